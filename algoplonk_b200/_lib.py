@@ -1,0 +1,88 @@
+"""ctypes binding of libb200plonk.so (include/b200plonk.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+usable, every entry point raises.  Build with `python -c "import
+__graft_entry__ as g; g.build()"` or `make -C algoplonk_b200/csrc -j8`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200plonk.so")
+
+B2P_BN254, B2P_BLS12_381 = 0, 1
+BASIS_CANONICAL, BASIS_LAGRANGE = 0, 1
+NTT_INVERSE, NTT_COSET = 1, 2
+STAT_NAMES = ["total_ms", "msm_ms", "msm_accum_ms", "ntt_ms", "quotient_ms", "msm_calls", "msm_accum_adds",
+              "h2d_bytes", "d2h_bytes", "launches"]
+STAT_COUNT = 16
+
+# every symbol include/b200plonk.h declares: (name, restype, argtypes)
+_vp, _u64, _u32, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+SYMBOLS = [
+    ("b2p_init", _int, [_int]),
+    ("b2p_last_error", C.c_char_p, []),
+    ("b2p_version", C.c_char_p, []),
+    ("b2p_launch_count", _u64, []),
+    ("b2p_srs_load", _int, [_int, _vp, _u64, _vp, _u64, C.POINTER(_vp)]),
+    ("b2p_srs_generate_unsafe", _int, [_int, _vp, _u64, C.POINTER(_vp)]),
+    ("b2p_srs_get_points", _int, [_vp, _u64, _u64, _vp]),
+    ("b2p_srs_size", _u64, [_vp]),
+    ("b2p_srs_msm_params", _int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_u64)]),
+    ("b2p_srs_free", None, [_vp]),
+    ("b2p_msm_g1", _int, [_vp, _int, _vp, _u64, _vp]),
+    ("b2p_ntt", _int, [_int, _vp, _u64, _int]),
+    ("b2p_circuit_load", _int, [_vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _u64,
+                                C.POINTER(_vp)]),
+    ("b2p_circuit_vk_commitments", _int, [_vp, _vp]),
+    ("b2p_circuit_free", None, [_vp]),
+    ("b2p_proof_raw_size", _u64, [_int, _u32]),
+    ("b2p_prove", _int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("b2p_proof_marshal_size", _u64, [_int, _u32]),
+    ("b2p_marshal_proof", _int, [_int, _u32, _vp, _vp, _vp]),
+    ("b2p_marshal_public_inputs", _int, [_int, _vp, _u32, _vp]),
+    ("b2p_circuit_set_profiling", _int, [_vp, _int]),
+    ("b2p_circuit_stats", _int, [_vp, C.POINTER(C.c_double)]),
+]
+
+
+class B200PlonkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200plonk error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the shared library and binds every declared symbol (no GPU needed for this)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build the CUDA extension first (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)   # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200PlonkError(rc, load().b2p_last_error().decode())
+
+
+_initialised = False
+
+
+def init(device: int = -1) -> None:
+    """b2p_init: raises B200PlonkError when no CUDA device is usable."""
+    global _initialised
+    check(load().b2p_init(device))
+    _initialised = True

@@ -1,0 +1,299 @@
+"""Host-side mirror of AlgoPlonk's public API for the proving path, bound to the
+CUDA library through the C ABI.
+
+Reference surface mirrored (same names, argument meaning and error behaviour):
+  Compile(circuit, curve, setup)            /root/reference/algoplonk.go:37-59
+  (*CompiledCircuit).Verify(assignment)     /root/reference/algoplonk.go:79-98  (witness -> Prove -> verify)
+  MarshalProof / MarshalPublicInputs        /root/reference/helper.go:13-24,91-110
+  setup names                                /root/reference/setup/setup.go:23-36
+In the real integration these stay Go (go/gpuplonk); this module
+is the harness tests and bench.py use to drive the same C entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+from . import _lib
+from . import frontend as fe
+
+# ---- curve ids / setup registry (setup/setup.go:23-36) -----------------------
+BN254, BLS12_381 = "BN254", "BLS12_381"
+CURVE_ID = {BN254: _lib.B2P_BN254, BLS12_381: _lib.B2P_BLS12_381}
+R_MOD = fe.R_MOD
+P_MOD = {
+    BN254: 21888242871839275222246405745257275088696311157297823662689037894645226208583,
+    BLS12_381: 4002409555221667393417789825735904156556882819939007885332058136124031650490837864442687629129015664037894272559787,
+}
+FP_BYTES = {BN254: 32, BLS12_381: 48}
+
+
+class SetupName:
+    TestOnlyBN254 = 0
+    TestOnlyBLS12381 = 1
+    PerpetualPowersOfTauBN254 = 2
+    EthereumKzgCeremonyBLS12381 = 3
+    DuskBLS12381 = 4
+
+
+_SETUPS = {
+    SetupName.TestOnlyBN254: (BN254, False),
+    SetupName.TestOnlyBLS12381: (BLS12_381, False),
+    SetupName.PerpetualPowersOfTauBN254: (BN254, True),
+    SetupName.EthereumKzgCeremonyBLS12381: (BLS12_381, True),
+    SetupName.DuskBLS12381: (BLS12_381, True),
+}
+
+# fixed tau of the TestOnly setups in this harness (unsafekzg draws a random one)
+TEST_TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+
+
+# ---- conversions between Python ints and gnark's in-memory layout -------------
+def fr_to_mont_bytes(curve: str, values: Sequence[int]) -> bytes:
+    r = R_MOD[curve]
+    R = 1 << 256
+    return b"".join(((v % r) * R % r).to_bytes(32, "little") for v in values)
+
+
+def fr_from_mont_bytes(curve: str, data: bytes) -> List[int]:
+    r = R_MOD[curve]
+    Rinv = pow(1 << 256, -1, r)
+    return [int.from_bytes(data[i:i + 32], "little") * Rinv % r for i in range(0, len(data), 32)]
+
+
+def points_to_mont_bytes(curve: str, points) -> bytes:
+    """affine (x, y) ints or None (infinity) -> G1Affine memory layout."""
+    p, nb = P_MOD[curve], FP_BYTES[curve]
+    R = 1 << (8 * nb)
+    out = bytearray()
+    for P in points:
+        if P is None:
+            out += bytes(2 * nb)
+        else:
+            out += (P[0] * R % p).to_bytes(nb, "little") + (P[1] * R % p).to_bytes(nb, "little")
+    return bytes(out)
+
+
+def points_from_mont_bytes(curve: str, data: bytes):
+    p, nb = P_MOD[curve], FP_BYTES[curve]
+    Rinv = pow(1 << (8 * nb), -1, p)
+    out = []
+    for i in range(0, len(data), 2 * nb):
+        x = int.from_bytes(data[i:i + nb], "little") * Rinv % p
+        y = int.from_bytes(data[i + nb:i + 2 * nb], "little") * Rinv % p
+        out.append(None if x == 0 and y == 0 else (x, y))
+    return out
+
+
+def _buf(data: bytes):
+    return C.create_string_buffer(data, len(data))
+
+
+# ---- SRS ------------------------------------------------------------------------
+class SRS:
+    """kzg.SRS resident on the GPU (canonical basis + windowed multiples)."""
+
+    def __init__(self, curve: str, handle: int, tau: Optional[int] = None):
+        self.curve, self.handle, self.tau = curve, handle, tau
+
+    @classmethod
+    def from_points(cls, curve: str, points) -> "SRS":
+        """points: affine int pairs, or bytes already in G1Affine layout."""
+        _lib.init()
+        data = points if isinstance(points, (bytes, bytearray)) else points_to_mont_bytes(curve, points)
+        n = len(data) // (2 * FP_BYTES[curve])
+        h = C.c_void_p()
+        buf = _buf(bytes(data))
+        _lib.check(_lib.load().b2p_srs_load(CURVE_ID[curve], buf, n, None, 0, C.byref(h)))
+        return cls(curve, h.value)
+
+    @classmethod
+    def unsafe(cls, curve: str, size: int, tau: int = TEST_TAU) -> "SRS":
+        """unsafekzg.NewSRS (setup/setup.go:102-108)."""
+        _lib.init()
+        h = C.c_void_p()
+        t = _buf(fr_to_mont_bytes(curve, [tau]))
+        _lib.check(_lib.load().b2p_srs_generate_unsafe(CURVE_ID[curve], t, size, C.byref(h)))
+        return cls(curve, h.value, tau % R_MOD[curve])
+
+    @property
+    def size(self) -> int:
+        return _lib.load().b2p_srs_size(self.handle)
+
+    def msm_params(self):
+        c, w, b = C.c_int(), C.c_int(), C.c_uint64()
+        _lib.check(_lib.load().b2p_srs_msm_params(self.handle, C.byref(c), C.byref(w), C.byref(b)))
+        return c.value, w.value, b.value
+
+    def points(self, first: int, count: int):
+        out = C.create_string_buffer(count * 2 * FP_BYTES[self.curve])
+        _lib.check(_lib.load().b2p_srs_get_points(self.handle, first, count, out))
+        return points_from_mont_bytes(self.curve, out.raw)
+
+    def msm(self, scalars: Sequence[int], basis: int = _lib.BASIS_CANONICAL):
+        """G1Affine.MultiExp / kzg.Commit: returns an affine int pair (None = infinity)."""
+        data = _buf(fr_to_mont_bytes(self.curve, scalars)) if len(scalars) else None
+        out = C.create_string_buffer(2 * FP_BYTES[self.curve])
+        _lib.check(_lib.load().b2p_msm_g1(self.handle, basis, data, len(scalars), out))
+        return points_from_mont_bytes(self.curve, out.raw)[0]
+
+    def msm_raw(self, scalars_mont: bytes, basis: int = _lib.BASIS_CANONICAL) -> bytes:
+        out = C.create_string_buffer(2 * FP_BYTES[self.curve])
+        _lib.check(_lib.load().b2p_msm_g1(self.handle, basis, _buf(scalars_mont), len(scalars_mont) // 32, out))
+        return out.raw
+
+    def free(self):
+        if self.handle:
+            _lib.load().b2p_srs_free(self.handle)
+            self.handle = None
+
+
+def ntt(curve: str, values: Sequence[int], inverse: bool = False, coset: bool = False) -> List[int]:
+    """fft.Domain.FFT / FFTInverse (natural order in and out)."""
+    _lib.init()
+    buf = _buf(fr_to_mont_bytes(curve, values))
+    flags = (_lib.NTT_INVERSE if inverse else 0) | (_lib.NTT_COSET if coset else 0)
+    _lib.check(_lib.load().b2p_ntt(CURVE_ID[curve], buf, len(values), flags))
+    return fr_from_mont_bytes(curve, buf.raw)
+
+
+# ---- proofs -----------------------------------------------------------------------
+@dataclass
+class Proof:
+    """plonk.Proof: raw = 9 G1Affine + (7+k) Fr in gnark memory layout, plus the BSB22 commitments."""
+    curve: str
+    k: int
+    raw: bytes
+    bsb22: bytes = b""
+
+
+@dataclass
+class VerifiedProof:
+    """algoplonk.go:28-31."""
+    Proof: Proof
+    Witness: List[int]          # public inputs (canonical ints)
+
+    def ExportProofAndPublicInputs(self, proof_path: str, public_inputs_path: str) -> None:
+        """algoplonk.go:103-131."""
+        with open(proof_path, "wb") as f:
+            f.write(MarshalProof(self.Proof))
+        with open(public_inputs_path, "wb") as f:
+            f.write(MarshalPublicInputs(self.Proof.curve, self.Witness))
+
+
+def MarshalProof(proof: Proof) -> bytes:
+    """helper.go:13-24."""
+    lib = _lib.load()
+    out = C.create_string_buffer(lib.b2p_proof_marshal_size(CURVE_ID[proof.curve], proof.k))
+    _lib.check(lib.b2p_marshal_proof(CURVE_ID[proof.curve], proof.k, _buf(proof.raw),
+                                     _buf(proof.bsb22) if proof.k else None, out))
+    return out.raw
+
+
+def MarshalPublicInputs(curve: str, public_values: Sequence[int]) -> bytes:
+    """helper.go:91-110 (public witness minus its 12-byte header)."""
+    lib = _lib.load()
+    n = len(public_values)
+    out = C.create_string_buffer(32 * n)
+    vals = _buf(fr_to_mont_bytes(curve, public_values)) if n else None
+    _lib.check(lib.b2p_marshal_public_inputs(CURVE_ID[curve], vals, n, out))
+    return out.raw
+
+
+# ---- compiled circuit ----------------------------------------------------------------
+class CompiledCircuit:
+    """algoplonk.go:21-26: Ccs + Pk + Vk + Curve, with Pk resident on the GPU."""
+
+    def __init__(self, cs: fe.SparseR1CS, trace: fe.TraceColumns, srs: SRS, handle: int):
+        self.Ccs, self.trace, self.srs, self.handle = cs, trace, srs, handle
+        self.Curve = cs.curve
+        self._vk_points = None
+
+    # verifying-key commitments S1 S2 S3 Ql Qr Qm Qo Qk Qcp* (affine ints)
+    def vk_commitments(self):
+        if self._vk_points is None:
+            k = len(self.trace.qcp)
+            out = C.create_string_buffer((8 + k) * 2 * FP_BYTES[self.Curve])
+            _lib.check(_lib.load().b2p_circuit_vk_commitments(self.handle, out))
+            self._vk_points = points_from_mont_bytes(self.Curve, out.raw)
+        return self._vk_points
+
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(_lib.load().b2p_circuit_set_profiling(self.handle, 1 if on else 0))
+
+    def stats(self) -> dict:
+        arr = (C.c_double * _lib.STAT_COUNT)()
+        _lib.check(_lib.load().b2p_circuit_stats(self.handle, arr))
+        return {name: arr[i] for i, name in enumerate(_lib.STAT_NAMES)}
+
+    def prove_raw(self, L: bytes, R: bytes, O: bytes, blinding: bytes, pi2: Sequence[bytes] = (),
+                  bsb22: bytes = b"") -> Proof:
+        """plonk.Prove on buffers already in gnark layout (what the Go shim passes)."""
+        lib = _lib.load()
+        k = len(self.trace.qcp)
+        cid = CURVE_ID[self.Curve]
+        out = C.create_string_buffer(lib.b2p_proof_raw_size(cid, k))
+        bufs = [_buf(p) for p in pi2]
+        arr = (C.c_void_p * max(k, 1))(*[C.cast(b, C.c_void_p) for b in bufs]) if k else None
+        _lib.check(lib.b2p_prove(self.handle, _buf(L) if not isinstance(L, C.Array) else L,
+                                 _buf(R) if not isinstance(R, C.Array) else R,
+                                 _buf(O) if not isinstance(O, C.Array) else O,
+                                 arr, _buf(bsb22) if k else None, _buf(blinding), out))
+        return Proof(self.Curve, k, out.raw, bsb22)
+
+    def Prove(self, L: Sequence[int], R: Sequence[int], O: Sequence[int], blinding: Sequence[int],
+              pi2: Sequence[Sequence[int]] = (), bsb22_points=()) -> Proof:
+        cv = self.Curve
+        return self.prove_raw(fr_to_mont_bytes(cv, L), fr_to_mont_bytes(cv, R), fr_to_mont_bytes(cv, O),
+                              fr_to_mont_bytes(cv, blinding), [fr_to_mont_bytes(cv, v) for v in pi2],
+                              points_to_mont_bytes(cv, bsb22_points))
+
+    def Verify(self, L, R, O, blinding, pi2=(), bsb22_points=(), verifier: Optional[Callable] = None) -> VerifiedProof:
+        """algoplonk.go:79-98: prove, then check the proof with `verifier(proof_bytes, public_bytes)`
+        (plonk.Verify in the reference; tests inject the oracle's restatement of the AVM verifier)."""
+        proof = self.Prove(L, R, O, blinding, pi2, bsb22_points)
+        public = [v % R_MOD[self.Curve] for v in L[: self.trace.nb_public]]
+        if verifier is not None:
+            if not verifier(MarshalProof(proof), MarshalPublicInputs(self.Curve, public)):
+                raise ValueError("error verifying proof")
+        return VerifiedProof(proof, public)
+
+    def free(self):
+        if self.handle:
+            _lib.load().b2p_circuit_free(self.handle)
+            self.handle = None
+
+
+def Compile(cs: fe.SparseR1CS, curve: str, setup_name: int, srs: Optional[SRS] = None) -> CompiledCircuit:
+    """algoplonk.go:37-59.  `cs` is the already-built constraint system (gnark's frontend.Compile
+    stays on the CPU); a trusted setup needs its SRS passed in (the embedded pk.bin files of the
+    reference are loaded by the caller, setup/setup.go:196-228)."""
+    if curve not in CURVE_ID:
+        raise ValueError(f"unsupported curve: {curve}")
+    if setup_name not in _SETUPS:
+        raise ValueError(f"unknown setup: {setup_name}")
+    s_curve, trusted = _SETUPS[setup_name]
+    if s_curve != curve:
+        raise ValueError("curve and trusted setup do not match")
+    if cs.curve != curve:
+        raise ValueError("constraint system was built for another curve")
+    _lib.init()
+    tc = fe.build_trace(cs)
+    n = tc.n
+    if srs is None:
+        if trusted:
+            raise ValueError("trusted setups need their SRS points (pk.bin) passed in")
+        srs = SRS.unsafe(curve, n + 3)
+    if srs.size < n + 3:
+        raise ValueError(f"pk.bin too small for {n + 3} elements")      # setup/setup.go:219-223
+    lib = _lib.load()
+    cols = [_buf(fr_to_mont_bytes(curve, c)) for c in (tc.ql, tc.qr, tc.qm, tc.qo, tc.qk)]
+    perm = (C.c_int64 * (3 * n))(*tc.perm)
+    k = len(tc.qcp)
+    qcp_bufs = [_buf(fr_to_mont_bytes(curve, c)) for c in tc.qcp]
+    qcp_arr = (C.c_void_p * max(k, 1))(*[C.cast(b, C.c_void_p) for b in qcp_bufs]) if k else None
+    cidx = (C.c_uint64 * max(k, 1))(*tc.commitment_constraint_indexes) if k else None
+    h = C.c_void_p()
+    _lib.check(lib.b2p_circuit_load(srs.handle, n, tc.nb_public, *cols, perm, k, qcp_arr, cidx, None, 0, C.byref(h)))
+    return CompiledCircuit(cs, tc, srs, h.value)

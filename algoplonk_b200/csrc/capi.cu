@@ -1,0 +1,180 @@
+// extern "C" surface of libb200plonk.so -- see include/b200plonk.h for the contract
+// and the reference interface each entry point replaces.  This file only does
+// argument checking, curve dispatch and error translation; the work is in the
+// per-curve instantiations (inst_*.cu).
+#include <cuda_runtime.h>
+#include <cstring>
+#include <new>
+#include <string>
+#include "../../include/b200plonk.h"
+#include "iface.hpp"
+
+namespace b2p {
+unsigned long long g_launch_count = 0;
+}
+using namespace b2p;
+
+#define API extern "C" __attribute__((visibility("default")))
+
+static thread_local std::string g_err;
+
+static void require(bool cond, const char* msg) {
+    if (!cond) throw Error(B2P_ERR_ARG, msg);
+}
+
+template <class Fn>
+static int guarded(Fn fn) {
+    try {
+        fn();
+        return B2P_OK;
+    } catch (const Error& e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_err = "host allocation failed";
+        return B2P_ERR_INTERNAL;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return B2P_ERR_INTERNAL;
+    } catch (...) {
+        g_err = "unknown error";
+        return B2P_ERR_INTERNAL;
+    }
+}
+
+static const CurveOps* ops_for(int curve) {
+    if (curve == B2P_BN254) return curve_ops_bn254();
+    if (curve == B2P_BLS12_381) return curve_ops_bls12381();
+    throw Error(B2P_ERR_ARG, "unsupported curve id (B2P_BN254 = 0, B2P_BLS12_381 = 1)");
+}
+
+API const char* b2p_last_error(void) { return g_err.c_str(); }
+API const char* b2p_version(void) { return "b200plonk 0.1 (sm_100a)"; }
+API uint64_t b2p_launch_count(void) { return g_launch_count; }
+
+API int b2p_init(int device) {
+    return guarded([&] {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error(B2P_ERR_CUDA, std::string("CUDA error: no usable device: ") + cudaGetErrorString(e));
+        if (device >= 0) {
+            require(device < count, "device index out of range");
+            e = cudaSetDevice(device);
+            if (e != cudaSuccess) throw Error(B2P_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+        }
+        e = cudaFree(nullptr);
+        if (e != cudaSuccess) throw Error(B2P_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    });
+}
+
+API int b2p_srs_load(int curve, const void* g1, uint64_t n_can, const void* g1_lag, uint64_t n_lag, b2p_srs** out) {
+    (void)g1_lag; (void)n_lag;   // see header: Lagrange commitments are iNTT + canonical MSM
+    return guarded([&] {
+        require(g1 && out, "null argument");
+        SrsBase* s = ops_for(curve)->new_srs();
+        try { s->load(g1, n_can); } catch (...) { delete s; throw; }
+        *out = reinterpret_cast<b2p_srs*>(s);
+    });
+}
+
+API int b2p_srs_generate_unsafe(int curve, const void* tau, uint64_t n_can, b2p_srs** out) {
+    return guarded([&] {
+        require(tau && out, "null argument");
+        SrsBase* s = ops_for(curve)->new_srs();
+        try { s->generate_unsafe(tau, n_can); } catch (...) { delete s; throw; }
+        *out = reinterpret_cast<b2p_srs*>(s);
+    });
+}
+
+API int b2p_srs_get_points(const b2p_srs* srs, uint64_t first, uint64_t count, void* out) {
+    return guarded([&] {
+        require(srs && out, "null argument");
+        reinterpret_cast<const SrsBase*>(srs)->get_points(first, count, out);
+    });
+}
+API uint64_t b2p_srs_size(const b2p_srs* srs) { return srs ? reinterpret_cast<const SrsBase*>(srs)->size() : 0; }
+API int b2p_srs_msm_params(const b2p_srs* srs, int* c, int* windows, uint64_t* buckets) {
+    return guarded([&] {
+        require(srs, "null argument");
+        reinterpret_cast<const SrsBase*>(srs)->msm_params(c, windows, buckets);
+    });
+}
+API void b2p_srs_free(b2p_srs* srs) { delete reinterpret_cast<SrsBase*>(srs); }
+
+API int b2p_msm_g1(b2p_srs* srs, int basis, const void* scalars, uint64_t n, void* out_affine) {
+    return guarded([&] {
+        require(srs && out_affine && (scalars || n == 0), "null argument");
+        reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, scalars, n, out_affine);
+    });
+}
+
+API int b2p_ntt(int curve, void* data, uint64_t n, int flags) {
+    return guarded([&] {
+        require(data, "null argument");
+        ops_for(curve)->ntt(data, n, flags);
+    });
+}
+
+API int b2p_circuit_load(b2p_srs* srs, uint64_t n, uint32_t nb_public, const void* ql, const void* qr, const void* qm,
+                         const void* qo, const void* qk, const int64_t* perm, uint32_t k, const void* const* qcp,
+                         const uint64_t* cidx, const void* vkb, uint64_t vkb_len, b2p_circuit** out) {
+    return guarded([&] {
+        require(srs && ql && qr && qm && qo && qk && perm && out, "null argument");
+        require(k == 0 || (qcp && cidx), "BSB22 columns missing");
+        SrsBase* s = reinterpret_cast<SrsBase*>(srs);
+        CircuitBase* c = ops_for(s->curve)->new_circuit();
+        try { c->load(s, n, nb_public, ql, qr, qm, qo, qk, perm, k, qcp, cidx, vkb, vkb_len); }
+        catch (...) { delete c; throw; }
+        *out = reinterpret_cast<b2p_circuit*>(c);
+    });
+}
+API int b2p_circuit_vk_commitments(b2p_circuit* c, void* out_points) {
+    return guarded([&] {
+        require(c && out_points, "null argument");
+        reinterpret_cast<CircuitBase*>(c)->vk_commitments(out_points);
+    });
+}
+API void b2p_circuit_free(b2p_circuit* c) { delete reinterpret_cast<CircuitBase*>(c); }
+
+API uint64_t b2p_proof_raw_size(int curve, uint32_t k) {
+    const uint64_t pt = curve == B2P_BN254 ? 64 : 96;
+    return 9 * pt + (7 + (uint64_t)k) * 32;
+}
+
+API int b2p_prove(b2p_circuit* c, const void* L, const void* R, const void* O, const void* const* pi2,
+                  const void* bsb22, const void* blinding, void* out_raw) {
+    return guarded([&] {
+        require(c && L && R && O && blinding && out_raw, "null argument");
+        reinterpret_cast<CircuitBase*>(c)->prove(L, R, O, pi2, bsb22, blinding, out_raw);
+    });
+}
+
+API uint64_t b2p_proof_marshal_size(int curve, uint32_t k) {
+    return curve == B2P_BN254 ? (24 + 3 * (uint64_t)k) * 32 : (33 + 4 * (uint64_t)k) * 32;
+}
+API int b2p_marshal_proof(int curve, uint32_t k, const void* raw, const void* bsb22, void* out_bytes) {
+    return guarded([&] {
+        require(raw && out_bytes && (k == 0 || bsb22), "null argument");
+        ops_for(curve)->marshal_proof(k, raw, bsb22, static_cast<uint8_t*>(out_bytes));
+    });
+}
+API int b2p_marshal_public_inputs(int curve, const void* values, uint32_t nb_public, void* out_bytes) {
+    return guarded([&] {
+        require((values && out_bytes) || nb_public == 0, "null argument");
+        ops_for(curve)->marshal_public_inputs(values, nb_public, static_cast<uint8_t*>(out_bytes));
+    });
+}
+
+API int b2p_circuit_set_profiling(b2p_circuit* c, int enable) {
+    return guarded([&] {
+        require(c, "null argument");
+        reinterpret_cast<CircuitBase*>(c)->set_profiling(enable != 0);
+    });
+}
+API int b2p_circuit_stats(const b2p_circuit* c, double* out) {
+    return guarded([&] {
+        require(c && out, "null argument");
+        memcpy(out, reinterpret_cast<const CircuitBase*>(c)->stats, sizeof(double) * B2P_STAT_COUNT);
+    });
+}

@@ -1,0 +1,235 @@
+// Prime-field arithmetic in Montgomery form, 32-bit limbs, register resident.
+// One template serves the four fields of the hot path; the in-memory layout is
+// gnark-crypto's fr.Element / fp.Element (little-endian limbs, R = 2^(32N)), so
+// buffers handed over the C-ABI by the Go shim are used as they are
+// ("pass unsafe.Pointer(&pk.Kzg.G1[0])").
+#pragma once
+#include <cstdint>
+#include "ptx.cuh"
+#include "field_params.cuh"
+
+namespace b2p {
+
+template <class P>
+struct Field {
+    static constexpr int N = P::N;
+    using Params = P;
+    uint32_t v[N];
+
+    // ---- constants ------------------------------------------------------
+    HD static Field zero() {
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r;
+    }
+    HD static Field one() {
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+        return r;
+    }
+    HD static Field r2() {
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::r2(i);
+        return r;
+    }
+    HD static Field modulus() {
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::mod(i);
+        return r;
+    }
+
+    HD bool is_zero() const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i];
+        return acc == 0;
+    }
+    HD bool operator==(const Field& o) const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i] ^ o.v[i];
+        return acc == 0;
+    }
+    HD bool operator!=(const Field& o) const { return !(*this == o); }
+
+    // ---- add / sub ------------------------------------------------------
+    // r = a - p if a >= p else a   (a < 2p)
+    HD static void final_sub(uint32_t* a) {
+        uint32_t t[N];
+        t[0] = ptx::sub_cc(a[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(a[i], P::mod(i));
+        uint32_t borrow = ptx::subc(0, 0);   // 0 or 0xffffffff
+#pragma unroll
+        for (int i = 0; i < N; i++) a[i] = borrow ? a[i] : t[i];
+    }
+
+    HD friend Field operator+(const Field& a, const Field& b) {
+        Field r;
+        r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+        r.v[N - 1] = ptx::addc(a.v[N - 1], b.v[N - 1]);   // moduli leave >= 1 spare bit: no carry out
+        final_sub(r.v);
+        return r;
+    }
+
+    HD friend Field operator-(const Field& a, const Field& b) {
+        Field r;
+        r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+        uint32_t borrow = ptx::subc(0, 0);
+        // add p back when the subtraction borrowed (masked add keeps it branch-free)
+        uint32_t t0 = ptx::add_cc(r.v[0], P::mod(0) & borrow);
+        r.v[0] = t0;
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(r.v[i], P::mod(i) & borrow);
+        r.v[N - 1] = ptx::addc(r.v[N - 1], P::mod(N - 1) & borrow);
+        return r;
+    }
+
+    HD Field neg() const { return is_zero() ? *this : (modulus_raw_sub(*this)); }
+
+    HD static Field modulus_raw_sub(const Field& a) {   // p - a, a != 0
+        Field r;
+        r.v[0] = ptx::sub_cc(P::mod(0), a.v[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = ptx::subc_cc(P::mod(i), a.v[i]);
+        r.v[N - 1] = ptx::subc(P::mod(N - 1), a.v[N - 1]);
+        return r;
+    }
+
+    HD Field dbl() const { return *this + *this; }
+
+    // ---- Montgomery multiplication --------------------------------------
+    // Coarsely-integrated operand scanning with the products of even and odd
+    // limbs of `a` kept in two accumulators, so that every (lo,hi) pair lands on
+    // adjacent registers of one carry chain: ptxas fuses each
+    // mad.lo.cc/madc.hi.cc pair into one IMAD.WIDE.U32(.X).
+    //   acc[j] of `even` is column j, acc[j] of `odd` is column j+1.
+
+    // acc[0..N) = a[0], a[2], ... times bi (disjoint 64-bit products)
+    HD static void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            acc[j] = ptx::mul_lo(a[j], bi);
+            acc[j + 1] = ptx::mul_hi(a[j], bi);
+        }
+    }
+    // acc += a[0], a[2], ... times bi; leaves the carry out in CC
+    HD static void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+        acc[0] = ptx::mad_lo_cc(a[0], bi, acc[0]);
+        acc[1] = ptx::madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j]);
+            acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 1]);
+        }
+    }
+    // same, modulus limbs as the multiplicand (compile-time immediates)
+    template <int OFF>
+    HD static void cmad_mod(uint32_t* acc, uint32_t mi) {
+        acc[0] = ptx::mad_lo_cc(P::mod(OFF), mi, acc[0]);
+        acc[1] = ptx::madc_hi_cc(P::mod(OFF), mi, acc[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            acc[j] = ptx::madc_lo_cc(P::mod(OFF + j), mi, acc[j]);
+            acc[j + 1] = ptx::madc_hi_cc(P::mod(OFF + j), mi, acc[j + 1]);
+        }
+    }
+    // odd[j] = a[j]*bi + odd[j+2] with the incoming carry (CC), i.e. add and shift right by two limbs
+    HD static void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < N - 2; j += 2) {
+            odd[j] = ptx::madc_lo_cc(a[j], bi, odd[j + 2]);
+            odd[j + 1] = ptx::madc_hi_cc(a[j], bi, odd[j + 3]);
+        }
+        odd[N - 2] = ptx::madc_lo_cc(a[N - 2], bi, 0);
+        odd[N - 1] = ptx::madc_hi(a[N - 2], bi, 0);
+    }
+    template <bool FIRST>
+    HD static void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
+        if (FIRST) {
+            mul_n(odd, a + 1, bi);
+            mul_n(even, a, bi);
+        } else {
+            even[0] = ptx::add_cc(even[0], odd[1]);
+            madc_n_rshift(odd, a + 1, bi);
+            cmad_n(even, a, bi);
+            odd[N - 1] = ptx::addc(odd[N - 1], 0);
+        }
+        uint32_t mi = even[0] * P::INV;
+        cmad_mod<1>(odd, mi);
+        cmad_mod<0>(even, mi);
+        odd[N - 1] = ptx::addc(odd[N - 1], 0);
+    }
+
+    HD friend Field operator*(const Field& a, const Field& b) {
+        uint32_t even[N], odd[N];
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            if (i == 0) mad_n_redc<true>(even, odd, a.v, b.v[0]);
+            else        mad_n_redc<false>(even, odd, a.v, b.v[i]);
+            mad_n_redc<false>(odd, even, a.v, b.v[i + 1]);
+        }
+        // merge: result column j = even[j] + odd[j+1]
+        Field r;
+        r.v[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(even[i], odd[i + 1]);
+        r.v[N - 1] = ptx::addc(even[N - 1], 0);
+        final_sub(r.v);
+        return r;
+    }
+
+    HD Field sqr() const { return (*this) * (*this); }
+
+    HD Field& operator+=(const Field& o) { *this = *this + o; return *this; }
+    HD Field& operator-=(const Field& o) { *this = *this - o; return *this; }
+    HD Field& operator*=(const Field& o) { *this = *this * o; return *this; }
+
+    // ---- conversions ----------------------------------------------------
+    HD Field to_mont() const { return (*this) * r2(); }
+    HD Field from_mont() const {
+        Field o = zero();
+        o.v[0] = 1;
+        return (*this) * o;
+    }
+    HD static Field from_u32(uint32_t x) {
+        Field o = zero();
+        o.v[0] = x;
+        return o.to_mont();
+    }
+
+    // ---- exponentiation / inversion -------------------------------------
+    HDN Field pow_u64(uint64_t e) const {
+        Field acc = one(), base = *this;
+        while (e) {
+            if (e & 1) acc = acc * base;
+            base = base.sqr();
+            e >>= 1;
+        }
+        return acc;
+    }
+    // a^(p-2); zero maps to zero (gnark's Inverse convention)
+    HDN Field inverse() const {
+        Field acc = one();
+        for (int i = P::BITS - 1; i >= 0; i--) {
+            acc = acc.sqr();
+            if ((P::pm2(i >> 5) >> (i & 31)) & 1) acc = acc * (*this);
+        }
+        return acc;
+    }
+};
+
+using FrBn254 = Field<Bn254FrParams>;
+using FpBn254 = Field<Bn254FpParams>;
+using FrBls12381 = Field<Bls12381FrParams>;
+using FpBls12381 = Field<Bls12381FpParams>;
+
+}  // namespace b2p

@@ -1,0 +1,53 @@
+// Curve-erased interfaces between the C ABI (capi.cu) and the per-curve
+// template instantiations (inst_prover_*.cu).  Keeping capi.cu free of the
+// templates keeps its compile time in seconds.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+namespace b2p {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+struct SrsBase {
+    int curve = -1;
+    virtual ~SrsBase() {}
+    virtual void load(const void* points, uint64_t n) = 0;
+    virtual void generate_unsafe(const void* tau, uint64_t n) = 0;
+    virtual void get_points(uint64_t first, uint64_t count, void* out) const = 0;
+    virtual uint64_t size() const = 0;
+    virtual void msm_params(int* c, int* windows, uint64_t* buckets) const = 0;
+    virtual void msm_g1(int basis, const void* scalars, uint64_t n, void* out_affine) = 0;
+};
+
+struct CircuitBase {
+    int curve = -1;
+    double stats[16] = {0};
+    virtual ~CircuitBase() {}
+    virtual void load(SrsBase* srs, uint64_t n, uint32_t nb_public, const void* ql, const void* qr, const void* qm,
+                      const void* qo, const void* qk, const int64_t* perm, uint32_t k, const void* const* qcp,
+                      const uint64_t* cidx, const void* vkb, uint64_t vkb_len) = 0;
+    virtual void vk_commitments(void* out_points) = 0;
+    virtual void prove(const void* L, const void* R, const void* O, const void* const* pi2, const void* bsb22,
+                       const void* blinding, void* out_raw) = 0;
+    virtual void set_profiling(bool on) = 0;
+};
+
+struct CurveOps {
+    virtual ~CurveOps() {}
+    virtual SrsBase* new_srs() const = 0;
+    virtual CircuitBase* new_circuit() const = 0;
+    virtual void ntt(void* data, uint64_t n, int flags) const = 0;
+    virtual void marshal_proof(uint32_t k, const void* raw, const void* bsb22, uint8_t* out) const = 0;
+    virtual void marshal_public_inputs(const void* values, uint32_t nb_public, uint8_t* out) const = 0;
+};
+const CurveOps* curve_ops_bn254();
+const CurveOps* curve_ops_bls12381();
+
+extern unsigned long long g_launch_count;
+
+}  // namespace b2p

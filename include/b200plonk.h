@@ -1,0 +1,153 @@
+/* b200plonk.h -- C ABI of the B200-native PLONK prover.
+ *
+ * This is the drop-in boundary for the one hot call AlgoPlonk makes:
+ *
+ *     proof, err := plonk.Prove(cc.Ccs, cc.Pk, witness)     reference algoplonk.go:89
+ *                                                           (and testutils/testutils.go:47)
+ *
+ * The reference has no FFI of its own (pure Go over gnark v0.15.0 / gnark-crypto
+ * v0.20.1, go.mod:8-9); the entry points below are what a cgo shim with the
+ * signature of plonk.Prove binds (go/gpuplonk/prove.go).  Every
+ * buffer uses gnark-crypto's in-memory layout so the shim passes
+ * unsafe.Pointer(&slice[0]) with no conversion:
+ *
+ *   Fr        32 bytes : 4 x u64 little-endian limbs, Montgomery form (R = 2^256)
+ *   G1Affine  BN254 64 bytes / BLS12-381 96 bytes : X || Y, each Fp in Montgomery
+ *             form (R = 2^256 / 2^384), little-endian limbs; (0,0) = infinity.
+ *
+ * All functions return 0 on success and a negative code on failure; the message
+ * is available from b2p_last_error() (thread local).  Nothing aborts, nothing
+ * throws across the boundary, no caller pointer is retained after a call returns
+ * (cgo rule).  Handles may be used from any thread, one call at a time per handle.
+ */
+#ifndef B200PLONK_H
+#define B200PLONK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2P_BN254      0   /* ecc.BN254      (algoplonk.go:39) */
+#define B2P_BLS12_381  1   /* ecc.BLS12_381  (algoplonk.go:39) */
+
+#define B2P_OK             0
+#define B2P_ERR_ARG       -1   /* bad argument / unsupported size */
+#define B2P_ERR_CUDA      -2   /* CUDA runtime failure (no device, OOM, launch error) */
+#define B2P_ERR_INTERNAL  -3
+
+#define B2P_BASIS_CANONICAL 0  /* pk.Kzg          : [tau^j]_1            */
+#define B2P_BASIS_LAGRANGE  1  /* pk.KzgLagrange  : [L_j(tau)]_1, size n */
+
+typedef struct b2p_srs b2p_srs;
+typedef struct b2p_circuit b2p_circuit;
+
+/* ---- process -------------------------------------------------------------- */
+
+/* Selects the CUDA device for the calling thread's subsequent handle creation
+ * (-1 keeps the current device).  Fails with B2P_ERR_CUDA when no GPU is usable:
+ * there is no CPU fallback inside this library. */
+int b2p_init(int device);
+const char* b2p_last_error(void);
+const char* b2p_version(void);
+/* Kernel launches issued by this library since process start (for bench.py's gpu_launches). */
+uint64_t b2p_launch_count(void);
+
+/* ---- SRS  (replaces: kzg.SRS as loaded by setup/setup.go:165-193) ---------- */
+
+/* g1_canonical: n_can points [tau^j]_1 (what srs.Pk.ReadFrom produced, setup.go:173,189).
+ * g1_lagrange : optional (may be NULL, n_lag = 0).  Lagrange-basis commitments are
+ * computed as iNTT + canonical MSM, which is the same group element as
+ * MSM(kzg.ToLagrangeG1(...)) (setup.go:124,138); the argument exists so the shim
+ * can pass the whole gnark ProvingKey.  Builds the windowed point table in HBM. */
+int b2p_srs_load(int curve, const void* g1_canonical, uint64_t n_can,
+                 const void* g1_lagrange, uint64_t n_lag, b2p_srs** out);
+
+/* unsafekzg.NewSRS (setup.go:102-108, the TestOnly setups): [tau^j]_1 for j < n_can,
+ * generated on the device from a known tau (Fr, Montgomery form). */
+int b2p_srs_generate_unsafe(int curve, const void* tau, uint64_t n_can, b2p_srs** out);
+
+/* Copies canonical points [first, first+count) back to the host (G1Affine layout). */
+int b2p_srs_get_points(const b2p_srs* srs, uint64_t first, uint64_t count, void* out);
+uint64_t b2p_srs_size(const b2p_srs* srs);
+/* window bits / number of windows / buckets chosen for this SRS (reporting) */
+int b2p_srs_msm_params(const b2p_srs* srs, int* c, int* windows, uint64_t* buckets);
+void b2p_srs_free(b2p_srs* srs);
+
+/* ---- primitives (replace gnark-crypto G1Affine.MultiExp / fft.Domain.FFT) -- */
+
+/* out_affine = sum_i scalars[i] * basis[i], n <= SRS size (Lagrange: n a power of two).
+ * Used by the shim for the BSB22 commitment hint (kzg.Commit on pk.KzgLagrange). */
+int b2p_msm_g1(b2p_srs* srs, int basis, const void* scalars, uint64_t n, void* out_affine);
+
+#define B2P_NTT_INVERSE   1   /* FFTInverse (includes the 1/n scaling) */
+#define B2P_NTT_COSET     2   /* on the coset FrMultiplicativeGen * <omega> */
+/* In-place, natural order in and out (gnark: FFT(DIF)+BitReverse / BitReverse+FFTInverse(DIT)). */
+int b2p_ntt(int curve, void* data, uint64_t n, int flags);
+
+/* ---- circuit (replaces: the trace + domains inside gnark's plonk.ProvingKey) */
+
+/* ql..qk: Lagrange-form selector columns, n Fr each (pk trace; qk WITHOUT public inputs).
+ * perm  : gnark trace.S, 3n entries.
+ * qcp / commitment_constraint_idx: k BSB22 selector columns and vk.CommitmentConstraintIndexes.
+ * vk_transcript: the bytes gnark binds into the gamma challenge before the public inputs
+ *   (S1 S2 S3 Ql Qr Qm Qo Qk Qcp*, G1Affine.Marshal() each; reference
+ *   verifier/templateLogicSigBN254.go:131-132).  NULL: the library commits to the
+ *   columns itself (what plonk.Setup does, setup.go:149) and derives the bytes. */
+int b2p_circuit_load(b2p_srs* srs, uint64_t n, uint32_t nb_public,
+                     const void* ql, const void* qr, const void* qm, const void* qo, const void* qk,
+                     const int64_t* perm, uint32_t k, const void* const* qcp,
+                     const uint64_t* commitment_constraint_idx,
+                     const void* vk_transcript, uint64_t vk_transcript_len,
+                     b2p_circuit** out);
+/* The verifying key's commitments: 8+k G1Affine in the order S1 S2 S3 Ql Qr Qm Qo Qk Qcp*. */
+int b2p_circuit_vk_commitments(b2p_circuit* c, void* out_points);
+void b2p_circuit_free(b2p_circuit* c);
+
+/* ---- prove (replaces: plonk.Prove, algoplonk.go:89) ------------------------ */
+
+/* Raw proof = 9 G1Affine (LRO[0..2], Z, H[0..2], BatchedProof.H, ZShiftedOpening.H)
+ * followed by 7+k Fr (BatchedProof.ClaimedValues[0..5+k], ZShiftedOpening.ClaimedValue),
+ * all in gnark's in-memory layout: the shim memcpy's them into *plonk_bn254.Proof. */
+uint64_t b2p_proof_raw_size(int curve, uint32_t k);
+
+/* L, R, O  : solved wire columns (Lagrange, n Fr each) from gnark's solver.
+ * pi2      : k committed-value columns (Lagrange, n Fr each), NULL when k = 0.
+ * bsb22    : k G1Affine commitments (proof.Bsb22Commitments), NULL when k = 0.
+ * blinding : 9 Fr  bl0 bl1 br0 br1 bo0 bo1 bz0 bz1 bz2  -- the coefficients gnark draws
+ *            with fr.SetRandom for the blinding polynomials b_L, b_R, b_O (order 1) and
+ *            b_Z (order 2).  They are an INPUT so that proofs are reproducible
+ *            bit for bit; the shim draws them from crypto/rand. */
+int b2p_prove(b2p_circuit* c, const void* L, const void* R, const void* O,
+              const void* const* pi2, const void* bsb22,
+              const void* blinding, void* out_proof_raw);
+
+/* ---- marshalling (replaces: MarshalProof / MarshalPublicInputs, helper.go:13-110) */
+
+uint64_t b2p_proof_marshal_size(int curve, uint32_t k);      /* (24+3k)*32 / (33+4k)*32 */
+int b2p_marshal_proof(int curve, uint32_t k, const void* proof_raw, const void* bsb22, void* out_bytes);
+/* public inputs: nb_public Fr (Montgomery) -> nb_public * 32 bytes big-endian */
+int b2p_marshal_public_inputs(int curve, const void* values, uint32_t nb_public, void* out_bytes);
+
+/* ---- instrumentation -------------------------------------------------------- */
+
+#define B2P_STAT_TOTAL_MS        0   /* b2p_prove wall time incl. H2D/D2H               */
+#define B2P_STAT_MSM_MS          1   /* device time in MSM launches (CUDA events)        */
+#define B2P_STAT_MSM_ACCUM_MS    2   /* ... of which bucket accumulation                 */
+#define B2P_STAT_NTT_MS          3
+#define B2P_STAT_QUOTIENT_MS     4
+#define B2P_STAT_MSM_CALLS       5
+#define B2P_STAT_MSM_ACCUM_ADDS  6   /* mixed additions performed by the accumulation    */
+#define B2P_STAT_H2D_BYTES       7
+#define B2P_STAT_D2H_BYTES       8
+#define B2P_STAT_LAUNCHES        9
+#define B2P_STAT_COUNT          16
+/* enable!=0: time phases of subsequent b2p_prove calls with CUDA events (adds syncs). */
+int b2p_circuit_set_profiling(b2p_circuit* c, int enable);
+int b2p_circuit_stats(const b2p_circuit* c, double* out /* B2P_STAT_COUNT doubles */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PLONK_H */

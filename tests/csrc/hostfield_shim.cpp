@@ -1,0 +1,31 @@
+// Test-only shim: exposes the product's field / curve templates (host emulation
+// path of ptx.cuh) through a C ABI so pytest can check them against Python ints
+// on a machine without a GPU.
+#include <cstring>
+#include "../../algoplonk_b200/csrc/field.cuh"
+using namespace b2p;
+
+template <class F> static void binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* o) {
+    F x, y, r;
+    memcpy(x.v, a, sizeof x.v); memcpy(y.v, b, sizeof y.v);
+    switch (op) {
+        case 0: r = x * y; break;
+        case 1: r = x + y; break;
+        case 2: r = x - y; break;
+        case 3: r = x.neg(); break;
+        case 4: r = x.inverse(); break;
+        case 5: r = x.to_mont(); break;
+        case 6: r = x.from_mont(); break;
+        case 7: r = x.sqr(); break;
+        default: r = F::zero();
+    }
+    memcpy(o, r.v, sizeof r.v);
+}
+extern "C" void ht_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* o) {
+    switch (field) {
+        case 0: binop<FrBn254>(op, a, b, o); break;
+        case 1: binop<FpBn254>(op, a, b, o); break;
+        case 2: binop<FrBls12381>(op, a, b, o); break;
+        case 3: binop<FpBls12381>(op, a, b, o); break;
+    }
+}
