@@ -602,7 +602,7 @@ struct Circuit : CircuitBase {
         pow_table(powzi.p, zeta.inverse(), n + 3);
         pow_table(powzw.p, zw, n + 3);
         pow_table(powzwi.p, zw.inverse(), n + 3);
-        std::vector<Fr> ev(6 + k);   // l r o s1 s2 qcp*  (lin comes later)
+        std::vector<Fr> ev(5 + k);   // l r o s1 s2 qcp*  (lin comes later)
         {
             std::vector<std::pair<const Fr*, uint64_t>> polys = {
                 {cl.p, n + 2}, {cr.p, n + 2}, {co.p, n + 2}, {c_s1.p, n}, {c_s2.p, n}};
