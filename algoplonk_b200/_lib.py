@@ -40,6 +40,8 @@ SYMBOLS = [
     ("b2p_circuit_free", None, [_vp]),
     ("b2p_proof_raw_size", _u64, [_int, _u32]),
     ("b2p_prove", _int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("b2p_prove_dev", _int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("b2p_circuit_stream", _vp, [_vp]),
     ("b2p_proof_marshal_size", _u64, [_int, _u32]),
     ("b2p_marshal_proof", _int, [_int, _u32, _vp, _vp, _vp]),
     ("b2p_marshal_public_inputs", _int, [_int, _vp, _u32, _vp]),

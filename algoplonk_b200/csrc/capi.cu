@@ -146,9 +146,17 @@ API int b2p_prove(b2p_circuit* c, const void* L, const void* R, const void* O, c
                   const void* bsb22, const void* blinding, void* out_raw) {
     return guarded([&] {
         require(c && L && R && O && blinding && out_raw, "null argument");
-        reinterpret_cast<CircuitBase*>(c)->prove(L, R, O, pi2, bsb22, blinding, out_raw);
+        reinterpret_cast<CircuitBase*>(c)->prove(L, R, O, pi2, bsb22, blinding, out_raw, false);
     });
 }
+API int b2p_prove_dev(b2p_circuit* c, const void* dL, const void* dR, const void* dO, const void* const* d_pi2,
+                      const void* bsb22, const void* blinding, void* out_raw) {
+    return guarded([&] {
+        require(c && dL && dR && dO && blinding && out_raw, "null argument");
+        reinterpret_cast<CircuitBase*>(c)->prove(dL, dR, dO, d_pi2, bsb22, blinding, out_raw, true);
+    });
+}
+API void* b2p_circuit_stream(b2p_circuit* c) { return c ? reinterpret_cast<CircuitBase*>(c)->stream_handle() : nullptr; }
 
 API uint64_t b2p_proof_marshal_size(int curve, uint32_t k) {
     return curve == B2P_BN254 ? (24 + 3 * (uint64_t)k) * 32 : (33 + 4 * (uint64_t)k) * 32;

@@ -194,7 +194,11 @@ struct Field {
     HD Field& operator*=(const Field& o) { *this = *this * o; return *this; }
 
     // ---- conversions ----------------------------------------------------
-    HD Field to_mont() const { return (*this) * r2(); }
+    HD Field to_mont() const { return (*this) * r2(); }   // *this must be canonical (< p)
+    // Any N-limb value (e.g. a 256-bit hash, possibly >= p) -> Montgomery form of (x mod p).
+    // The unreduced value must be the operand that is scanned limb by limb (the right one):
+    // the running sum then stays below 2p; as the left operand it can overflow N limbs.
+    HD static Field reduce_to_mont(const Field& raw) { return r2() * raw; }
     HD Field from_mont() const {
         Field o = zero();
         o.v[0] = 1;

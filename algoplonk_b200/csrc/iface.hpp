@@ -33,7 +33,8 @@ struct CircuitBase {
                       const uint64_t* cidx, const void* vkb, uint64_t vkb_len) = 0;
     virtual void vk_commitments(void* out_points) = 0;
     virtual void prove(const void* L, const void* R, const void* O, const void* const* pi2, const void* bsb22,
-                       const void* blinding, void* out_raw) = 0;
+                       const void* blinding, void* out_raw, bool device_inputs) = 0;
+    virtual void* stream_handle() = 0;
     virtual void set_profiling(bool on) = 0;
 };
 

@@ -207,10 +207,12 @@ k_msm_reduce_level(const XYZZ<Fp>* __restrict__ Pin, const XYZZ<Fp>* __restrict_
 }
 
 template <class Fp>
-__global__ void k_msm_final(const XYZZ<Fp>* __restrict__ P, const XYZZ<Fp>* __restrict__ A, XYZZ<Fp>* __restrict__ out) {
+__global__ void k_msm_final(const XYZZ<Fp>* __restrict__ P, const XYZZ<Fp>* __restrict__ A, XYZZ<Fp>* __restrict__ out,
+                            const uint32_t* __restrict__ total_entries, unsigned long long* __restrict__ adds_total) {
     XYZZ<Fp> r = ld_xyzz(A);
     r.add(ld_xyzz(P));
     st_xyzz(out, r);
+    *adds_total += *total_entries;   // single thread, stream ordered: mixed additions done by the accumulation
 }
 
 // ---------------------------------------------------------------------------
@@ -233,7 +235,7 @@ struct MsmEngine {
     uint32_t max_items = 0;
     Profiler* prof = nullptr;
     DevBuf<uint32_t> total_entries;
-    double adds_accum = 0;            // mixed additions of profiled runs (sum of non-zero digits)
+    DevBuf<unsigned long long> adds_total;   // running count of mixed additions (non-zero digits), device side
 
     void load(const void* host_points, uint64_t n, int force_c, cudaStream_t st) {
         npoints = n;
@@ -259,6 +261,8 @@ struct MsmEngine {
         scan_scratch.alloc(scan_scratch_words(nb));
         total_items.alloc(1);
         total_entries.alloc(1);
+        adds_total.alloc(1);
+        B2P_CUDA(cudaMemset(adds_total.p, 0, sizeof(unsigned long long)));
         max_items = nb + (uint32_t)(((uint64_t)plan.W * npoints) / MSM_CAP) + 1;
         partial.alloc(max_items);
         const uint32_t m1 = div_up(nb, MSM_SEG);
@@ -281,12 +285,6 @@ struct MsmEngine {
         B2P_LAUNCH((k_msm_accumulate<Fp>), div_up(max_items, MSM_THREADS), MSM_THREADS, 0, st, table.p, entries.p,
                    counts.p, offsets.p, item_off.p, total_items.p, nb, partial.p);
         if (prof) prof->end(span, st);
-        if (prof && prof->on) {
-            uint32_t te = 0;
-            B2P_CUDA(cudaMemcpyAsync(&te, total_entries.p, sizeof te, cudaMemcpyDeviceToHost, st));
-            B2P_CUDA(cudaStreamSynchronize(st));
-            adds_accum += te;
-        }
         // reduction tree
         uint32_t m = nb;
         int level = 0;
@@ -306,7 +304,7 @@ struct MsmEngine {
                            item_off.p, total_items.p, m, level * log_seg, Pout, Aout);
             Pin = Pout; Ain = Aout; m = mout; level++;
         } while (m > 1);
-        B2P_LAUNCH((k_msm_final<Fp>), 1, 1, 0, st, Pin, Ain, result.p);
+        B2P_LAUNCH((k_msm_final<Fp>), 1, 1, 0, st, Pin, Ain, result.p, total_entries.p, adds_total.p);
     }
 
     // synchronous convenience: returns the affine result (host)

@@ -35,8 +35,7 @@ inline Fr fr_from_be32_mod(const uint8_t* in) {
     for (int i = 0; i < 8; i++)
         raw.v[i] = ((uint32_t)in[31 - 4 * i]) | ((uint32_t)in[30 - 4 * i] << 8) | ((uint32_t)in[29 - 4 * i] << 16) |
                    ((uint32_t)in[28 - 4 * i] << 24);
-    // Montgomery multiplication by R^2 reduces any value < 2^256
-    return raw.to_mont();
+    return Fr::reduce_to_mont(raw);
 }
 template <class C>
 inline void point_marshal(const Affine<typename C::Fp>& p, uint8_t* out, bool gnark_inf_flag) {
@@ -442,26 +441,33 @@ struct Circuit : CircuitBase {
     }
 
     // ---- the prover -------------------------------------------------------
+    void* stream_handle() override { return (void*)st; }
+
     void prove(const void* hL, const void* hR, const void* hO, const void* const* h_pi2, const void* h_bsb22,
-               const void* h_blinding, void* out_raw) override {
+               const void* h_blinding, void* out_raw, bool device_inputs) override {
         auto t0 = std::chrono::steady_clock::now();
         for (auto& s : stats) s = 0;
         const unsigned long long launches0 = g_launch_count;
         srs->prof = prof.on ? &prof : nullptr;
-        srs->msm.adds_accum = 0;
-        const Fr* hLf = static_cast<const Fr*>(hL);
+        B2P_CUDA(cudaMemsetAsync(srs->msm.adds_total.p, 0, sizeof(unsigned long long), st));
+        // wire columns: host buffers (the cgo path) or buffers already resident in HBM
+        const cudaMemcpyKind in_kind = device_inputs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        std::vector<Fr> pub_host(nb_public);
+        if (device_inputs && nb_public)
+            B2P_CUDA(cudaMemcpyAsync(pub_host.data(), hL, nb_public * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        const Fr* hLf = device_inputs ? pub_host.data() : static_cast<const Fr*>(hL);
         const Aff* bsb = static_cast<const Aff*>(h_bsb22);
         B2P_REQUIRE(k == 0 || (h_pi2 && h_bsb22), "BSB22 inputs missing");
 
         // -- upload -----------------------------------------------------------
-        B2P_CUDA(cudaMemcpyAsync(L.p, hL, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
-        B2P_CUDA(cudaMemcpyAsync(R.p, hR, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
-        B2P_CUDA(cudaMemcpyAsync(O.p, hO, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        B2P_CUDA(cudaMemcpyAsync(L.p, hL, n * sizeof(Fr), in_kind, st));
+        B2P_CUDA(cudaMemcpyAsync(R.p, hR, n * sizeof(Fr), in_kind, st));
+        B2P_CUDA(cudaMemcpyAsync(O.p, hO, n * sizeof(Fr), in_kind, st));
         B2P_CUDA(cudaMemcpyAsync(small.p, h_blinding, 9 * sizeof(Fr), cudaMemcpyHostToDevice, st));
-        stats[B2P_STAT_H2D_BYTES] += 3.0 * n * sizeof(Fr) + 9 * sizeof(Fr);
+        stats[B2P_STAT_H2D_BYTES] += (device_inputs ? 0.0 : 3.0 * n * sizeof(Fr)) + 9 * sizeof(Fr);
         for (uint32_t c = 0; c < k; c++) {
-            B2P_CUDA(cudaMemcpyAsync(c_pi2[c].p, h_pi2[c], n * sizeof(Fr), cudaMemcpyHostToDevice, st));
-            stats[B2P_STAT_H2D_BYTES] += (double)n * sizeof(Fr);
+            B2P_CUDA(cudaMemcpyAsync(c_pi2[c].p, h_pi2[c], n * sizeof(Fr), in_kind, st));
+            if (!device_inputs) stats[B2P_STAT_H2D_BYTES] += (double)n * sizeof(Fr);
         }
 
         // -- round 1: l, r, o -------------------------------------------------
@@ -708,7 +714,12 @@ struct Circuit : CircuitBase {
         if (prof.on) prof.collect(stats);
         srs->prof = nullptr;
         stats[B2P_STAT_MSM_CALLS] = 10;
-        stats[B2P_STAT_MSM_ACCUM_ADDS] = srs->msm.adds_accum;
+        {
+            unsigned long long adds = 0;
+            B2P_CUDA(cudaMemcpyAsync(&adds, srs->msm.adds_total.p, sizeof adds, cudaMemcpyDeviceToHost, st));
+            B2P_CUDA(cudaStreamSynchronize(st));
+            stats[B2P_STAT_MSM_ACCUM_ADDS] = (double)adds;
+        }
         stats[B2P_STAT_LAUNCHES] = (double)(g_launch_count - launches0);
         stats[B2P_STAT_TOTAL_MS] =
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

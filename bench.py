@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""bench.py -- PLONK proofs/sec on the BASELINE.json workload (2^20-constraint BN254 circuit).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--log2 20] [--curve BN254]
+
+One "step" = one proof (b2p_prove: 10 MSMs, ~10 NTTs of size 4n, quotient, openings) of the synthetic
+squaring-chain circuit of SURVEY 8d on a known-tau SRS.  N > 1 runs one replica per GPU (proofs are
+independent: no data-path collective, "scaling": "weak"); timing is CUDA events on the library's stream,
+max over ranks.  Rank 0 prints ONE JSON line.
+
+  value      proofs/s with L, R, O already resident in HBM (b2p_prove_dev)
+  e2e        proofs/s through the reference-facing C-ABI call b2p_prove with pinned HOST buffers
+             (H2D of 3*32*n bytes and D2H of the proof inside the timed region)
+  roofline   dominant kernel (k_msm_accumulate): algorithmic bytes n*(64+32) per launch
+             / CUDA-event launch duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the C++ CPU oracle (oracle/cpu_plonk.cpp, OpenMP) on a bounded sample, rank 0, N = 1
+
+--impl reference times that CPU oracle alone (the reference is pure Go over un-vendored gnark and no Go
+toolchain exists here, so oracle/_ref cannot be built: kind "port").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "plonk_proofs_per_sec"
+UNIT = "proofs/s"
+TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+
+
+# ---------------------------------------------------------------------------------------
+# pieces shared with tests/test_bench_host.py
+# ---------------------------------------------------------------------------------------
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def reduce_over_ranks(local_ms: float, local_units: float, world: int, device=None):
+    """Whole-job figures: elapsed = max over ranks, units = sum over ranks (replicas, no data collective)."""
+    if world == 1:
+        return local_ms, local_units
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([local_ms], dtype=torch.float64, device=device)
+    u = torch.tensor([local_units], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return float(t.item()), float(u.item())
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def msm_algorithmic_bytes(n_scalars: int, curve: str) -> int:
+    """MSM(n) moves n * (affine point + scalar) bytes."""
+    return n_scalars * ((64 if curve == "BN254" else 96) + 32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------
+def build_workload(curve: str, log2_rows: int):
+    """Synthetic squaring-chain circuit with exactly 2^log2_rows rows."""
+    from algoplonk_b200 import frontend as fe
+    cs, values = fe.squaring_chain(curve, log2_rows)
+    tc = fe.build_trace(cs)
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    return cs, tc, L, R, O
+
+
+# ---------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------
+def cpu_prove_seconds(curve: str, log2_rows: int, repeats: int = 1, warmup: int = 0):
+    """Times oracle proofs of a 2^log2_rows circuit; returns the list of timed step durations."""
+    from oracle import cpu_oracle as co
+    cid = co.CURVE_ID[curve]
+    cs, tc, L, R, O = build_workload(curve, log2_rows)
+    srs = co.srs_from_tau_bytes(cid, TAU, tc.n + 3)
+    circ = co.Circuit(cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs)
+    Lb, Rb, Ob = co.scalars_le(L), co.scalars_le(R), co.scalars_le(O)
+    bl = co.scalars_le(range(1, 10))
+    out = []
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        circ.prove(Lb, Rb, Ob, bl)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            out.append(dt)
+    circ.free()
+    return out
+
+
+def choose_sample_log2(curve: str, target_log2: int, seconds_per_step: float):
+    """Largest sample size <= target whose predicted proof time fits the per-step budget
+    (prediction: linear in n from a 2^12 calibration proof)."""
+    cal_log2 = min(12, target_log2)
+    t_cal = min(cpu_prove_seconds(curve, cal_log2, repeats=2))
+    s = cal_log2
+    while s < target_log2 and t_cal * (1 << (s + 1 - cal_log2)) <= seconds_per_step:
+        s += 1
+    return s
+
+
+def cpu_baseline(curve: str, target_log2: int, seconds_per_step: float = 25.0):
+    from oracle import cpu_oracle as co
+    s = choose_sample_log2(curve, target_log2, seconds_per_step)
+    t = min(cpu_prove_seconds(curve, s, repeats=1))
+    scale = 1 << (target_log2 - s)
+    sample = f"one 2^{s}-row {curve} proof in {t:.2f} s"
+    if scale > 1:
+        sample += f", scaled x{scale} linearly in n to 2^{target_log2} rows (favours the CPU: the work grows n log n)"
+    return {"value": 1.0 / (t * scale), "unit": UNIT, "cores": co.threads(), "kind": "port", "sample": sample}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import cpu_oracle as co
+    budget = max(2.0, 150.0 / max(1, args.steps + args.warmup))
+    s = choose_sample_log2(args.curve, args.log2, budget)
+    times = cpu_prove_seconds(args.curve, s, repeats=args.steps, warmup=args.warmup)
+    scale = 1 << (args.log2 - s)
+    per_step = sum(times) / len(times) * scale
+    value = 1.0 / per_step
+    sample = (f"each step = one 2^{s}-row {args.curve} proof on the host cores"
+              + (f", scaled x{scale} linearly in n" if scale > 1 else ""))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": co.threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of gnark's prover (oracle/cpu_plonk.cpp, OpenMP); gnark itself needs Go, absent here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"synthetic squaring-chain circuit, 2^{args.log2} constraints, {args.curve}, "
+                        f"known-tau SRS of 2^{args.log2}+3 points, k=0",
+            "log2_constraints": args.log2, "curve": args.curve, "parallelism": f"replicas x{args.gpus}",
+            "l2": "inputs larger than L2: per-proof working set (13-window SRS table + 4n evaluations) "
+                  "is > 1 GB vs 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    from algoplonk_b200 import _lib, api
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    _lib.init(local_rank)          # raises without a usable GPU: there is no CPU fallback
+    lib = _lib.load()
+    curve = args.curve
+
+    cs, tc, L, R, O = build_workload(curve, args.log2)
+    n = tc.n
+    setup = api.SetupName.TestOnlyBN254 if curve == "BN254" else api.SetupName.TestOnlyBLS12381
+    t0 = time.perf_counter()
+    cc = api.Compile(cs, curve, setup)
+    load_s = time.perf_counter() - t0
+    c_bits, windows, buckets = cc.srs.msm_params()
+
+    # pinned host buffers (what the cgo shim would pass) and their device-resident copies
+    def pinned(data: bytes):
+        t = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+        return t
+    hL, hR, hO = (pinned(api.fr_to_mont_bytes(curve, col)) for col in (L, R, O))
+    dL, dR, dO = (t.to(device) for t in (hL, hR, hO))
+    blinding = C.create_string_buffer(api.fr_to_mont_bytes(curve, list(range(1, 10))))
+    cid = api.CURVE_ID[curve]
+    out = C.create_string_buffer(lib.b2p_proof_raw_size(cid, 0))
+    stream = torch.cuda.ExternalStream(lib.b2p_circuit_stream(cc.handle), device=device)
+    torch.cuda.synchronize()
+
+    def prove_dev():
+        _lib.check(lib.b2p_prove_dev(cc.handle, dL.data_ptr(), dR.data_ptr(), dO.data_ptr(), None, None, blinding, out))
+
+    def prove_host():
+        _lib.check(lib.b2p_prove(cc.handle, hL.data_ptr(), hR.data_ptr(), hO.data_ptr(), None, None, blinding, out))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    cc.set_profiling(True)         # CUDA-event spans around MSM / accumulate / NTT / quotient; no extra syncs
+    for _ in range(args.warmup):
+        prove_dev()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.b2p_launch_count()
+    ms = timed(prove_dev, args.steps)
+    launches = lib.b2p_launch_count() - launches0
+    stats = cc.stats()             # spans of the last timed proof
+    proof_resident = bytes(out.raw)
+    for _ in range(min(1, args.warmup)):
+        prove_host()
+    ms_e2e = timed(prove_host, args.steps)
+    clocks = sampler.stop()
+    assert bytes(out.raw) == proof_resident, "host-buffer and resident-buffer proofs differ"
+
+    tot_ms, units = reduce_over_ranks(ms, args.steps, world, device)
+    tot_ms_e2e, _ = reduce_over_ranks(ms_e2e, args.steps, world, device)
+    if rank != 0:
+        return
+    value = units / (tot_ms / 1e3)
+    e2e_value = units / (tot_ms_e2e / 1e3)
+
+    hbm_peak, peak_src = peaks()
+    msm_calls = int(stats["msm_calls"])
+    accum_ms = stats["msm_accum_ms"] / msm_calls
+    alg_bytes = msm_algorithmic_bytes(n + 2, curve)
+    achieved = alg_bytes / (accum_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "launch_ms": accum_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "256-bit modular arithmetic makes this kernel INT32-ALU-bound, not HBM-bound (DESIGN.md); "
+                        "see msm_g1_adds_per_sec"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) if False else 3 * 32 * n + 9 * 32,
+                "d2h_bytes_per_step": int(lib.b2p_proof_raw_size(cid, 0)), "ms_per_step": tot_ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "clocks": clocks,
+        "msm": {"c": c_bits, "windows": windows, "buckets": buckets, "calls_per_proof": msm_calls,
+                "accum_adds_per_proof": stats["msm_accum_adds"],
+                "msm_g1_adds_per_sec": stats["msm_accum_adds"] / (stats["msm_accum_ms"] * 1e-3),
+                "msm_ms_per_proof": stats["msm_ms"]},
+        "phases_ms": {"msm": stats["msm_ms"], "msm_accumulate": stats["msm_accum_ms"], "ntt": stats["ntt_ms"],
+                      "quotient": stats["quotient_ms"], "total_host_wall": stats["total_ms"]},
+        "circuit_load_s": load_s,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(curve, args.log2)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2", type=int, default=20, help="log2 of the constraint count (BASELINE: 20)")
+    ap.add_argument("--curve", default="BN254", choices=["BN254", "BLS12_381"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print(f"note: --warmup {args.warmup} < 3 breaks the timing rules", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,17 @@ int b2p_prove(b2p_circuit* c, const void* L, const void* R, const void* O,
               const void* const* pi2, const void* bsb22,
               const void* blinding, void* out_proof_raw);
 
+/* Same as b2p_prove with L, R, O and the pi2 columns already resident in device memory
+ * (device pointers, Montgomery form); bsb22 / blinding / out_proof_raw stay host pointers.
+ * Used by a prover service that keeps witnesses in HBM, and by bench.py's resident-input
+ * measurement.  Not reachable from the reference's API (gnark's solver output is host memory). */
+int b2p_prove_dev(b2p_circuit* c, const void* dL, const void* dR, const void* dO,
+                  const void* const* d_pi2, const void* bsb22,
+                  const void* blinding, void* out_proof_raw);
+/* The cudaStream_t every launch of this circuit (and its SRS) is issued on, for callers
+ * that bracket calls with their own CUDA events. */
+void* b2p_circuit_stream(b2p_circuit* c);
+
 /* ---- marshalling (replaces: MarshalProof / MarshalPublicInputs, helper.go:13-110) */
 
 uint64_t b2p_proof_marshal_size(int curve, uint32_t k);      /* (24+3k)*32 / (33+4k)*32 */

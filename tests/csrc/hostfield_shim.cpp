@@ -17,6 +17,7 @@ template <class F> static void binop(int op, const uint32_t* a, const uint32_t* 
         case 5: r = x.to_mont(); break;
         case 6: r = x.from_mont(); break;
         case 7: r = x.sqr(); break;
+        case 8: r = F::reduce_to_mont(x); break;
         default: r = F::zero();
     }
     memcpy(o, r.v, sizeof r.v);

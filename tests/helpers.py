@@ -1,10 +1,15 @@
-"""Shared test plumbing: builds the same circuit for the CUDA path and for the oracle."""
+"""Shared test plumbing: builds the same circuit for the CUDA path and for the oracles,
+and reloads the committed golden fixtures (tests/golden/, made by tools/gen_golden.py)."""
+import functools
+import json
+import os
 import random
 
 from oracle import plonk_oracle as po
 from algoplonk_b200 import frontend as fe
 
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def oracle_trace(tc: fe.TraceColumns) -> po.Trace:
@@ -44,3 +49,82 @@ def vk_from_points(tc: fe.TraceColumns, pts, g1, tau=None, g2=None) -> po.Verify
                            Qr=pts[4], Qm=pts[5], Qo=pts[6], Qk=pts[7], Qcp=list(pts[8:]),
                            commitment_constraint_indexes=list(tc.commitment_constraint_indexes), g1=g1, tau=tau,
                            g2=g2)
+
+
+# ---- golden fixtures ---------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def srs_kat():
+    with open(os.path.join(GOLDEN, "srs_kat.json")) as f:
+        return json.load(f)
+
+
+@functools.lru_cache(maxsize=None)
+def golden_proofs():
+    with open(os.path.join(GOLDEN, "proofs.json")) as f:
+        return json.load(f)
+
+
+@functools.lru_cache(maxsize=None)
+def real_srs_points(name: str):
+    """Decompressed G1 points of the committed slice of a reference SRS file."""
+    ent = srs_kat()[name]
+    cv = po.CURVES[ent["curve"]]
+    raw = bytes.fromhex(ent["first"])
+    return [po.g1_decompress(cv, raw[i * cv.fp_bytes:(i + 1) * cv.fp_bytes]) for i in range(ent["count"])]
+
+
+def case_id(case) -> str:
+    return f"{case['curve']}-{case['name']}-{case['srs'][:4]}"
+
+
+def build_case(case):
+    """Rebuilds the prover inputs of a golden case.  Returns dict(cs, tc, L, R, O, pi2, coms, srs, tau)."""
+    curve = case["curve"]
+    cv = po.CURVES[curve]
+    if case["name"] == "basic":
+        B = fe.basic_circuit(curve)
+        cs, values, pi2s, coms = B.build(), B.values, [], []
+    elif case["name"].startswith("bsb22"):
+        k = case["k"]
+        n_dry = fe.bsb22_circuit(curve, k, lambda a, b, c: 1).build().domain_size
+        srs_o = po.srs_from_tau(cv, TAU, n_dry + 3)
+        trd = type("T", (), {"curve": cv, "n": n_dry})
+        cs, values, pi2s, coms = build_bsb22(curve, k, lambda col: po.bsb22_commit(trd, srs_o, col))
+        assert [po.g1_raw_bytes(cv, P).hex() for P in coms] == case["bsb22"]
+    elif case["name"].startswith("squaring_2p"):
+        cs, values = fe.squaring_chain(curve, int(case["name"].split("2p")[1]), x0=3)
+        pi2s, coms = [], []
+    else:
+        raise KeyError(case["name"])
+    tc = fe.build_trace(cs)
+    assert tc.n == case["n"]
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    if case["srs"] == "tau":
+        srs, tau = po.srs_from_tau(cv, TAU, tc.n + 3), TAU
+    else:
+        srs, tau = real_srs_points(case["srs"])[: tc.n + 3], None
+    return dict(cs=cs, tc=tc, L=L, R=R, O=O, pi2=pi2s, coms=coms, srs=srs, tau=tau, cv=cv,
+                blinding=case["blinding"])
+
+
+# ---- scalar distributions (SURVEY 8d) -------------------------------------------------
+def scalars_uniform(r: int, n: int, seed: int):
+    rng = random.Random(seed)
+    return [rng.randrange(r) for _ in range(n)]
+
+
+def scalars_witness_like(r: int, n: int, seed: int):
+    """40 % zero, 20 % one, 10 % < 2^16, 30 % uniform: the bucket-skew case."""
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n):
+        t = rng.random()
+        if t < 0.4:
+            out.append(0)
+        elif t < 0.6:
+            out.append(1)
+        elif t < 0.7:
+            out.append(rng.randrange(1 << 16))
+        else:
+            out.append(rng.randrange(r))
+    return out

@@ -1,0 +1,129 @@
+"""GPU parity: b2p_prove (plonk.Prove, /root/reference/algoplonk.go:89) -- proofs byte-identical to the
+oracles given the same blinding scalars, accepted by the restated reference verifier, on the reference's
+own circuits (examples/basic, bsb22_test.go), on real-SRS slices and at the BASELINE config sizes."""
+import pytest
+
+import helpers as H
+from algoplonk_b200 import _lib, api, frontend as fe
+from oracle import cpu_oracle as co
+from oracle import plonk_oracle as po
+
+pytestmark = pytest.mark.gpu
+SETUP = {"BN254": api.SetupName.TestOnlyBN254, "BLS12_381": api.SetupName.TestOnlyBLS12381}
+
+
+def _compile(c, case):
+    curve = case["curve"]
+    if case["srs"] == "tau":
+        return api.Compile(c["cs"], curve, SETUP[curve])
+    real = {"PerpetualPowersOfTauBN254": api.SetupName.PerpetualPowersOfTauBN254,
+            "DuskBLS12_381": api.SetupName.DuskBLS12381}[case["srs"]]
+    return api.Compile(c["cs"], curve, real, srs=api.SRS.from_points(curve, c["srs"]))
+
+
+@pytest.mark.parametrize("case", H.golden_proofs(), ids=H.case_id)
+def test_golden_proofs_byte_identical(gpu, case):
+    c = H.build_case(case)
+    cc = _compile(c, case)
+    vk_pts = cc.vk_commitments()
+    assert b"".join(po.g1_raw_bytes(c["cv"], P, gnark_infinity_flag=True) for P in vk_pts).hex() == case["vk"]
+    vp = cc.Verify(c["L"], c["R"], c["O"], c["blinding"], c["pi2"], c["coms"])
+    blob = api.MarshalProof(vp.Proof)
+    assert blob.hex() == case["proof"]
+    assert api.MarshalPublicInputs(case["curve"], vp.Witness).hex() == case["public_inputs"]
+    if c["tau"] is not None:
+        vk = H.vk_from_points(c["tc"], vk_pts, c["cv"].g1, tau=c["tau"])
+        assert po.verify_proof(vk, blob, bytes.fromhex(case["public_inputs"]))
+    cc.free()
+
+
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+@pytest.mark.parametrize("k", (1, 2))
+def test_bsb22_commitment_hint_on_gpu(gpu, curve, k):
+    """The BSB22 solver hint commits through b2p_msm_g1 on the Lagrange basis (what the Go shim does)."""
+    cv = po.CURVES[curve]
+    n_dry = fe.bsb22_circuit(curve, k, lambda a, b, c: 1).build().domain_size
+    srs = api.SRS.unsafe(curve, n_dry + 3, H.TAU)
+    cs, values, pi2s, coms = H.build_bsb22(curve, k, lambda col: srs.msm(col, basis=_lib.BASIS_LAGRANGE))
+    case = next(c for c in H.golden_proofs() if c["curve"] == curve and c["name"] == f"bsb22_k{k}")
+    assert [po.g1_raw_bytes(cv, P).hex() for P in coms] == case["bsb22"]
+    cc = api.Compile(cs, curve, SETUP[curve], srs=srs)
+    L, R, O = fe.solve_lro(cs, values, cc.trace.n)
+    blob = api.MarshalProof(cc.Prove(L, R, O, case["blinding"], pi2s, coms))
+    assert blob.hex() == case["proof"]
+    cc.free()
+    srs.free()
+
+
+@pytest.mark.parametrize("curve,logn", [("BN254", 10), ("BN254", 14), ("BLS12_381", 12)])
+def test_mid_size_byte_identical_to_cpp_oracle(gpu, curve, logn):
+    cv = po.CURVES[curve]
+    cs, values = fe.squaring_chain(curve, logn, x0=5)
+    cc = api.Compile(cs, curve, SETUP[curve])
+    tc = cc.trace
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    blinding = H.scalars_uniform(cv.r, 9, logn)
+    blob = api.MarshalProof(cc.Prove(L, R, O, blinding))
+    srs_le = co.srs_from_tau_bytes(cv.cid, api.TEST_TAU, tc.n + 3)
+    circ = co.Circuit(cv.cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
+    assert cc.vk_commitments() == circ.vk_points()
+    assert blob == circ.prove(L, R, O, blinding)
+    vk = H.vk_from_points(tc, cc.vk_commitments(), cv.g1, tau=api.TEST_TAU)
+    pub = api.MarshalPublicInputs(curve, L[: tc.nb_public])
+    assert po.verify_proof(vk, blob, pub)
+    # blinding really enters: different scalars, different proof, still accepted
+    blob2 = api.MarshalProof(cc.Prove(L, R, O, H.scalars_uniform(cv.r, 9, 999)))
+    assert blob2 != blob and po.verify_proof(vk, blob2, pub)
+    # proving twice with the same inputs is deterministic
+    assert api.MarshalProof(cc.Prove(L, R, O, blinding)) == blob
+    circ.free()
+    cc.free()
+
+
+@pytest.mark.parametrize("curve,logn", [("BN254", 17), ("BN254", 20), ("BLS12_381", 17)])
+def test_config_sizes_accepted_by_reference_verifier(gpu, curve, logn):
+    """BASELINE configs[1], [2] (2^17 and 2^20 BN254) and a 2^17 BLS12-381 run: size-independent
+    check -- the restated AVM verifier accepts, and rejects a tampered public input.  The 2^17 BN254
+    case is additionally compared byte for byte with the C++ oracle."""
+    cv = po.CURVES[curve]
+    cs, values = fe.squaring_chain(curve, logn, x0=7)
+    cc = api.Compile(cs, curve, SETUP[curve])
+    tc = cc.trace
+    assert tc.n == 1 << logn
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    blinding = H.scalars_uniform(cv.r, 9, logn)
+    blob = api.MarshalProof(cc.Prove(L, R, O, blinding))
+    vk = H.vk_from_points(tc, cc.vk_commitments(), cv.g1, tau=api.TEST_TAU)
+    pub = api.MarshalPublicInputs(curve, L[: tc.nb_public])
+    assert po.verify_proof(vk, blob, pub)
+    bad = bytearray(pub)
+    bad[31] ^= 1
+    assert not po.verify_proof(vk, blob, bytes(bad))
+    if (curve, logn) == ("BN254", 17):
+        srs_le = co.srs_from_tau_bytes(cv.cid, api.TEST_TAU, tc.n + 3)
+        circ = co.Circuit(cv.cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
+        assert blob == circ.prove(L, R, O, blinding)
+        circ.free()
+    cc.free()
+
+
+def test_prove_errors(gpu):
+    B = fe.basic_circuit("BN254")
+    cs = B.build()
+    small = api.SRS.unsafe("BN254", 8, H.TAU)           # needs n + 3 = 11
+    with pytest.raises(ValueError, match="too small"):  # setup/setup.go:219-223
+        api.Compile(cs, "BN254", api.SetupName.TestOnlyBN254, srs=small)
+    lib = gpu.load()
+    import ctypes as C
+    h = C.c_void_p()
+    col = C.create_string_buffer(32 * 8)
+    perm = (C.c_int64 * 24)(*range(24))
+    assert lib.b2p_circuit_load(small.handle, 8, 0, col, col, col, col, col, perm, 0, None, None, None, 0,
+                                C.byref(h)) == -1
+    assert b"n+3" in lib.b2p_last_error()
+    bls = api.SRS.unsafe("BLS12_381", 16, H.TAU)
+    perm[0] = 99                                         # out-of-range permutation entry
+    assert lib.b2p_circuit_load(bls.handle, 8, 0, col, col, col, col, col, perm, 0, None, None, None, 0,
+                                C.byref(h)) == -1
+    small.free()
+    bls.free()

@@ -1,0 +1,196 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, host-only entry points (marshalling) match the reference layout, the field
+templates' host emulation matches Python integers, and the front-end / API mirror behaves
+like the reference (compile_test.go, setup/registry_test.go)."""
+import ctypes as C
+import os
+import random
+import re
+import subprocess
+
+import pytest
+
+import helpers as H
+from algoplonk_b200 import _lib, api, frontend as fe
+from oracle import plonk_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+# ---- C ABI ------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "b200plonk.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(b2p_[a-z0-9_]+)\s*\(", header))
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert declared == bound, f"header/binding mismatch: {declared ^ bound}"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.b2p_version()
+
+
+def test_sizes():
+    lib = _lib.load()
+    for k in (0, 1, 2):
+        assert lib.b2p_proof_marshal_size(0, k) == (24 + 3 * k) * 32      # templateLogicSigBN254.go:50
+        assert lib.b2p_proof_marshal_size(1, k) == (33 + 4 * k) * 32      # templateLogicSigBLS12_381.go:50
+        assert lib.b2p_proof_raw_size(0, k) == 9 * 64 + (7 + k) * 32
+        assert lib.b2p_proof_raw_size(1, k) == 9 * 96 + (7 + k) * 32
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU error path")
+def test_init_fails_loudly_without_gpu():
+    with pytest.raises(_lib.B200PlonkError) as e:
+        _lib.init()
+    assert e.value.code == -2 and "CUDA" in str(e.value)
+    # ... and so does the public API: there is no CPU fallback
+    with pytest.raises(_lib.B200PlonkError):
+        api.SRS.unsafe("BN254", 8)
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    assert lib.b2p_ntt(7, C.create_string_buffer(32), 1, 0) == -1
+    assert b"unsupported curve" in lib.b2p_last_error()
+    assert lib.b2p_marshal_proof(0, 0, None, None, None) == -1
+    assert lib.b2p_srs_size(None) == 0
+
+
+@pytest.mark.parametrize("case", H.golden_proofs(), ids=H.case_id)
+def test_marshal_proof_matches_reference_layout(case):
+    """b2p_marshal_proof is host-only: raw gnark-layout proof -> helper.go:27-88 byte layout."""
+    curve, k = case["curve"], case["k"]
+    cv = po.CURVES[curve]
+    blob = bytes.fromhex(case["proof"])
+    pb = 2 * cv.fp_bytes
+    # parse the golden blob (Appendix B) back into points / scalars
+    pos = 0
+
+    def P():
+        nonlocal pos
+        pt = po.g1_from_raw_bytes(cv, blob[pos:pos + pb])
+        pos += pb
+        return pt
+
+    def S():
+        nonlocal pos
+        v = int.from_bytes(blob[pos:pos + 32], "big")
+        pos += 32
+        return v
+
+    lro = [P(), P(), P()]
+    h = [P(), P(), P()]
+    claimed = [S() for _ in range(5)]
+    z = P()
+    zs = S()
+    wz, wzw = P(), P()
+    qcp = [S() for _ in range(k)]
+    bsb = [P() for _ in range(k)]
+    raw = api.points_to_mont_bytes(curve, lro + [z] + h + [wz, wzw]) + \
+        api.fr_to_mont_bytes(curve, [12345] + claimed + qcp + [zs])
+    out = api.MarshalProof(api.Proof(curve, k, raw, api.points_to_mont_bytes(curve, bsb)))
+    assert out == blob
+
+
+def test_marshal_public_inputs():
+    vals = [0, 1, 35, po.BN254.r - 1]
+    assert api.MarshalPublicInputs("BN254", vals) == po.marshal_public_inputs(vals)   # helper.go:96-109
+
+
+# ---- field templates (host emulation of the PTX carry chains) ---------------------------------
+@pytest.fixture(scope="module")
+def hostfield(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hf") / "hostfield.so"
+    src = os.path.join(ROOT, "tests", "csrc", "hostfield_shim.cpp")
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O1", "-std=c++17", "-shared",
+                    "-fPIC", "-x", "c++", src, "-o", str(out)], check=True)
+    return C.CDLL(str(out))
+
+
+@pytest.mark.parametrize("fid,mod,nlimb", [(0, po.BN254.r, 8), (1, po.BN254.p, 8), (2, po.BLS12_381.r, 8),
+                                          (3, po.BLS12_381.p, 12)])
+def test_device_field_code_on_host(hostfield, fid, mod, nlimb):
+    """The very field.cuh the kernels use, run through its host emulation, against Python ints."""
+    R = 1 << (32 * nlimb)
+    rng = random.Random(fid)
+
+    def call(op, a, b=0):
+        A = (C.c_uint32 * nlimb)(*[(a >> (32 * i)) & 0xFFFFFFFF for i in range(nlimb)])
+        B = (C.c_uint32 * nlimb)(*[(b >> (32 * i)) & 0xFFFFFFFF for i in range(nlimb)])
+        O = (C.c_uint32 * nlimb)()
+        hostfield.ht_field_op(fid, op, A, B, O)
+        return sum(int(O[i]) << (32 * i) for i in range(nlimb))
+
+    Rinv = pow(R, -1, mod)
+    vals = [0, 1, mod - 1, mod - 2, (1 << 32) - 1, 1 << 32] + [rng.randrange(mod) for _ in range(60)]
+    for a in vals:
+        b = rng.choice(vals)
+        assert call(0, a, b) == a * b * Rinv % mod          # Montgomery product
+        assert call(1, a, b) == (a + b) % mod
+        assert call(2, a, b) == (a - b) % mod
+        assert call(3, a) == (-a) % mod
+        assert call(7, a) == a * a * Rinv % mod
+        assert call(5, a) == a * R % mod
+        assert call(6, a) == a * Rinv % mod
+    # hashes are reduced mod r from raw 256-bit values (Fiat-Shamir challenges): any N-limb input
+    for _ in range(300):
+        a = rng.randrange(R)
+        assert call(8, a) == a * R % mod
+    assert call(8, R - 1) == (R - 1) * R % mod
+    for a in vals[:12]:
+        am = a * R % mod
+        inv = call(4, am)
+        assert inv == (pow(a, -1, mod) * R % mod if a else 0)
+
+
+# ---- front-end ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+def test_frontend_basic_and_permutation(curve):
+    B = fe.basic_circuit(curve)
+    cs, values = B.build(), B.values
+    tc = fe.build_trace(cs)
+    assert tc.n == 8 and tc.nb_public == 2
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    assert fe.check_gates(tc, L, R, O)
+    assert sorted(tc.perm) == list(range(3 * tc.n))
+    # positions on one cycle carry one value
+    wires = L + R + O
+    assert all(wires[i] == wires[tc.perm[i]] for i in range(3 * tc.n))
+
+
+def test_frontend_squaring_chain_sizes():
+    for lg in (3, 6, 10):
+        cs, values = fe.squaring_chain("BN254", lg)
+        assert cs.nb_public + cs.nb_constraints == 1 << lg == cs.domain_size
+        tc = fe.build_trace(cs)
+        L, R, O = fe.solve_lro(cs, values, tc.n)
+        assert fe.check_gates(tc, L, R, O)
+
+
+def test_compile_rejects_like_the_reference():
+    B = fe.basic_circuit("BN254")
+    cs = B.build()
+    with pytest.raises(ValueError, match="unknown setup"):          # compile_test.go:22-30
+        api.Compile(cs, api.BN254, 999)
+    with pytest.raises(ValueError, match="unsupported curve"):      # algoplonk.go:39-41
+        api.Compile(cs, "BW6_761", api.SetupName.TestOnlyBN254)
+    with pytest.raises(ValueError, match="do not match"):           # algoplonk.go:46-49
+        api.Compile(cs, api.BN254, api.SetupName.DuskBLS12381)
+
+
+def test_conversions_roundtrip():
+    for curve in ("BN254", "BLS12_381"):
+        cv = po.CURVES[curve]
+        vals = H.scalars_uniform(cv.r, 5, 1)
+        assert api.fr_from_mont_bytes(curve, api.fr_to_mont_bytes(curve, vals)) == vals
+        pts = po.srs_from_tau(cv, 5, 3) + [None]
+        assert api.points_from_mont_bytes(curve, api.points_to_mont_bytes(curve, pts)) == pts
