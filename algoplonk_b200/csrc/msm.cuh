@@ -115,42 +115,100 @@ __global__ void k_msm_scatter(const Fr* __restrict__ scalars, uint64_t n, uint64
 }
 
 // ---------------------------------------------------------------------------
-// bucket accumulation: thread t handles slice `sub` of bucket b
+// Work items.  A bucket with cnt entries is cut into ceil(cnt / CAP) items of at
+// most CAP entries; one thread accumulates one item.  Bucket sizes are Poisson
+// distributed, so handing a warp 32 neighbouring buckets leaves ~30 % of its lanes
+// idle (measured: 22 of 32 lanes active).  Items are therefore counting-sorted by
+// length, longest first: lanes of a warp get equal trip counts and the long items
+// do not end up in the tail of the launch.
+//   hist[(CAP - len) * nblk + blk]  -> exclusive scan ->  start of (len, blk) in `order`
+// Buckets with more than MSM_BIG items (skewed scalars: many 0/1/small witness
+// values land in one bucket) are listed so that their partial sums are added by a
+// whole block instead of one thread.
 // ---------------------------------------------------------------------------
+constexpr int MSM_SORT_THREADS = 256;
+constexpr uint32_t MSM_BIG = 8;
+
+static __global__ void __launch_bounds__(MSM_SORT_THREADS)
+k_msm_len_hist(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t nblk, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[MSM_CAP + 1];
+    for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) {
+        const uint32_t cnt = counts[b], nfull = cnt / MSM_CAP, rem = cnt % MSM_CAP;
+        if (nfull) atomicAdd(&sh[MSM_CAP], nfull);
+        if (rem) atomicAdd(&sh[rem], 1u);
+    }
+    __syncthreads();
+    for (int len = 1 + threadIdx.x; len <= MSM_CAP; len += blockDim.x)
+        hist[(uint32_t)(MSM_CAP - len) * nblk + blockIdx.x] = sh[len];
+}
+
+static __global__ void __launch_bounds__(MSM_SORT_THREADS)
+k_msm_len_scatter(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ item_off, uint32_t nb,
+                  uint32_t nblk, const uint32_t* __restrict__ start, uint2* __restrict__ order,
+                  uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_count) {
+    __shared__ uint32_t sh[MSM_CAP + 1];
+    for (int len = 1 + threadIdx.x; len <= MSM_CAP; len += blockDim.x)
+        sh[len] = start[(uint32_t)(MSM_CAP - len) * nblk + blockIdx.x];
+    __syncthreads();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t cnt = counts[b], nfull = cnt / MSM_CAP, rem = cnt % MSM_CAP;
+    if (nfull) {
+        const uint32_t p = atomicAdd(&sh[MSM_CAP], nfull);
+        for (uint32_t k = 0; k < nfull; k++) order[p + k] = make_uint2(b, k);
+    }
+    if (rem) order[atomicAdd(&sh[rem], 1u)] = make_uint2(b, nfull);
+    if (nfull + (rem ? 1u : 0u) > MSM_BIG) big_list[atomicAdd(big_count, 1u)] = b;
+    (void)item_off;
+}
+
+// ---------------------------------------------------------------------------
+// bucket accumulation: thread t handles item order[t] = (bucket, slice)
+// ---------------------------------------------------------------------------
+template <class Fp> struct XYZZ;
+template <class Fp> __device__ __forceinline__ void st_xyzz_fwd(XYZZ<Fp>* p, const XYZZ<Fp>& r) {
+    st_field(&p->X, r.X); st_field(&p->Y, r.Y); st_field(&p->ZZ, r.ZZ); st_field(&p->ZZZ, r.ZZZ);
+}
+template <class Fp>
+__device__ __forceinline__ Affine<Fp> ldg_point(const Affine<Fp>* src) {
+    Affine<Fp> p;
+    p.x = ldg_field(&src->x);
+    p.y = ldg_field(&src->y);
+    return p;
+}
+
 template <class Fp>
 __global__ void __launch_bounds__(MSM_THREADS)
 k_msm_accumulate(const Affine<Fp>* __restrict__ table, const uint32_t* __restrict__ entries,
                  const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                  const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ total_items,
-                 uint32_t nbuckets, XYZZ<Fp>* __restrict__ partial) {
+                 const uint2* __restrict__ order, XYZZ<Fp>* __restrict__ partial) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *total_items) return;
-    // bucket = last b with item_off[b] <= t
-    uint32_t lo = 0, hi = nbuckets - 1;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi + 1) >> 1;
-        if (item_off[mid] <= t) lo = mid; else hi = mid - 1;
-    }
-    const uint32_t b = lo;
-    const uint32_t sub = t - item_off[b];
+    const uint2 it = order[t];
+    const uint32_t b = it.x, sub = it.y;
     const uint32_t cnt = counts[b];
     const uint32_t begin = sub * MSM_CAP;
     const uint32_t len = min((uint32_t)MSM_CAP, cnt - begin);
     const uint32_t* e = entries + offsets[b] + begin;
     XYZZ<Fp> acc = XYZZ<Fp>::inf();
+    // software pipeline: the gather of point j+1 is in flight while point j is added
+    uint32_t ent = e[0];
+    Affine<Fp> p = ldg_point(table + (ent & 0x7fffffffu));
+#pragma unroll 1
     for (uint32_t j = 0; j < len; j++) {
-        const uint32_t ent = e[j];
-        const Affine<Fp>* src = table + (ent & 0x7fffffffu);
-        Affine<Fp> p;
-        p.x = ldg_field(&src->x);
-        p.y = ldg_field(&src->y);
-        acc.add_affine_signed(p, ent >> 31);
+        const uint32_t ent_cur = ent;
+        const Affine<Fp> cur = p;
+        if (j + 1 < len) {
+            ent = e[j + 1];
+            p = ldg_point(table + (ent & 0x7fffffffu));
+        }
+        acc.add_affine_signed(cur, ent_cur >> 31);
     }
-    XYZZ<Fp>* dst = partial + t;
-    st_field(&dst->X, acc.X);
-    st_field(&dst->Y, acc.Y);
-    st_field(&dst->ZZ, acc.ZZ);
-    st_field(&dst->ZZZ, acc.ZZZ);
+    st_xyzz_fwd(partial + item_off[b] + sub, acc);
 }
 
 template <class Fp>
@@ -190,8 +248,12 @@ k_msm_reduce_level(const XYZZ<Fp>* __restrict__ Pin, const XYZZ<Fp>* __restrict_
                 // bucket sum = sum of its item partials
                 const uint32_t b0 = item_off[i];
                 const uint32_t b1 = (i + 1 < m) ? item_off[i + 1] : *total_items;
-                p = XYZZ<Fp>::inf();
-                for (uint32_t t = b0; t < b1; t++) p.add(ld_xyzz(Pin + t));
+                if (b1 - b0 > MSM_BIG) {
+                    p = ld_xyzz(Pin + b0);          // total left there by k_msm_big_buckets
+                } else {
+                    p = XYZZ<Fp>::inf();
+                    for (uint32_t t = b0; t < b1; t++) p.add(ld_xyzz(Pin + t));
+                }
             } else {
                 p = ld_xyzz(Pin + i);
                 asum.add(ld_xyzz(Ain + i));
@@ -206,13 +268,134 @@ k_msm_reduce_level(const XYZZ<Fp>* __restrict__ Pin, const XYZZ<Fp>* __restrict_
     st_xyzz(Aout + s, asum);
 }
 
+// ---------------------------------------------------------------------------
+// Tail of the bucket reduction.  After level 0, m entries (P_s, A_s) remain and
+//     result = sum_s A_s + sum_s P_s + SEG * sum_s s * P_s.
+// A chain of further running-sum levels is latency-bound (a few hundred threads,
+// ~16 dependent point additions per level).  Instead the weighted sum is split by
+// the bits of s:   sum_s s P_s = sum_j 2^j Q_j,   Q_j = sum_{s : bit j of s set} P_s,
+// which are plain sums: log-depth tree reductions that fill the machine.
+//   sums 0..nbits-1 : Q_j     sum nbits : sum_s P_s     sum nbits+1 : sum_s A_s
+// ---------------------------------------------------------------------------
+constexpr int MSM_BS_THREADS = 256;
+constexpr int MSM_BS_ITEMS = 8;   // entries per thread
+
 template <class Fp>
-__global__ void k_msm_final(const XYZZ<Fp>* __restrict__ P, const XYZZ<Fp>* __restrict__ A, XYZZ<Fp>* __restrict__ out,
-                            const uint32_t* __restrict__ total_entries, unsigned long long* __restrict__ adds_total) {
-    XYZZ<Fp> r = ld_xyzz(A);
-    r.add(ld_xyzz(P));
-    st_xyzz(out, r);
-    *adds_total += *total_entries;   // single thread, stream ordered: mixed additions done by the accumulation
+__device__ __forceinline__ XYZZ<Fp> shfl_down_xyzz(const XYZZ<Fp>& p, int d) {
+    XYZZ<Fp> r;
+#pragma unroll
+    for (int i = 0; i < Fp::N; i++) {
+        r.X.v[i] = __shfl_down_sync(0xffffffffu, p.X.v[i], d);
+        r.Y.v[i] = __shfl_down_sync(0xffffffffu, p.Y.v[i], d);
+        r.ZZ.v[i] = __shfl_down_sync(0xffffffffu, p.ZZ.v[i], d);
+        r.ZZZ.v[i] = __shfl_down_sync(0xffffffffu, p.ZZZ.v[i], d);
+    }
+    return r;
+}
+// sum over the warp; valid in lane 0 (upper lanes add garbage-free copies of valid points, harmlessly)
+template <class Fp>
+__device__ __forceinline__ XYZZ<Fp> warp_sum_xyzz(XYZZ<Fp> v) {
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        XYZZ<Fp> o = shfl_down_xyzz(v, d);
+        v.add(o);
+    }
+    return v;
+}
+
+// Big buckets (more than MSM_BIG items): one block adds the bucket's partial sums and leaves the
+// total in the bucket's first partial slot; level 0 of the reduction then reads only that slot.
+template <class Fp>
+__global__ void __launch_bounds__(256)
+k_msm_big_buckets(const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_count,
+                  const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ total_items, uint32_t nb,
+                  XYZZ<Fp>* __restrict__ partial) {
+    __shared__ XYZZ<Fp> wsum[8];
+    const uint32_t nbig = *big_count;
+    for (uint32_t k = blockIdx.x; k < nbig; k += gridDim.x) {
+        const uint32_t b = big_list[k];
+        const uint32_t b0 = item_off[b];
+        const uint32_t b1 = (b + 1 < nb) ? item_off[b + 1] : *total_items;
+        XYZZ<Fp> acc = XYZZ<Fp>::inf();
+#pragma unroll 1
+        for (uint32_t t = b0 + threadIdx.x; t < b1; t += blockDim.x) acc.add(ld_xyzz(partial + t));
+        acc = warp_sum_xyzz(acc);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        __syncthreads();          // every read of this bucket's partials is done
+        if (lane == 0) wsum[wid] = acc;
+        __syncthreads();
+        if (wid == 0) {
+            XYZZ<Fp> v = lane < 8 ? wsum[lane] : XYZZ<Fp>::inf();
+#pragma unroll 1
+            for (int d = 4; d >= 1; d >>= 1) {
+                XYZZ<Fp> o = shfl_down_xyzz(v, d);
+                v.add(o);
+            }
+            if (lane == 0) st_xyzz(partial + b0, v);
+        }
+        __syncthreads();
+    }
+}
+
+template <class Fp>
+__global__ void __launch_bounds__(MSM_BS_THREADS)
+k_msm_bitsum(const XYZZ<Fp>* __restrict__ P, const XYZZ<Fp>* __restrict__ A, uint32_t m, int nbits,
+             XYZZ<Fp>* __restrict__ partial) {
+    __shared__ XYZZ<Fp> wsum[MSM_BS_THREADS / 32];
+    const int sum = blockIdx.y;
+    const XYZZ<Fp>* src = (sum == nbits + 1) ? A : P;
+    const uint32_t base = blockIdx.x * (MSM_BS_THREADS * MSM_BS_ITEMS);
+    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+#pragma unroll 1
+    for (int i = 0; i < MSM_BS_ITEMS; i++) {
+        const uint32_t s = base + i * MSM_BS_THREADS + threadIdx.x;
+        if (s < m && (sum >= nbits || ((s >> sum) & 1u))) acc.add(ld_xyzz(src + s));
+    }
+    acc = warp_sum_xyzz(acc);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) wsum[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        XYZZ<Fp> v = lane < MSM_BS_THREADS / 32 ? wsum[lane] : XYZZ<Fp>::inf();
+#pragma unroll 1
+        for (int d = MSM_BS_THREADS / 64; d >= 1; d >>= 1) {
+            XYZZ<Fp> o = shfl_down_xyzz(v, d);
+            v.add(o);
+        }
+        if (lane == 0) st_xyzz(partial + (size_t)sum * gridDim.x + blockIdx.x, v);
+    }
+}
+
+// one warp per sum: adds the per-chunk partials and applies the weight 2^(j + log_seg) to Q_j
+template <class Fp>
+__global__ void __launch_bounds__(32)
+k_msm_bitsum_finish(const XYZZ<Fp>* __restrict__ partial, int nchunks, int nbits, int log_seg,
+                    XYZZ<Fp>* __restrict__ T) {
+    const int sum = blockIdx.x;
+    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+#pragma unroll 1
+    for (int i = threadIdx.x; i < nchunks; i += 32) acc.add(ld_xyzz(partial + (size_t)sum * nchunks + i));
+    acc = warp_sum_xyzz(acc);
+    if (threadIdx.x == 0) {
+        if (sum < nbits) {
+#pragma unroll 1
+            for (int k = 0; k < sum + log_seg; k++) acc = acc.dbl();
+        }
+        st_xyzz(T + sum, acc);
+    }
+}
+
+// result = sum of the nsums (<= 32) weighted sums
+template <class Fp>
+__global__ void __launch_bounds__(32)
+k_msm_final(const XYZZ<Fp>* __restrict__ T, int nsums, XYZZ<Fp>* __restrict__ out,
+            const uint32_t* __restrict__ total_entries, unsigned long long* __restrict__ adds_total) {
+    XYZZ<Fp> v = (int)threadIdx.x < nsums ? ld_xyzz(T + threadIdx.x) : XYZZ<Fp>::inf();
+    v = warp_sum_xyzz(v);
+    if (threadIdx.x == 0) {
+        st_xyzz(out, v);
+        *adds_total += *total_entries;   // stream ordered: mixed additions done by the accumulation
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -231,10 +414,12 @@ struct MsmEngine {
 
     // scratch (sized for npoints scalars)
     DevBuf<uint32_t> counts, offsets, cursor, item_off, entries, scan_scratch, total_items;
-    DevBuf<Ext> partial, lvlP[2], lvlA[2], result;
+    DevBuf<Ext> partial, lvlP[1], lvlA[1], bs_partial, bs_T, result;
     uint32_t max_items = 0;
     Profiler* prof = nullptr;
-    DevBuf<uint32_t> total_entries;
+    DevBuf<uint32_t> total_entries, len_hist, len_start, big_list, big_count;
+    DevBuf<uint2> order;
+    uint32_t sort_blocks = 0;
     DevBuf<unsigned long long> adds_total;   // running count of mixed additions (non-zero digits), device side
 
     void load(const void* host_points, uint64_t n, int force_c, cudaStream_t st) {
@@ -258,15 +443,23 @@ struct MsmEngine {
         const uint32_t nb = plan.nbuckets;
         counts.alloc(nb); offsets.alloc(nb); cursor.alloc(nb); item_off.alloc(nb);
         entries.alloc((size_t)plan.W * npoints);
-        scan_scratch.alloc(scan_scratch_words(nb));
+        sort_blocks = div_up(nb, MSM_SORT_THREADS);
+        const uint32_t hist_len = MSM_CAP * sort_blocks;
+        scan_scratch.alloc(scan_scratch_words(nb > hist_len ? nb : hist_len));
+        len_hist.alloc(hist_len); len_start.alloc(hist_len);
         total_items.alloc(1);
         total_entries.alloc(1);
         adds_total.alloc(1);
         B2P_CUDA(cudaMemset(adds_total.p, 0, sizeof(unsigned long long)));
         max_items = nb + (uint32_t)(((uint64_t)plan.W * npoints) / MSM_CAP) + 1;
         partial.alloc(max_items);
+        order.alloc(max_items);
+        big_list.alloc(max_items / MSM_BIG + 1);
+        big_count.alloc(1);
         const uint32_t m1 = div_up(nb, MSM_SEG);
-        for (int k = 0; k < 2; k++) { lvlP[k].alloc(m1); lvlA[k].alloc(m1); }
+        lvlP[0].alloc(m1); lvlA[0].alloc(m1);
+        bs_partial.alloc((size_t)34 * div_up(m1, MSM_BS_THREADS * MSM_BS_ITEMS));
+        bs_T.alloc(34);
         result.alloc(1);
     }
 
@@ -281,30 +474,33 @@ struct MsmEngine {
         exclusive_scan_u32(counts.p, item_off.p, nb, scan_scratch.p, total_items.p, st, ScanCeilDiv{MSM_CAP});
         if (n) B2P_LAUNCH((k_msm_scatter<Fr>), div_up(n, 256), 256, 0, st, d_scalars, n, npoints, plan.c, plan.W, (int)mont,
                           offsets.p, cursor.p, entries.p);
+        // items sorted by length, longest first
+        B2P_CUDA(cudaMemsetAsync(big_count.p, 0, sizeof(uint32_t), st));
+        B2P_LAUNCH(k_msm_len_hist, sort_blocks, MSM_SORT_THREADS, 0, st, counts.p, nb, sort_blocks, len_hist.p);
+        exclusive_scan_u32(len_hist.p, len_start.p, MSM_CAP * sort_blocks, scan_scratch.p, (uint32_t*)nullptr, st,
+                           ScanIdentity{});
+        B2P_LAUNCH(k_msm_len_scatter, sort_blocks, MSM_SORT_THREADS, 0, st, counts.p, item_off.p, nb, sort_blocks,
+                   len_start.p, order.p, big_list.p, big_count.p);
         const int span = prof ? prof->begin(B2P_STAT_MSM_ACCUM_MS, st) : -1;
         B2P_LAUNCH((k_msm_accumulate<Fp>), div_up(max_items, MSM_THREADS), MSM_THREADS, 0, st, table.p, entries.p,
-                   counts.p, offsets.p, item_off.p, total_items.p, nb, partial.p);
+                   counts.p, offsets.p, item_off.p, total_items.p, order.p, partial.p);
         if (prof) prof->end(span, st);
-        // reduction tree
-        uint32_t m = nb;
-        int level = 0;
+        B2P_LAUNCH((k_msm_big_buckets<Fp>), 148, 256, 0, st, big_list.p, big_count.p, item_off.p, total_items.p, nb,
+                   partial.p);
+        // reduction: one running-sum level over SEG-bucket segments, then bit-decomposed plain sums
         int log_seg = 0;
         while ((1 << log_seg) < MSM_SEG) log_seg++;
-        const Ext* Pin = partial.p;
-        const Ext* Ain = nullptr;
-        do {
-            const uint32_t mout = div_up(m, MSM_SEG);
-            Ext* Pout = lvlP[level & 1].p;
-            Ext* Aout = lvlA[level & 1].p;
-            if (level == 0)
-                B2P_LAUNCH((k_msm_reduce_level<Fp, true>), div_up(mout, MSM_THREADS), MSM_THREADS, 0, st, Pin, Ain,
-                           item_off.p, total_items.p, m, 0, Pout, Aout);
-            else
-                B2P_LAUNCH((k_msm_reduce_level<Fp, false>), div_up(mout, MSM_THREADS), MSM_THREADS, 0, st, Pin, Ain,
-                           item_off.p, total_items.p, m, level * log_seg, Pout, Aout);
-            Pin = Pout; Ain = Aout; m = mout; level++;
-        } while (m > 1);
-        B2P_LAUNCH((k_msm_final<Fp>), 1, 1, 0, st, Pin, Ain, result.p, total_entries.p, adds_total.p);
+        const uint32_t m1 = div_up(nb, MSM_SEG);
+        B2P_LAUNCH((k_msm_reduce_level<Fp, true>), div_up(m1, MSM_THREADS), MSM_THREADS, 0, st, partial.p,
+                   (const Ext*)nullptr, item_off.p, total_items.p, nb, 0, lvlP[0].p, lvlA[0].p);
+        int nbits = 0;
+        while ((1u << nbits) < m1) nbits++;
+        const int nsums = nbits + 2;
+        const unsigned nchunks = div_up(m1, MSM_BS_THREADS * MSM_BS_ITEMS);
+        B2P_LAUNCH((k_msm_bitsum<Fp>), dim3(nchunks, nsums), MSM_BS_THREADS, 0, st, lvlP[0].p, lvlA[0].p, m1, nbits,
+                   bs_partial.p);
+        B2P_LAUNCH((k_msm_bitsum_finish<Fp>), nsums, 32, 0, st, bs_partial.p, (int)nchunks, nbits, log_seg, bs_T.p);
+        B2P_LAUNCH((k_msm_final<Fp>), 1, 32, 0, st, bs_T.p, nsums, result.p, total_entries.p, adds_total.p);
     }
 
     // synchronous convenience: returns the affine result (host)

@@ -22,7 +22,7 @@ __global__ void k_imad(uint32_t* out, int iters, uint32_t seed) {
         for (int it = 0; it < iters; it++) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[i]) : "r"(a), "r"(b));
+                asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(c[i]) : "r"(b));
         }
         uint64_t s = 0;
 #pragma unroll
@@ -35,7 +35,7 @@ __global__ void k_imad(uint32_t* out, int iters, uint32_t seed) {
         for (int it = 0; it < iters; it++) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c[i]) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(c[i]) : "r"(b), "r"(a));
         }
         uint32_t s = 0;
 #pragma unroll
@@ -48,6 +48,8 @@ template <class F>
 __global__ void __launch_bounds__(256) k_fmul(F* out, int iters) {
     F a = F::one(), b = F::r2(), c = F::r2();
     a.v[0] += threadIdx.x;
+    c.v[0] += 3 * threadIdx.x + blockIdx.x;   // keep both chains off the uniform datapath
+    b.v[1] += threadIdx.x;
     for (int it = 0; it < iters; it++) {
         a = a * b;      // two independent chains
         c = c * b;
