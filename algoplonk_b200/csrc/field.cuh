@@ -169,7 +169,74 @@ struct Field {
         odd[N - 1] = ptx::addc(odd[N - 1], 0);
     }
 
+#if !defined(__CUDA_ARCH__) && !defined(B2P_HOST_EMULATE_DEVICE_MUL)
+    // Host build: the same Montgomery product on 64-bit limbs with a 128-bit accumulator
+    // (the carry-flag emulation of ptx.cuh is exact but ~20x slower; the prover's host side
+    // inverts a few scalars and converts the proof points to affine with this).
+    // -DB2P_HOST_EMULATE_DEVICE_MUL keeps the emulated device code path (tests/test_host.py).
+    static uint64_t inv64() {
+        // P::INV = -p^-1 mod 2^32; one Newton step lifts p^-1 to 64 bits
+        const uint64_t p0 = (uint64_t)P::mod(0) | ((uint64_t)P::mod(1) << 32);
+        uint64_t y = (uint64_t)(uint32_t)(0u - P::INV);
+        y *= 2 - p0 * y;
+        return 0 - y;
+    }
+    static Field mul_host(const Field& a, const Field& b) {
+        constexpr int M = N / 2;
+        typedef unsigned __int128 u128;
+        uint64_t A[M], B[M], Pm[M], t[M + 2];
+        for (int i = 0; i < M; i++) {
+            A[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+            B[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+            Pm[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
+        }
+        for (int i = 0; i < M + 2; i++) t[i] = 0;
+        static const uint64_t ninv = inv64();
+        for (int i = 0; i < M; i++) {
+            u128 c = 0;
+            for (int j = 0; j < M; j++) {
+                c += (u128)A[j] * B[i] + t[j];
+                t[j] = (uint64_t)c;
+                c >>= 64;
+            }
+            c += t[M];
+            t[M] = (uint64_t)c;
+            t[M + 1] = (uint64_t)(c >> 64);
+            const uint64_t m = t[0] * ninv;
+            c = (u128)m * Pm[0] + t[0];
+            c >>= 64;
+            for (int j = 1; j < M; j++) {
+                c += (u128)m * Pm[j] + t[j];
+                t[j - 1] = (uint64_t)c;
+                c >>= 64;
+            }
+            c += t[M];
+            t[M - 1] = (uint64_t)c;
+            t[M] = t[M + 1] + (uint64_t)(c >> 64);
+        }
+        // t < 2p (operands < p, or one operand any N-limb value as in reduce_to_mont): one conditional subtraction
+        uint64_t d[M];
+        unsigned char borrow = 0;
+        for (int i = 0; i < M; i++) {
+            u128 s = (u128)t[i] - Pm[i] - borrow;
+            d[i] = (uint64_t)s;
+            borrow = (unsigned char)((s >> 64) & 1);
+        }
+        const bool ge = t[M] != 0 || !borrow;
+        Field r;
+        for (int i = 0; i < M; i++) {
+            const uint64_t x = ge ? d[i] : t[i];
+            r.v[2 * i] = (uint32_t)x;
+            r.v[2 * i + 1] = (uint32_t)(x >> 32);
+        }
+        return r;
+    }
+#endif
+
     HD friend Field operator*(const Field& a, const Field& b) {
+#if !defined(__CUDA_ARCH__) && !defined(B2P_HOST_EMULATE_DEVICE_MUL)
+        return mul_host(a, b);
+#else
         uint32_t even[N], odd[N];
 #pragma unroll
         for (int i = 0; i < N; i += 2) {
@@ -185,6 +252,7 @@ struct Field {
         r.v[N - 1] = ptx::addc(even[N - 1], 0);
         final_sub(r.v);
         return r;
+#endif
     }
 
     HD Field sqr() const { return (*this) * (*this); }

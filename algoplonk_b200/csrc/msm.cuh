@@ -22,7 +22,6 @@
 namespace b2p {
 
 constexpr int MSM_CAP = 64;        // max entries accumulated by one thread
-constexpr int MSM_SEG = 8;         // radix of the bucket-reduction tree
 constexpr int MSM_THREADS = 128;
 
 struct MsmPlan {
@@ -218,67 +217,25 @@ __device__ __forceinline__ XYZZ<Fp> ld_xyzz(const XYZZ<Fp>* p) {
     return r;
 }
 template <class Fp>
+__device__ __forceinline__ XYZZ<Fp> ld_xyzz_cg(const XYZZ<Fp>* p) {   // L2-coherent loads
+    XYZZ<Fp> r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(XYZZ<Fp>) / 16); i++) {
+        const uint4 t = __ldcg(q + i);
+        w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+    }
+    return r;
+}
+template <class Fp>
 __device__ __forceinline__ void st_xyzz(XYZZ<Fp>* p, const XYZZ<Fp>& r) {
     st_field(&p->X, r.X); st_field(&p->Y, r.Y); st_field(&p->ZZ, r.ZZ); st_field(&p->ZZZ, r.ZZZ);
 }
 
 // ---------------------------------------------------------------------------
-// bucket reduction.  Invariant over levels (m entries, index i has weight i):
-//     result = sum_i A_i + scale * sum_i i * P_i + sum_i P_i
-// One step groups SEG consecutive entries:  A'_s = sum_j A_j + scale * sum_j j * P_j,
-// P'_s = sum_j P_j, scale' = scale * SEG.  At m == 1: result = A_0 + P_0.
-// Level 0 reads the per-item partial sums (A absent).
+// warp-level sums of XYZZ points
 // ---------------------------------------------------------------------------
-template <class Fp, bool FIRST>
-__global__ void __launch_bounds__(MSM_THREADS)
-k_msm_reduce_level(const XYZZ<Fp>* __restrict__ Pin, const XYZZ<Fp>* __restrict__ Ain,
-                   const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ total_items,
-                   uint32_t m, int log_scale, XYZZ<Fp>* __restrict__ Pout, XYZZ<Fp>* __restrict__ Aout) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t mout = (m + MSM_SEG - 1) / MSM_SEG;
-    if (s >= mout) return;
-    XYZZ<Fp> running = XYZZ<Fp>::inf();   // sum of P_j seen so far (descending j)
-    XYZZ<Fp> weighted = XYZZ<Fp>::inf();  // sum_j j * P_j
-    XYZZ<Fp> asum = XYZZ<Fp>::inf();
-    for (int j = MSM_SEG - 1; j >= 0; j--) {
-        const uint32_t i = s * MSM_SEG + j;
-        if (i < m) {
-            XYZZ<Fp> p;
-            if (FIRST) {
-                // bucket sum = sum of its item partials
-                const uint32_t b0 = item_off[i];
-                const uint32_t b1 = (i + 1 < m) ? item_off[i + 1] : *total_items;
-                if (b1 - b0 > MSM_BIG) {
-                    p = ld_xyzz(Pin + b0);          // total left there by k_msm_big_buckets
-                } else {
-                    p = XYZZ<Fp>::inf();
-                    for (uint32_t t = b0; t < b1; t++) p.add(ld_xyzz(Pin + t));
-                }
-            } else {
-                p = ld_xyzz(Pin + i);
-                asum.add(ld_xyzz(Ain + i));
-            }
-            running.add(p);
-        }
-        if (j > 0) weighted.add(running);
-    }
-    for (int k = 0; k < log_scale; k++) weighted = weighted.dbl();
-    asum.add(weighted);
-    st_xyzz(Pout + s, running);
-    st_xyzz(Aout + s, asum);
-}
-
-// ---------------------------------------------------------------------------
-// Tail of the bucket reduction.  After level 0, m entries (P_s, A_s) remain and
-//     result = sum_s A_s + sum_s P_s + SEG * sum_s s * P_s.
-// A chain of further running-sum levels is latency-bound (a few hundred threads,
-// ~16 dependent point additions per level).  Instead the weighted sum is split by
-// the bits of s:   sum_s s P_s = sum_j 2^j Q_j,   Q_j = sum_{s : bit j of s set} P_s,
-// which are plain sums: log-depth tree reductions that fill the machine.
-//   sums 0..nbits-1 : Q_j     sum nbits : sum_s P_s     sum nbits+1 : sum_s A_s
-// ---------------------------------------------------------------------------
-constexpr int MSM_BS_THREADS = 256;
-constexpr int MSM_BS_ITEMS = 8;   // entries per thread
 
 template <class Fp>
 __device__ __forceinline__ XYZZ<Fp> shfl_down_xyzz(const XYZZ<Fp>& p, int d) {
@@ -292,13 +249,19 @@ __device__ __forceinline__ XYZZ<Fp> shfl_down_xyzz(const XYZZ<Fp>& p, int d) {
     }
     return r;
 }
+// Out-of-line point addition for the reduction kernels: keeps their register count at the cost of one
+// call per ~2000-instruction addition (the accumulation kernel inlines its mixed addition instead).
+template <class Fp>
+__device__ __noinline__ XYZZ<Fp> xyzz_add_fn(XYZZ<Fp> a, const XYZZ<Fp> b) { a.add(b); return a; }
+#define xyzz_add(a, b) ((a) = xyzz_add_fn((a), (b)))
+
 // sum over the warp; valid in lane 0 (upper lanes add garbage-free copies of valid points, harmlessly)
 template <class Fp>
 __device__ __forceinline__ XYZZ<Fp> warp_sum_xyzz(XYZZ<Fp> v) {
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
         XYZZ<Fp> o = shfl_down_xyzz(v, d);
-        v.add(o);
+        xyzz_add(v, o);
     }
     return v;
 }
@@ -318,7 +281,7 @@ k_msm_big_buckets(const uint32_t* __restrict__ big_list, const uint32_t* __restr
         const uint32_t b1 = (b + 1 < nb) ? item_off[b + 1] : *total_items;
         XYZZ<Fp> acc = XYZZ<Fp>::inf();
 #pragma unroll 1
-        for (uint32_t t = b0 + threadIdx.x; t < b1; t += blockDim.x) acc.add(ld_xyzz(partial + t));
+        for (uint32_t t = b0 + threadIdx.x; t < b1; t += blockDim.x) xyzz_add(acc, ld_xyzz(partial + t));
         acc = warp_sum_xyzz(acc);
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         __syncthreads();          // every read of this bucket's partials is done
@@ -329,7 +292,7 @@ k_msm_big_buckets(const uint32_t* __restrict__ big_list, const uint32_t* __restr
 #pragma unroll 1
             for (int d = 4; d >= 1; d >>= 1) {
                 XYZZ<Fp> o = shfl_down_xyzz(v, d);
-                v.add(o);
+                xyzz_add(v, o);
             }
             if (lane == 0) st_xyzz(partial + b0, v);
         }
@@ -337,64 +300,132 @@ k_msm_big_buckets(const uint32_t* __restrict__ big_list, const uint32_t* __restr
     }
 }
 
+// ---------------------------------------------------------------------------
+// Bucket reduction  result = sum_b (b+1) * B_b  over nb = 2^(c-1) buckets.
+// Write b = h * 2^s + l (l: s low bits).  With column sums C_l = sum_h B_{h,l} and row
+// sums R_h = sum_l B_{h,l}
+//     result = sum_l (l+1) * C_l  +  2^s * sum_h h * R_h :
+// 2^s + 2^(c-1-s) PLAIN sums (one warp each: lanes stride over the terms, then a
+// shuffle tree) followed by one small weighted sum over ncols + nrows points, which
+// is split by the bits of the weights into plain sums again
+//     sum_i w_i X_i = sum_j 2^j Q_j,   Q_j = sum_{i : bit j of w_i} X_i.
+// Nothing here is a long dependent chain of point additions (the first version, a
+// radix-8 running-sum level plus bit-decomposed sums over 65536 entries, was
+// latency-bound: 1.07 ms of a 3.4 ms MSM at c = 20).
+// ---------------------------------------------------------------------------
+constexpr int MSM_RC_WARPS = 4;     // rows/columns per block of k_msm_rowcol
+constexpr int MSM_TAIL_THREADS = 256;
+
+// sum of bucket b: its item partials, or the block-reduced total of a big bucket
 template <class Fp>
-__global__ void __launch_bounds__(MSM_BS_THREADS)
-k_msm_bitsum(const XYZZ<Fp>* __restrict__ P, const XYZZ<Fp>* __restrict__ A, uint32_t m, int nbits,
-             XYZZ<Fp>* __restrict__ partial) {
-    __shared__ XYZZ<Fp> wsum[MSM_BS_THREADS / 32];
-    const int sum = blockIdx.y;
-    const XYZZ<Fp>* src = (sum == nbits + 1) ? A : P;
-    const uint32_t base = blockIdx.x * (MSM_BS_THREADS * MSM_BS_ITEMS);
+__device__ __forceinline__ XYZZ<Fp> load_bucket(const XYZZ<Fp>* __restrict__ partial, const uint32_t* __restrict__ item_off,
+                                                const uint32_t* __restrict__ total_items, uint32_t b, uint32_t nb) {
+    const uint32_t b0 = item_off[b];
+    const uint32_t b1 = (b + 1 < nb) ? item_off[b + 1] : *total_items;
+    if (b1 == b0) return XYZZ<Fp>::inf();
+    XYZZ<Fp> p = ld_xyzz(partial + b0);            // big buckets: total left here by k_msm_big_buckets
+    if (b1 - b0 <= MSM_BIG)
+        for (uint32_t t = b0 + 1; t < b1; t++) xyzz_add(p, ld_xyzz(partial + t));
+    return p;
+}
+
+// Level 1: every thread adds MSM_RC_CHUNK buckets of one column (threads [0, ncols * nch_r)) or of one row
+// (the rest): 2 * nb point additions spread over ~2 * nb / 16 threads with no tree in the way -- this is where
+// the reduction's work is, and it runs at the machine's addition throughput.
+//   Pc[l * nch_r + ch] = sum_{h in chunk ch} B_{h,l}      Pr[h * nch_c + ch] = sum_{l in chunk ch} B_{h,l}
+constexpr int MSM_RC_CHUNK = 16;
+template <class Fp>
+__global__ void __launch_bounds__(128, 4)
+k_msm_rowcol_partial(const XYZZ<Fp>* __restrict__ partial, const uint32_t* __restrict__ item_off,
+                     const uint32_t* __restrict__ total_items, int s, uint32_t nb, XYZZ<Fp>* __restrict__ Pc,
+                     XYZZ<Fp>* __restrict__ Pr) {
+    const uint32_t ncols = 1u << s, nrows = nb >> s;
+    const uint32_t nch_r = (nrows + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK, nch_c = (ncols + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+    if (t < ncols * nch_r) {
+        const uint32_t l = t % ncols, ch = t / ncols;      // lanes along l: neighbouring buckets
+        const uint32_t h1 = min(nrows, (ch + 1) * MSM_RC_CHUNK);
+#pragma unroll 1
+        for (uint32_t h = ch * MSM_RC_CHUNK; h < h1; h++) xyzz_add(acc, load_bucket(partial, item_off, total_items, (h << s) | l, nb));
+        st_xyzz(Pc + (size_t)l * nch_r + ch, acc);
+        return;
+    }
+    t -= ncols * nch_r;
+    if (t >= nrows * nch_c) return;
+    const uint32_t h = t / nch_c, ch = t % nch_c;
+    const uint32_t l1 = min(ncols, (ch + 1) * MSM_RC_CHUNK);
+#pragma unroll 1
+    for (uint32_t l = ch * MSM_RC_CHUNK; l < l1; l++) xyzz_add(acc, load_bucket(partial, item_off, total_items, (h << s) | l, nb));
+    st_xyzz(Pr + (size_t)h * nch_c + ch, acc);
+}
+
+// Level 2: X[l] = C_l for l < ncols, X[ncols + h] = R_h for h < nrows.  One warp per sum of <= 64 partials.
+template <class Fp>
+__global__ void __launch_bounds__(32 * MSM_RC_WARPS)
+k_msm_rowcol(const XYZZ<Fp>* __restrict__ Pc, const XYZZ<Fp>* __restrict__ Pr, int s, uint32_t nb,
+             XYZZ<Fp>* __restrict__ X) {
+    const uint32_t ncols = 1u << s, nrows = nb >> s;
+    const uint32_t nch_r = (nrows + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK, nch_c = (ncols + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK;
+    const uint32_t w = blockIdx.x * MSM_RC_WARPS + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (w >= ncols + nrows) return;
+    const XYZZ<Fp>* src = w < ncols ? Pc + (size_t)w * nch_r : Pr + (size_t)(w - ncols) * nch_c;
+    const uint32_t cnt = w < ncols ? nch_r : nch_c;
     XYZZ<Fp> acc = XYZZ<Fp>::inf();
 #pragma unroll 1
-    for (int i = 0; i < MSM_BS_ITEMS; i++) {
-        const uint32_t s = base + i * MSM_BS_THREADS + threadIdx.x;
-        if (s < m && (sum >= nbits || ((s >> sum) & 1u))) acc.add(ld_xyzz(src + s));
-    }
+    for (uint32_t i = lane; i < cnt; i += 32) xyzz_add(acc, ld_xyzz(src + i));
+    acc = warp_sum_xyzz(acc);
+    if (lane == 0) st_xyzz(X + w, acc);
+}
+
+// weight of entry i of X in the final sum
+__device__ __forceinline__ uint32_t msm_tail_weight(uint32_t i, int s) {
+    const uint32_t ncols = 1u << s;
+    return i < ncols ? i + 1 : (i - ncols) << s;
+}
+
+// block j: T[j] = 2^j * sum_{i : bit j of w_i} X_i; the last block to finish adds the T[j] up.
+template <class Fp>
+__global__ void __launch_bounds__(MSM_TAIL_THREADS)
+k_msm_tail(const XYZZ<Fp>* __restrict__ X, uint32_t ntot, int s, XYZZ<Fp>* __restrict__ T, uint32_t* __restrict__ done,
+           XYZZ<Fp>* __restrict__ out, const uint32_t* __restrict__ total_entries,
+           unsigned long long* __restrict__ adds_total) {
+    __shared__ XYZZ<Fp> wsum[MSM_TAIL_THREADS / 32];
+    __shared__ bool last;
+    const int j = blockIdx.x;
+    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+#pragma unroll 1
+    for (uint32_t i = threadIdx.x; i < ntot; i += MSM_TAIL_THREADS)
+        if ((msm_tail_weight(i, s) >> j) & 1u) xyzz_add(acc, ld_xyzz(X + i));
     acc = warp_sum_xyzz(acc);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) wsum[wid] = acc;
     __syncthreads();
     if (wid == 0) {
-        XYZZ<Fp> v = lane < MSM_BS_THREADS / 32 ? wsum[lane] : XYZZ<Fp>::inf();
+        XYZZ<Fp> v = lane < MSM_TAIL_THREADS / 32 ? wsum[lane] : XYZZ<Fp>::inf();
 #pragma unroll 1
-        for (int d = MSM_BS_THREADS / 64; d >= 1; d >>= 1) {
+        for (int d = MSM_TAIL_THREADS / 64; d >= 1; d >>= 1) {
             XYZZ<Fp> o = shfl_down_xyzz(v, d);
-            v.add(o);
+            xyzz_add(v, o);
         }
-        if (lane == 0) st_xyzz(partial + (size_t)sum * gridDim.x + blockIdx.x, v);
-    }
-}
-
-// one warp per sum: adds the per-chunk partials and applies the weight 2^(j + log_seg) to Q_j
-template <class Fp>
-__global__ void __launch_bounds__(32)
-k_msm_bitsum_finish(const XYZZ<Fp>* __restrict__ partial, int nchunks, int nbits, int log_seg,
-                    XYZZ<Fp>* __restrict__ T) {
-    const int sum = blockIdx.x;
-    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+        if (lane == 0) {
 #pragma unroll 1
-    for (int i = threadIdx.x; i < nchunks; i += 32) acc.add(ld_xyzz(partial + (size_t)sum * nchunks + i));
-    acc = warp_sum_xyzz(acc);
-    if (threadIdx.x == 0) {
-        if (sum < nbits) {
-#pragma unroll 1
-            for (int k = 0; k < sum + log_seg; k++) acc = acc.dbl();
+            for (int k = 0; k < j; k++) v = v.dbl();
+            st_xyzz(T + j, v);
+            __threadfence();
+            last = atomicAdd(done, 1u) == gridDim.x - 1;
         }
-        st_xyzz(T + sum, acc);
     }
-}
-
-// result = sum of the nsums (<= 32) weighted sums
-template <class Fp>
-__global__ void __launch_bounds__(32)
-k_msm_final(const XYZZ<Fp>* __restrict__ T, int nsums, XYZZ<Fp>* __restrict__ out,
-            const uint32_t* __restrict__ total_entries, unsigned long long* __restrict__ adds_total) {
-    XYZZ<Fp> v = (int)threadIdx.x < nsums ? ld_xyzz(T + threadIdx.x) : XYZZ<Fp>::inf();
+    __syncthreads();
+    if (!last || wid != 0) return;
+    __threadfence();
+    XYZZ<Fp> v = lane < (int)gridDim.x ? ld_xyzz_cg(T + lane) : XYZZ<Fp>::inf();   // written by other SMs: bypass L1
     v = warp_sum_xyzz(v);
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
         st_xyzz(out, v);
         *adds_total += *total_entries;   // stream ordered: mixed additions done by the accumulation
+        *done = 0;                       // ready for the next MSM on this stream
     }
 }
 
@@ -414,7 +445,8 @@ struct MsmEngine {
 
     // scratch (sized for npoints scalars)
     DevBuf<uint32_t> counts, offsets, cursor, item_off, entries, scan_scratch, total_items;
-    DevBuf<Ext> partial, lvlP[1], lvlA[1], bs_partial, bs_T, result;
+    DevBuf<Ext> partial, rc_col, rc_row, rc_sums, tail_T, result;
+    DevBuf<uint32_t> tail_done;
     uint32_t max_items = 0;
     Profiler* prof = nullptr;
     DevBuf<uint32_t> total_entries, len_hist, len_start, big_list, big_count;
@@ -439,6 +471,8 @@ struct MsmEngine {
         B2P_LAUNCH((k_msm_build_table<Fp>), div_up(n, 128), 128, 0, st, table.p, n, plan.c, plan.W);
         alloc_scratch();
     }
+    // low bits of the bucket index that select the column in the 2D reduction
+    int split_bits() const { return (plan.c - 1) / 2; }
     void alloc_scratch() {
         const uint32_t nb = plan.nbuckets;
         counts.alloc(nb); offsets.alloc(nb); cursor.alloc(nb); item_off.alloc(nb);
@@ -456,10 +490,15 @@ struct MsmEngine {
         order.alloc(max_items);
         big_list.alloc(max_items / MSM_BIG + 1);
         big_count.alloc(1);
-        const uint32_t m1 = div_up(nb, MSM_SEG);
-        lvlP[0].alloc(m1); lvlA[0].alloc(m1);
-        bs_partial.alloc((size_t)34 * div_up(m1, MSM_BS_THREADS * MSM_BS_ITEMS));
-        bs_T.alloc(34);
+        {
+            const uint32_t ncols = 1u << split_bits(), nrows = nb >> split_bits();
+            rc_col.alloc((size_t)ncols * div_up(nrows, MSM_RC_CHUNK));
+            rc_row.alloc((size_t)nrows * div_up(ncols, MSM_RC_CHUNK));
+            rc_sums.alloc((size_t)ncols + nrows);
+        }
+        tail_T.alloc(32);
+        tail_done.alloc(1);
+        B2P_CUDA(cudaMemset(tail_done.p, 0, sizeof(uint32_t)));
         result.alloc(1);
     }
 
@@ -487,20 +526,17 @@ struct MsmEngine {
         if (prof) prof->end(span, st);
         B2P_LAUNCH((k_msm_big_buckets<Fp>), 148, 256, 0, st, big_list.p, big_count.p, item_off.p, total_items.p, nb,
                    partial.p);
-        // reduction: one running-sum level over SEG-bucket segments, then bit-decomposed plain sums
-        int log_seg = 0;
-        while ((1 << log_seg) < MSM_SEG) log_seg++;
-        const uint32_t m1 = div_up(nb, MSM_SEG);
-        B2P_LAUNCH((k_msm_reduce_level<Fp, true>), div_up(m1, MSM_THREADS), MSM_THREADS, 0, st, partial.p,
-                   (const Ext*)nullptr, item_off.p, total_items.p, nb, 0, lvlP[0].p, lvlA[0].p);
-        int nbits = 0;
-        while ((1u << nbits) < m1) nbits++;
-        const int nsums = nbits + 2;
-        const unsigned nchunks = div_up(m1, MSM_BS_THREADS * MSM_BS_ITEMS);
-        B2P_LAUNCH((k_msm_bitsum<Fp>), dim3(nchunks, nsums), MSM_BS_THREADS, 0, st, lvlP[0].p, lvlA[0].p, m1, nbits,
-                   bs_partial.p);
-        B2P_LAUNCH((k_msm_bitsum_finish<Fp>), nsums, 32, 0, st, bs_partial.p, (int)nchunks, nbits, log_seg, bs_T.p);
-        B2P_LAUNCH((k_msm_final<Fp>), 1, 32, 0, st, bs_T.p, nsums, result.p, total_entries.p, adds_total.p);
+        // reduction: row/column plain sums (two levels), then the bit-decomposed weighted sum of those
+        const int s = split_bits();
+        const uint32_t ncols = 1u << s, nrows = nb >> s, ntot = ncols + nrows;
+        const uint32_t nthreads = ncols * div_up(nrows, MSM_RC_CHUNK) + nrows * div_up(ncols, MSM_RC_CHUNK);
+        B2P_LAUNCH((k_msm_rowcol_partial<Fp>), div_up(nthreads, 128), 128, 0, st, partial.p, item_off.p, total_items.p, s,
+                   nb, rc_col.p, rc_row.p);
+        B2P_LAUNCH((k_msm_rowcol<Fp>), div_up(ntot, MSM_RC_WARPS), 32 * MSM_RC_WARPS, 0, st, rc_col.p, rc_row.p, s, nb,
+                   rc_sums.p);
+        const int nbits = plan.c;                     // weights are < 2^(c-1) + 1
+        B2P_LAUNCH((k_msm_tail<Fp>), nbits, MSM_TAIL_THREADS, 0, st, rc_sums.p, ntot, s, tail_T.p, tail_done.p, result.p,
+                   total_entries.p, adds_total.p);
     }
 
     // synchronous convenience: returns the affine result (host)

@@ -4,7 +4,8 @@
 // Forward = decimation in frequency: natural order in, bit-reversed order out.
 // Inverse = decimation in time: bit-reversed order in, natural order out.
 // Each launch ("pass") runs up to NTT_MAX_STAGES consecutive butterfly stages on
-// a tile held in shared memory, so a 2^22 transform is two trips through HBM.
+// a tile held in shared memory, so a 2^22 transform is two trips through HBM; zero
+// padding, coset scaling and the 1/n of the inverse are fused into the first / last pass.
 // Twiddles omega^k (k < n/2) are a resident table streamed through L2.
 #pragma once
 #include "common.cuh"
@@ -39,13 +40,36 @@ __global__ void k_bitrev_permute(Fr* __restrict__ data, int logn) {
     st_field(data + j, a);
 }
 
+// What a pass does besides its butterflies (fused so the scaling steps of the coset transforms and
+// the zero padding of the coefficient vectors cost no extra trip through HBM):
+enum NttFuse {
+    NTT_PLAIN = 0,
+    NTT_LOAD_PAD_SCALE = 1,   // first DIF pass: in[i] = i < src_len ? src[i] * scale_tab[i] : 0   (out of place)
+    NTT_STORE_SCALE_TAB = 2,  // last DIT pass:  out[i] = v[i] * scale_tab[i]                       (g^-i / n)
+    NTT_STORE_SCALE = 3,      // last DIT pass:  out[i] = v[i] * scale                              (1 / n)
+};
+
+template <class Fr>
+struct NttPassArgs {
+    Fr* data;                 // in place (destination of NTT_LOAD_PAD_SCALE)
+    const Fr* tw;             // omega^k, k < n/2
+    const Fr* src;            // NTT_LOAD_PAD_SCALE: coefficient vector
+    uint64_t src_len;
+    const Fr* scale_tab;
+    Fr scale;
+    int logn, s_lo, nst;
+};
+
 // One pass: stages s_hi .. s_hi-nst+1 (DIF, descending) or s_lo .. s_lo+nst-1 (DIT, ascending).
 // Tile element k (0 <= k < 2^nst) lives at global index (hi << (s_hi+1)) | (k << s_lo) | lo.
-template <class Fr, bool DIF>
+template <class Fr, bool DIF, int FUSE>
 __global__ void __launch_bounds__(1 << (NTT_MAX_STAGES - 1))
-k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, int logn, int s_lo, int nst) {
+k_ntt_pass(const NttPassArgs<Fr> a) {
     extern __shared__ uint4 smem4[];
     constexpr int Q = Fr::N / 4;              // uint4 per element
+    Fr* __restrict__ data = a.data;
+    const Fr* __restrict__ tw = a.tw;
+    const int logn = a.logn, s_lo = a.s_lo, nst = a.nst;
     const int tile = 1 << nst;
     const uint32_t lo_mask = (1u << s_lo) - 1;
     const uint32_t lo = blockIdx.x & lo_mask;
@@ -57,27 +81,44 @@ k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, int logn, int s_lo,
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const int k = t + r * (tile >> 1);
-        const uint4* src = reinterpret_cast<const uint4*>(data + (base + ((uint64_t)k << s_lo)));
+        const uint64_t g = base + ((uint64_t)k << s_lo);
+        if (FUSE == NTT_LOAD_PAD_SCALE) {
+            Fr v = Fr::zero();
+            if (g < a.src_len) v = ld_field(a.src + g) * ldg_field(a.scale_tab + g);
 #pragma unroll
-        for (int q = 0; q < Q; q++) smem4[q * tile + k] = src[q];
+            for (int q = 0; q < Q; q++)
+                smem4[q * tile + k] = make_uint4(v.v[4 * q], v.v[4 * q + 1], v.v[4 * q + 2], v.v[4 * q + 3]);
+        } else {
+            const uint4* src = reinterpret_cast<const uint4*>(data + g);
+#pragma unroll
+            for (int q = 0; q < Q; q++) smem4[q * tile + k] = src[q];
+        }
     }
     __syncthreads();
 
+    // twiddle of this thread's butterfly at iteration `it` (depends on the thread, not on the data):
+    // fetched one stage ahead so its L2 latency hides behind the butterfly and the barrier
+    auto twiddle = [&](int it) {
+        const int ls = DIF ? (nst - 1 - it) : it;
+        const int half = 1 << ls;
+        // position inside the half-block at the global stage s = s_lo + ls
+        const uint32_t pos = ((uint32_t)(t & (half - 1)) << s_lo) | lo;
+        return ldg_field(tw + ((uint64_t)pos << (logn - 1 - (s_lo + ls))));
+    };
+    Fr w = twiddle(0);
     for (int it = 0; it < nst; it++) {
         const int ls = DIF ? (nst - 1 - it) : it;
         const int half = 1 << ls;
         const int i = ((t >> ls) << (ls + 1)) | (t & (half - 1));
         const int j = i + half;
-        // position inside the half-block at the global stage s = s_lo + ls
-        const uint32_t pos = ((uint32_t)(i & (half - 1)) << s_lo) | lo;
-        const int s = s_lo + ls;
-        const Fr w = ldg_field(tw + ((uint64_t)pos << (logn - 1 - s)));
+        Fr w_next;
+        if (it + 1 < nst) w_next = twiddle(it + 1);
         Fr x, y;
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            uint4 a = smem4[q * tile + i], b = smem4[q * tile + j];
-            x.v[4 * q] = a.x; x.v[4 * q + 1] = a.y; x.v[4 * q + 2] = a.z; x.v[4 * q + 3] = a.w;
-            y.v[4 * q] = b.x; y.v[4 * q + 1] = b.y; y.v[4 * q + 2] = b.z; y.v[4 * q + 3] = b.w;
+            uint4 a4 = smem4[q * tile + i], b4 = smem4[q * tile + j];
+            x.v[4 * q] = a4.x; x.v[4 * q + 1] = a4.y; x.v[4 * q + 2] = a4.z; x.v[4 * q + 3] = a4.w;
+            y.v[4 * q] = b4.x; y.v[4 * q + 1] = b4.y; y.v[4 * q + 2] = b4.z; y.v[4 * q + 3] = b4.w;
         }
         Fr u, v;
         if (DIF) { u = x + y; v = (x - y) * w; }
@@ -88,14 +129,27 @@ k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, int logn, int s_lo,
             smem4[q * tile + j] = make_uint4(v.v[4 * q], v.v[4 * q + 1], v.v[4 * q + 2], v.v[4 * q + 3]);
         }
         __syncthreads();
+        if (it + 1 < nst) w = w_next;
     }
 
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const int k = t + r * (tile >> 1);
-        uint4* dst = reinterpret_cast<uint4*>(data + (base + ((uint64_t)k << s_lo)));
+        const uint64_t g = base + ((uint64_t)k << s_lo);
+        uint4* dst = reinterpret_cast<uint4*>(data + g);
+        if (FUSE == NTT_STORE_SCALE_TAB || FUSE == NTT_STORE_SCALE) {
+            Fr v;
 #pragma unroll
-        for (int q = 0; q < Q; q++) dst[q] = smem4[q * tile + k];
+            for (int q = 0; q < Q; q++) {
+                uint4 c = smem4[q * tile + k];
+                v.v[4 * q] = c.x; v.v[4 * q + 1] = c.y; v.v[4 * q + 2] = c.z; v.v[4 * q + 3] = c.w;
+            }
+            v = v * (FUSE == NTT_STORE_SCALE_TAB ? ldg_field(a.scale_tab + g) : a.scale);
+            st_field(data + g, v);
+        } else {
+#pragma unroll
+            for (int q = 0; q < Q; q++) dst[q] = smem4[q * tile + k];
+        }
     }
 }
 
@@ -158,46 +212,64 @@ struct NttDomain {
         }
     }
 
-    template <bool DIF>
-    void passes(Fr* d, const Fr* table, cudaStream_t st) const {
-        if (logn == 0) return;
+    // FIRST / LAST: fusion applied by the first / last pass of the transform (NttFuse)
+    template <bool DIF, int FIRST, int LAST>
+    void passes(Fr* d, const Fr* table, cudaStream_t st, const Fr* src = nullptr, uint64_t src_len = 0,
+                const Fr* scale_tab = nullptr, const Fr* scale = nullptr) const {
+        if (logn == 0) {
+            // a single point: only the fused copy / scaling remains
+            if (FIRST == NTT_LOAD_PAD_SCALE) {
+                if (!src_len) {
+                    B2P_CUDA(cudaMemsetAsync(d, 0, sizeof(Fr), st));
+                } else {
+                    if (src != d) B2P_CUDA(cudaMemcpyAsync(d, src, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+                    B2P_LAUNCH((k_mul_table<Fr>), 1, 32, 0, st, d, scale_tab, 1);
+                }
+            }
+            if (LAST == NTT_STORE_SCALE_TAB) B2P_LAUNCH((k_mul_table<Fr>), 1, 32, 0, st, d, scale_tab, 1);
+            if (LAST == NTT_STORE_SCALE) B2P_LAUNCH((k_mul_scalar<Fr>), 1, 32, 0, st, d, *scale, 1);
+            return;
+        }
         const int npass = (logn + NTT_MAX_STAGES - 1) / NTT_MAX_STAGES;
         // split stages as evenly as possible
         int sizes[8];
         for (int p = 0; p < npass; p++) sizes[p] = logn / npass + (p < logn % npass ? 1 : 0);
-        auto kern = k_ntt_pass<Fr, DIF>;
+        NttPassArgs<Fr> a;
+        a.data = d; a.tw = table; a.src = src; a.src_len = src_len; a.scale_tab = scale_tab;
+        a.scale = scale ? *scale : Fr::zero();
+        a.logn = logn;
+        int s_next = DIF ? logn - 1 : 0;
+        for (int p = 0; p < npass; p++) {
+            a.nst = sizes[p];
+            a.s_lo = DIF ? s_next - a.nst + 1 : s_next;
+            s_next = DIF ? a.s_lo - 1 : a.s_lo + a.nst;
+            const int fuse = (p == 0 ? FIRST : NTT_PLAIN) | (p == npass - 1 ? LAST : NTT_PLAIN);
+            if (fuse == NTT_PLAIN) launch_pass<DIF, NTT_PLAIN>(a, st);
+            else if (fuse == FIRST) launch_pass<DIF, FIRST>(a, st);
+            else if (fuse == LAST) launch_pass<DIF, LAST>(a, st);
+            else B2P_REQUIRE(false, "unsupported NTT fusion");   // a first-pass and a last-pass fusion never meet
+        }
+    }
+    template <bool DIF, int FUSE>
+    void launch_pass(const NttPassArgs<Fr>& a, cudaStream_t st) const {
+        auto kern = k_ntt_pass<Fr, DIF, FUSE>;
         static bool attr_set = false;
         if (!attr_set) {
             B2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(sizeof(Fr) << NTT_MAX_STAGES)));
             attr_set = true;
         }
-        if (DIF) {
-            int s_hi = logn - 1;
-            for (int p = 0; p < npass; p++) {
-                const int nst = sizes[p], s_lo = s_hi - nst + 1;
-                B2P_LAUNCH(kern, (unsigned)(n >> nst), 1 << (nst - 1), sizeof(Fr) << nst, st, d, table, logn, s_lo, nst);
-                s_hi = s_lo - 1;
-            }
-        } else {
-            int s_lo = 0;
-            for (int p = 0; p < npass; p++) {
-                const int nst = sizes[p];
-                B2P_LAUNCH(kern, (unsigned)(n >> nst), 1 << (nst - 1), sizeof(Fr) << nst, st, d, table, logn, s_lo, nst);
-                s_lo += nst;
-            }
-        }
+        B2P_LAUNCH(kern, (unsigned)(n >> a.nst), 1 << (a.nst - 1), sizeof(Fr) << a.nst, st, a);
     }
 
     void bitrev(Fr* d, cudaStream_t st) const {
         B2P_LAUNCH((k_bitrev_permute<Fr>), div_up(n, 256), 256, 0, st, d, logn);
     }
     // natural -> bit-reversed evaluations
-    void forward_dif(Fr* d, cudaStream_t st) const { passes<true>(d, tw.p, st); }
-    // bit-reversed evaluations -> natural coefficients (scaled by 1/n)
+    void forward_dif(Fr* d, cudaStream_t st) const { passes<true, NTT_PLAIN, NTT_PLAIN>(d, tw.p, st); }
+    // bit-reversed evaluations -> natural coefficients (scaled by 1/n in the last pass)
     void inverse_dit(Fr* d, cudaStream_t st) const {
-        passes<false>(d, tw_inv.p, st);
-        B2P_LAUNCH((k_mul_scalar<Fr>), div_up(n, 256), 256, 0, st, d, n_inv, n);
+        passes<false, NTT_PLAIN, NTT_STORE_SCALE>(d, tw_inv.p, st, nullptr, 0, nullptr, &n_inv);
     }
     // natural -> natural variants (explicit bit reversal)
     void forward_natural(Fr* d, cudaStream_t st) const {
@@ -208,17 +280,18 @@ struct NttDomain {
         B2P_LAUNCH((k_bitrev_permute<Fr>), div_up(n, 256), 256, 0, st, d, logn);
         inverse_dit(d, st);
     }
-    // coefficients (natural) -> evaluations on g*<omega> in bit-reversed order
-    void coset_forward_dif(Fr* d, cudaStream_t st) const {
+    // coefficients (natural) -> evaluations on g*<omega> in bit-reversed order, in place
+    void coset_forward_dif(Fr* d, cudaStream_t st) const { coset_forward_dif_from(d, d, n, st); }
+    // same, reading len <= n coefficients from src (zero padded) and writing the n evaluations to dst
+    void coset_forward_dif_from(Fr* dst, const Fr* src, uint64_t len, cudaStream_t st) const {
         B2P_REQUIRE(has_coset, "domain built without coset tables");
-        B2P_LAUNCH((k_mul_table<Fr>), div_up(n, 256), 256, 0, st, d, coset_pow.p, n);
-        forward_dif(d, st);
+        B2P_REQUIRE(len <= n, "more coefficients than domain points");
+        passes<true, NTT_LOAD_PAD_SCALE, NTT_PLAIN>(dst, tw.p, st, src, len, coset_pow.p);
     }
-    // evaluations on g*<omega> (bit-reversed) -> coefficients (natural)
+    // evaluations on g*<omega> (bit-reversed) -> coefficients (natural); g^-i / n applied by the last pass
     void coset_inverse_dit(Fr* d, cudaStream_t st) const {
         B2P_REQUIRE(has_coset, "domain built without coset tables");
-        passes<false>(d, tw_inv.p, st);
-        B2P_LAUNCH((k_mul_table<Fr>), div_up(n, 256), 256, 0, st, d, coset_pow_inv.p, n);
+        passes<false, NTT_PLAIN, NTT_STORE_SCALE_TAB>(d, tw_inv.p, st, nullptr, 0, coset_pow_inv.p);
     }
 };
 

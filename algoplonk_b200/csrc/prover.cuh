@@ -49,6 +49,56 @@ inline void point_marshal(const Affine<typename C::Fp>& p, uint8_t* out, bool gn
     field_to_be(p.y, out + NB);
 }
 
+// inverse of point_marshal: uncompressed X || Y big-endian (gnark G1Affine.Marshal()); the flag bits gnark
+// keeps in the top of the first byte are masked, an infinity flag or all-zero coordinates give infinity
+template <class C>
+inline Affine<typename C::Fp> point_unmarshal(const uint8_t* in) {
+    using Fp = typename C::Fp;
+    constexpr int NB = Fp::N * 4;
+    const uint8_t mask = C::ID == B2P_BLS12_381 ? 0xE0 : 0xC0;
+    if ((in[0] & mask) == 0x40) return Affine<Fp>::inf();
+    Fp c[2];
+    for (int k = 0; k < 2; k++) {
+        for (int i = 0; i < Fp::N; i++) c[k].v[i] = 0;
+        for (int b = 0; b < NB; b++) {
+            uint8_t byte = in[k * NB + NB - 1 - b];
+            if (k == 0 && b == NB - 1) byte &= (uint8_t)~mask;
+            c[k].v[b >> 2] |= (uint32_t)byte << (8 * (b & 3));
+        }
+    }
+    if (c[0].is_zero() && c[1].is_zero()) return Affine<Fp>::inf();
+    return Affine<Fp>{c[0].to_mont(), c[1].to_mont()};
+}
+
+// sum_i s_i * P_i for a handful of points, on the host (Straus, 4-bit windows, shared doublings).
+// Used for the commitment to the linearised polynomial, which is a combination of commitments
+// that are already known (the verifier computes the same combination,
+// templateLogicSigBN254.go:256-278); runs while the device is busy with an MSM.
+template <class C>
+inline Affine<typename C::Fp> host_msm_small(const Affine<typename C::Fp>* pts, const typename C::Fr* scalars_mont,
+                                             int cnt) {
+    using Fp = typename C::Fp;
+    using Fr = typename C::Fr;
+    std::vector<XYZZ<Fp>> tbl((size_t)cnt * 16);
+    std::vector<Fr> sc(cnt);
+    for (int i = 0; i < cnt; i++) {
+        sc[i] = scalars_mont[i].from_mont();
+        XYZZ<Fp>* t = &tbl[(size_t)i * 16];
+        t[0] = XYZZ<Fp>::inf();
+        t[1] = XYZZ<Fp>::from_affine(pts[i]);
+        for (int j = 2; j < 16; j++) { t[j] = t[j - 1]; t[j].add(t[1]); }
+    }
+    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+    for (int w = Fr::N * 8 - 1; w >= 0; w--) {
+        for (int k = 0; k < 4; k++) acc = acc.dbl();
+        for (int i = 0; i < cnt; i++) {
+            const uint32_t d = (sc[i].v[w >> 3] >> (4 * (w & 7))) & 15u;
+            if (d) acc.add(tbl[(size_t)i * 16 + d]);
+        }
+    }
+    return acc.to_affine();
+}
+
 // hash_to_field with DST "BSB22-Plonk" (templateLogicSigBN254.go:386-397)
 template <class C>
 inline typename C::Fr hash_fr(const uint8_t* point_bytes, size_t len) {
@@ -69,16 +119,6 @@ inline typename C::Fr hash_fr(const uint8_t* point_bytes, size_t len) {
     Fr hi = fr_from_be32_mod<Fr>(b1);
     Fr two128 = Fr::from_u32(2).pow_u64(128);
     return hi * two128 + fr_from_be32_mod<Fr>(lo);
-}
-
-template <class Fp>
-__global__ void k_xyzz_to_affine(const XYZZ<Fp>* __restrict__ in, Affine<Fp>* __restrict__ out, int cnt) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cnt) return;
-    XYZZ<Fp> p = ld_xyzz(in + i);
-    Affine<Fp> a = p.to_affine();
-    st_field(&out[i].x, a.x);
-    st_field(&out[i].y, a.y);
 }
 
 // [tau^j] G1 for j < n  (unsafekzg.NewSRS)
@@ -136,7 +176,6 @@ struct Srs : SrsBase {
     cudaStream_t stream = nullptr;
     MsmEngine<C> msm;
     DevBuf<Ext> msm_out;        // result slots
-    DevBuf<Aff> msm_out_aff;
     DevBuf<Fr> scratch;         // scalar staging for b2p_msm_g1
     Profiler* prof = nullptr;
     static constexpr int OUT_SLOTS = 16;
@@ -146,7 +185,6 @@ struct Srs : SrsBase {
 
     void finish_init() {
         msm_out.alloc(OUT_SLOTS);
-        msm_out_aff.alloc(OUT_SLOTS);
         B2P_CUDA(cudaStreamSynchronize(stream));
     }
     void load(const void* pts, uint64_t n) override {
@@ -209,11 +247,15 @@ struct Srs : SrsBase {
         B2P_CUDA(cudaMemcpyAsync(msm_out.p + slot, msm.result.p, sizeof(Ext), cudaMemcpyDeviceToDevice, stream));
         if (prof) prof->end(id, stream);
     }
-    // convert slots [first, first+cnt) to affine and bring them to the host (synchronises)
+    // bring slots [first, first+cnt) to the host (synchronises) and convert them to affine there:
+    // one field inversion per point takes ~10 us on a host core, against ~160 us for a
+    // single-thread kernel on the device.
     void fetch(int first, int cnt, Aff* host_out) {
-        B2P_LAUNCH((k_xyzz_to_affine<Fp>), 1, 32, 0, stream, msm_out.p + first, msm_out_aff.p + first, cnt);
-        B2P_CUDA(cudaMemcpyAsync(host_out, msm_out_aff.p + first, cnt * sizeof(Aff), cudaMemcpyDeviceToHost, stream));
+        Ext h[OUT_SLOTS];
+        B2P_REQUIRE(first >= 0 && cnt >= 0 && first + cnt <= OUT_SLOTS, "result slot out of range");
+        B2P_CUDA(cudaMemcpyAsync(h, msm_out.p + first, cnt * sizeof(Ext), cudaMemcpyDeviceToHost, stream));
         B2P_CUDA(cudaStreamSynchronize(stream));
+        for (int i = 0; i < cnt; i++) host_out[i] = h[i].to_affine();
     }
 };
 
@@ -245,6 +287,7 @@ struct Circuit : CircuitBase {
     Fr u, u2;
     std::vector<uint8_t> vk_bytes;
     std::vector<Aff> vk_points;        // S1 S2 S3 Ql Qr Qm Qo Qk Qcp*
+    std::vector<Aff> vk_lin_points;    // the same commitments as the transcript binds them (used for [Lin])
     bool have_vk_points = false;
 
     // per-proof workspace
@@ -260,8 +303,10 @@ struct Circuit : CircuitBase {
     void vk_commitments(void* out) override {
         if (!have_vk_points) {
             auto keep = vk_bytes;
+            auto keep_pts = vk_lin_points;
             compute_vk();
             vk_bytes = keep;   // the caller-supplied transcript bytes stay authoritative
+            vk_lin_points = keep_pts;
         }
         memcpy(out, vk_points.data(), vk_points.size() * sizeof(Aff));
     }
@@ -272,10 +317,8 @@ struct Circuit : CircuitBase {
     void to_canonical(Fr* d) { d0.inverse_natural(d, st); }
     // canonical coefficients (len <= m) -> evaluations on the big coset (bit-reversed) into dst (m)
     void to_coset(Fr* dst, const Fr* coeffs, uint64_t len) {
-        B2P_CUDA(cudaMemcpyAsync(dst, coeffs, len * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-        B2P_CUDA(cudaMemsetAsync(dst + len, 0, (m - len) * sizeof(Fr), st));
         int id = prof.begin(B2P_STAT_NTT_MS, st);
-        d1.coset_forward_dif(dst, st);
+        d1.coset_forward_dif_from(dst, coeffs, len, st);
         prof.end(id, st);
     }
     void upload_column_canonical(DevBuf<Fr>& c, const void* host_lagrange) {
@@ -369,8 +412,10 @@ struct Circuit : CircuitBase {
         alloc_workspace();
 
         if (vkb) {
-            vk_bytes.assign((const uint8_t*)vkb, (const uint8_t*)vkb + vkb_len);
             B2P_REQUIRE(vkb_len == (size_t)(8 + k) * PB, "vk_transcript has the wrong length");
+            vk_bytes.assign((const uint8_t*)vkb, (const uint8_t*)vkb + vkb_len);
+            vk_lin_points.resize(8 + k);
+            for (uint32_t i = 0; i < 8 + k; i++) vk_lin_points[i] = point_unmarshal<C>(&vk_bytes[(size_t)i * PB]);
         } else {
             compute_vk();
         }
@@ -413,6 +458,7 @@ struct Circuit : CircuitBase {
         vk_bytes.resize((size_t)(8 + k) * PB);
         for (size_t i = 0; i < vk_points.size(); i++) point_marshal<C>(vk_points[i], &vk_bytes[i * PB], true);
         have_vk_points = true;
+        vk_lin_points = vk_points;
     }
 
     // ---- evaluation helpers ---------------------------------------------
@@ -615,13 +661,14 @@ struct Circuit : CircuitBase {
             for (uint32_t c = 0; c < k; c++) polys.push_back({c_qcp[c].p, n});
             // z(omega zeta) needs the other power table: queue first, fetch with the rest
             divide_linear(cz.p, n + 3, powzw.p, powzwi.p);   // T[n+2] = z(omega zeta) as a by-product
-            srs->commit_async(quot.p, n + 2, 8);
             B2P_CUDA(cudaMemcpyAsync(dot_out.p + MAX_DOT - 1, T.p + (n + 2), sizeof(Fr), cudaMemcpyDeviceToDevice, st));
             eval_many(polys, powz.p, ev.data());
         }
         Fr z_zw;
         B2P_CUDA(cudaMemcpyAsync(&z_zw, dot_out.p + MAX_DOT - 1, sizeof(Fr), cudaMemcpyDeviceToHost, st));
         B2P_CUDA(cudaStreamSynchronize(st));
+        // the opening MSM runs on the device while the host derives the linearisation and [Lin]
+        srs->commit_async(quot.p, n + 2, 8);
         const Fr l_z = ev[0], r_z = ev[1], o_z = ev[2], s1_z = ev[3], s2_z = ev[4];
 
         // -- round 5: linearised polynomial --------------------------------------------------
@@ -634,33 +681,38 @@ struct Circuit : CircuitBase {
         const Fr bz = beta * zeta;
         const Fr s2p = a2l - alpha * (l_z + bz + gamma) * (r_z + bz * u + gamma) * (o_z + bz * u2 + gamma);
         const Fr zn2 = zeta.pow_u64(n + 2);
+        // [Lin] is the same combination of commitments that are already known: S1 S2 S3 Ql Qr Qm Qo Qk Qcp*
+        // from the key, the BSB22 commitments, [Z] and [h_j] from this proof
+        std::vector<Aff> lin_pts;
+        std::vector<Fr> lin_coef;
         {
             LinCombArgs<Fr> a;
             int t = 0;
-            auto term = [&](const Fr* p, uint64_t len, const Fr& coef, bool unit) {
+            auto term = [&](const Fr* p, uint64_t len, const Fr& coef, bool unit, const Aff& com) {
                 a.poly[t] = p; a.len[t] = len; a.coef[t] = coef; a.unit[t] = unit ? 1 : 0; t++;
+                lin_pts.push_back(com); lin_coef.push_back(coef);
             };
-            term(c_ql.p, n, l_z, false);
-            term(c_qr.p, n, r_z, false);
-            term(c_qm.p, n, l_z * r_z, false);
-            term(c_qo.p, n, o_z, false);
-            term(c_qk.p, n, one, true);
-            for (uint32_t c = 0; c < k; c++) term(c_pi2[c].p, n, ev[5 + c], false);
-            term(c_s3.p, n, s1p, false);
-            term(cz.p, n + 3, s2p, false);
+            term(c_ql.p, n, l_z, false, vk_lin_points[3]);
+            term(c_qr.p, n, r_z, false, vk_lin_points[4]);
+            term(c_qm.p, n, l_z * r_z, false, vk_lin_points[5]);
+            term(c_qo.p, n, o_z, false, vk_lin_points[6]);
+            term(c_qk.p, n, one, true, vk_lin_points[7]);
+            for (uint32_t c = 0; c < k; c++) term(c_pi2[c].p, n, ev[5 + c], false, bsb[c]);
+            term(c_s3.p, n, s1p, false, vk_lin_points[2]);
+            term(cz.p, n + 3, s2p, false, pts[3]);
             const Fr mzh = zh_z.neg();
-            term(h.p, n + 2, mzh, false);
-            term(h.p + (n + 2), n + 2, mzh * zn2, false);
-            term(h.p + 2 * (n + 2), n + 2, mzh * zn2 * zn2, false);
+            term(h.p, n + 2, mzh, false, pts[4]);
+            term(h.p + (n + 2), n + 2, mzh * zn2, false, pts[5]);
+            term(h.p + 2 * (n + 2), n + 2, mzh * zn2 * zn2, false, pts[6]);
             a.nterms = t;
             a.out = lin.p;
             a.out_len = n + 3;
             B2P_LAUNCH((k_lincomb<Fr>), div_up(n + 3, 256), 256, 0, st, a);
         }
-        srs->commit_async(lin.p, n + 3, 9);
+        pts[9] = host_msm_small<C>(lin_pts.data(), lin_coef.data(), (int)lin_pts.size());
         Fr lin_z;
         eval_many({{lin.p, n + 3}}, powz.p, &lin_z);
-        srs->fetch(8, 2, pts + 8);   // pts[8] = W_{omega zeta}, pts[9] = [Lin]
+        srs->fetch(8, 1, pts + 8);   // W_{omega zeta}
 
         // -- fold challenge (kzg.BatchOpenSinglePoint; templateLogicSigBN254.go:280-286) --------
         uint8_t v_pre[32], b32[32];
@@ -713,7 +765,7 @@ struct Circuit : CircuitBase {
 
         if (prof.on) prof.collect(stats);
         srs->prof = nullptr;
-        stats[B2P_STAT_MSM_CALLS] = 10;
+        stats[B2P_STAT_MSM_CALLS] = 9;
         {
             unsigned long long adds = 0;
             B2P_CUDA(cudaMemcpyAsync(&adds, srs->msm.adds_total.p, sizeof adds, cudaMemcpyDeviceToHost, st));

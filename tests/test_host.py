@@ -107,12 +107,16 @@ def test_marshal_public_inputs():
 
 
 # ---- field templates (host emulation of the PTX carry chains) ---------------------------------
-@pytest.fixture(scope="module")
-def hostfield(tmp_path_factory):
+@pytest.fixture(scope="module", params=["emulated-device-code", "host-u128"])
+def hostfield(request, tmp_path_factory):
+    """field.cuh compiled for the host twice: with the device multiplication code running on the carry-flag
+    emulation of ptx.cuh (-DB2P_HOST_EMULATE_DEVICE_MUL), and with the 64-bit-limb host product the library's
+    host side uses."""
     out = tmp_path_factory.mktemp("hf") / "hostfield.so"
     src = os.path.join(ROOT, "tests", "csrc", "hostfield_shim.cpp")
+    flags = ["-DB2P_HOST_EMULATE_DEVICE_MUL"] if request.param == "emulated-device-code" else []
     subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O1", "-std=c++17", "-shared",
-                    "-fPIC", "-x", "c++", src, "-o", str(out)], check=True)
+                    "-fPIC", *flags, "-x", "c++", src, "-o", str(out)], check=True)
     return C.CDLL(str(out))
 
 
