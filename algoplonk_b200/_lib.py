@@ -28,11 +28,15 @@ SYMBOLS = [
     ("b2p_launch_count", _u64, []),
     ("b2p_srs_load", _int, [_int, _vp, _u64, _vp, _u64, C.POINTER(_vp)]),
     ("b2p_srs_generate_unsafe", _int, [_int, _vp, _u64, C.POINTER(_vp)]),
+    ("b2p_srs_generate_unsafe_range", _int, [_int, _vp, _u64, _u64, C.POINTER(_vp)]),
     ("b2p_srs_get_points", _int, [_vp, _u64, _u64, _vp]),
     ("b2p_srs_size", _u64, [_vp]),
     ("b2p_srs_msm_params", _int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_u64)]),
     ("b2p_srs_free", None, [_vp]),
     ("b2p_msm_g1", _int, [_vp, _int, _vp, _u64, _vp]),
+    ("b2p_msm_g1_dev", _int, [_vp, _int, _vp, _u64, _vp]),
+    ("b2p_g1_sum", _int, [_int, _vp, _u64, _vp]),
+    ("b2p_srs_stream", _vp, [_vp]),
     ("b2p_ntt", _int, [_int, _vp, _u64, _int]),
     ("b2p_circuit_load", _int, [_vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _u64,
                                 C.POINTER(_vp)]),

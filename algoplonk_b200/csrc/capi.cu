@@ -82,7 +82,16 @@ API int b2p_srs_generate_unsafe(int curve, const void* tau, uint64_t n_can, b2p_
     return guarded([&] {
         require(tau && out, "null argument");
         SrsBase* s = ops_for(curve)->new_srs();
-        try { s->generate_unsafe(tau, n_can); } catch (...) { delete s; throw; }
+        try { s->generate_unsafe(tau, 0, n_can); } catch (...) { delete s; throw; }
+        *out = reinterpret_cast<b2p_srs*>(s);
+    });
+}
+
+API int b2p_srs_generate_unsafe_range(int curve, const void* tau, uint64_t first, uint64_t count, b2p_srs** out) {
+    return guarded([&] {
+        require(tau && out, "null argument");
+        SrsBase* s = ops_for(curve)->new_srs();
+        try { s->generate_unsafe(tau, first, count); } catch (...) { delete s; throw; }
         *out = reinterpret_cast<b2p_srs*>(s);
     });
 }
@@ -105,9 +114,22 @@ API void b2p_srs_free(b2p_srs* srs) { delete reinterpret_cast<SrsBase*>(srs); }
 API int b2p_msm_g1(b2p_srs* srs, int basis, const void* scalars, uint64_t n, void* out_affine) {
     return guarded([&] {
         require(srs && out_affine && (scalars || n == 0), "null argument");
-        reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, scalars, n, out_affine);
+        reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, scalars, n, out_affine, false);
     });
 }
+API int b2p_msm_g1_dev(b2p_srs* srs, int basis, const void* d_scalars, uint64_t n, void* out_affine) {
+    return guarded([&] {
+        require(srs && out_affine && (d_scalars || n == 0), "null argument");
+        reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, d_scalars, n, out_affine, true);
+    });
+}
+API int b2p_g1_sum(int curve, const void* points, uint64_t n, void* out_affine) {
+    return guarded([&] {
+        require(out_affine && (points || n == 0), "null argument");
+        ops_for(curve)->g1_sum(points, n, out_affine);
+    });
+}
+API void* b2p_srs_stream(b2p_srs* srs) { return srs ? reinterpret_cast<SrsBase*>(srs)->stream_handle() : nullptr; }
 
 API int b2p_ntt(int curve, void* data, uint64_t n, int flags) {
     return guarded([&] {

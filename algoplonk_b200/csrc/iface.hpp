@@ -17,11 +17,12 @@ struct SrsBase {
     int curve = -1;
     virtual ~SrsBase() {}
     virtual void load(const void* points, uint64_t n) = 0;
-    virtual void generate_unsafe(const void* tau, uint64_t n) = 0;
+    virtual void generate_unsafe(const void* tau, uint64_t first, uint64_t n) = 0;
     virtual void get_points(uint64_t first, uint64_t count, void* out) const = 0;
     virtual uint64_t size() const = 0;
     virtual void msm_params(int* c, int* windows, uint64_t* buckets) const = 0;
-    virtual void msm_g1(int basis, const void* scalars, uint64_t n, void* out_affine) = 0;
+    virtual void* stream_handle() = 0;
+    virtual void msm_g1(int basis, const void* scalars, uint64_t n, void* out_affine, bool device_scalars) = 0;
 };
 
 struct CircuitBase {
@@ -43,6 +44,7 @@ struct CurveOps {
     virtual SrsBase* new_srs() const = 0;
     virtual CircuitBase* new_circuit() const = 0;
     virtual void ntt(void* data, uint64_t n, int flags) const = 0;
+    virtual void g1_sum(const void* points, uint64_t n, void* out_affine) const = 0;
     virtual void marshal_proof(uint32_t k, const void* raw, const void* bsb22, uint8_t* out) const = 0;
     virtual void marshal_public_inputs(const void* values, uint32_t nb_public, uint8_t* out) const = 0;
 };

@@ -21,8 +21,10 @@
 
 namespace b2p {
 
-constexpr int MSM_CAP = 64;        // max entries accumulated by one thread
+constexpr int MSM_CAP = 128;       // max entries accumulated by one thread (the partial top window puts
+                                   // ~n / 2^(bits - (W-1)c) entries into each of its buckets: ~90 at n = 2^20, c = 20)
 constexpr int MSM_THREADS = 128;
+constexpr int MSM_SLOTS = 16;      // MSMs that can be queued before their results are fetched
 
 struct MsmPlan {
     int c = 0;        // window bits
@@ -121,12 +123,12 @@ __global__ void k_msm_scatter(const Fr* __restrict__ scalars, uint64_t n, uint64
 // length, longest first: lanes of a warp get equal trip counts and the long items
 // do not end up in the tail of the launch.
 //   hist[(CAP - len) * nblk + blk]  -> exclusive scan ->  start of (len, blk) in `order`
-// Buckets with more than MSM_BIG items (skewed scalars: many 0/1/small witness
-// values land in one bucket) are listed so that their partial sums are added by a
-// whole block instead of one thread.
+// A bucket with a single item (the rule: Poisson(26) against CAP = 64) is written
+// straight into the dense bucket array; buckets with more items (skewed scalars: many
+// 0/1/small witness values land in one bucket) are listed and their item sums are
+// added by one warp each (k_msm_multi_buckets).
 // ---------------------------------------------------------------------------
 constexpr int MSM_SORT_THREADS = 256;
-constexpr uint32_t MSM_BIG = 8;
 
 static __global__ void __launch_bounds__(MSM_SORT_THREADS)
 k_msm_len_hist(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t nblk, uint32_t* __restrict__ hist) {
@@ -160,7 +162,7 @@ k_msm_len_scatter(const uint32_t* __restrict__ counts, const uint32_t* __restric
         for (uint32_t k = 0; k < nfull; k++) order[p + k] = make_uint2(b, k);
     }
     if (rem) order[atomicAdd(&sh[rem], 1u)] = make_uint2(b, nfull);
-    if (nfull + (rem ? 1u : 0u) > MSM_BIG) big_list[atomicAdd(big_count, 1u)] = b;
+    if (nfull + (rem ? 1u : 0u) > 1u) big_list[atomicAdd(big_count, 1u)] = b;   // more than one item
     (void)item_off;
 }
 
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(MSM_THREADS)
 k_msm_accumulate(const Affine<Fp>* __restrict__ table, const uint32_t* __restrict__ entries,
                  const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                  const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ total_items,
-                 const uint2* __restrict__ order, XYZZ<Fp>* __restrict__ partial) {
+                 const uint2* __restrict__ order, XYZZ<Fp>* __restrict__ partial, XYZZ<Fp>* __restrict__ buckets) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *total_items) return;
     const uint2 it = order[t];
@@ -207,7 +209,7 @@ k_msm_accumulate(const Affine<Fp>* __restrict__ table, const uint32_t* __restric
         }
         acc.add_affine_signed(cur, ent_cur >> 31);
     }
-    st_xyzz_fwd(partial + item_off[b] + sub, acc);
+    st_xyzz_fwd(cnt <= MSM_CAP ? buckets + b : partial + item_off[b] + sub, acc);
 }
 
 template <class Fp>
@@ -266,117 +268,133 @@ __device__ __forceinline__ XYZZ<Fp> warp_sum_xyzz(XYZZ<Fp> v) {
     return v;
 }
 
-// Big buckets (more than MSM_BIG items): one block adds the bucket's partial sums and leaves the
-// total in the bucket's first partial slot; level 0 of the reduction then reads only that slot.
+// Buckets with more than one item: one warp adds the bucket's item sums and writes the dense slot.
 template <class Fp>
-__global__ void __launch_bounds__(256)
-k_msm_big_buckets(const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_count,
-                  const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ total_items, uint32_t nb,
-                  XYZZ<Fp>* __restrict__ partial) {
-    __shared__ XYZZ<Fp> wsum[8];
-    const uint32_t nbig = *big_count;
-    for (uint32_t k = blockIdx.x; k < nbig; k += gridDim.x) {
-        const uint32_t b = big_list[k];
+__global__ void __launch_bounds__(128)
+k_msm_multi_buckets(const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
+                    const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ total_items, uint32_t nb,
+                    const XYZZ<Fp>* __restrict__ partial, XYZZ<Fp>* __restrict__ buckets) {
+    const uint32_t nlist = *list_count;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nlist; k += nwarps) {
+        const uint32_t b = list[k];
         const uint32_t b0 = item_off[b];
         const uint32_t b1 = (b + 1 < nb) ? item_off[b + 1] : *total_items;
         XYZZ<Fp> acc = XYZZ<Fp>::inf();
 #pragma unroll 1
-        for (uint32_t t = b0 + threadIdx.x; t < b1; t += blockDim.x) xyzz_add(acc, ld_xyzz(partial + t));
+        for (uint32_t t = b0 + lane; t < b1; t += 32) xyzz_add(acc, ld_xyzz(partial + t));
         acc = warp_sum_xyzz(acc);
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        __syncthreads();          // every read of this bucket's partials is done
-        if (lane == 0) wsum[wid] = acc;
-        __syncthreads();
-        if (wid == 0) {
-            XYZZ<Fp> v = lane < 8 ? wsum[lane] : XYZZ<Fp>::inf();
-#pragma unroll 1
-            for (int d = 4; d >= 1; d >>= 1) {
-                XYZZ<Fp> o = shfl_down_xyzz(v, d);
-                xyzz_add(v, o);
-            }
-            if (lane == 0) st_xyzz(partial + b0, v);
-        }
-        __syncthreads();
+        if (lane == 0) st_xyzz(buckets + b, acc);
     }
 }
 
+// one thread, once per MSM: running count of the mixed additions the accumulation performed
+static __global__ void k_msm_count_adds(const uint32_t* __restrict__ total_entries, unsigned long long* __restrict__ adds_total) {
+    *adds_total += *total_entries;
+}
+
 // ---------------------------------------------------------------------------
-// Bucket reduction  result = sum_b (b+1) * B_b  over nb = 2^(c-1) buckets.
+// Bucket reduction  result = sum_b (b+1) * B_b  over the dense array of nb = 2^(c-1) bucket sums.
 // Write b = h * 2^s + l (l: s low bits).  With column sums C_l = sum_h B_{h,l} and row
 // sums R_h = sum_l B_{h,l}
 //     result = sum_l (l+1) * C_l  +  2^s * sum_h h * R_h :
-// 2^s + 2^(c-1-s) PLAIN sums (one warp each: lanes stride over the terms, then a
-// shuffle tree) followed by one small weighted sum over ncols + nrows points, which
+// 2^s + 2^(c-1-s) PLAIN sums, followed by one small weighted sum over ncols + nrows points, which
 // is split by the bits of the weights into plain sums again
 //     sum_i w_i X_i = sum_j 2^j Q_j,   Q_j = sum_{i : bit j of w_i} X_i.
 // Nothing here is a long dependent chain of point additions (the first version, a
 // radix-8 running-sum level plus bit-decomposed sums over 65536 entries, was
 // latency-bound: 1.07 ms of a 3.4 ms MSM at c = 20).
 // ---------------------------------------------------------------------------
-constexpr int MSM_RC_WARPS = 4;     // rows/columns per block of k_msm_rowcol
+constexpr int MSM_RC_WARPS = 8;     // rows/columns per block of k_msm_rowcol
 constexpr int MSM_TAIL_THREADS = 256;
-
-// sum of bucket b: its item partials, or the block-reduced total of a big bucket
-template <class Fp>
-__device__ __forceinline__ XYZZ<Fp> load_bucket(const XYZZ<Fp>* __restrict__ partial, const uint32_t* __restrict__ item_off,
-                                                const uint32_t* __restrict__ total_items, uint32_t b, uint32_t nb) {
-    const uint32_t b0 = item_off[b];
-    const uint32_t b1 = (b + 1 < nb) ? item_off[b + 1] : *total_items;
-    if (b1 == b0) return XYZZ<Fp>::inf();
-    XYZZ<Fp> p = ld_xyzz(partial + b0);            // big buckets: total left here by k_msm_big_buckets
-    if (b1 - b0 <= MSM_BIG)
-        for (uint32_t t = b0 + 1; t < b1; t++) xyzz_add(p, ld_xyzz(partial + t));
-    return p;
-}
+constexpr int MSM_RC_CHUNK = 16;
 
 // Level 1: every thread adds MSM_RC_CHUNK buckets of one column (threads [0, ncols * nch_r)) or of one row
 // (the rest): 2 * nb point additions spread over ~2 * nb / 16 threads with no tree in the way -- this is where
-// the reduction's work is, and it runs at the machine's addition throughput.
+// the reduction's work is.  The next bucket is fetched while the current one is added.
 //   Pc[l * nch_r + ch] = sum_{h in chunk ch} B_{h,l}      Pr[h * nch_c + ch] = sum_{l in chunk ch} B_{h,l}
-constexpr int MSM_RC_CHUNK = 16;
 template <class Fp>
-__global__ void __launch_bounds__(128, 4)
-k_msm_rowcol_partial(const XYZZ<Fp>* __restrict__ partial, const uint32_t* __restrict__ item_off,
-                     const uint32_t* __restrict__ total_items, int s, uint32_t nb, XYZZ<Fp>* __restrict__ Pc,
+__global__ void __launch_bounds__(128, 3)
+k_msm_rowcol_partial(const XYZZ<Fp>* __restrict__ B, int s, uint32_t nb, XYZZ<Fp>* __restrict__ Pc,
                      XYZZ<Fp>* __restrict__ Pr) {
     const uint32_t ncols = 1u << s, nrows = nb >> s;
     const uint32_t nch_r = (nrows + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK, nch_c = (ncols + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+    uint32_t first, stride, cnt;
+    XYZZ<Fp>* dst;
     if (t < ncols * nch_r) {
         const uint32_t l = t % ncols, ch = t / ncols;      // lanes along l: neighbouring buckets
-        const uint32_t h1 = min(nrows, (ch + 1) * MSM_RC_CHUNK);
-#pragma unroll 1
-        for (uint32_t h = ch * MSM_RC_CHUNK; h < h1; h++) xyzz_add(acc, load_bucket(partial, item_off, total_items, (h << s) | l, nb));
-        st_xyzz(Pc + (size_t)l * nch_r + ch, acc);
-        return;
+        first = ((ch * MSM_RC_CHUNK) << s) | l;
+        stride = ncols;
+        cnt = min(nrows, (ch + 1) * MSM_RC_CHUNK) - ch * MSM_RC_CHUNK;
+        dst = Pc + (size_t)l * nch_r + ch;
+    } else {
+        t -= ncols * nch_r;
+        if (t >= nrows * nch_c) return;
+        const uint32_t h = t / nch_c, ch = t % nch_c;
+        first = (h << s) | (ch * MSM_RC_CHUNK);
+        stride = 1;
+        cnt = min(ncols, (ch + 1) * MSM_RC_CHUNK) - ch * MSM_RC_CHUNK;
+        dst = Pr + (size_t)h * nch_c + ch;
     }
-    t -= ncols * nch_r;
-    if (t >= nrows * nch_c) return;
-    const uint32_t h = t / nch_c, ch = t % nch_c;
-    const uint32_t l1 = min(ncols, (ch + 1) * MSM_RC_CHUNK);
+    XYZZ<Fp> acc = ld_xyzz(B + first);
+    XYZZ<Fp> nxt = cnt > 1 ? ld_xyzz(B + first + stride) : XYZZ<Fp>::inf();
 #pragma unroll 1
-    for (uint32_t l = ch * MSM_RC_CHUNK; l < l1; l++) xyzz_add(acc, load_bucket(partial, item_off, total_items, (h << s) | l, nb));
-    st_xyzz(Pr + (size_t)h * nch_c + ch, acc);
+    for (uint32_t i = 1; i < cnt; i++) {
+        const XYZZ<Fp> cur = nxt;
+        if (i + 1 < cnt) nxt = ld_xyzz(B + first + (size_t)(i + 1) * stride);
+        acc.add(cur);
+    }
+    st_xyzz(dst, acc);
 }
 
-// Level 2: X[l] = C_l for l < ncols, X[ncols + h] = R_h for h < nrows.  One warp per sum of <= 64 partials.
+// Level 2: X[l] = C_l for l < ncols, X[ncols + h] = R_h for h < nrows: each is the sum of its <= 64 chunk
+// partials.  A block takes MSM_RC_WARPS sums at a time and adds them up as one pairwise tree through
+// shared memory, so that all lanes work on the wide levels (a shuffle tree per warp spends 5 of its 7
+// additions with most lanes idle).
+// Levels 2 and 3 are latency-bound (~10 dependent additions each), so they are deferred until the
+// results are fetched and run once for all MSMs queued since (grid.y = slots).
 template <class Fp>
 __global__ void __launch_bounds__(32 * MSM_RC_WARPS)
 k_msm_rowcol(const XYZZ<Fp>* __restrict__ Pc, const XYZZ<Fp>* __restrict__ Pr, int s, uint32_t nb,
              XYZZ<Fp>* __restrict__ X) {
+    extern __shared__ uint4 rc_smem[];
+    XYZZ<Fp>* sh = reinterpret_cast<XYZZ<Fp>*>(rc_smem);       // 32 * MSM_RC_WARPS points
     const uint32_t ncols = 1u << s, nrows = nb >> s;
     const uint32_t nch_r = (nrows + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK, nch_c = (ncols + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK;
-    const uint32_t w = blockIdx.x * MSM_RC_WARPS + (threadIdx.x >> 5);
-    const uint32_t lane = threadIdx.x & 31;
-    if (w >= ncols + nrows) return;
-    const XYZZ<Fp>* src = w < ncols ? Pc + (size_t)w * nch_r : Pr + (size_t)(w - ncols) * nch_c;
-    const uint32_t cnt = w < ncols ? nch_r : nch_c;
+    // blockIdx.y: result slot (several MSMs are finished by one launch)
+    Pc += (size_t)blockIdx.y * ncols * nch_r;
+    Pr += (size_t)blockIdx.y * nrows * nch_c;
+    X += (size_t)blockIdx.y * (ncols + nrows);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * MSM_RC_WARPS + wid;         // the sum this warp's slice of the tree belongs to
     XYZZ<Fp> acc = XYZZ<Fp>::inf();
+    if (w < ncols + nrows) {
+        const XYZZ<Fp>* src = w < ncols ? Pc + (size_t)w * nch_r : Pr + (size_t)(w - ncols) * nch_c;
+        const uint32_t cnt = w < ncols ? nch_r : nch_c;
 #pragma unroll 1
-    for (uint32_t i = lane; i < cnt; i += 32) xyzz_add(acc, ld_xyzz(src + i));
-    acc = warp_sum_xyzz(acc);
-    if (lane == 0) st_xyzz(X + w, acc);
+        for (uint32_t i = lane; i < cnt; i += 32) xyzz_add(acc, ld_xyzz(src + i));
+    }
+    // tree over the 32 lane sums of every warp: entry (wid, lane) at sh[wid * 32 + lane]
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t width = 16; width >= 1; width >>= 1) {
+        // MSM_RC_WARPS * width additions, packed onto the first threads of the block
+        const uint32_t t = threadIdx.x;
+        XYZZ<Fp> r;
+        const bool active = t < MSM_RC_WARPS * width;
+        if (active) {
+            const uint32_t g = t / width, i = t % width;
+            r = sh[g * 32 + i];
+            xyzz_add(r, sh[g * 32 + i + width]);
+        }
+        __syncthreads();
+        if (active) sh[(t / width) * 32 + (t % width)] = r;
+        __syncthreads();
+    }
+    if (lane == 0 && w < ncols + nrows) st_xyzz(X + w, sh[wid * 32]);
 }
 
 // weight of entry i of X in the final sum
@@ -389,11 +407,14 @@ __device__ __forceinline__ uint32_t msm_tail_weight(uint32_t i, int s) {
 template <class Fp>
 __global__ void __launch_bounds__(MSM_TAIL_THREADS)
 k_msm_tail(const XYZZ<Fp>* __restrict__ X, uint32_t ntot, int s, XYZZ<Fp>* __restrict__ T, uint32_t* __restrict__ done,
-           XYZZ<Fp>* __restrict__ out, const uint32_t* __restrict__ total_entries,
-           unsigned long long* __restrict__ adds_total) {
+           XYZZ<Fp>* __restrict__ out) {
     __shared__ XYZZ<Fp> wsum[MSM_TAIL_THREADS / 32];
     __shared__ bool last;
     const int j = blockIdx.x;
+    X += (size_t)blockIdx.y * ntot;       // blockIdx.y: result slot
+    T += (size_t)blockIdx.y * 32;
+    done += blockIdx.y;
+    out += blockIdx.y;
     XYZZ<Fp> acc = XYZZ<Fp>::inf();
 #pragma unroll 1
     for (uint32_t i = threadIdx.x; i < ntot; i += MSM_TAIL_THREADS)
@@ -424,8 +445,7 @@ k_msm_tail(const XYZZ<Fp>* __restrict__ X, uint32_t ntot, int s, XYZZ<Fp>* __res
     v = warp_sum_xyzz(v);
     if (lane == 0) {
         st_xyzz(out, v);
-        *adds_total += *total_entries;   // stream ordered: mixed additions done by the accumulation
-        *done = 0;                       // ready for the next MSM on this stream
+        *done = 0;                       // ready for the next MSM that uses this slot
     }
 }
 
@@ -445,7 +465,7 @@ struct MsmEngine {
 
     // scratch (sized for npoints scalars)
     DevBuf<uint32_t> counts, offsets, cursor, item_off, entries, scan_scratch, total_items;
-    DevBuf<Ext> partial, rc_col, rc_row, rc_sums, tail_T, result;
+    DevBuf<Ext> partial, buckets, rc_col, rc_row, rc_sums, tail_T, result;
     DevBuf<uint32_t> tail_done;
     uint32_t max_items = 0;
     Profiler* prof = nullptr;
@@ -473,6 +493,8 @@ struct MsmEngine {
     }
     // low bits of the bucket index that select the column in the 2D reduction
     int split_bits() const { return (plan.c - 1) / 2; }
+    size_t col_partials() const { return (size_t)(1u << split_bits()) * div_up(plan.nbuckets >> split_bits(), MSM_RC_CHUNK); }
+    size_t row_partials() const { return (size_t)(plan.nbuckets >> split_bits()) * div_up(1u << split_bits(), MSM_RC_CHUNK); }
     void alloc_scratch() {
         const uint32_t nb = plan.nbuckets;
         counts.alloc(nb); offsets.alloc(nb); cursor.alloc(nb); item_off.alloc(nb);
@@ -488,23 +510,23 @@ struct MsmEngine {
         max_items = nb + (uint32_t)(((uint64_t)plan.W * npoints) / MSM_CAP) + 1;
         partial.alloc(max_items);
         order.alloc(max_items);
-        big_list.alloc(max_items / MSM_BIG + 1);
+        buckets.alloc(nb);
+        big_list.alloc(nb);
         big_count.alloc(1);
-        {
-            const uint32_t ncols = 1u << split_bits(), nrows = nb >> split_bits();
-            rc_col.alloc((size_t)ncols * div_up(nrows, MSM_RC_CHUNK));
-            rc_row.alloc((size_t)nrows * div_up(ncols, MSM_RC_CHUNK));
-            rc_sums.alloc((size_t)ncols + nrows);
-        }
-        tail_T.alloc(32);
-        tail_done.alloc(1);
-        B2P_CUDA(cudaMemset(tail_done.p, 0, sizeof(uint32_t)));
-        result.alloc(1);
+        rc_col.alloc((size_t)MSM_SLOTS * col_partials());
+        rc_row.alloc((size_t)MSM_SLOTS * row_partials());
+        rc_sums.alloc((size_t)MSM_SLOTS * ((1u << split_bits()) + (nb >> split_bits())));
+        tail_T.alloc((size_t)MSM_SLOTS * 32);
+        tail_done.alloc(MSM_SLOTS);
+        B2P_CUDA(cudaMemset(tail_done.p, 0, MSM_SLOTS * sizeof(uint32_t)));
+        result.alloc(MSM_SLOTS);
     }
 
-    // d_scalars: device pointer, n <= npoints scalars; result (XYZZ, device) in this->result.
-    void run_async(const Fr* d_scalars, uint64_t n, bool mont, cudaStream_t st) {
+    // Queues sort + accumulation + level 1 of the reduction for n <= npoints device scalars; the MSM's
+    // row/column partial sums land in result slot `slot`.  finish_async() completes the queued slots.
+    void run_async(const Fr* d_scalars, uint64_t n, bool mont, cudaStream_t st, int slot = 0) {
         B2P_REQUIRE(n <= npoints, "MSM: more scalars than SRS points");
+        B2P_REQUIRE(slot >= 0 && slot < MSM_SLOTS, "MSM result slot out of range");
         const uint32_t nb = plan.nbuckets;
         B2P_CUDA(cudaMemsetAsync(counts.p, 0, nb * sizeof(uint32_t), st));
         B2P_CUDA(cudaMemsetAsync(cursor.p, 0, nb * sizeof(uint32_t), st));
@@ -520,28 +542,39 @@ struct MsmEngine {
                            ScanIdentity{});
         B2P_LAUNCH(k_msm_len_scatter, sort_blocks, MSM_SORT_THREADS, 0, st, counts.p, item_off.p, nb, sort_blocks,
                    len_start.p, order.p, big_list.p, big_count.p);
+        B2P_CUDA(cudaMemsetAsync(buckets.p, 0, (size_t)nb * sizeof(Ext), st));     // empty buckets = infinity
         const int span = prof ? prof->begin(B2P_STAT_MSM_ACCUM_MS, st) : -1;
         B2P_LAUNCH((k_msm_accumulate<Fp>), div_up(max_items, MSM_THREADS), MSM_THREADS, 0, st, table.p, entries.p,
-                   counts.p, offsets.p, item_off.p, total_items.p, order.p, partial.p);
+                   counts.p, offsets.p, item_off.p, total_items.p, order.p, partial.p, buckets.p);
         if (prof) prof->end(span, st);
-        B2P_LAUNCH((k_msm_big_buckets<Fp>), 148, 256, 0, st, big_list.p, big_count.p, item_off.p, total_items.p, nb,
-                   partial.p);
-        // reduction: row/column plain sums (two levels), then the bit-decomposed weighted sum of those
+        B2P_LAUNCH((k_msm_multi_buckets<Fp>), 148, 128, 0, st, big_list.p, big_count.p, item_off.p, total_items.p, nb,
+                   partial.p, buckets.p);
+        B2P_LAUNCH(k_msm_count_adds, 1, 1, 0, st, total_entries.p, adds_total.p);
+        // reduction level 1: row/column chunk sums of the dense bucket array
+        const int s = split_bits();
+        const uint32_t nthreads = (uint32_t)(col_partials() + row_partials());
+        B2P_LAUNCH((k_msm_rowcol_partial<Fp>), div_up(nthreads, 128), 128, 0, st, buckets.p, s, nb,
+                   rc_col.p + (size_t)slot * col_partials(), rc_row.p + (size_t)slot * row_partials());
+    }
+    // Reduction levels 2 and 3 for slots [first, first + cnt), one launch each; results (XYZZ) in result[slot].
+    void finish_async(int first, int cnt, cudaStream_t st) {
+        B2P_REQUIRE(first >= 0 && cnt >= 1 && first + cnt <= MSM_SLOTS, "MSM result slot out of range");
+        const uint32_t nb = plan.nbuckets;
         const int s = split_bits();
         const uint32_t ncols = 1u << s, nrows = nb >> s, ntot = ncols + nrows;
-        const uint32_t nthreads = ncols * div_up(nrows, MSM_RC_CHUNK) + nrows * div_up(ncols, MSM_RC_CHUNK);
-        B2P_LAUNCH((k_msm_rowcol_partial<Fp>), div_up(nthreads, 128), 128, 0, st, partial.p, item_off.p, total_items.p, s,
-                   nb, rc_col.p, rc_row.p);
-        B2P_LAUNCH((k_msm_rowcol<Fp>), div_up(ntot, MSM_RC_WARPS), 32 * MSM_RC_WARPS, 0, st, rc_col.p, rc_row.p, s, nb,
-                   rc_sums.p);
+        B2P_LAUNCH((k_msm_rowcol<Fp>), dim3(div_up(ntot, MSM_RC_WARPS), cnt), 32 * MSM_RC_WARPS,
+                   32 * MSM_RC_WARPS * sizeof(Ext), st,
+                   rc_col.p + (size_t)first * col_partials(), rc_row.p + (size_t)first * row_partials(), s, nb,
+                   rc_sums.p + (size_t)first * ntot);
         const int nbits = plan.c;                     // weights are < 2^(c-1) + 1
-        B2P_LAUNCH((k_msm_tail<Fp>), nbits, MSM_TAIL_THREADS, 0, st, rc_sums.p, ntot, s, tail_T.p, tail_done.p, result.p,
-                   total_entries.p, adds_total.p);
+        B2P_LAUNCH((k_msm_tail<Fp>), dim3(nbits, cnt), MSM_TAIL_THREADS, 0, st, rc_sums.p + (size_t)first * ntot, ntot, s,
+                   tail_T.p + (size_t)first * 32, tail_done.p + first, result.p + first);
     }
 
     // synchronous convenience: returns the affine result (host)
     Aff run(const Fr* d_scalars, uint64_t n, bool mont, cudaStream_t st) {
-        run_async(d_scalars, n, mont, st);
+        run_async(d_scalars, n, mont, st, 0);
+        finish_async(0, 1, st);
         Ext h;
         B2P_CUDA(cudaMemcpyAsync(&h, result.p, sizeof(Ext), cudaMemcpyDeviceToHost, st));
         B2P_CUDA(cudaStreamSynchronize(st));

@@ -8,6 +8,7 @@
 // padding, coset scaling and the 1/n of the inverse are fused into the first / last pass.
 // Twiddles omega^k (k < n/2) are a resident table streamed through L2.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 namespace b2p {
@@ -153,6 +154,133 @@ k_ntt_pass(const NttPassArgs<Fr> a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same pass with eight elements per thread: three butterfly stages run in registers between two
+// trips through shared memory (the kernel above makes one trip per stage), the four butterflies of a
+// stage are independent (ILP for the IMAD pipe, which is what bounds a 254-bit NTT), and a thread
+// fetches 7 twiddles per 12 butterflies instead of 12.  Used for tiles of >= 2^8 elements.
+//   round: a window of three bits [p, p+3) of the tile index; thread t holds the elements whose
+//   index is t with j = 0..7 spliced in at bit p; the stages of the round are the live bits of the
+//   window (all three, except in the last round when nst is not a multiple of 3).
+// Shared-memory slot of element k is k ^ ((k >> 3) & 7): conflict-free 128-bit accesses both for
+// the window at p = 0 (a thread's elements are neighbours) and for the higher ones.
+// ---------------------------------------------------------------------------
+constexpr int NTT_R8_MIN_STAGES = 8;
+__device__ __forceinline__ int ntt_swz(int k) { return k ^ ((k >> 3) & 7); }
+
+template <class Fr>
+__device__ __forceinline__ Fr ntt_lds(const uint4* smem4, int tile, int k) {
+    constexpr int Q = Fr::N / 4;
+    Fr x;
+    const int sk = ntt_swz(k);
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const uint4 c = smem4[q * tile + sk];
+        x.v[4 * q] = c.x; x.v[4 * q + 1] = c.y; x.v[4 * q + 2] = c.z; x.v[4 * q + 3] = c.w;
+    }
+    return x;
+}
+template <class Fr>
+__device__ __forceinline__ void ntt_sts(uint4* smem4, int tile, int k, const Fr& x) {
+    constexpr int Q = Fr::N / 4;
+    const int sk = ntt_swz(k);
+#pragma unroll
+    for (int q = 0; q < Q; q++)
+        smem4[q * tile + sk] = make_uint4(x.v[4 * q], x.v[4 * q + 1], x.v[4 * q + 2], x.v[4 * q + 3]);
+}
+
+// butterflies of window bit B on the 8 register-resident elements
+template <class Fr, bool DIF, int B>
+__device__ __forceinline__ void ntt_r8_stage(Fr (&e)[8], const Fr* __restrict__ tw, uint32_t tl, int p, int s_lo,
+                                             uint32_t lo, int logn) {
+    const int s = s_lo + p + B;               // global stage
+#pragma unroll
+    for (int grp = 0; grp < (1 << B); grp++) {
+        // twiddle shared by the pairs whose lower index has low window bits == grp
+        const uint32_t pos = ((tl | ((uint32_t)grp << p)) << s_lo) | lo;
+        const Fr w = ldg_field(tw + ((uint64_t)pos << (logn - 1 - s)));
+#pragma unroll
+        for (int up = 0; up < (4 >> B); up++) {
+            const int j = grp | (up << (B + 1));
+            const int jj = j | (1 << B);
+            if (DIF) {
+                const Fr u = e[j] + e[jj];
+                e[jj] = (e[j] - e[jj]) * w;
+                e[j] = u;
+            } else {
+                const Fr wy = e[jj] * w;
+                e[jj] = e[j] - wy;
+                e[j] = e[j] + wy;
+            }
+        }
+    }
+}
+
+template <class Fr, bool DIF, int FUSE>
+__global__ void __launch_bounds__(1 << (NTT_MAX_STAGES - 3), 2)
+k_ntt_pass8(const NttPassArgs<Fr> a) {
+    extern __shared__ uint4 smem4[];
+    Fr* __restrict__ data = a.data;
+    const Fr* __restrict__ tw = a.tw;
+    const int logn = a.logn, s_lo = a.s_lo, nst = a.nst;
+    const int tile = 1 << nst, nthr = tile >> 3;
+    const uint32_t lo = blockIdx.x & ((1u << s_lo) - 1);
+    const uint32_t hi = blockIdx.x >> s_lo;
+    const uint64_t base = ((uint64_t)hi << (s_lo + nst)) | lo;
+    const int t = threadIdx.x;                // 2^(nst-3) threads
+
+    // load: eight elements per thread, neighbouring threads take neighbouring elements
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int k = t + r * nthr;
+        const uint64_t g = base + ((uint64_t)k << s_lo);
+        Fr v;
+        if (FUSE == NTT_LOAD_PAD_SCALE) {
+            v = Fr::zero();
+            if (g < a.src_len) v = ld_field(a.src + g) * ldg_field(a.scale_tab + g);
+        } else {
+            v = ld_field(data + g);
+        }
+        ntt_sts(smem4, tile, k, v);
+    }
+    __syncthreads();
+
+    for (int done = 0; done < nst;) {
+        const int r = min(3, nst - done);
+        int p, b0;                           // window position, first live bit of the window
+        if (DIF) { p = r == 3 ? nst - done - 3 : 0; b0 = 0; }             // stages nst-done-1 .. nst-done-r
+        else     { p = r == 3 ? done : nst - 3; b0 = 3 - r; }             // stages done .. done+r-1
+        const uint32_t tl = (uint32_t)t & ((1u << p) - 1);
+        const int kbase = ((t >> p) << (p + 3)) | (int)tl;
+        Fr e[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) e[j] = ntt_lds<Fr>(smem4, tile, kbase | (j << p));
+        if (DIF) {
+            if (b0 + r > 2) ntt_r8_stage<Fr, DIF, 2>(e, tw, tl, p, s_lo, lo, logn);
+            if (b0 + r > 1) ntt_r8_stage<Fr, DIF, 1>(e, tw, tl, p, s_lo, lo, logn);
+            ntt_r8_stage<Fr, DIF, 0>(e, tw, tl, p, s_lo, lo, logn);
+        } else {
+            if (b0 == 0) ntt_r8_stage<Fr, DIF, 0>(e, tw, tl, p, s_lo, lo, logn);
+            if (b0 <= 1) ntt_r8_stage<Fr, DIF, 1>(e, tw, tl, p, s_lo, lo, logn);
+            ntt_r8_stage<Fr, DIF, 2>(e, tw, tl, p, s_lo, lo, logn);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) ntt_sts(smem4, tile, kbase | (j << p), e[j]);
+        __syncthreads();
+        done += r;
+    }
+
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int k = t + r * nthr;
+        const uint64_t g = base + ((uint64_t)k << s_lo);
+        Fr v = ntt_lds<Fr>(smem4, tile, k);
+        if (FUSE == NTT_STORE_SCALE_TAB) v = v * ldg_field(a.scale_tab + g);
+        if (FUSE == NTT_STORE_SCALE) v = v * a.scale;
+        st_field(data + g, v);
+    }
+}
+
 // out[i] = a[i] * table[i]   (coset scaling: table = g^i, or g^-i / n)
 template <class Fr>
 __global__ void k_mul_table(Fr* __restrict__ a, const Fr* __restrict__ table, uint64_t n) {
@@ -252,6 +380,17 @@ struct NttDomain {
     }
     template <bool DIF, int FUSE>
     void launch_pass(const NttPassArgs<Fr>& a, cudaStream_t st) const {
+        if (a.nst >= NTT_R8_MIN_STAGES && !force_radix2()) {
+            auto kern = k_ntt_pass8<Fr, DIF, FUSE>;
+            static bool attr_set = false;
+            if (!attr_set) {
+                B2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(Fr) << NTT_MAX_STAGES)));
+                attr_set = true;
+            }
+            B2P_LAUNCH(kern, (unsigned)(n >> a.nst), 1 << (a.nst - 3), sizeof(Fr) << a.nst, st, a);
+            return;
+        }
         auto kern = k_ntt_pass<Fr, DIF, FUSE>;
         static bool attr_set = false;
         if (!attr_set) {
@@ -260,6 +399,11 @@ struct NttDomain {
             attr_set = true;
         }
         B2P_LAUNCH(kern, (unsigned)(n >> a.nst), 1 << (a.nst - 1), sizeof(Fr) << a.nst, st, a);
+    }
+    // B2P_NTT_RADIX2=1 keeps every pass on the one-butterfly-per-thread kernel (tests compare the two)
+    static bool force_radix2() {
+        static const bool v = [] { const char* e = getenv("B2P_NTT_RADIX2"); return e && atoi(e) != 0; }();
+        return v;
     }
 
     void bitrev(Fr* d, cudaStream_t st) const {

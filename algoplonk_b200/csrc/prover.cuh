@@ -121,15 +121,15 @@ inline typename C::Fr hash_fr(const uint8_t* point_bytes, size_t len) {
     return hi * two128 + fr_from_be32_mod<Fr>(lo);
 }
 
-// [tau^j] G1 for j < n  (unsafekzg.NewSRS)
+// [tau^(first+j)] G1 for j < n  (unsafekzg.NewSRS; first > 0: one rank's shard of it)
 template <class C>
-__global__ void k_srs_from_tau(Affine<typename C::Fp>* __restrict__ out, uint64_t n, typename C::Fr tau,
-                               Affine<typename C::Fp> g) {
+__global__ void k_srs_from_tau(Affine<typename C::Fp>* __restrict__ out, uint64_t first, uint64_t n,
+                               typename C::Fr tau, Affine<typename C::Fp> g) {
     using Fr = typename C::Fr;
     using Fp = typename C::Fp;
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    Fr s = tau.pow_u64(j).from_mont();
+    Fr s = tau.pow_u64(first + j).from_mont();
     XYZZ<Fp> acc = XYZZ<Fp>::inf();
     for (int b = Fr::Params::BITS - 1; b >= 0; b--) {
         acc = acc.dbl();
@@ -175,16 +175,14 @@ struct Srs : SrsBase {
     using Ext = XYZZ<Fp>;
     cudaStream_t stream = nullptr;
     MsmEngine<C> msm;
-    DevBuf<Ext> msm_out;        // result slots
     DevBuf<Fr> scratch;         // scalar staging for b2p_msm_g1
     Profiler* prof = nullptr;
-    static constexpr int OUT_SLOTS = 16;
+    static constexpr int OUT_SLOTS = MSM_SLOTS;
 
     Srs() { curve = C::ID; B2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); }
     ~Srs() override { if (stream) cudaStreamDestroy(stream); }
 
     void finish_init() {
-        msm_out.alloc(OUT_SLOTS);
         B2P_CUDA(cudaStreamSynchronize(stream));
     }
     void load(const void* pts, uint64_t n) override {
@@ -197,16 +195,18 @@ struct Srs : SrsBase {
         B2P_CUDA(cudaMemcpy(out, msm.table.p + first, count * sizeof(Aff), cudaMemcpyDeviceToHost));
     }
     uint64_t size() const override { return msm.npoints; }
+    void* stream_handle() override { return (void*)stream; }
     void msm_params(int* c, int* windows, uint64_t* buckets) const override {
         if (c) *c = msm.plan.c;
         if (windows) *windows = msm.plan.W;
         if (buckets) *buckets = msm.plan.nbuckets;
     }
     // b2p_msm_g1: host scalars (Montgomery) -> affine result on the host
-    void msm_g1(int basis, const void* scalars, uint64_t n, void* out) override {
+    void msm_g1(int basis, const void* scalars, uint64_t n, void* out, bool device_scalars) override {
         B2P_REQUIRE(n <= msm.npoints, "more scalars than SRS points");
         if (scratch.n < n + 1) scratch.alloc(n + 1);
-        if (n) B2P_CUDA(cudaMemcpyAsync(scratch.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, stream));
+        if (n) B2P_CUDA(cudaMemcpyAsync(scratch.p, scalars, n * sizeof(Fr),
+                                        device_scalars ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
         if (basis == B2P_BASIS_LAGRANGE) {
             // MSM(Lagrange SRS, v) == commit(iNTT(v)) on the canonical SRS
             B2P_REQUIRE(n >= 1 && (n & (n - 1)) == 0, "Lagrange basis needs a power-of-two length");
@@ -224,14 +224,14 @@ struct Srs : SrsBase {
         fetch(0, 1, &a);
         memcpy(out, &a, sizeof a);
     }
-    void generate_unsafe(const void* tau_p, uint64_t n) override {
+    void generate_unsafe(const void* tau_p, uint64_t first, uint64_t n) override {
         Fr tau;
         memcpy(&tau, tau_p, sizeof tau);
         B2P_REQUIRE(n >= 1, "empty SRS");
         MsmPlan pl = msm_plan(n, Fr::Params::BITS, env_force_c());
         B2P_REQUIRE((uint64_t)pl.W * n < (1ull << 31), "SRS too large for 31-bit table indices");
         DevBuf<Aff> tbl((size_t)pl.W * n);
-        B2P_LAUNCH((k_srs_from_tau<C>), div_up(n, 128), 128, 0, stream, tbl.p, n, tau, CurveConsts<C>::generator());
+        B2P_LAUNCH((k_srs_from_tau<C>), div_up(n, 128), 128, 0, stream, tbl.p, first, n, tau, CurveConsts<C>::generator());
         msm.load_device(std::move(tbl), n, pl, stream);
         finish_init();
     }
@@ -243,8 +243,7 @@ struct Srs : SrsBase {
     void commit_async(const Fr* d_scalars, uint64_t n, int slot) {
         int id = prof ? prof->begin(B2P_STAT_MSM_MS, stream) : -1;
         msm.prof = prof;
-        msm.run_async(d_scalars, n, true, stream);
-        B2P_CUDA(cudaMemcpyAsync(msm_out.p + slot, msm.result.p, sizeof(Ext), cudaMemcpyDeviceToDevice, stream));
+        msm.run_async(d_scalars, n, true, stream, slot);
         if (prof) prof->end(id, stream);
     }
     // bring slots [first, first+cnt) to the host (synchronises) and convert them to affine there:
@@ -253,7 +252,10 @@ struct Srs : SrsBase {
     void fetch(int first, int cnt, Aff* host_out) {
         Ext h[OUT_SLOTS];
         B2P_REQUIRE(first >= 0 && cnt >= 0 && first + cnt <= OUT_SLOTS, "result slot out of range");
-        B2P_CUDA(cudaMemcpyAsync(h, msm_out.p + first, cnt * sizeof(Ext), cudaMemcpyDeviceToHost, stream));
+        int id = prof ? prof->begin(B2P_STAT_MSM_MS, stream) : -1;
+        msm.finish_async(first, cnt, stream);          // the latency-bound end of the reductions, once for all slots
+        if (prof) prof->end(id, stream);
+        B2P_CUDA(cudaMemcpyAsync(h, msm.result.p + first, cnt * sizeof(Ext), cudaMemcpyDeviceToHost, stream));
         B2P_CUDA(cudaStreamSynchronize(stream));
         for (int i = 0; i < cnt; i++) host_out[i] = h[i].to_affine();
     }
@@ -817,6 +819,15 @@ struct CurveOpsImpl : CurveOps {
             throw;
         }
         cudaStreamDestroy(st);
+    }
+
+    // sum of n affine points on the host (the G-point add that follows the all_gather of a sharded MSM)
+    void g1_sum(const void* points, uint64_t n, void* out_affine) const override {
+        const Aff* p = static_cast<const Aff*>(points);
+        XYZZ<typename C::Fp> acc = XYZZ<typename C::Fp>::inf();
+        for (uint64_t i = 0; i < n; i++) acc.add_affine_signed(p[i], false);
+        Aff a = acc.to_affine();
+        memcpy(out_affine, &a, sizeof a);
     }
 
     // helper.go:27-88 (and gnark's MarshalSolidity for BN254, helper.go:16-17): same field order on both curves

@@ -68,6 +68,10 @@ int b2p_srs_load(int curve, const void* g1_canonical, uint64_t n_can,
  * generated on the device from a known tau (Fr, Montgomery form). */
 int b2p_srs_generate_unsafe(int curve, const void* tau, uint64_t n_can, b2p_srs** out);
 
+/* One rank's shard of the same SRS: [tau^(first+j)]_1 for j < count (multi-GPU MSM, the point set is
+ * split across the GPUs of a box). */
+int b2p_srs_generate_unsafe_range(int curve, const void* tau, uint64_t first, uint64_t count, b2p_srs** out);
+
 /* Copies canonical points [first, first+count) back to the host (G1Affine layout). */
 int b2p_srs_get_points(const b2p_srs* srs, uint64_t first, uint64_t count, void* out);
 uint64_t b2p_srs_size(const b2p_srs* srs);
@@ -80,6 +84,14 @@ void b2p_srs_free(b2p_srs* srs);
 /* out_affine = sum_i scalars[i] * basis[i], n <= SRS size (Lagrange: n a power of two).
  * Used by the shim for the BSB22 commitment hint (kzg.Commit on pk.KzgLagrange). */
 int b2p_msm_g1(b2p_srs* srs, int basis, const void* scalars, uint64_t n, void* out_affine);
+
+/* Same with the scalars already resident in device memory (device pointer, Montgomery form). */
+int b2p_msm_g1_dev(b2p_srs* srs, int basis, const void* d_scalars, uint64_t n, void* out_affine);
+/* out_affine = sum of n affine points, computed on the host: the local add that follows the all_gather of
+ * the per-GPU partial sums of a point-set-sharded MSM (NCCL has no reduction over group elements). */
+int b2p_g1_sum(int curve, const void* points, uint64_t n, void* out_affine);
+/* The cudaStream_t every launch of this SRS handle is issued on. */
+void* b2p_srs_stream(b2p_srs* srs);
 
 #define B2P_NTT_INVERSE   1   /* FFTInverse (includes the 1/n scaling) */
 #define B2P_NTT_COSET     2   /* on the coset FrMultiplicativeGen * <omega> */

@@ -18,7 +18,7 @@ def _le_to_mont(curve, raw_le: bytes) -> bytes:
 
 
 @pytest.mark.parametrize("curve", CURVES)
-@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 8, 10, 11, 12, 13])
+@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 8, 9, 10, 11, 12, 13])
 def test_ntt_small_vs_bigint_oracle(gpu, curve, logn):
     cv = po.CURVES[curve]
     n = 1 << logn
@@ -37,7 +37,7 @@ def test_ntt_small_vs_bigint_oracle(gpu, curve, logn):
 
 
 @pytest.mark.parametrize("curve", CURVES)
-@pytest.mark.parametrize("logn", [16, 20])
+@pytest.mark.parametrize("logn", [16, 17, 19, 20])
 def test_ntt_large_vs_cpp_oracle(gpu, curve, logn):
     """Config sizes (2^17 / 2^20-row circuits use domains 2^17..2^22): multi-pass path."""
     cv = po.CURVES[curve]
