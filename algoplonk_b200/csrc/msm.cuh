@@ -8,8 +8,8 @@
 //     window w of scalar i then contributes  sign(d) * T[w][i]  to bucket |d|
 //     of ONE shared bucket set -- no per-window bucket sets, no window
 //     combination, and the window width can grow to c = 20 at n = 2^20.
-//   * digits -> buckets is a counting sort written here: histogram with
-//     global reductions, exclusive scan, scatter with fetch-add cursors.
+//   * digits -> buckets is a counting sort written here: histogram whose
+//     fetch-adds also rank every digit inside its bucket, exclusive scan, scatter.
 //   * bucket accumulation: one thread per <=CAP-entry slice of a bucket, XYZZ
 //     accumulator in registers, mixed additions (8M+2S), points gathered as
 //     full 64 B / 96 B sectors.
@@ -91,27 +91,28 @@ __device__ __forceinline__ void for_each_digit(const Fr& s, int c, int W, Fn f) 
     }
 }
 
+// Histogram pass.  The fetch-add that counts a digit also hands out its rank inside the bucket; the rank
+// is kept (ranks[w * n + i], coalesced) so that the scatter pass needs no second round of atomics.
 template <class Fr>
 __global__ void k_msm_count(const Fr* __restrict__ scalars, uint64_t n, int c, int W, int mont,
-                            uint32_t* __restrict__ counts) {
+                            uint32_t* __restrict__ counts, uint32_t* __restrict__ ranks) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr s = ld_field(scalars + i);
     if (mont) s = s.from_mont();
-    for_each_digit(s, c, W, [&](int, uint32_t b, bool) { atomicAdd(counts + b, 1u); });
+    for_each_digit(s, c, W, [&](int w, uint32_t b, bool) { ranks[(uint64_t)w * n + i] = atomicAdd(counts + b, 1u); });
 }
 
 template <class Fr>
 __global__ void k_msm_scatter(const Fr* __restrict__ scalars, uint64_t n, uint64_t npoints, int c, int W, int mont,
-                              const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                              const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ranks,
                               uint32_t* __restrict__ entries) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr s = ld_field(scalars + i);
     if (mont) s = s.from_mont();
     for_each_digit(s, c, W, [&](int w, uint32_t b, bool neg) {
-        uint32_t pos = atomicAdd(cursor + b, 1u);
-        entries[offsets[b] + pos] = (uint32_t)((uint64_t)w * npoints + i) | (neg ? 0x80000000u : 0u);
+        entries[offsets[b] + ranks[(uint64_t)w * n + i]] = (uint32_t)((uint64_t)w * npoints + i) | (neg ? 0x80000000u : 0u);
     });
 }
 
@@ -464,7 +465,7 @@ struct MsmEngine {
     DevBuf<Aff> table;
 
     // scratch (sized for npoints scalars)
-    DevBuf<uint32_t> counts, offsets, cursor, item_off, entries, scan_scratch, total_items;
+    DevBuf<uint32_t> counts, offsets, ranks, item_off, entries, scan_scratch, total_items;
     DevBuf<Ext> partial, buckets, rc_col, rc_row, rc_sums, tail_T, result;
     DevBuf<uint32_t> tail_done;
     uint32_t max_items = 0;
@@ -497,8 +498,9 @@ struct MsmEngine {
     size_t row_partials() const { return (size_t)(plan.nbuckets >> split_bits()) * div_up(1u << split_bits(), MSM_RC_CHUNK); }
     void alloc_scratch() {
         const uint32_t nb = plan.nbuckets;
-        counts.alloc(nb); offsets.alloc(nb); cursor.alloc(nb); item_off.alloc(nb);
+        counts.alloc(nb); offsets.alloc(nb); item_off.alloc(nb);
         entries.alloc((size_t)plan.W * npoints);
+        ranks.alloc((size_t)plan.W * npoints);
         sort_blocks = div_up(nb, MSM_SORT_THREADS);
         const uint32_t hist_len = MSM_CAP * sort_blocks;
         scan_scratch.alloc(scan_scratch_words(nb > hist_len ? nb : hist_len));
@@ -529,12 +531,12 @@ struct MsmEngine {
         B2P_REQUIRE(slot >= 0 && slot < MSM_SLOTS, "MSM result slot out of range");
         const uint32_t nb = plan.nbuckets;
         B2P_CUDA(cudaMemsetAsync(counts.p, 0, nb * sizeof(uint32_t), st));
-        B2P_CUDA(cudaMemsetAsync(cursor.p, 0, nb * sizeof(uint32_t), st));
-        if (n) B2P_LAUNCH((k_msm_count<Fr>), div_up(n, 256), 256, 0, st, d_scalars, n, plan.c, plan.W, (int)mont, counts.p);
+        if (n) B2P_LAUNCH((k_msm_count<Fr>), div_up(n, 256), 256, 0, st, d_scalars, n, plan.c, plan.W, (int)mont, counts.p,
+                          ranks.p);
         exclusive_scan_u32(counts.p, offsets.p, nb, scan_scratch.p, total_entries.p, st, ScanIdentity{});
         exclusive_scan_u32(counts.p, item_off.p, nb, scan_scratch.p, total_items.p, st, ScanCeilDiv{MSM_CAP});
         if (n) B2P_LAUNCH((k_msm_scatter<Fr>), div_up(n, 256), 256, 0, st, d_scalars, n, npoints, plan.c, plan.W, (int)mont,
-                          offsets.p, cursor.p, entries.p);
+                          offsets.p, ranks.p, entries.p);
         // items sorted by length, longest first
         B2P_CUDA(cudaMemsetAsync(big_count.p, 0, sizeof(uint32_t), st));
         B2P_LAUNCH(k_msm_len_hist, sort_blocks, MSM_SORT_THREADS, 0, st, counts.p, nb, sort_blocks, len_hist.p);

@@ -183,17 +183,21 @@ __global__ void k_perm_to_lagrange(F* __restrict__ s, const int64_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------
-// grand product terms:  f[i+1] = num_i, g[i+1] = den_i (i < n-1), f[0] = g[0] = 1
+// grand product terms:  f[i+1] = num_i (i < n-1), f[0] = 1;  the denominators are stored REVERSED,
+// gr[n-2-i] = den_i, gr[n-1] = 1, so that the prefix scan of gr yields the suffix products of den:
+//   Z_k = prod_{i<k} num_i / den_i = F_k * (prod_{i>=k} den_i) / (prod_all den_i) = F_k * PR[n-2-k] * Ginv
+// with F, PR the inclusive scans of f, gr and Ginv = 1 / PR[n-1]: ONE field inversion (on the host)
+// instead of a batch inversion of n prefix products.
 // ---------------------------------------------------------------------------
 template <class F>
-__global__ void k_z_terms(F* __restrict__ f, F* __restrict__ g, const F* __restrict__ L, const F* __restrict__ R,
+__global__ void k_z_terms(F* __restrict__ f, F* __restrict__ gr, const F* __restrict__ L, const F* __restrict__ R,
                           const F* __restrict__ O, const F* __restrict__ S /* 3n Lagrange */, const F* __restrict__ tw,
                           uint64_t n, F beta, F gamma, F u, F u2) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (i == n - 1) {
         st_field(f, F::one());
-        st_field(g, F::one());
+        st_field(gr + (n - 1), F::one());
         return;
     }
     const F l = ld_field(L + i) + gamma, r = ld_field(R + i) + gamma, o = ld_field(O + i) + gamma;
@@ -201,13 +205,23 @@ __global__ void k_z_terms(F* __restrict__ f, F* __restrict__ g, const F* __restr
     const F num = (l + bw) * (r + bw * u) * (o + bw * u2);
     const F den = (l + beta * ld_field(S + i)) * (r + beta * ld_field(S + n + i)) * (o + beta * ld_field(S + 2 * n + i));
     st_field(f + i + 1, num);
-    st_field(g + i + 1, den);
+    st_field(gr + (n - 2 - i), den);
+}
+// Z_k = F_k * PR[n-2-k] * ginv  (k = n-1: the empty suffix product)
+template <class F>
+__global__ void k_z_finish(F* __restrict__ z, const F* __restrict__ Fs, const F* __restrict__ PR, uint64_t n, F ginv) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    F v = ld_field(Fs + k) * ginv;
+    if (k + 1 < n) v = v * ld_field(PR + (n - 2 - k));
+    st_field(z + k, v);
 }
 
 // ---------------------------------------------------------------------------
 // quotient on the big coset, bit-reversed layout (position p <-> natural index brev(p))
 // ---------------------------------------------------------------------------
 constexpr int MAX_QCP = 8;
+constexpr int MAX_PI_DIRECT = 8;
 template <class F>
 struct QuotientArgs {
     const F *l, *r, *o, *z;               // blinded wire / grand product evaluations
@@ -222,6 +236,13 @@ struct QuotientArgs {
     int logm, log_rho;
     F beta, gamma, alpha, alpha2, u, u2;
     F zh_inv[8];                          // 1 / (X^n - 1) by natural index mod rho
+    // Public inputs and BSB22 commitment hashes sit in rows of qk (gnark completeQk).  With only a few of
+    // them, qk is NOT completed and transformed per proof: a.qk holds the key's qk and the missing part
+    //   sum_t pi_val[t] * L_{pi_row[t]}(x),   L_i(x) = L_0(x * omega^-i),
+    // is read off the resident L_0 evaluations (a rotation by rho * i in natural order).
+    int n_pi;
+    uint32_t pi_row[MAX_PI_DIRECT];
+    F pi_val[MAX_PI_DIRECT];
 };
 
 template <class F>
@@ -237,6 +258,10 @@ __global__ void __launch_bounds__(256) k_quotient(const QuotientArgs<F> a) {
     F gate = ld_field(a.ql + p) * l + ld_field(a.qr + p) * r + ld_field(a.qm + p) * (l * r)
            + ld_field(a.qo + p) * o + ld_field(a.qk + p);
     for (int c = 0; c < a.k; c++) gate = gate + ld_field(a.qcp[c] + p) * ld_field(a.pi2[c] + p);
+    for (int t = 0; t < a.n_pi; t++) {
+        const uint32_t q = brev32((nat - rho * a.pi_row[t]) & (m - 1), a.logm);
+        gate = gate + a.pi_val[t] * ld_field(a.l1 + q);
+    }
 
     const F z = ld_field(a.z + p), zs = ld_field(a.z + pshift);
     const F lg = l + a.gamma, rg = r + a.gamma, og = o + a.gamma;

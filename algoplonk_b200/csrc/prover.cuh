@@ -273,6 +273,8 @@ struct Circuit : CircuitBase {
 
     Srs<C>* srs;
     cudaStream_t st;
+    cudaStream_t copy_st = nullptr;            // host -> device uploads of the wire columns
+    cudaEvent_t ev_ready = nullptr, ev_col[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t n, m;
     int logn, logm, log_rho;
     uint32_t nb_public, k;
@@ -283,7 +285,7 @@ struct Circuit : CircuitBase {
     // resident circuit data
     DevBuf<Fr> lag_qk, lag_S;
     DevBuf<Fr> c_ql, c_qr, c_qm, c_qo, c_qk, c_s1, c_s2, c_s3;
-    DevBuf<Fr> e_ql, e_qr, e_qm, e_qo, e_s1, e_s2, e_s3, e_x, e_l1;
+    DevBuf<Fr> e_ql, e_qr, e_qm, e_qo, e_qk, e_s1, e_s2, e_s3, e_x, e_l1;
     std::vector<DevBuf<Fr>> c_qcp, e_qcp;
     Fr zh_inv[8];
     Fr u, u2;
@@ -387,7 +389,7 @@ struct Circuit : CircuitBase {
             to_canonical(cs[j]);
         }
         auto mk = [&](DevBuf<Fr>& e, const DevBuf<Fr>& c) { e.alloc(m); to_coset(e.p, c.p, n); };
-        mk(e_ql, c_ql); mk(e_qr, c_qr); mk(e_qm, c_qm); mk(e_qo, c_qo);
+        mk(e_ql, c_ql); mk(e_qr, c_qr); mk(e_qm, c_qm); mk(e_qo, c_qo); mk(e_qk, c_qk);
         mk(e_s1, c_s1); mk(e_s2, c_s2); mk(e_s3, c_s3);
         for (uint32_t c = 0; c < k; c++) mk(e_qcp[c], c_qcp[c]);
 
@@ -424,6 +426,11 @@ struct Circuit : CircuitBase {
         B2P_CUDA(cudaStreamSynchronize(st));
     }
 
+    // B2P_NO_PI_DIRECT=1 forces the general completeQk path (tests compare the two)
+    static bool env_no_pi_direct() {
+        const char* e = getenv("B2P_NO_PI_DIRECT");
+        return e && atoi(e) != 0;
+    }
     static Fr fr_from_u64(uint64_t x) {
         Fr r = Fr::zero();
         r.v[0] = (uint32_t)x;
@@ -431,7 +438,15 @@ struct Circuit : CircuitBase {
         return r.to_mont();
     }
 
+    ~Circuit() override {
+        if (copy_st) cudaStreamDestroy(copy_st);
+        if (ev_ready) cudaEventDestroy(ev_ready);
+        for (auto& e : ev_col) if (e) cudaEventDestroy(e);
+    }
     void alloc_workspace() {
+        B2P_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+        B2P_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+        for (auto& e : ev_col) B2P_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         L.alloc(n); R.alloc(n); O.alloc(n);
         cl.alloc(coeff_cap()); cr.alloc(coeff_cap()); co.alloc(coeff_cap()); cz.alloc(coeff_cap());
         Zf.alloc(n); Zg.alloc(n);
@@ -508,20 +523,33 @@ struct Circuit : CircuitBase {
         B2P_REQUIRE(k == 0 || (h_pi2 && h_bsb22), "BSB22 inputs missing");
 
         // -- upload -----------------------------------------------------------
-        B2P_CUDA(cudaMemcpyAsync(L.p, hL, n * sizeof(Fr), in_kind, st));
-        B2P_CUDA(cudaMemcpyAsync(R.p, hR, n * sizeof(Fr), in_kind, st));
-        B2P_CUDA(cudaMemcpyAsync(O.p, hO, n * sizeof(Fr), in_kind, st));
+        // Host columns go up on a copy stream, one event per column: the transform and commitment of L
+        // run while R and O are still on the wire (pinned host buffers; pageable ones are staged by the
+        // driver and simply serialise).
         B2P_CUDA(cudaMemcpyAsync(small.p, h_blinding, 9 * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        const void* hcols[3] = {hL, hR, hO};
+        Fr* dcols[3] = {L.p, R.p, O.p};
+        cudaStream_t up = device_inputs ? st : copy_st;
+        if (!device_inputs) {
+            B2P_CUDA(cudaEventRecord(ev_ready, st));            // the previous proof is done with L, R, O, pi2
+            B2P_CUDA(cudaStreamWaitEvent(copy_st, ev_ready, 0));
+        }
+        for (int j = 0; j < 3; j++) {
+            B2P_CUDA(cudaMemcpyAsync(dcols[j], hcols[j], n * sizeof(Fr), in_kind, up));
+            if (!device_inputs) B2P_CUDA(cudaEventRecord(ev_col[j], copy_st));
+        }
         stats[B2P_STAT_H2D_BYTES] += (device_inputs ? 0.0 : 3.0 * n * sizeof(Fr)) + 9 * sizeof(Fr);
         for (uint32_t c = 0; c < k; c++) {
-            B2P_CUDA(cudaMemcpyAsync(c_pi2[c].p, h_pi2[c], n * sizeof(Fr), in_kind, st));
+            B2P_CUDA(cudaMemcpyAsync(c_pi2[c].p, h_pi2[c], n * sizeof(Fr), in_kind, up));
             if (!device_inputs) stats[B2P_STAT_H2D_BYTES] += (double)n * sizeof(Fr);
         }
+        if (!device_inputs) B2P_CUDA(cudaEventRecord(ev_col[3], copy_st));   // pi2 columns
 
         // -- round 1: l, r, o -------------------------------------------------
         Fr* wires_c[3] = {cl.p, cr.p, co.p};
         const Fr* wires_l[3] = {L.p, R.p, O.p};
         for (int j = 0; j < 3; j++) {
+            if (!device_inputs) B2P_CUDA(cudaStreamWaitEvent(st, ev_col[j], 0));
             B2P_CUDA(cudaMemcpyAsync(wires_c[j], wires_l[j], n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
             B2P_CUDA(cudaMemsetAsync(wires_c[j] + n, 0, (coeff_cap() - n) * sizeof(Fr), st));
             int id = prof.begin(B2P_STAT_NTT_MS, st);
@@ -530,6 +558,7 @@ struct Circuit : CircuitBase {
             B2P_LAUNCH((k_blind<Fr>), 1, 32, 0, st, wires_c[j], n, 2, small.p + 2 * j);
             srs->commit_async(wires_c[j], n + 2, j);
         }
+        if (!device_inputs) B2P_CUDA(cudaStreamWaitEvent(st, ev_col[3], 0));
         Aff pts[10];   // LRO[3], Z, H[3], batched H, zshift H, [Lin]
         srs->fetch(0, 3, pts);
 
@@ -559,8 +588,12 @@ struct Circuit : CircuitBase {
         B2P_LAUNCH((k_z_terms<Fr>), div_up(n, 256), 256, 0, st, Zf.p, Zg.p, L.p, R.p, O.p, lag_S.p, d0.tw.p, n, beta, gamma, u, u2);
         field_scan_inclusive<Fr, OpMul>(Zf.p, n, fscratch.p, st);
         field_scan_inclusive<Fr, OpMul>(Zg.p, n, fscratch.p, st);
-        B2P_LAUNCH((k_batch_inverse<Fr>), div_up(div_up(n, BINV_CHUNK), 128), 128, 0, st, Zg.p, n);
-        B2P_LAUNCH((k_mul_pointwise<Fr>), div_up(n, 256), 256, 0, st, cz.p, Zf.p, Zg.p, n);
+        {
+            Fr gall;   // product of all denominators; a zero denominator (probability ~2^-230) zeroes Z
+            B2P_CUDA(cudaMemcpyAsync(&gall, Zg.p + (n - 1), sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            B2P_CUDA(cudaStreamSynchronize(st));
+            B2P_LAUNCH((k_z_finish<Fr>), div_up(n, 256), 256, 0, st, cz.p, Zf.p, Zg.p, n, gall.inverse());
+        }
         B2P_CUDA(cudaMemsetAsync(cz.p + n, 0, (coeff_cap() - n) * sizeof(Fr), st));
         {
             int id = prof.begin(B2P_STAT_NTT_MS, st);
@@ -590,8 +623,11 @@ struct Circuit : CircuitBase {
         const Fr alpha = fr_from_be32_mod<Fr>(alpha_pre);
 
         // -- round 3: quotient ------------------------------------------------------
-        // qk completed with public inputs and commitment hashes (gnark completeQk), built in `T`
-        {
+        // qk completed with public inputs and commitment hashes (gnark completeQk): with few of them the
+        // quotient kernel adds their Lagrange terms itself (QuotientArgs::n_pi), otherwise qk is completed
+        // in Lagrange form and transformed (iNTT(n) + coset NTT(4n)) like the wires
+        const bool pi_direct = nb_public + k <= (uint32_t)MAX_PI_DIRECT && !env_no_pi_direct();
+        if (!pi_direct) {
             Fr* tmp = h.p;   // h is free until the quotient kernel writes it
             B2P_CUDA(cudaMemcpyAsync(tmp, lag_qk.p, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
             if (nb_public) B2P_CUDA(cudaMemcpyAsync(tmp, L.p, nb_public * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
@@ -621,7 +657,16 @@ struct Circuit : CircuitBase {
         {
             QuotientArgs<Fr> a;
             a.l = el.p; a.r = er.p; a.o = eo.p; a.z = ez.p;
-            a.ql = e_ql.p; a.qr = e_qr.p; a.qm = e_qm.p; a.qo = e_qo.p; a.qk = eqk.p;
+            a.ql = e_ql.p; a.qr = e_qr.p; a.qm = e_qm.p; a.qo = e_qo.p;
+            a.qk = pi_direct ? e_qk.p : eqk.p;
+            a.n_pi = 0;
+            if (pi_direct) {
+                for (uint32_t i = 0; i < nb_public; i++) { a.pi_row[a.n_pi] = i; a.pi_val[a.n_pi++] = hLf[i]; }
+                for (uint32_t c = 0; c < k; c++) {
+                    a.pi_row[a.n_pi] = (uint32_t)(nb_public + commit_idx[c]);
+                    a.pi_val[a.n_pi++] = bsb_hash[c];
+                }
+            }
             a.s1 = e_s1.p; a.s2 = e_s2.p; a.s3 = e_s3.p; a.x = e_x.p; a.l1 = e_l1.p;
             for (uint32_t c = 0; c < k; c++) { a.qcp[c] = e_qcp[c].p; a.pi2[c] = e_pi2[c].p; }
             a.k = (int)k;

@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--log2 20] [--curve BN254]
 
-One "step" = one proof (b2p_prove: 10 MSMs, ~10 NTTs of size 4n, quotient, openings) of the synthetic
-squaring-chain circuit of SURVEY 8d on a known-tau SRS.  N > 1 runs one replica per GPU (proofs are
-independent: no data-path collective, "scaling": "weak"); timing is CUDA events on the library's stream,
-max over ranks.  Rank 0 prints ONE JSON line.
+One "step" = one proof (b2p_prove: 9 MSMs of ~n points, 6 NTTs of size 4n + 5 of size n, quotient, openings)
+of the synthetic squaring-chain circuit of SURVEY 8d on a known-tau SRS.  N > 1 runs one replica per GPU
+(proofs are independent: no data-path collective, "scaling": "weak"); timing is CUDA events on the library's
+stream, max over ranks.  Rank 0 prints ONE JSON line.  At N > 1 the line also carries "msm_sharded": one
+2^log2-point MSM with the point set split over the N GPUs (one all_gather of a point per rank over NCCL,
+DESIGN.md section 7), timed the same way.
 
   value      proofs/s with L, R, O already resident in HBM (b2p_prove_dev)
   e2e        proofs/s through the reference-facing C-ABI call b2p_prove with pinned HOST buffers
@@ -283,6 +285,8 @@ def run_b200(args):
     clocks = sampler.stop()
     assert bytes(out.raw) == proof_resident, "host-buffer and resident-buffer proofs differ"
 
+    sharded_line = measure_sharded_msm(args, rank, world, device) if world > 1 else None
+
     tot_ms, units = reduce_over_ranks(ms, args.steps, world, device)
     tot_ms_e2e, _ = reduce_over_ranks(ms_e2e, args.steps, world, device)
     if rank != 0:
@@ -317,6 +321,8 @@ def run_b200(args):
                       "quotient": stats["quotient_ms"], "total_host_wall": stats["total_ms"]},
         "circuit_load_s": load_s,
     }
+    if sharded_line is not None:
+        line["msm_sharded"] = sharded_line
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(curve, args.log2)
     else:
@@ -325,6 +331,60 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def measure_sharded_msm(args, rank, world, device, iters: int = 10):
+    """One MSM over 2^log2 points with the point set sharded over the ranks (algoplonk_b200/sharded.py):
+    local Pippenger on n/G resident scalars, one all_gather of the G partial sums over NCCL, local add.
+    Timed with CUDA events on the shard's stream (torch's current stream for the duration, so the NCCL
+    collective is ordered on it), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from algoplonk_b200 import _lib, api, sharded
+    lib = _lib.load()
+    curve, n = args.curve, 1 << args.log2
+    sh = sharded.ShardedSRS.unsafe(curve, n, rank, world, TAU)
+    gen = torch.Generator(device="cpu").manual_seed(0xB200 + rank)
+    # uniform 256-bit patterns taken as Montgomery representations: uniform scalars up to the top two bits
+    raw = torch.randint(-(1 << 31), 1 << 31, (sh.count, 8), generator=gen, dtype=torch.int64).to(torch.int32)
+    raw[:, 7] &= 0x0FFFFFFF                      # < 2^252 < r: a valid (canonical) field element
+    d_scalars = raw.to(device).contiguous()
+    stream = torch.cuda.ExternalStream(lib.b2p_srs_stream(sh.handle), device=device)
+    nb = 2 * api.FP_BYTES[curve]
+
+    def one():
+        local = sh.local_msm_dev_raw(d_scalars.data_ptr(), sh.count)
+        t = torch.frombuffer(bytearray(local), dtype=torch.uint8).to(device, non_blocking=True)
+        out = torch.empty(world * nb, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(out, t)
+        return sharded.g1_sum(curve, bytes(out.cpu().numpy().tobytes()))
+
+    with torch.cuda.stream(stream):
+        first = one()
+        for _ in range(2):
+            one()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            res = one()
+        e1.record(stream)
+        e1.synchronize()
+        dist.barrier()
+    assert res == first
+    # every rank must hold the same sum
+    chk = torch.frombuffer(bytearray(res), dtype=torch.uint8).to(device)
+    allr = torch.empty(world * nb, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allr, chk)
+    assert all(bytes(allr[i * nb:(i + 1) * nb].cpu().numpy().tobytes()) == res for i in range(world))
+    ms, _ = reduce_over_ranks(e0.elapsed_time(e1) / iters, 0, world, device)
+    c_bits, windows, _ = api.SRS(curve, sh.handle).msm_params()
+    sh.free()
+    return {"points": n, "points_per_gpu": sh.count, "ms_per_msm": ms, "msm_per_sec": 1e3 / ms,
+            "g1_adds_per_sec": n * windows / (ms * 1e-3), "c": c_bits, "windows": windows,
+            "collective": f"all_gather of one {nb}-byte point per rank (NCCL), then a local {world}-point add",
+            "scalars": "uniform, resident in HBM"}
 
 
 def main():

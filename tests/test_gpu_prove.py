@@ -80,6 +80,58 @@ def test_mid_size_byte_identical_to_cpp_oracle(gpu, curve, logn):
     cc.free()
 
 
+def _many_public_circuit(curve, nb_public):
+    """sum of nb_public public inputs == a secret, padded with a few multiplications."""
+    B = fe.Builder(curve)
+    pubs = [B.public(3 * i + 2) for i in range(nb_public)]
+    total = B.secret(sum(3 * i + 2 for i in range(nb_public)))
+    acc = pubs[0]
+    for v in pubs[1:]:
+        acc = B.add(acc, v)
+    B.assert_is_equal(acc, total)
+    sq = B.mul(total, total)
+    B.assert_is_equal(B.mul(sq, pubs[1]), B.secret(B.values[sq] * B.values[pubs[1]]))
+    return B
+
+
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+@pytest.mark.parametrize("nb_public", (8, 12))
+def test_many_public_inputs(gpu, curve, nb_public):
+    """8 public inputs: their Lagrange terms are added by the quotient kernel; 12: the general completeQk
+    path (qk completed in Lagrange form, iNTT + coset NTT).  Both byte-identical to the C++ oracle."""
+    cv = po.CURVES[curve]
+    B = _many_public_circuit(curve, nb_public)
+    cs = B.build()
+    cc = api.Compile(cs, curve, SETUP[curve])
+    tc = cc.trace
+    assert tc.nb_public == nb_public
+    L, R, O = fe.solve_lro(cs, B.values, tc.n)
+    assert fe.check_gates(tc, L, R, O)
+    blinding = H.scalars_uniform(cv.r, 9, nb_public)
+    blob = api.MarshalProof(cc.Prove(L, R, O, blinding))
+    srs_le = co.srs_from_tau_bytes(cv.cid, api.TEST_TAU, tc.n + 3)
+    circ = co.Circuit(cv.cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
+    assert blob == circ.prove(L, R, O, blinding)
+    vk = H.vk_from_points(tc, cc.vk_commitments(), cv.g1, tau=api.TEST_TAU)
+    assert po.verify_proof(vk, blob, api.MarshalPublicInputs(curve, L[: tc.nb_public]))
+    circ.free()
+    cc.free()
+
+
+@pytest.mark.parametrize("name", ("basic", "bsb22_k2"))
+def test_direct_public_input_terms_equal_completed_qk(gpu, name, monkeypatch):
+    """B2P_NO_PI_DIRECT=1 forces the general path on circuits that normally take the direct one."""
+    case = next(c for c in H.golden_proofs() if c["curve"] == "BN254" and c["name"] == name and c["srs"] == "tau")
+    c = H.build_case(case)
+    cc = _compile(c, case)
+    monkeypatch.setenv("B2P_NO_PI_DIRECT", "1")
+    general = api.MarshalProof(cc.Prove(c["L"], c["R"], c["O"], c["blinding"], c["pi2"], c["coms"]))
+    monkeypatch.delenv("B2P_NO_PI_DIRECT")
+    direct = api.MarshalProof(cc.Prove(c["L"], c["R"], c["O"], c["blinding"], c["pi2"], c["coms"]))
+    assert general.hex() == case["proof"] == direct.hex()
+    cc.free()
+
+
 @pytest.mark.parametrize("curve,logn", [("BN254", 17), ("BN254", 20), ("BLS12_381", 17)])
 def test_config_sizes_accepted_by_reference_verifier(gpu, curve, logn):
     """BASELINE configs[1], [2] (2^17 and 2^20 BN254) and a 2^17 BLS12-381 run: size-independent
