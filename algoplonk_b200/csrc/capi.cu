@@ -2,6 +2,7 @@
 // and the reference interface each entry point replaces.  This file only does
 // argument checking, curve dispatch and error translation; the work is in the
 // per-curve instantiations (inst_*.cu).
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cstring>
 #include <new>
@@ -10,7 +11,7 @@
 #include "iface.hpp"
 
 namespace b2p {
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 }
 using namespace b2p;
 

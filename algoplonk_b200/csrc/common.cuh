@@ -1,6 +1,7 @@
 // Shared plumbing: curve configs, CUDA error handling, device buffers, vector loads.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -41,7 +42,7 @@ struct Bls12381 {
 
 // Launch counter: every kernel launch of this library goes through B2P_LAUNCH so
 // that bench.py can report "gpu_launches" as a measured number.
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 
 #define B2P_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
     do {                                                                        \

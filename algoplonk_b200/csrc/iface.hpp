@@ -2,6 +2,7 @@
 // template instantiations (inst_prover_*.cu).  Keeping capi.cu free of the
 // templates keeps its compile time in seconds.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -51,6 +52,6 @@ struct CurveOps {
 const CurveOps* curve_ops_bn254();
 const CurveOps* curve_ops_bls12381();
 
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 
 }  // namespace b2p

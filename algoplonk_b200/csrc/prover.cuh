@@ -273,6 +273,7 @@ struct Circuit : CircuitBase {
 
     Srs<C>* srs;
     cudaStream_t st;
+    Fr* h_pub = nullptr;                       // pinned: public inputs of a device-resident witness
     cudaStream_t copy_st = nullptr;            // host -> device uploads of the wire columns
     cudaEvent_t ev_ready = nullptr, ev_col[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t n, m;
@@ -439,11 +440,13 @@ struct Circuit : CircuitBase {
     }
 
     ~Circuit() override {
+        if (h_pub) cudaFreeHost(h_pub);
         if (copy_st) cudaStreamDestroy(copy_st);
         if (ev_ready) cudaEventDestroy(ev_ready);
         for (auto& e : ev_col) if (e) cudaEventDestroy(e);
     }
     void alloc_workspace() {
+        B2P_CUDA(cudaMallocHost(&h_pub, (nb_public ? nb_public : 1) * sizeof(Fr)));
         B2P_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
         B2P_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
         for (auto& e : ev_col) B2P_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -515,10 +518,11 @@ struct Circuit : CircuitBase {
         B2P_CUDA(cudaMemsetAsync(srs->msm.adds_total.p, 0, sizeof(unsigned long long), st));
         // wire columns: host buffers (the cgo path) or buffers already resident in HBM
         const cudaMemcpyKind in_kind = device_inputs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        std::vector<Fr> pub_host(nb_public);
+        // public inputs on the host (transcript, quotient): with device-resident columns they come back through a
+        // pinned buffer; the copy is complete at the first fetch() below, before anything reads it
         if (device_inputs && nb_public)
-            B2P_CUDA(cudaMemcpyAsync(pub_host.data(), hL, nb_public * sizeof(Fr), cudaMemcpyDeviceToHost, st));
-        const Fr* hLf = device_inputs ? pub_host.data() : static_cast<const Fr*>(hL);
+            B2P_CUDA(cudaMemcpyAsync(h_pub, hL, nb_public * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        const Fr* hLf = device_inputs ? h_pub : static_cast<const Fr*>(hL);
         const Aff* bsb = static_cast<const Aff*>(h_bsb22);
         B2P_REQUIRE(k == 0 || (h_pi2 && h_bsb22), "BSB22 inputs missing");
 

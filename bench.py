@@ -37,6 +37,12 @@ if ROOT not in sys.path:
 METRIC = "plonk_proofs_per_sec"
 UNIT = "proofs/s"
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_msm_accumulate launch, from the ncu --set full capture
+# under profiles/ (per workload): the gather reads W = 13 table points per scalar, so ~13x the algorithmic bytes
+ACCUM_DRAM_TRAFFIC = {("BN254", 20): 1_887_123_792}
+# mixed additions / s at which the IMAD pipe saturates: measured field multiplications / s (tools/microbench.cu,
+# profiles/microbench_r1.json) / 10 multiplications per XYZZ mixed addition
+MADD_ROOFLINE = {"BN254": 6.78e9, "BLS12_381": 3.09e9}
 
 
 # ---------------------------------------------------------------------------------------
@@ -204,6 +210,7 @@ def workload_config(args):
     return {"workload": f"synthetic squaring-chain circuit, 2^{args.log2} constraints, {args.curve}, "
                         f"known-tau SRS of 2^{args.log2}+3 points, k=0",
             "log2_constraints": args.log2, "curve": args.curve, "parallelism": f"replicas x{args.gpus}",
+            "inflight_per_gpu": max(1, args.inflight),
             "l2": "inputs larger than L2: per-proof working set (13-window SRS table + 4n evaluations) "
                   "is > 1 GB vs 126 MB L2"}
 
@@ -225,32 +232,35 @@ def run_b200(args):
     _lib.init(local_rank)          # raises without a usable GPU: there is no CPU fallback
     lib = _lib.load()
     curve = args.curve
+    F = max(1, args.inflight)
 
     cs, tc, L, R, O = build_workload(curve, args.log2)
     n = tc.n
     setup = api.SetupName.TestOnlyBN254 if curve == "BN254" else api.SetupName.TestOnlyBLS12381
     t0 = time.perf_counter()
-    cc = api.Compile(cs, curve, setup)
-    load_s = time.perf_counter() - t0
-    c_bits, windows, buckets = cc.srs.msm_params()
+    # one proving key (SRS table + circuit + workspace + stream) per proof in flight
+    ccs = [api.Compile(cs, curve, setup) for _ in range(F)]
+    load_s = (time.perf_counter() - t0) / F
+    c_bits, windows, buckets = ccs[0].srs.msm_params()
 
     # pinned host buffers (what the cgo shim would pass) and their device-resident copies
     def pinned(data: bytes):
-        t = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
-        return t
+        return torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
     hL, hR, hO = (pinned(api.fr_to_mont_bytes(curve, col)) for col in (L, R, O))
     dL, dR, dO = (t.to(device) for t in (hL, hR, hO))
     blinding = C.create_string_buffer(api.fr_to_mont_bytes(curve, list(range(1, 10))))
     cid = api.CURVE_ID[curve]
-    out = C.create_string_buffer(lib.b2p_proof_raw_size(cid, 0))
-    stream = torch.cuda.ExternalStream(lib.b2p_circuit_stream(cc.handle), device=device)
+    outs = [C.create_string_buffer(lib.b2p_proof_raw_size(cid, 0)) for _ in range(F)]
+    streams = [torch.cuda.ExternalStream(lib.b2p_circuit_stream(cc.handle), device=device) for cc in ccs]
     torch.cuda.synchronize()
 
-    def prove_dev():
-        _lib.check(lib.b2p_prove_dev(cc.handle, dL.data_ptr(), dR.data_ptr(), dO.data_ptr(), None, None, blinding, out))
+    def prove_dev(i):
+        _lib.check(lib.b2p_prove_dev(ccs[i].handle, dL.data_ptr(), dR.data_ptr(), dO.data_ptr(), None, None,
+                                     blinding, outs[i]))
 
-    def prove_host():
-        _lib.check(lib.b2p_prove(cc.handle, hL.data_ptr(), hR.data_ptr(), hO.data_ptr(), None, None, blinding, out))
+    def prove_host(i):
+        _lib.check(lib.b2p_prove(ccs[i].handle, hL.data_ptr(), hR.data_ptr(), hO.data_ptr(), None, None,
+                                 blinding, outs[i]))
 
     def barrier():
         if world > 1:
@@ -258,37 +268,70 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        e1.synchronize()
-        barrier()
-        return e0.elapsed_time(e1)
+    # one persistent host thread per lane (a prover service keeps its workers alive; the first CUDA call of a
+    # fresh thread costs ~100 ms of one-time initialisation, which the warm-up absorbs)
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=F)
 
-    cc.set_profiling(True)         # CUDA-event spans around MSM / accumulate / NTT / quotient; no extra syncs
-    for _ in range(args.warmup):
-        prove_dev()
+    def timed(fn, steps, lanes):
+        """EXACTLY `steps` proofs, spread over `lanes` host threads (one proving key and stream each);
+        CUDA events on the library's streams, recorded by the workers: first start to last end."""
+        counts = [steps // lanes + (1 if i < steps % lanes else 0) for i in range(lanes)]
+        barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
+        gate = threading.Barrier(lanes)
+
+        def work(i):
+            gate.wait()
+            starts[i].record(streams[i])
+            tw = time.perf_counter()
+            for _ in range(counts[i]):
+                fn(i)
+            ends[i].record(streams[i])
+            if os.environ.get("B2P_BENCH_DEBUG"):
+                print(f"[lane {i}] {counts[i]} x {fn.__name__}: {(time.perf_counter() - tw) * 1e3:.1f} ms",
+                      file=sys.stderr)
+
+        for f in [pool.submit(work, i) for i in range(lanes)]:
+            f.result()                   # re-raises a worker's exception
+        for e in ends:
+            e.synchronize()
+        barrier()
+        if os.environ.get("B2P_BENCH_DEBUG"):
+            print("[events]", [[round(s.elapsed_time(e), 1) for e in ends] for s in starts], file=sys.stderr)
+        return max(s.elapsed_time(e) for s in starts for e in ends)
+
+    def warm(i):
+        for _ in range(args.warmup):
+            prove_dev(i)
+    for f in [pool.submit(warm, i) for i in range(F)]:
+        f.result()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # pass 1: one proof at a time, CUDA-event spans around MSM / accumulate / NTT / quotient (no extra syncs)
+    ccs[0].set_profiling(True)
+    ms_single = timed(prove_dev, args.steps, 1)
+    stats = ccs[0].stats()         # spans of the last timed proof
+    ccs[0].set_profiling(False)
+    proof_resident = bytes(outs[0].raw)
+    # pass 2 (value): F proofs in flight
     launches0 = lib.b2p_launch_count()
-    ms = timed(prove_dev, args.steps)
+    ms = timed(prove_dev, args.steps, F)
     launches = lib.b2p_launch_count() - launches0
-    stats = cc.stats()             # spans of the last timed proof
-    proof_resident = bytes(out.raw)
-    for _ in range(min(1, args.warmup)):
-        prove_host()
-    ms_e2e = timed(prove_host, args.steps)
+    # pass 3 (e2e): the same through b2p_prove with host buffers
+    for i in range(F):
+        prove_host(i)
+    ms_e2e = timed(prove_host, args.steps, F)
     clocks = sampler.stop()
-    assert bytes(out.raw) == proof_resident, "host-buffer and resident-buffer proofs differ"
+    for o in outs:
+        assert bytes(o.raw) == proof_resident, "host-buffer and resident-buffer proofs differ"
 
     sharded_line = measure_sharded_msm(args, rank, world, device) if world > 1 else None
 
     tot_ms, units = reduce_over_ranks(ms, args.steps, world, device)
     tot_ms_e2e, _ = reduce_over_ranks(ms_e2e, args.steps, world, device)
+    tot_ms_single, _ = reduce_over_ranks(ms_single, args.steps, world, device)
     if rank != 0:
         return
     value = units / (tot_ms / 1e3)
@@ -300,22 +343,28 @@ def run_b200(args):
     alg_bytes = msm_algorithmic_bytes(n + 2, curve)
     achieved = alg_bytes / (accum_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "launch_ms": accum_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "256-bit modular arithmetic makes this kernel INT32-ALU-bound, not HBM-bound (DESIGN.md); "
-                        "see msm_g1_adds_per_sec"}
+                "frac": achieved / hbm_peak, "traffic": ACCUM_DRAM_TRAFFIC.get((curve, args.log2)),
+                "peak_source": peak_src, "launch_ms": accum_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "measured_in": "the one-proof-at-a-time pass (CUDA events around every launch of the kernel)",
+                "note": "254-bit modular arithmetic makes this kernel INT32-multiplier-bound, not HBM-bound: ncu shows "
+                        "sm__pipe_fmaheavy_cycles_active at 91 % (DESIGN.md section 4); the honest roofline is "
+                        "msm.msm_g1_adds_per_sec against msm.madd_roofline_per_sec"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic", "config": workload_config(args),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) if False else 3 * 32 * n + 9 * 32,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * 32 * n + 9 * 32,
                 "d2h_bytes_per_step": int(lib.b2p_proof_raw_size(cid, 0)), "ms_per_step": tot_ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks,
+        "single_stream": {"value": units / (tot_ms_single / 1e3), "ms_per_proof": tot_ms_single / args.steps,
+                          "note": "one proof at a time on one stream (latency); `value` keeps "
+                                  f"{F} proofs in flight on {F} streams"},
         "msm": {"c": c_bits, "windows": windows, "buckets": buckets, "calls_per_proof": msm_calls,
                 "accum_adds_per_proof": stats["msm_accum_adds"],
                 "msm_g1_adds_per_sec": stats["msm_accum_adds"] / (stats["msm_accum_ms"] * 1e-3),
+                "madd_roofline_per_sec": MADD_ROOFLINE.get(curve),
                 "msm_ms_per_proof": stats["msm_ms"]},
         "phases_ms": {"msm": stats["msm_ms"], "msm_accumulate": stats["msm_accum_ms"], "ntt": stats["ntt_ms"],
                       "quotient": stats["quotient_ms"], "total_host_wall": stats["total_ms"]},
@@ -396,6 +445,8 @@ def main():
     ap.add_argument("--log2", type=int, default=20, help="log2 of the constraint count (BASELINE: 20)")
     ap.add_argument("--curve", default="BN254", choices=["BN254", "BLS12_381"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3,
+                    help="proofs in flight per GPU (one proving key + stream each; SURVEY 8d timing protocol)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print(f"note: --warmup {args.warmup} < 3 breaks the timing rules", file=sys.stderr)
