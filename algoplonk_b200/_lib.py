@@ -27,6 +27,7 @@ SYMBOLS = [
     ("b2p_version", C.c_char_p, []),
     ("b2p_launch_count", _u64, []),
     ("b2p_srs_load", _int, [_int, _vp, _u64, _vp, _u64, C.POINTER(_vp)]),
+    ("b2p_srs_load_compressed", _int, [_int, _vp, _u64, _u64, C.POINTER(_vp)]),
     ("b2p_srs_generate_unsafe", _int, [_int, _vp, _u64, C.POINTER(_vp)]),
     ("b2p_srs_generate_unsafe_range", _int, [_int, _vp, _u64, _u64, C.POINTER(_vp)]),
     ("b2p_srs_get_points", _int, [_vp, _u64, _u64, _vp]),

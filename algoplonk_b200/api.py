@@ -109,6 +109,16 @@ class SRS:
         return cls(curve, h.value)
 
     @classmethod
+    def from_pk_bin(cls, curve: str, pk_bin: bytes, count: int) -> "SRS":
+        """setup/setup.go:165-228: the first `count` points of an embedded pk.bin (u32 BE count + compressed
+        G1), decompressed on the GPU."""
+        _lib.init()
+        h = C.c_void_p()
+        _lib.check(_lib.load().b2p_srs_load_compressed(CURVE_ID[curve], _buf(bytes(pk_bin)), len(pk_bin), count,
+                                                       C.byref(h)))
+        return cls(curve, h.value)
+
+    @classmethod
     def unsafe(cls, curve: str, size: int, tau: int = TEST_TAU) -> "SRS":
         """unsafekzg.NewSRS (setup/setup.go:102-108)."""
         _lib.init()

@@ -43,6 +43,28 @@ static int guarded(Fn fn) {
     }
 }
 
+// Handles are bound to the device that was current when they were created; calls may arrive on any host
+// thread (cgo moves goroutines between OS threads, Python worker threads start on device 0), so every entry
+// point that touches a handle makes that device current for the duration of the call.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) throw Error(B2P_ERR_CUDA, "CUDA error: no current device");
+        if (prev != dev) {
+            if (cudaSetDevice(dev) != cudaSuccess) throw Error(B2P_ERR_CUDA, "CUDA error: cannot switch device");
+            switched = true;
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+static int current_device() {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) throw Error(B2P_ERR_CUDA, "CUDA error: no current device");
+    return d;
+}
+
 static const CurveOps* ops_for(int curve) {
     if (curve == B2P_BN254) return curve_ops_bn254();
     if (curve == B2P_BLS12_381) return curve_ops_bls12381();
@@ -74,7 +96,25 @@ API int b2p_srs_load(int curve, const void* g1, uint64_t n_can, const void* g1_l
     return guarded([&] {
         require(g1 && out, "null argument");
         SrsBase* s = ops_for(curve)->new_srs();
+        s->device = current_device();
         try { s->load(g1, n_can); } catch (...) { delete s; throw; }
+        *out = reinterpret_cast<b2p_srs*>(s);
+    });
+}
+
+API int b2p_srs_load_compressed(int curve, const void* pk_bin, uint64_t len, uint64_t count, b2p_srs** out) {
+    return guarded([&] {
+        require(pk_bin && out, "null argument");
+        const uint64_t nb = curve == B2P_BN254 ? 32 : 48;
+        const uint8_t* p = static_cast<const uint8_t*>(pk_bin);
+        require(len >= 4, "pk.bin too small: no header");
+        const uint64_t declared = ((uint64_t)p[0] << 24) | ((uint64_t)p[1] << 16) | ((uint64_t)p[2] << 8) | p[3];
+        // setup/setup.go:219-223: "pk.bin too small for %d elements"
+        if (declared < count || len < 4 + count * nb)
+            throw Error(B2P_ERR_ARG, "pk.bin too small for " + std::to_string(count) + " elements");
+        SrsBase* s = ops_for(curve)->new_srs();
+        s->device = current_device();
+        try { s->load_compressed(p + 4, count); } catch (...) { delete s; throw; }
         *out = reinterpret_cast<b2p_srs*>(s);
     });
 }
@@ -83,6 +123,7 @@ API int b2p_srs_generate_unsafe(int curve, const void* tau, uint64_t n_can, b2p_
     return guarded([&] {
         require(tau && out, "null argument");
         SrsBase* s = ops_for(curve)->new_srs();
+        s->device = current_device();
         try { s->generate_unsafe(tau, 0, n_can); } catch (...) { delete s; throw; }
         *out = reinterpret_cast<b2p_srs*>(s);
     });
@@ -92,6 +133,7 @@ API int b2p_srs_generate_unsafe_range(int curve, const void* tau, uint64_t first
     return guarded([&] {
         require(tau && out, "null argument");
         SrsBase* s = ops_for(curve)->new_srs();
+        s->device = current_device();
         try { s->generate_unsafe(tau, first, count); } catch (...) { delete s; throw; }
         *out = reinterpret_cast<b2p_srs*>(s);
     });
@@ -100,6 +142,7 @@ API int b2p_srs_generate_unsafe_range(int curve, const void* tau, uint64_t first
 API int b2p_srs_get_points(const b2p_srs* srs, uint64_t first, uint64_t count, void* out) {
     return guarded([&] {
         require(srs && out, "null argument");
+        DeviceGuard g(reinterpret_cast<const SrsBase*>(srs)->device);
         reinterpret_cast<const SrsBase*>(srs)->get_points(first, count, out);
     });
 }
@@ -110,17 +153,25 @@ API int b2p_srs_msm_params(const b2p_srs* srs, int* c, int* windows, uint64_t* b
         reinterpret_cast<const SrsBase*>(srs)->msm_params(c, windows, buckets);
     });
 }
-API void b2p_srs_free(b2p_srs* srs) { delete reinterpret_cast<SrsBase*>(srs); }
+API void b2p_srs_free(b2p_srs* srs) {
+    if (!srs) return;
+    guarded([&] {
+        DeviceGuard g(reinterpret_cast<SrsBase*>(srs)->device);
+        delete reinterpret_cast<SrsBase*>(srs);
+    });
+}
 
 API int b2p_msm_g1(b2p_srs* srs, int basis, const void* scalars, uint64_t n, void* out_affine) {
     return guarded([&] {
         require(srs && out_affine && (scalars || n == 0), "null argument");
+        DeviceGuard g(reinterpret_cast<SrsBase*>(srs)->device);
         reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, scalars, n, out_affine, false);
     });
 }
 API int b2p_msm_g1_dev(b2p_srs* srs, int basis, const void* d_scalars, uint64_t n, void* out_affine) {
     return guarded([&] {
         require(srs && out_affine && (d_scalars || n == 0), "null argument");
+        DeviceGuard g(reinterpret_cast<SrsBase*>(srs)->device);
         reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, d_scalars, n, out_affine, true);
     });
 }
@@ -146,7 +197,9 @@ API int b2p_circuit_load(b2p_srs* srs, uint64_t n, uint32_t nb_public, const voi
         require(srs && ql && qr && qm && qo && qk && perm && out, "null argument");
         require(k == 0 || (qcp && cidx), "BSB22 columns missing");
         SrsBase* s = reinterpret_cast<SrsBase*>(srs);
+        DeviceGuard g(s->device);
         CircuitBase* c = ops_for(s->curve)->new_circuit();
+        c->device = s->device;
         try { c->load(s, n, nb_public, ql, qr, qm, qo, qk, perm, k, qcp, cidx, vkb, vkb_len); }
         catch (...) { delete c; throw; }
         *out = reinterpret_cast<b2p_circuit*>(c);
@@ -155,10 +208,17 @@ API int b2p_circuit_load(b2p_srs* srs, uint64_t n, uint32_t nb_public, const voi
 API int b2p_circuit_vk_commitments(b2p_circuit* c, void* out_points) {
     return guarded([&] {
         require(c && out_points, "null argument");
+        DeviceGuard g(reinterpret_cast<CircuitBase*>(c)->device);
         reinterpret_cast<CircuitBase*>(c)->vk_commitments(out_points);
     });
 }
-API void b2p_circuit_free(b2p_circuit* c) { delete reinterpret_cast<CircuitBase*>(c); }
+API void b2p_circuit_free(b2p_circuit* c) {
+    if (!c) return;
+    guarded([&] {
+        DeviceGuard g(reinterpret_cast<CircuitBase*>(c)->device);
+        delete reinterpret_cast<CircuitBase*>(c);
+    });
+}
 
 API uint64_t b2p_proof_raw_size(int curve, uint32_t k) {
     const uint64_t pt = curve == B2P_BN254 ? 64 : 96;
@@ -169,6 +229,7 @@ API int b2p_prove(b2p_circuit* c, const void* L, const void* R, const void* O, c
                   const void* bsb22, const void* blinding, void* out_raw) {
     return guarded([&] {
         require(c && L && R && O && blinding && out_raw, "null argument");
+        DeviceGuard g(reinterpret_cast<CircuitBase*>(c)->device);
         reinterpret_cast<CircuitBase*>(c)->prove(L, R, O, pi2, bsb22, blinding, out_raw, false);
     });
 }
@@ -176,6 +237,7 @@ API int b2p_prove_dev(b2p_circuit* c, const void* dL, const void* dR, const void
                       const void* bsb22, const void* blinding, void* out_raw) {
     return guarded([&] {
         require(c && dL && dR && dO && blinding && out_raw, "null argument");
+        DeviceGuard g(reinterpret_cast<CircuitBase*>(c)->device);
         reinterpret_cast<CircuitBase*>(c)->prove(dL, dR, dO, d_pi2, bsb22, blinding, out_raw, true);
     });
 }

@@ -16,8 +16,10 @@ struct Error : std::runtime_error {
 
 struct SrsBase {
     int curve = -1;
+    int device = -1;      // CUDA device the handle lives on; every entry point switches to it
     virtual ~SrsBase() {}
     virtual void load(const void* points, uint64_t n) = 0;
+    virtual void load_compressed(const uint8_t* bytes, uint64_t n) = 0;
     virtual void generate_unsafe(const void* tau, uint64_t first, uint64_t n) = 0;
     virtual void get_points(uint64_t first, uint64_t count, void* out) const = 0;
     virtual uint64_t size() const = 0;
@@ -28,6 +30,7 @@ struct SrsBase {
 
 struct CircuitBase {
     int curve = -1;
+    int device = -1;
     double stats[16] = {0};
     virtual ~CircuitBase() {}
     virtual void load(SrsBase* srs, uint64_t n, uint32_t nb_public, const void* ql, const void* qr, const void* qm,

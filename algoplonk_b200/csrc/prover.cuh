@@ -140,8 +140,73 @@ __global__ void k_srs_from_tau(Affine<typename C::Fp>* __restrict__ out, uint64_
     st_field(&out[j].y, a.y);
 }
 
+// Compressed G1 stream -> affine Montgomery points: what srs.Pk.ReadFrom does to the embedded pk.bin files
+// (setup/setup.go:173,189; format pinned by setup/trusted_setup_test.go:53-59,132,290-303).  One thread per
+// point: x from the big-endian bytes under the flag bits, y = (x^3 + b)^((p+1)/4) (both base fields are
+// 3 mod 4), the flag picks the lexicographically smallest / largest root.  err: 0 ok, 1 bad flag,
+// 2 x >= p, 3 x^3 + b is not a square (x not on the curve).
+template <class C>
+__global__ void k_g1_decompress(const uint8_t* __restrict__ in, Affine<typename C::Fp>* __restrict__ out, uint64_t n,
+                                typename C::Fp exp_p1_4 /* (p+1)/4, plain limbs */, uint32_t curve_b,
+                                uint32_t* __restrict__ err) {
+    using Fp = typename C::Fp;
+    constexpr int NB = Fp::N * 4;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* b = in + i * NB;
+    const bool bls = C::ID == B2P_BLS12_381;
+    const uint32_t flag = bls ? (b[0] >> 5) : (b[0] >> 6);
+    const uint8_t mask = bls ? 0x1F : 0x3F;
+    const uint32_t f_small = bls ? 4u : 2u, f_large = bls ? 5u : 3u, f_inf = bls ? 6u : 1u;
+    if (flag == f_inf) {
+        st_field(&out[i].x, Fp::zero());
+        st_field(&out[i].y, Fp::zero());
+        return;
+    }
+    if (flag != f_small && flag != f_large) { atomicMax(err, 1u); return; }
+    Fp x;
+#pragma unroll
+    for (int l = 0; l < Fp::N; l++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int idx = NB - 1 - (4 * l + k);           // byte of weight 8 * (4l + k)
+            uint32_t byte = b[idx];
+            if (idx == 0) byte &= mask;
+            w |= byte << (8 * k);
+        }
+        x.v[l] = w;
+    }
+    // canonical? (x < p)
+    bool lt = false, decided = false;
+    for (int l = Fp::N - 1; l >= 0 && !decided; l--) {
+        const uint32_t pm = Fp::Params::mod(l);
+        if (x.v[l] != pm) { lt = x.v[l] < pm; decided = true; }
+    }
+    if (!lt) { atomicMax(err, 2u); return; }
+    x = x.to_mont();
+    const Fp rhs = x.sqr() * x + Fp::from_u32(curve_b);
+    Fp y = Fp::one();
+    for (int bit = Fp::Params::BITS - 1; bit >= 0; bit--) {
+        y = y.sqr();
+        if ((exp_p1_4.v[bit >> 5] >> (bit & 31)) & 1) y = y * rhs;
+    }
+    if (y.sqr() != rhs) { atomicMax(err, 3u); return; }
+    // lexicographically largest root?  y > p - y as integers
+    const Fp yc = y.from_mont();
+    const Fp ny = y.neg().from_mont();
+    bool larger = false;
+    decided = false;
+    for (int l = Fp::N - 1; l >= 0 && !decided; l--)
+        if (yc.v[l] != ny.v[l]) { larger = yc.v[l] > ny.v[l]; decided = true; }
+    if (larger != (flag == f_large)) y = y.neg();
+    st_field(&out[i].x, x);
+    st_field(&out[i].y, y);
+}
+
 template <class C> struct CurveConsts;
 template <> struct CurveConsts<Bn254> {
+    static constexpr uint32_t B = 3;      // y^2 = x^3 + 3
     static Affine<FpBn254> generator() {
         Affine<FpBn254> g;
         g.x = FpBn254::from_u32(1);
@@ -150,6 +215,7 @@ template <> struct CurveConsts<Bn254> {
     }
 };
 template <> struct CurveConsts<Bls12381> {
+    static constexpr uint32_t B = 4;      // y^2 = x^3 + 4
     static Affine<FpBls12381> generator() {
         // canonical little-endian 32-bit limbs of the standard generator
         static const uint32_t gx[12] = {0xdb22c6bbu, 0xfb3af00au, 0xf97a1aefu, 0x6c55e83fu, 0x171bac58u, 0xa14e3a3fu,
@@ -188,6 +254,37 @@ struct Srs : SrsBase {
     void load(const void* pts, uint64_t n) override {
         B2P_REQUIRE(n >= 1, "empty SRS");
         msm.load(pts, n, env_force_c(), stream);
+        finish_init();
+    }
+    // pk.bin payload (count compressed points, header already stripped by the caller)
+    void load_compressed(const uint8_t* bytes, uint64_t n) override {
+        B2P_REQUIRE(n >= 1, "empty SRS");
+        constexpr int NB = Fp::N * 4;
+        MsmPlan pl = msm_plan(n, Fr::Params::BITS, env_force_c());
+        B2P_REQUIRE((uint64_t)pl.W * n < (1ull << 31), "SRS too large for 31-bit table indices");
+        DevBuf<Aff> tbl((size_t)pl.W * n);
+        DevBuf<uint8_t> raw(n * NB);
+        DevBuf<uint32_t> err(1);
+        B2P_CUDA(cudaMemcpyAsync(raw.p, bytes, n * NB, cudaMemcpyHostToDevice, stream));
+        B2P_CUDA(cudaMemsetAsync(err.p, 0, sizeof(uint32_t), stream));
+        // (p + 1) / 4 as plain limbs
+        Fp e;
+        uint64_t carry = 1;
+        for (int l = 0; l < Fp::N; l++) {
+            const uint64_t v = (uint64_t)Fp::Params::mod(l) + carry;
+            e.v[l] = (uint32_t)v;
+            carry = v >> 32;
+        }
+        for (int l = 0; l < Fp::N; l++)
+            e.v[l] = (e.v[l] >> 2) | (l + 1 < Fp::N ? e.v[l + 1] << 30 : 0u);
+        B2P_LAUNCH((k_g1_decompress<C>), div_up(n, 128), 128, 0, stream, raw.p, tbl.p, n, e, CurveConsts<C>::B, err.p);
+        uint32_t herr = 0;
+        B2P_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof herr, cudaMemcpyDeviceToHost, stream));
+        B2P_CUDA(cudaStreamSynchronize(stream));
+        B2P_REQUIRE(herr != 1, "compressed SRS: invalid point flag");
+        B2P_REQUIRE(herr != 2, "compressed SRS: coordinate not reduced");
+        B2P_REQUIRE(herr != 3, "compressed SRS: point not on the curve");
+        msm.load_device(std::move(tbl), n, pl, stream);
         finish_init();
     }
     void get_points(uint64_t first, uint64_t count, void* out) const override {

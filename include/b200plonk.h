@@ -64,6 +64,14 @@ uint64_t b2p_launch_count(void);
 int b2p_srs_load(int curve, const void* g1_canonical, uint64_t n_can,
                  const void* g1_lagrange, uint64_t n_lag, b2p_srs** out);
 
+/* The embedded trusted setups as they sit on disk (setup/<name>/pk.bin, gnark kzg.ProvingKey.WriteTo):
+ * u32 big-endian point count, then compressed G1 points (BN254 32 B with 2 flag bits, BLS12-381 48 B with
+ * 3 flag bits).  Replaces loadTrustedSetupBytes + srs.Pk.ReadFrom (setup.go:165-228) for the first `count`
+ * points: the square roots of the decompression run on the GPU.  Fails with "pk.bin too small for N
+ * elements" like setup.go:219-223.  gnark's decoder also checks subgroup membership of BLS12-381 points;
+ * this loader, like gnark's UnsafeReadFrom, does not (the files are audited ceremony outputs). */
+int b2p_srs_load_compressed(int curve, const void* pk_bin, uint64_t len, uint64_t count, b2p_srs** out);
+
 /* unsafekzg.NewSRS (setup.go:102-108, the TestOnly setups): [tau^j]_1 for j < n_can,
  * generated on the device from a known tau (Fr, Montgomery form). */
 int b2p_srs_generate_unsafe(int curve, const void* tau, uint64_t n_can, b2p_srs** out);
