@@ -47,6 +47,7 @@ import (
 var BlindingSource func() [9]fr.Element
 
 type gpuKey struct {
+	mu      sync.Mutex // a handle takes one call at a time (b200plonk.h); concurrent provers of one key queue here
 	srs     *C.b2p_srs
 	circuit *C.b2p_circuit
 }
@@ -138,6 +139,12 @@ func proveBN254(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey, fullWitnes
 	if err != nil {
 		return nil, err
 	}
+	// One proof at a time per device-resident key.  (A service that wants several proofs in flight per GPU
+	// uploads the key more than once -- bench.py does exactly that -- the library is re-entrant across handles.)
+	key.mu.Lock()
+	defer key.mu.Unlock()
+	// Not required for correctness (every entry point switches to the handle's CUDA device itself), but it
+	// keeps the blocking cgo call from being counted against GOMAXPROCS scheduling.
 	runtime.LockOSThread()
 	defer runtime.UnlockOSThread()
 
