@@ -39,7 +39,7 @@ UNIT = "proofs/s"
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_msm_accumulate launch, from the ncu --set full capture
 # under profiles/ (per workload): the gather reads W = 13 table points per scalar, so ~13x the algorithmic bytes
-ACCUM_DRAM_TRAFFIC = {("BN254", 20): 1_887_123_792}
+ACCUM_DRAM_TRAFFIC = {("BN254", 20): 1_852_200_000}
 # mixed additions / s at which the IMAD pipe saturates: measured field multiplications / s (tools/microbench.cu,
 # profiles/microbench_r1.json) / 10 multiplications per XYZZ mixed addition
 MADD_ROOFLINE = {"BN254": 6.78e9, "BLS12_381": 3.09e9}
