@@ -37,7 +37,7 @@ struct XYZZ {
         Fp xx = x.sqr();
         Fp M = xx.dbl() + xx;
         r.X = M.sqr() - S.dbl();
-        r.Y = M * (S - r.X) - W * y;
+        r.Y = Fp::mul_sub(M, S - r.X, W, y);
         r.ZZ = V;
         r.ZZZ = W;
         return r;
@@ -60,7 +60,7 @@ struct XYZZ {
         Fp PPP = Pv * PP;
         Fp Q = X * PP;
         Fp X3 = Rv.sqr() - PPP - Q.dbl();
-        Y = Rv * (Q - X3) - Y * PPP;
+        Y = Fp::mul_sub(Rv, Q - X3, Y, PPP);       // two products, one Montgomery reduction
         X = X3;
         ZZ = ZZ * PP;
         ZZZ = ZZZ * PPP;
@@ -83,7 +83,7 @@ struct XYZZ {
         Fp xx = X.sqr();
         Fp M = xx.dbl() + xx;
         r.X = M.sqr() - S.dbl();
-        r.Y = M * (S - r.X) - W * Y;
+        r.Y = Fp::mul_sub(M, S - r.X, W, Y);
         r.ZZ = V * ZZ;
         r.ZZZ = W * ZZZ;
         return r;
@@ -108,7 +108,7 @@ struct XYZZ {
         Fp PPP = Pv * PP;
         Fp Q = U1 * PP;
         Fp X3 = Rv.sqr() - PPP - Q.dbl();
-        Y = Rv * (Q - X3) - S1 * PPP;
+        Y = Fp::mul_sub(Rv, Q - X3, S1, PPP);
         X = X3;
         ZZ = ZZ * o.ZZ * PP;
         ZZZ = ZZZ * o.ZZZ * PPP;

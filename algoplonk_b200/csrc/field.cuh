@@ -106,6 +106,22 @@ struct Field {
 
     HD Field dbl() const { return *this + *this; }
 
+    // K * x for a small compile-time K as a chain of modular additions: the coset shifts (5, 7) and their
+    // squares multiply on the ALU pipe instead of occupying the IMAD pipe with a full Montgomery product
+    template <uint32_t K>
+    HD Field mul_small() const {
+        static_assert(K >= 1, "mul_small needs K >= 1");
+        int top = 31;
+        while (!((K >> top) & 1u)) top--;
+        Field acc = *this;
+#pragma unroll
+        for (int b = top - 1; b >= 0; b--) {
+            acc = acc.dbl();
+            if ((K >> b) & 1u) acc = acc + *this;
+        }
+        return acc;
+    }
+
     // ---- Montgomery multiplication --------------------------------------
     // Coarsely-integrated operand scanning with the products of even and odd
     // limbs of `a` kept in two accumulators, so that every (lo,hi) pair lands on
@@ -255,7 +271,166 @@ struct Field {
 #endif
     }
 
-    HD Field sqr() const { return (*this) * (*this); }
+    // ---- separated product / reduction: squaring, a*b - c*d ------------------
+    // A 2N-limb value is kept as two accumulators of aligned (lo, hi) pairs, like the product above:
+    //   value = sum_k E[k] 2^(32k) + sum_k O[k] 2^(32(k+1)).
+    // acc[col .. col+2*cnt) += x[0], x[2], ... (cnt limbs, stride 2) times y, carry into acc[col + 2*cnt]
+    template <int CNT>
+    HD static void wide_mad_chain(uint32_t* acc, const uint32_t* x, uint32_t y) {
+        if (CNT <= 0) return;
+        acc[0] = ptx::mad_lo_cc(x[0], y, acc[0]);
+        acc[1] = ptx::madc_hi_cc(x[0], y, acc[1]);
+#pragma unroll
+        for (int t = 1; t < CNT; t++) {
+            acc[2 * t] = ptx::madc_lo_cc(x[2 * t], y, acc[2 * t]);
+            acc[2 * t + 1] = ptx::madc_hi_cc(x[2 * t], y, acc[2 * t + 1]);
+        }
+        acc[2 * CNT] = ptx::addc(acc[2 * CNT], 0);
+    }
+    // flat[0..2N) = E + (O << 32)
+    HD static void wide_merge(uint32_t* flat, const uint32_t* E, const uint32_t* O) {
+        flat[0] = E[0];
+        flat[1] = ptx::add_cc(E[1], O[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; k++) flat[k] = ptx::addc_cc(E[k], O[k - 1]);
+        flat[2 * N - 1] = ptx::addc(E[2 * N - 1], O[2 * N - 2]);
+    }
+    // flat = a * b (2N limbs)
+    HD static void wide_mul(uint32_t* flat, const uint32_t* a, const uint32_t* b) {
+        uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+        for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            // a[j] * b[i] lands on column i + j: even columns -> E, odd columns -> O (column c is O[c-1])
+            if (i % 2 == 0) {
+                wide_mad_chain<N / 2>(E + i, a, b[i]);            // j = 0, 2, ...
+                wide_mad_chain<N / 2>(O + i, a + 1, b[i]);        // j = 1, 3, ...: column i + j - 1 in O
+            } else {
+                wide_mad_chain<N / 2>(O + i - 1, a, b[i]);        // j even, i odd: odd column i + j
+                wide_mad_chain<N / 2>(E + i + 1, a + 1, b[i]);    // j odd: even column i + j
+            }
+        }
+        wide_merge(flat, E, O);
+    }
+    // flat = a^2: the off-diagonal products once, doubled, plus the diagonal
+    HD static void wide_sqr(uint32_t* flat, const uint32_t* a) {
+        uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+        for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) {
+            // j = i+1, i+3, ...: odd column 2i+1, ... -> O[2i ...];  j = i+2, i+4, ...: even column 2i+2 ... -> E
+            wide_mad_chain_rt(O + 2 * i, a + i + 1, a[i], (N - i) / 2);
+            wide_mad_chain_rt(E + 2 * i + 2, a + i + 2, a[i], (N - i - 1) / 2);
+        }
+        uint32_t S[2 * N];
+        wide_merge(S, E, O);
+        // flat = 2 S + sum_i a_i^2 2^(64 i): operands first, then one uninterrupted carry chain
+        uint32_t D[2 * N], S2[2 * N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            D[2 * i] = ptx::mul_lo(a[i], a[i]);
+            D[2 * i + 1] = ptx::mul_hi(a[i], a[i]);
+        }
+        S2[0] = S[0] << 1;
+#pragma unroll
+        for (int k = 1; k < 2 * N; k++) S2[k] = (S[k] << 1) | (S[k - 1] >> 31);
+        flat[0] = ptx::add_cc(D[0], S2[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) flat[k] = ptx::addc_cc(D[k], S2[k]);
+        flat[2 * N - 1] = ptx::addc(D[2 * N - 1], S2[2 * N - 1]);
+    }
+    // same chain with a trip count that is a compile-time constant after unrolling
+    HD static void wide_mad_chain_rt(uint32_t* acc, const uint32_t* x, uint32_t y, int cnt) {
+        if (cnt <= 0) return;
+        acc[0] = ptx::mad_lo_cc(x[0], y, acc[0]);
+        acc[1] = ptx::madc_hi_cc(x[0], y, acc[1]);
+#pragma unroll
+        for (int t = 1; t < N / 2; t++) {
+            if (t < cnt) {
+                acc[2 * t] = ptx::madc_lo_cc(x[2 * t], y, acc[2 * t]);
+                acc[2 * t + 1] = ptx::madc_hi_cc(x[2 * t], y, acc[2 * t + 1]);
+            }
+        }
+        acc[2 * cnt] = ptx::addc(acc[2 * cnt], 0);
+    }
+    // Montgomery reduction of a 2N-limb value T < 2 p R:  T / R mod p  =  mul_by_1(T_lo) + T_hi, reduced.
+    // mul_by_1 is the product loop above with the a * b_i rows left out (N rows of m_i * p).
+    template <bool FIRST>
+    HD static void redc_row(uint32_t* even, uint32_t* odd) {
+        if (!FIRST) {
+            even[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+            for (int j = 0; j < N - 2; j++) odd[j] = ptx::addc_cc(odd[j + 2], 0);
+            odd[N - 2] = ptx::addc(0, 0);
+            odd[N - 1] = 0;
+        }
+        uint32_t mi = even[0] * P::INV;
+        cmad_mod<1>(odd, mi);
+        cmad_mod<0>(even, mi);
+        odd[N - 1] = ptx::addc(odd[N - 1], 0);
+    }
+    template <int SUBS>
+    HD static Field wide_redc(const uint32_t* flat) {
+        uint32_t even[N], odd[N];
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            even[j] = flat[j]; even[j + 1] = 0;
+            odd[j] = flat[j + 1]; odd[j + 1] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            if (i == 0) redc_row<true>(even, odd);
+            else        redc_row<false>(even, odd);
+            redc_row<false>(odd, even);
+        }
+        // (T_lo + M p) / R  <=  p, then + T_hi
+        Field r;
+        r.v[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(even[i], odd[i + 1]);
+        r.v[N - 1] = ptx::addc(even[N - 1], 0);
+        r.v[0] = ptx::add_cc(r.v[0], flat[N]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(r.v[i], flat[N + i]);
+        r.v[N - 1] = ptx::addc(r.v[N - 1], flat[2 * N - 1]);
+#pragma unroll
+        for (int k = 0; k < SUBS; k++) final_sub(r.v);
+        return r;
+    }
+
+    HD Field sqr() const {
+#if !defined(__CUDA_ARCH__) && !defined(B2P_HOST_EMULATE_DEVICE_MUL)
+        return mul_host(*this, *this);
+#else
+        uint32_t T[2 * N];
+        wide_sqr(T, v);
+        return wide_redc<1>(T);
+#endif
+    }
+    // a * b - c * d with ONE Montgomery reduction (the two products are subtracted as 2N-limb integers,
+    // biased by p * R to stay positive)
+    HD static Field mul_sub(const Field& a, const Field& b, const Field& c, const Field& d) {
+        static_assert(P::BITS + 2 <= 32 * N, "mul_sub needs 3p < 2^(32N)");
+#if !defined(__CUDA_ARCH__) && !defined(B2P_HOST_EMULATE_DEVICE_MUL)
+        return mul_host(a, b) - mul_host(c, d);
+#else
+        uint32_t T[2 * N], U[2 * N];
+        wide_mul(T, a.v, b.v);
+        wide_mul(U, c.v, d.v);
+        T[0] = ptx::sub_cc(T[0], U[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) T[k] = ptx::subc_cc(T[k], U[k]);
+        T[2 * N - 1] = ptx::subc(T[2 * N - 1], U[2 * N - 1]);
+        // + p * R: the high half gets p added (wraps correctly when the difference was negative)
+        T[N] = ptx::add_cc(T[N], P::mod(0));
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) T[N + k] = ptx::addc_cc(T[N + k], P::mod(k));
+        T[2 * N - 1] = ptx::addc(T[2 * N - 1], P::mod(N - 1));
+        return wide_redc<2>(T);      // T < 2 p R: the result is below 3 p before the subtractions
+#endif
+    }
 
     HD Field& operator+=(const Field& o) { *this = *this + o; return *this; }
     HD Field& operator-=(const Field& o) { *this = *this - o; return *this; }

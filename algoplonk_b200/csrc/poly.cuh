@@ -202,7 +202,8 @@ __global__ void k_z_terms(F* __restrict__ f, F* __restrict__ gr, const F* __rest
     }
     const F l = ld_field(L + i) + gamma, r = ld_field(R + i) + gamma, o = ld_field(O + i) + gamma;
     const F bw = beta * omega_pow(tw, i, n);
-    const F num = (l + bw) * (r + bw * u) * (o + bw * u2);
+    constexpr uint32_t US = F::Params::SHIFT_SMALL;     // u and u^2 are small integers: additions, not products
+    const F num = (l + bw) * (r + bw.template mul_small<US>()) * (o + bw.template mul_small<US * US>());
     const F den = (l + beta * ld_field(S + i)) * (r + beta * ld_field(S + n + i)) * (o + beta * ld_field(S + 2 * n + i));
     st_field(f + i + 1, num);
     st_field(gr + (n - 2 - i), den);
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256) k_quotient(const QuotientArgs<F> a) {
     const uint32_t pshift = brev32((nat + rho) & (m - 1), a.logm);
 
     const F l = ld_field(a.l + p), r = ld_field(a.r + p), o = ld_field(a.o + p);
-    F gate = ld_field(a.ql + p) * l + ld_field(a.qr + p) * r + ld_field(a.qm + p) * (l * r)
+    F gate = (ld_field(a.ql + p) + ld_field(a.qm + p) * r) * l + ld_field(a.qr + p) * r
            + ld_field(a.qo + p) * o + ld_field(a.qk + p);
     for (int c = 0; c < a.k; c++) gate = gate + ld_field(a.qcp[c] + p) * ld_field(a.pi2[c] + p);
     for (int t = 0; t < a.n_pi; t++) {
@@ -268,7 +269,8 @@ __global__ void __launch_bounds__(256) k_quotient(const QuotientArgs<F> a) {
     const F pa = (lg + a.beta * ld_field(a.s1 + p)) * (rg + a.beta * ld_field(a.s2 + p))
                * (og + a.beta * ld_field(a.s3 + p)) * zs;
     const F bx = a.beta * ld_field(a.x + p);
-    const F pb = (lg + bx) * (rg + bx * a.u) * (og + bx * a.u2) * z;
+    constexpr uint32_t US = F::Params::SHIFT_SMALL;     // u = 5 / 7: multiples by additions (ALU pipe)
+    const F pb = (lg + bx) * (rg + bx.template mul_small<US>()) * (og + bx.template mul_small<US * US>()) * z;
     const F loc = ld_field(a.l1 + p) * (z - F::one());
     const F num = gate + a.alpha * (pa - pb) + a.alpha2 * loc;
     st_field(a.h + p, num * a.zh_inv[nat & (rho - 1)]);

@@ -5,6 +5,11 @@
 #include "../../algoplonk_b200/csrc/field.cuh"
 using namespace b2p;
 
+// mul_sub exists for the fields with two spare bits (the base fields of the EC formulas)
+template <class F> static F mulsub(const F& a, const F& b, const F& c, const F& d) {
+    if constexpr (F::Params::BITS + 2 <= 32 * F::N) return F::mul_sub(a, b, c, d);
+    else return a * b - c * d;
+}
 template <class F> static void binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* o) {
     F x, y, r;
     memcpy(x.v, a, sizeof x.v); memcpy(y.v, b, sizeof y.v);
@@ -18,6 +23,8 @@ template <class F> static void binop(int op, const uint32_t* a, const uint32_t* 
         case 6: r = x.from_mont(); break;
         case 7: r = x.sqr(); break;
         case 8: r = F::reduce_to_mont(x); break;
+        case 9: r = mulsub<F>(x, y, y, x + F::one()); break;   // x*y - y*(x+1) = -y / R
+        case 10: r = mulsub<F>(x, x, y, y); break;
         default: r = F::zero();
     }
     memcpy(o, r.v, sizeof r.v);

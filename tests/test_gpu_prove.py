@@ -159,6 +159,40 @@ def test_config_sizes_accepted_by_reference_verifier(gpu, curve, logn):
     cc.free()
 
 
+def test_two_proofs_in_flight_on_two_handles(gpu):
+    """The library is re-entrant across handles and calls may come from any host thread (fresh threads start
+    on CUDA device 0; every entry point switches to its handle's device): two keys, two threads, the same
+    bytes as a lone proof."""
+    import threading
+    curve, cv = "BN254", po.CURVES["BN254"]
+    cs, values = fe.squaring_chain(curve, 12, x0=3)
+    ccs = [api.Compile(cs, curve, SETUP[curve]) for _ in range(2)]
+    L, R, O = fe.solve_lro(cs, values, ccs[0].trace.n)
+    blindings = [H.scalars_uniform(cv.r, 9, s) for s in (1, 2)]
+    want = [api.MarshalProof(ccs[i].Prove(L, R, O, blindings[i])) for i in range(2)]
+    got = [[None] * 4 for _ in range(2)]
+    errs = []
+
+    def work(i):
+        try:
+            for rep in range(4):
+                got[i][rep] = api.MarshalProof(ccs[i].Prove(L, R, O, blindings[i]))
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for i in range(2):
+        assert all(g == want[i] for g in got[i])
+    assert want[0] != want[1]
+    for cc in ccs:
+        cc.free()
+
+
 def test_prove_errors(gpu):
     B = fe.basic_circuit("BN254")
     cs = B.build()

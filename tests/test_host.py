@@ -143,8 +143,17 @@ def test_device_field_code_on_host(hostfield, fid, mod, nlimb):
         assert call(2, a, b) == (a - b) % mod
         assert call(3, a) == (-a) % mod
         assert call(7, a) == a * a * Rinv % mod
+        if mod.bit_length() + 2 <= 32 * nlimb:               # base fields: a*b - c*d with one reduction
+            assert call(9, a, b) == (-b) % mod                 # x*y - y*(x + R) = -y*R, reduced once
+            assert call(10, a, b) == (a * a - b * b) * Rinv % mod
         assert call(5, a) == a * R % mod
         assert call(6, a) == a * Rinv % mod
+    # the separated product / reduction paths (squaring, a*b - c*d) on many more operands
+    for _ in range(1500):
+        a, b = rng.randrange(mod), rng.randrange(mod)
+        assert call(7, a) == a * a * Rinv % mod
+        if mod.bit_length() + 2 <= 32 * nlimb:
+            assert call(10, a, b) == (a * a - b * b) * Rinv % mod
     # hashes are reduced mod r from raw 256-bit values (Fiat-Shamir challenges): any N-limb input
     for _ in range(300):
         a = rng.randrange(R)
