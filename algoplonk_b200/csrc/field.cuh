@@ -295,11 +295,8 @@ struct Field {
         for (int k = 2; k < 2 * N - 1; k++) flat[k] = ptx::addc_cc(E[k], O[k - 1]);
         flat[2 * N - 1] = ptx::addc(E[2 * N - 1], O[2 * N - 2]);
     }
-    // flat = a * b (2N limbs)
-    HD static void wide_mul(uint32_t* flat, const uint32_t* a, const uint32_t* b) {
-        uint32_t E[2 * N + 2], O[2 * N + 2];
-#pragma unroll
-        for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+    // (E, O) += a * b
+    HD static void wide_mul_acc(uint32_t* E, uint32_t* O, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
         for (int i = 0; i < N; i++) {
             // a[j] * b[i] lands on column i + j: even columns -> E, odd columns -> O (column c is O[c-1])
@@ -311,7 +308,6 @@ struct Field {
                 wide_mad_chain<N / 2>(E + i + 1, a + 1, b[i]);    // j odd: even column i + j
             }
         }
-        wide_merge(flat, E, O);
     }
     // flat = a^2: the off-diagonal products once, doubled, plus the diagonal
     HD static void wide_sqr(uint32_t* flat, const uint32_t* a) {
@@ -409,26 +405,26 @@ struct Field {
         return wide_redc<1>(T);
 #endif
     }
-    // a * b - c * d with ONE Montgomery reduction (the two products are subtracted as 2N-limb integers,
-    // biased by p * R to stay positive)
+    // a * b - c * d with ONE Montgomery reduction
     HD static Field mul_sub(const Field& a, const Field& b, const Field& c, const Field& d) {
         static_assert(P::BITS + 2 <= 32 * N, "mul_sub needs 3p < 2^(32N)");
 #if !defined(__CUDA_ARCH__) && !defined(B2P_HOST_EMULATE_DEVICE_MUL)
         return mul_host(a, b) - mul_host(c, d);
 #else
-        uint32_t T[2 * N], U[2 * N];
-        wide_mul(T, a.v, b.v);
-        wide_mul(U, c.v, d.v);
-        T[0] = ptx::sub_cc(T[0], U[0]);
+        // a*b - c*d == a*b + (p - c)*d (mod p): both products are accumulated into ONE pair of accumulators
+        uint32_t nc[N];
+        nc[0] = ptx::sub_cc(P::mod(0), c.v[0]);
 #pragma unroll
-        for (int k = 1; k < 2 * N - 1; k++) T[k] = ptx::subc_cc(T[k], U[k]);
-        T[2 * N - 1] = ptx::subc(T[2 * N - 1], U[2 * N - 1]);
-        // + p * R: the high half gets p added (wraps correctly when the difference was negative)
-        T[N] = ptx::add_cc(T[N], P::mod(0));
+        for (int i = 1; i < N - 1; i++) nc[i] = ptx::subc_cc(P::mod(i), c.v[i]);
+        nc[N - 1] = ptx::subc(P::mod(N - 1), c.v[N - 1]);
+        uint32_t E[2 * N + 2], O[2 * N + 2];
 #pragma unroll
-        for (int k = 1; k < N - 1; k++) T[N + k] = ptx::addc_cc(T[N + k], P::mod(k));
-        T[2 * N - 1] = ptx::addc(T[2 * N - 1], P::mod(N - 1));
-        return wide_redc<2>(T);      // T < 2 p R: the result is below 3 p before the subtractions
+        for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+        wide_mul_acc(E, O, a.v, b.v);
+        wide_mul_acc(E, O, nc, d.v);
+        uint32_t T[2 * N];
+        wide_merge(T, E, O);
+        return wide_redc<2>(T);      // T < 2 p^2 < 2 p R: the result is below 3 p before the subtractions
 #endif
     }
 

@@ -183,7 +183,7 @@ __device__ __forceinline__ Affine<Fp> ldg_point(const Affine<Fp>* src) {
 }
 
 template <class Fp>
-__global__ void __launch_bounds__(MSM_THREADS)
+__global__ void __launch_bounds__(MSM_THREADS, 4)
 k_msm_accumulate(const Affine<Fp>* __restrict__ table, const uint32_t* __restrict__ entries,
                  const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                  const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ total_items,

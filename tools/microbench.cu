@@ -47,9 +47,12 @@ __global__ void k_imad(uint32_t* out, int iters, uint32_t seed) {
 template <class F>
 __global__ void __launch_bounds__(256) k_fmul(F* out, int iters) {
     F a = F::one(), b = F::r2(), c = F::r2();
-    a.v[0] += threadIdx.x;
-    c.v[0] += 3 * threadIdx.x + blockIdx.x;   // keep both chains off the uniform datapath
-    b.v[1] += threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < F::N - 1; i++) {      // every limb differs per lane: nothing lands on the uniform datapath
+        a.v[i] += (threadIdx.x + 1) * (2 * i + 1);
+        b.v[i] ^= (threadIdx.x + 7) * (2 * i + 3);
+        c.v[i] += 3 * threadIdx.x + blockIdx.x + i;
+    }
     for (int it = 0; it < iters; it++) {
         a = a * b;      // two independent chains
         c = c * b;
@@ -61,7 +64,8 @@ template <class Fp>
 __global__ void __launch_bounds__(128) k_madd(XYZZ<Fp>* out, int iters) {
     // accumulate a fixed affine-looking operand; values need not be on the curve for timing
     Fp x = Fp::r2(), y = Fp::one();
-    x.v[0] += threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < Fp::N - 1; i++) { x.v[i] += (threadIdx.x + 1) * (2 * i + 1); y.v[i] ^= (threadIdx.x + 5) * (2 * i + 3); }
     XYZZ<Fp> acc = XYZZ<Fp>::from_affine(Affine<Fp>{x, y});
     acc.ZZ = Fp::r2(); acc.ZZZ = x;
     for (int it = 0; it < iters; it++) {
@@ -75,10 +79,11 @@ template <class K, class... A>
 static float time_kernel(K kern, dim3 grid, dim3 block, A... args) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    kern<<<grid, block>>>(args...);
+    // warm-up: clocks ramp from idle, the first launches of a fresh process are not representative
+    for (int r = 0; r < 8; r++) kern<<<grid, block>>>(args...);
     cudaDeviceSynchronize();
     float best = 1e30f;
-    for (int r = 0; r < 3; r++) {
+    for (int r = 0; r < 5; r++) {
         cudaEventRecord(e0);
         kern<<<grid, block>>>(args...);
         cudaEventRecord(e1);
