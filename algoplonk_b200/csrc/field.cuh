@@ -295,17 +295,25 @@ struct Field {
         for (int k = 2; k < 2 * N - 1; k++) flat[k] = ptx::addc_cc(E[k], O[k - 1]);
         flat[2 * N - 1] = ptx::addc(E[2 * N - 1], O[2 * N - 2]);
     }
-    // (E, O) += a * b
-    HD static void wide_mul_acc(uint32_t* E, uint32_t* O, const uint32_t* a, const uint32_t* b) {
+    // (E, O) = a * b + c * d, E and O zero on entry.  The rows of the two products are interleaved: the limb
+    // that receives the carry out of a chain (acc[2 * CNT] in wide_mad_chain) must hold nothing but earlier
+    // carries, or the addition could overflow it -- adding the second product after the first one is complete
+    // would hit full limbs there (a 2^-32 event per row: about one wrong point addition per 30 proofs).
+    HD static void wide_mul2(uint32_t* E, uint32_t* O, const uint32_t* a, const uint32_t* b, const uint32_t* c,
+                             const uint32_t* d) {
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            // a[j] * b[i] lands on column i + j: even columns -> E, odd columns -> O (column c is O[c-1])
+            // x[j] * y[i] lands on column i + j: even columns -> E, odd columns -> O (column k is O[k-1])
             if (i % 2 == 0) {
                 wide_mad_chain<N / 2>(E + i, a, b[i]);            // j = 0, 2, ...
+                wide_mad_chain<N / 2>(E + i, c, d[i]);
                 wide_mad_chain<N / 2>(O + i, a + 1, b[i]);        // j = 1, 3, ...: column i + j - 1 in O
+                wide_mad_chain<N / 2>(O + i, c + 1, d[i]);
             } else {
                 wide_mad_chain<N / 2>(O + i - 1, a, b[i]);        // j even, i odd: odd column i + j
+                wide_mad_chain<N / 2>(O + i - 1, c, d[i]);
                 wide_mad_chain<N / 2>(E + i + 1, a + 1, b[i]);    // j odd: even column i + j
+                wide_mad_chain<N / 2>(E + i + 1, c + 1, d[i]);
             }
         }
     }
@@ -420,8 +428,7 @@ struct Field {
         uint32_t E[2 * N + 2], O[2 * N + 2];
 #pragma unroll
         for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
-        wide_mul_acc(E, O, a.v, b.v);
-        wide_mul_acc(E, O, nc, d.v);
+        wide_mul2(E, O, a.v, b.v, nc, d.v);
         uint32_t T[2 * N];
         wide_merge(T, E, O);
         return wide_redc<2>(T);      // T < 2 p^2 < 2 p R: the result is below 3 p before the subtractions

@@ -25,6 +25,9 @@ template <class F> static void binop(int op, const uint32_t* a, const uint32_t* 
         case 8: r = F::reduce_to_mont(x); break;
         case 9: r = mulsub<F>(x, y, y, x + F::one()); break;   // x*y - y*(x+1) = -y / R
         case 10: r = mulsub<F>(x, x, y, y); break;
+        case 11: { F c; for (int i = 0; i < F::N; i++) c.v[i] = 0; /* (p-1)/3, plain limbs as a Montgomery value */
+                   F pm1 = F::modulus(); pm1.v[0] -= 1; uint64_t rem = 0; for (int i = F::N - 1; i >= 0; i--) { uint64_t cur = (rem << 32) | pm1.v[i]; c.v[i] = (uint32_t)(cur / 3); rem = cur % 3; }
+                   r = mulsub<F>(x, y, y, c); break; }
         default: r = F::zero();
     }
     memcpy(o, r.v, sizeof r.v);

@@ -154,6 +154,21 @@ def test_device_field_code_on_host(hostfield, fid, mod, nlimb):
         assert call(7, a) == a * a * Rinv % mod
         if mod.bit_length() + 2 <= 32 * nlimb:
             assert call(10, a, b) == (a * a - b * b) * Rinv % mod
+    # carry-propagation corner cases: operands built from saturated / empty limbs make limbs of the partial
+    # sums hit 0xffffffff, where a dropped carry shows (a 2^-32 event per row on random operands: an earlier
+    # mul_sub that added its second product after the first lost one carry per ~10^9 additions)
+    structured_c = (mod - 1) // 3
+
+    def structured():
+        limbs = [rng.choice((0, 1, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, rng.randrange(1 << 32))) for _ in range(nlimb)]
+        return sum(v << (32 * i) for i, v in enumerate(limbs)) % mod
+    for _ in range(3000):
+        a, b = structured(), structured()
+        assert call(0, a, b) == a * b * Rinv % mod
+        assert call(7, a) == a * a * Rinv % mod
+        if mod.bit_length() + 2 <= 32 * nlimb:
+            assert call(10, a, b) == (a * a - b * b) * Rinv % mod
+            assert call(11, a, b) == (a * b - b * structured_c) * Rinv % mod
     # hashes are reduced mod r from raw 256-bit values (Fiat-Shamir challenges): any N-limb input
     for _ in range(300):
         a = rng.randrange(R)
