@@ -309,34 +309,35 @@ static __global__ void k_msm_count_adds(const uint32_t* __restrict__ total_entri
 // ---------------------------------------------------------------------------
 constexpr int MSM_RC_WARPS = 8;     // rows/columns per block of k_msm_rowcol
 constexpr int MSM_TAIL_THREADS = 256;
-constexpr int MSM_RC_CHUNK = 16;
+constexpr int MSM_RC_MIN_CHUNK = 16;  // buckets per thread in level 1 (raised until the launch is one wave)
+constexpr int MSM_RC_BLOCKS_PER_SM = 3; // resident blocks of k_msm_rowcol_partial (its __launch_bounds__)
 
-// Level 1: every thread adds MSM_RC_CHUNK buckets of one column (threads [0, ncols * nch_r)) or of one row
+// Level 1: every thread adds `chunk` buckets of one column (threads [0, ncols * nch_r)) or of one row
 // (the rest): 2 * nb point additions spread over ~2 * nb / 16 threads with no tree in the way -- this is where
 // the reduction's work is.  The next bucket is fetched while the current one is added.
 //   Pc[l * nch_r + ch] = sum_{h in chunk ch} B_{h,l}      Pr[h * nch_c + ch] = sum_{l in chunk ch} B_{h,l}
 template <class Fp>
-__global__ void __launch_bounds__(128, 3)
-k_msm_rowcol_partial(const XYZZ<Fp>* __restrict__ B, int s, uint32_t nb, XYZZ<Fp>* __restrict__ Pc,
+__global__ void __launch_bounds__(128, MSM_RC_BLOCKS_PER_SM)
+k_msm_rowcol_partial(const XYZZ<Fp>* __restrict__ B, int s, uint32_t nb, uint32_t chunk, XYZZ<Fp>* __restrict__ Pc,
                      XYZZ<Fp>* __restrict__ Pr) {
     const uint32_t ncols = 1u << s, nrows = nb >> s;
-    const uint32_t nch_r = (nrows + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK, nch_c = (ncols + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK;
+    const uint32_t nch_r = (nrows + chunk - 1) / chunk, nch_c = (ncols + chunk - 1) / chunk;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t first, stride, cnt;
     XYZZ<Fp>* dst;
     if (t < ncols * nch_r) {
         const uint32_t l = t % ncols, ch = t / ncols;      // lanes along l: neighbouring buckets
-        first = ((ch * MSM_RC_CHUNK) << s) | l;
+        first = ((ch * chunk) << s) | l;
         stride = ncols;
-        cnt = min(nrows, (ch + 1) * MSM_RC_CHUNK) - ch * MSM_RC_CHUNK;
+        cnt = min(nrows, (ch + 1) * chunk) - ch * chunk;
         dst = Pc + (size_t)l * nch_r + ch;
     } else {
         t -= ncols * nch_r;
         if (t >= nrows * nch_c) return;
         const uint32_t h = t / nch_c, ch = t % nch_c;
-        first = (h << s) | (ch * MSM_RC_CHUNK);
+        first = (h << s) | (ch * chunk);
         stride = 1;
-        cnt = min(ncols, (ch + 1) * MSM_RC_CHUNK) - ch * MSM_RC_CHUNK;
+        cnt = min(ncols, (ch + 1) * chunk) - ch * chunk;
         dst = Pr + (size_t)h * nch_c + ch;
     }
     XYZZ<Fp> acc = ld_xyzz(B + first);
@@ -358,12 +359,12 @@ k_msm_rowcol_partial(const XYZZ<Fp>* __restrict__ B, int s, uint32_t nb, XYZZ<Fp
 // results are fetched and run once for all MSMs queued since (grid.y = slots).
 template <class Fp>
 __global__ void __launch_bounds__(32 * MSM_RC_WARPS)
-k_msm_rowcol(const XYZZ<Fp>* __restrict__ Pc, const XYZZ<Fp>* __restrict__ Pr, int s, uint32_t nb,
+k_msm_rowcol(const XYZZ<Fp>* __restrict__ Pc, const XYZZ<Fp>* __restrict__ Pr, int s, uint32_t nb, uint32_t chunk,
              XYZZ<Fp>* __restrict__ X) {
     extern __shared__ uint4 rc_smem[];
     XYZZ<Fp>* sh = reinterpret_cast<XYZZ<Fp>*>(rc_smem);       // 32 * MSM_RC_WARPS points
     const uint32_t ncols = 1u << s, nrows = nb >> s;
-    const uint32_t nch_r = (nrows + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK, nch_c = (ncols + MSM_RC_CHUNK - 1) / MSM_RC_CHUNK;
+    const uint32_t nch_r = (nrows + chunk - 1) / chunk, nch_c = (ncols + chunk - 1) / chunk;
     // blockIdx.y: result slot (several MSMs are finished by one launch)
     Pc += (size_t)blockIdx.y * ncols * nch_r;
     Pr += (size_t)blockIdx.y * nrows * nch_c;
@@ -494,8 +495,19 @@ struct MsmEngine {
     }
     // low bits of the bucket index that select the column in the 2D reduction
     int split_bits() const { return (plan.c - 1) / 2; }
-    size_t col_partials() const { return (size_t)(1u << split_bits()) * div_up(plan.nbuckets >> split_bits(), MSM_RC_CHUNK); }
-    size_t row_partials() const { return (size_t)(plan.nbuckets >> split_bits()) * div_up(1u << split_bits(), MSM_RC_CHUNK); }
+    uint32_t rc_chunk = MSM_RC_MIN_CHUNK;
+    size_t col_partials() const { return (size_t)(1u << split_bits()) * div_up(plan.nbuckets >> split_bits(), rc_chunk); }
+    size_t row_partials() const { return (size_t)(plan.nbuckets >> split_bits()) * div_up(1u << split_bits(), rc_chunk); }
+    // Level 1 of the reduction is one long dependent chain per thread: a second, partly filled wave of blocks
+    // would double its time, so the chunk grows until all blocks are resident at once.
+    void choose_rc_chunk() {
+        int dev = 0, sms = 148;
+        B2P_CUDA(cudaGetDevice(&dev));
+        B2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const size_t capacity = (size_t)sms * MSM_RC_BLOCKS_PER_SM * 128;
+        const uint32_t longest = plan.nbuckets >> split_bits();          // rows >= columns
+        for (rc_chunk = MSM_RC_MIN_CHUNK; rc_chunk < longest && col_partials() + row_partials() > capacity; rc_chunk++) {}
+    }
     void alloc_scratch() {
         const uint32_t nb = plan.nbuckets;
         counts.alloc(nb); offsets.alloc(nb); item_off.alloc(nb);
@@ -515,6 +527,7 @@ struct MsmEngine {
         buckets.alloc(nb);
         big_list.alloc(nb);
         big_count.alloc(1);
+        choose_rc_chunk();
         rc_col.alloc((size_t)MSM_SLOTS * col_partials());
         rc_row.alloc((size_t)MSM_SLOTS * row_partials());
         rc_sums.alloc((size_t)MSM_SLOTS * ((1u << split_bits()) + (nb >> split_bits())));
@@ -555,7 +568,7 @@ struct MsmEngine {
         // reduction level 1: row/column chunk sums of the dense bucket array
         const int s = split_bits();
         const uint32_t nthreads = (uint32_t)(col_partials() + row_partials());
-        B2P_LAUNCH((k_msm_rowcol_partial<Fp>), div_up(nthreads, 128), 128, 0, st, buckets.p, s, nb,
+        B2P_LAUNCH((k_msm_rowcol_partial<Fp>), div_up(nthreads, 128), 128, 0, st, buckets.p, s, nb, rc_chunk,
                    rc_col.p + (size_t)slot * col_partials(), rc_row.p + (size_t)slot * row_partials());
     }
     // Reduction levels 2 and 3 for slots [first, first + cnt), one launch each; results (XYZZ) in result[slot].
@@ -566,7 +579,7 @@ struct MsmEngine {
         const uint32_t ncols = 1u << s, nrows = nb >> s, ntot = ncols + nrows;
         B2P_LAUNCH((k_msm_rowcol<Fp>), dim3(div_up(ntot, MSM_RC_WARPS), cnt), 32 * MSM_RC_WARPS,
                    32 * MSM_RC_WARPS * sizeof(Ext), st,
-                   rc_col.p + (size_t)first * col_partials(), rc_row.p + (size_t)first * row_partials(), s, nb,
+                   rc_col.p + (size_t)first * col_partials(), rc_row.p + (size_t)first * row_partials(), s, nb, rc_chunk,
                    rc_sums.p + (size_t)first * ntot);
         const int nbits = plan.c;                     // weights are < 2^(c-1) + 1
         B2P_LAUNCH((k_msm_tail<Fp>), dim3(nbits, cnt), MSM_TAIL_THREADS, 0, st, rc_sums.p + (size_t)first * ntot, ntot, s,

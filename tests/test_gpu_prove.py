@@ -193,6 +193,42 @@ def test_two_proofs_in_flight_on_two_handles(gpu):
         cc.free()
 
 
+def test_concurrent_proofs_are_deterministic_at_benchmark_size(gpu):
+    """3 proving keys, 3 host threads, 2^20 rows: every proof equals the lone reference proof, with resident
+    and with host inputs.  (Bucket contents are summed in a different order in every run -- the ranks come
+    from atomics -- so a value-dependent arithmetic slip shows up here as a rare mismatch; this caught a
+    dropped carry that hit one point addition in 10^9.)"""
+    import ctypes as C
+    import threading
+    curve, lanes, reps = "BN254", 3, 8
+    cs, values = fe.squaring_chain(curve, 20, x0=11)
+    ccs = [api.Compile(cs, curve, SETUP[curve]) for _ in range(lanes)]
+    n = ccs[0].trace.n
+    L, R, O = fe.solve_lro(cs, values, n)
+    bufs = [C.create_string_buffer(api.fr_to_mont_bytes(curve, col)) for col in (L, R, O)]
+    bl = api.fr_to_mont_bytes(curve, list(range(11, 20)))
+    ref = ccs[0].prove_raw(bufs[0], bufs[1], bufs[2], bl).raw
+    bad, errs = [], []
+
+    def work(i):
+        try:
+            for k in range(reps):
+                if ccs[i].prove_raw(bufs[0], bufs[1], bufs[2], bl).raw != ref:
+                    bad.append((i, k))
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(lanes)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    assert not bad, f"proofs differ from the reference proof: {sorted(bad)}"
+    for cc in ccs:
+        cc.free()
+
+
 def test_prove_errors(gpu):
     B = fe.basic_circuit("BN254")
     cs = B.build()
