@@ -39,7 +39,7 @@ UNIT = "proofs/s"
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_msm_accumulate launch, from the ncu --set full capture
 # under profiles/ (per workload): the gather reads W = 13 table points per scalar, so ~13x the algorithmic bytes
-ACCUM_DRAM_TRAFFIC = {("BN254", 20): 1_852_200_000}
+ACCUM_DRAM_TRAFFIC = {("BN254", 20): 1_872_500_000}
 # mixed additions / s at which the IMAD pipe saturates: measured field multiplications / s (tools/microbench.cu,
 # profiles/microbench_r1.json: 6.68e10 BN254 Fp, 3.01e10 BLS12-381 Fp) / 9.4 multiplication-equivalents per XYZZ
 # mixed addition (6 products, 2 squarings at 0.94, one a*b - c*d with a single reduction at 1.5; SASS-counted)

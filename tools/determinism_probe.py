@@ -5,15 +5,16 @@ import torch
 import bench
 from algoplonk_b200 import _lib, api
 _lib.init(0); lib = _lib.load()
-curve, log2, F, K = "BN254", int(os.environ.get("LOG2", 20)), int(os.environ.get("F", 3)), int(os.environ.get("K", 6))
+curve, log2, F, K = os.environ.get("CURVE", "BN254"), int(os.environ.get("LOG2", 20)), int(os.environ.get("F", 3)), int(os.environ.get("K", 6))
 cs, tc, L, R, O = bench.build_workload(curve, log2)
-ccs = [api.Compile(cs, curve, api.SetupName.TestOnlyBN254) for _ in range(F)]
+setup = api.SetupName.TestOnlyBN254 if curve == "BN254" else api.SetupName.TestOnlyBLS12381
+ccs = [api.Compile(cs, curve, setup) for _ in range(F)]
 dev = torch.device("cuda", 0)
 pin = lambda d: torch.frombuffer(bytearray(d), dtype=torch.uint8).pin_memory()
 hL, hR, hO = (pin(api.fr_to_mont_bytes(curve, c)) for c in (L, R, O))
 dL, dR, dO = (t.to(dev) for t in (hL, hR, hO))
 bl = C.create_string_buffer(api.fr_to_mont_bytes(curve, list(range(1, 10))))
-size = lib.b2p_proof_raw_size(0, 0)
+size = lib.b2p_proof_raw_size(api.CURVE_ID[curve], 0)
 def prove(i, host):
     out = C.create_string_buffer(size)
     if host:
@@ -29,8 +30,9 @@ for mode in ("dev", "host"):
             got = prove(i, mode == "host")
             if got != ref:
                 # raw proof: 9 points of 64 B (LRO Z H0 H1 H2 Wz Wzw), then 32 B scalars
-                pts = [j for j in range(9) if got[64 * j:64 * j + 64] != ref[64 * j:64 * j + 64]]
-                frs = [j for j in range((len(ref) - 576) // 32) if got[576 + 32 * j:608 + 32 * j] != ref[576 + 32 * j:608 + 32 * j]]
+                pb = 2 * api.FP_BYTES[curve]
+                pts = [j for j in range(9) if got[pb * j:pb * j + pb] != ref[pb * j:pb * j + pb]]
+                frs = [j for j in range((len(ref) - 9 * pb) // 32) if got[9 * pb + 32 * j:9 * pb + 32 * j + 32] != ref[9 * pb + 32 * j:9 * pb + 32 * j + 32]]
                 bad.append((i, k, "pts", pts, "frs", frs))
     ths = [threading.Thread(target=work, args=(i,)) for i in range(F)]
     [t.start() for t in ths]; [t.join() for t in ths]
