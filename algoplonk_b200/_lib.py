@@ -26,6 +26,8 @@ SYMBOLS = [
     ("b2p_last_error", C.c_char_p, []),
     ("b2p_version", C.c_char_p, []),
     ("b2p_launch_count", _u64, []),
+    ("b2p_host_alloc", _int, [_u64, C.POINTER(_vp)]),
+    ("b2p_host_free", None, [_vp]),
     ("b2p_srs_load", _int, [_int, _vp, _u64, _vp, _u64, C.POINTER(_vp)]),
     ("b2p_srs_load_compressed", _int, [_int, _vp, _u64, _u64, C.POINTER(_vp)]),
     ("b2p_srs_generate_unsafe", _int, [_int, _vp, _u64, C.POINTER(_vp)]),

@@ -91,6 +91,17 @@ API int b2p_init(int device) {
     });
 }
 
+API int b2p_host_alloc(uint64_t bytes, void** out) {
+    return guarded([&] {
+        require(out && bytes > 0, "null argument");
+        cudaError_t e = cudaMallocHost(out, bytes);
+        if (e != cudaSuccess) throw Error(B2P_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    });
+}
+API void b2p_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 API int b2p_srs_load(int curve, const void* g1, uint64_t n_can, const void* g1_lag, uint64_t n_lag, b2p_srs** out) {
     (void)g1_lag; (void)n_lag;   // see header: Lagrange commitments are iNTT + canonical MSM
     return guarded([&] {

@@ -173,6 +173,7 @@ func proveBN254(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey, fullWitnes
 	}
 	s := sol.(*cs_bn254.SparseR1CSSolution)
 	L, R, O := pad(s.L, n), pad(s.R, n), pad(s.O, n)
+	defer release(L, R, O)
 
 	var blinding [9]fr.Element
 	if BlindingSource != nil {
@@ -216,8 +217,35 @@ func proveBN254(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey, fullWitnes
 	return proof, nil
 }
 
+// pad copies a solver column into a page-locked buffer of n elements (zero padded): pinned memory uploads at
+// PCIe speed and overlaps with the first transforms; the buffer is returned to the pool after the proof.
 func pad(v []fr.Element, n int) []fr.Element {
-	out := make([]fr.Element, n)
-	copy(out, v)
+	var p unsafe.Pointer
+	if rc := C.b2p_host_alloc(C.uint64_t(n)*C.uint64_t(unsafe.Sizeof(fr.Element{})), &p); rc != 0 {
+		out := make([]fr.Element, n) // pageable fallback: correct, slower upload
+		copy(out, v)
+		return out
+	}
+	out := unsafe.Slice((*fr.Element)(p), n)
+	k := copy(out, v)
+	for i := k; i < n; i++ {
+		out[i] = fr.Element{}
+	}
+	pinned.Store(p, struct{}{})
 	return out
+}
+
+// pinned tracks the page-locked columns of proofs in progress; release frees them.
+var pinned sync.Map
+
+func release(cols ...[]fr.Element) {
+	for _, c := range cols {
+		if len(c) == 0 {
+			continue
+		}
+		p := unsafe.Pointer(&c[0])
+		if _, ok := pinned.LoadAndDelete(p); ok {
+			C.b2p_host_free(p)
+		}
+	}
 }

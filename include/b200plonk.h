@@ -54,6 +54,12 @@ const char* b2p_version(void);
 /* Kernel launches issued by this library since process start (for bench.py's gpu_launches). */
 uint64_t b2p_launch_count(void);
 
+/* Page-locked host memory for the wire columns.  b2p_prove accepts any host pointer, but only pinned buffers
+ * upload at PCIe speed and overlap with compute (pageable memory is staged by the driver at a fraction of
+ * that); the Go shim copies gnark's solver output into buffers from here instead of into fresh slices. */
+int b2p_host_alloc(uint64_t bytes, void** out);
+void b2p_host_free(void* p);
+
 /* ---- SRS  (replaces: kzg.SRS as loaded by setup/setup.go:165-193) ---------- */
 
 /* g1_canonical: n_can points [tau^j]_1 (what srs.Pk.ReadFrom produced, setup.go:173,189).

@@ -229,6 +229,32 @@ def test_concurrent_proofs_are_deterministic_at_benchmark_size(gpu):
         cc.free()
 
 
+def test_prove_from_pinned_host_buffers(gpu):
+    """b2p_host_alloc / b2p_host_free: the page-locked staging the Go shim copies the solver's columns into."""
+    import ctypes as C
+    lib = _lib.load()
+    curve, cv = "BN254", po.CURVES["BN254"]
+    cs, values = fe.squaring_chain(curve, 11, x0=9)
+    cc = api.Compile(cs, curve, SETUP[curve])
+    n = cc.trace.n
+    L, R, O = fe.solve_lro(cs, values, n)
+    blinding = api.fr_to_mont_bytes(curve, H.scalars_uniform(cv.r, 9, 5))
+    want = cc.prove_raw(*(api.fr_to_mont_bytes(curve, c) for c in (L, R, O)), blinding).raw
+    ptrs = []
+    for col in (L, R, O):
+        p = C.c_void_p()
+        _lib.check(lib.b2p_host_alloc(32 * n, C.byref(p)))
+        C.memmove(p, api.fr_to_mont_bytes(curve, col), 32 * n)
+        ptrs.append(p)
+    out = C.create_string_buffer(lib.b2p_proof_raw_size(api.CURVE_ID[curve], 0))
+    _lib.check(lib.b2p_prove(cc.handle, ptrs[0], ptrs[1], ptrs[2], None, None, C.create_string_buffer(blinding), out))
+    assert out.raw == want
+    for p in ptrs:
+        lib.b2p_host_free(p)
+    lib.b2p_host_free(None)
+    cc.free()
+
+
 def test_prove_errors(gpu):
     B = fe.basic_circuit("BN254")
     cs = B.build()
