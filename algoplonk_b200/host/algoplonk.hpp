@@ -1,0 +1,240 @@
+// algoplonk.hpp -- compiled-language mirror of AlgoPlonk's public API for the proving path, over the C ABI
+// of include/b200plonk.h (header only; needs libb200plonk.so at link time and a B200 at run time).
+//
+// The reference is Go (package algoplonk) and no Go toolchain exists in the build image, so the binding a
+// maintainer adds is shipped as source (go/gpuplonk).  This header is the same surface in C++, with the
+// reference's names, argument meaning and error behaviour:
+//
+//   Compile(circuit, curve, setup)            /root/reference/algoplonk.go:37-59
+//   CompiledCircuit::Verify(assignment)       /root/reference/algoplonk.go:79-98   (witness -> Prove -> verify)
+//   VerifiedProof::ExportProofAndPublicInputs /root/reference/algoplonk.go:103-131
+//   MarshalProof / MarshalPublicInputs        /root/reference/helper.go:13-24,91-110
+//   setup::Name                               /root/reference/setup/setup.go:23-36
+//
+// The circuit front end (gnark's frontend.Compile + NewTrace) is restated minimally: public rows first,
+// last-seen-position permutation, padding rows on variable 0 -- enough for the circuits of the reference's
+// examples and tests (BasicCircuit, the squaring chain).  Field values are held in Montgomery form with the
+// library's own host arithmetic (csrc/field.cuh compiles for the host), i.e. in gnark's memory layout.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200plonk.h"
+#include "../csrc/field.cuh"
+
+namespace algoplonk {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+inline void check(int rc, const char* what) {
+    if (rc != B2P_OK) throw Error(std::string(what) + ": " + b2p_last_error());
+}
+
+namespace setup {
+// setup/setup.go:23-36
+enum class Name { TestOnlyBN254 = 0, TestOnlyBLS12381, PerpetualPowersOfTauBN254, EthereumKzgCeremonyBLS12381, DuskBLS12381 };
+inline bool trusted(Name n) { return n >= Name::PerpetualPowersOfTauBN254; }
+inline int curve_of(Name n) { return (n == Name::TestOnlyBN254 || n == Name::PerpetualPowersOfTauBN254) ? B2P_BN254 : B2P_BLS12_381; }
+}  // namespace setup
+
+template <int CURVE> struct ScalarField;
+template <> struct ScalarField<B2P_BN254> { using Fr = b2p::FrBn254; };
+template <> struct ScalarField<B2P_BLS12_381> { using Fr = b2p::FrBls12381; };
+
+// canonical big-endian hex (no 0x) -> Montgomery element; throws on overlong input
+template <class Fr>
+inline Fr fr_from_hex(const std::string& hex) {
+    Fr raw = Fr::zero();
+    if (hex.size() > (size_t)Fr::N * 8) throw Error("scalar does not fit the field");
+    for (size_t i = 0; i < hex.size(); i++) {
+        const char ch = hex[hex.size() - 1 - i];
+        const int d = ch >= '0' && ch <= '9' ? ch - '0' : ch >= 'a' && ch <= 'f' ? ch - 'a' + 10 : ch >= 'A' && ch <= 'F' ? ch - 'A' + 10 : -1;
+        if (d < 0) throw Error("bad hex digit");
+        raw.v[i / 8] |= (uint32_t)d << (4 * (i % 8));
+    }
+    return Fr::reduce_to_mont(raw);
+}
+template <class Fr>
+inline Fr fr_from_u64(uint64_t x) {
+    Fr r = Fr::zero();
+    r.v[0] = (uint32_t)x;
+    r.v[1] = (uint32_t)(x >> 32);
+    return r.to_mont();
+}
+
+// ---- constraint system (gnark SparseR1CS, the subset the proving path needs) ------------------------
+template <class Fr>
+struct SparseR1CS {
+    struct Constraint { Fr ql, qr, qm, qo, qk; uint32_t xa, xb, xc; };
+    uint32_t nb_public = 0;
+    std::vector<Fr> values;                 // solved witness, public variables first
+    std::vector<Constraint> constraints;
+
+    uint64_t domain_size() const {          // NextPowerOfTwo(nbConstraints + nbPublic), setup.go:113
+        uint64_t need = constraints.size() + nb_public, n = 1;
+        while (n < need) n <<= 1;
+        return n < 2 ? 2 : n;
+    }
+};
+
+// Eager builder: variables carry their values, one pass yields the system and its witness
+template <class Fr>
+struct Builder {
+    SparseR1CS<Fr> cs;
+    bool secret_started = false;
+    uint32_t Public(const Fr& v) {
+        if (secret_started) throw Error("public variables first (gnark witness order)");
+        cs.values.push_back(v);
+        return cs.nb_public++;
+    }
+    uint32_t Secret(const Fr& v) { secret_started = true; cs.values.push_back(v); return (uint32_t)cs.values.size() - 1; }
+    void Constrain(const Fr& ql, const Fr& qr, const Fr& qm, const Fr& qo, const Fr& qk, uint32_t a, uint32_t b, uint32_t c) {
+        cs.constraints.push_back({ql, qr, qm, qo, qk, a, b, c});
+    }
+    uint32_t Mul(uint32_t a, uint32_t b) {
+        const uint32_t c = Secret(cs.values[a] * cs.values[b]);
+        Constrain(Fr::zero(), Fr::zero(), Fr::one(), Fr::one().neg(), Fr::zero(), a, b, c);
+        return c;
+    }
+    uint32_t Add(uint32_t a, uint32_t b) {
+        const uint32_t c = Secret(cs.values[a] + cs.values[b]);
+        Constrain(Fr::one(), Fr::one(), Fr::zero(), Fr::one().neg(), Fr::zero(), a, b, c);
+        return c;
+    }
+    void AssertIsEqual(uint32_t a, uint32_t b) {
+        Constrain(Fr::one(), Fr::one().neg(), Fr::zero(), Fr::zero(), Fr::zero(), a, b, 0);
+    }
+};
+
+// ---- proofs -----------------------------------------------------------------------------------------
+template <int CURVE>
+struct VerifiedProof {                      // algoplonk.go:28-31
+    using Fr = typename ScalarField<CURVE>::Fr;
+    std::vector<uint8_t> raw;               // plonk.Proof in gnark memory layout (b2p_proof_raw_size bytes)
+    std::vector<Fr> witness;                // public inputs
+
+    std::vector<uint8_t> MarshalProof() const {                      // helper.go:13-24
+        std::vector<uint8_t> out(b2p_proof_marshal_size(CURVE, 0));
+        check(b2p_marshal_proof(CURVE, 0, raw.data(), nullptr, out.data()), "MarshalProof");
+        return out;
+    }
+    std::vector<uint8_t> MarshalPublicInputs() const {               // helper.go:91-110
+        std::vector<uint8_t> out(32 * witness.size());
+        check(b2p_marshal_public_inputs(CURVE, witness.data(), (uint32_t)witness.size(), out.data()), "MarshalPublicInputs");
+        return out;
+    }
+    void ExportProofAndPublicInputs(const std::string& proof_path, const std::string& public_inputs_path) const {
+        const auto p = MarshalProof(), w = MarshalPublicInputs();    // algoplonk.go:103-131
+        std::ofstream(proof_path, std::ios::binary).write((const char*)p.data(), (std::streamsize)p.size());
+        std::ofstream(public_inputs_path, std::ios::binary).write((const char*)w.data(), (std::streamsize)w.size());
+    }
+};
+
+// ---- compiled circuit (algoplonk.go:21-26: Ccs + Pk + Vk + Curve; Pk resident on the GPU) ------------
+template <int CURVE>
+class CompiledCircuit {
+public:
+    using Fr = typename ScalarField<CURVE>::Fr;
+    SparseR1CS<Fr> ccs;
+    uint64_t n = 0;
+
+    CompiledCircuit() = default;
+    CompiledCircuit(const CompiledCircuit&) = delete;
+    CompiledCircuit& operator=(const CompiledCircuit&) = delete;
+    ~CompiledCircuit() {
+        if (circuit_) b2p_circuit_free(circuit_);
+        if (srs_) b2p_srs_free(srs_);
+    }
+
+    // algoplonk.go:79-98: witness -> Prove -> (verify with `verifier`, if given)
+    // `blinding`: the 9 scalars gnark draws with fr.SetRandom (an input, so proofs are reproducible).
+    template <class Verifier = std::nullptr_t>
+    VerifiedProof<CURVE> Verify(const std::vector<Fr>& blinding, Verifier verifier = nullptr) const {
+        if (blinding.size() != 9) throw Error("9 blinding scalars expected");
+        std::vector<Fr> L(n, ccs.values.empty() ? Fr::zero() : ccs.values[0]), R = L, O = L;   // padding rows: variable 0
+        for (uint32_t i = 0; i < ccs.nb_public; i++) L[i] = ccs.values[i];
+        for (size_t j = 0; j < ccs.constraints.size(); j++) {
+            const auto& c = ccs.constraints[j];
+            L[ccs.nb_public + j] = ccs.values[c.xa];
+            R[ccs.nb_public + j] = ccs.values[c.xb];
+            O[ccs.nb_public + j] = ccs.values[c.xc];
+        }
+        VerifiedProof<CURVE> vp;
+        vp.raw.resize(b2p_proof_raw_size(CURVE, 0));
+        check(b2p_prove(circuit_, L.data(), R.data(), O.data(), nullptr, nullptr, blinding.data(), vp.raw.data()), "plonk.Prove");
+        vp.witness.assign(ccs.values.begin(), ccs.values.begin() + ccs.nb_public);
+        if constexpr (!std::is_same<Verifier, std::nullptr_t>::value) {
+            if (!verifier(vp.MarshalProof(), vp.MarshalPublicInputs())) throw Error("error verifying proof");
+        }
+        return vp;
+    }
+    // S1 S2 S3 Ql Qr Qm Qo Qk commitments of the verifying key (G1Affine memory layout)
+    std::vector<uint8_t> VkCommitments() const {
+        std::vector<uint8_t> out(8 * (CURVE == B2P_BN254 ? 64 : 96));
+        check(b2p_circuit_vk_commitments(circuit_, out.data()), "vk commitments");
+        return out;
+    }
+
+    template <int C> friend CompiledCircuit<C>* CompileInto(CompiledCircuit<C>*, const SparseR1CS<typename ScalarField<C>::Fr>&,
+                                                           setup::Name, const typename ScalarField<C>::Fr*, const void*, uint64_t);
+private:
+    b2p_srs* srs_ = nullptr;
+    b2p_circuit* circuit_ = nullptr;
+};
+
+template <int CURVE>
+inline CompiledCircuit<CURVE>* CompileInto(CompiledCircuit<CURVE>* cc, const SparseR1CS<typename ScalarField<CURVE>::Fr>& cs,
+                                           setup::Name name, const typename ScalarField<CURVE>::Fr* test_tau,
+                                           const void* pk_bin, uint64_t pk_len) {
+    using Fr = typename ScalarField<CURVE>::Fr;
+    if ((int)name < 0 || (int)name > (int)setup::Name::DuskBLS12381) throw Error("unknown setup");   // compile_test.go:22-30
+    if (setup::curve_of(name) != CURVE) throw Error("curve and trusted setup do not match");          // algoplonk.go:46-48
+    check(b2p_init(-1), "b2p_init");
+    cc->ccs = cs;
+    const uint64_t n = cc->n = cs.domain_size();
+    if (setup::trusted(name)) {
+        if (!pk_bin) throw Error("trusted setups need their pk.bin bytes");
+        check(b2p_srs_load_compressed(CURVE, pk_bin, pk_len, n + 3, &cc->srs_), "setup.Run");          // setup.go:113-139
+    } else {
+        if (!test_tau) throw Error("TestOnly setups need a tau");
+        check(b2p_srs_generate_unsafe(CURVE, test_tau, n + 3, &cc->srs_), "unsafekzg.NewSRS");         // setup.go:102-108
+    }
+    // trace: Lagrange columns + permutation (gnark NewTrace / buildPermutation)
+    std::vector<Fr> ql(n, Fr::zero()), qr = ql, qm = ql, qo = ql, qk = ql;
+    const uint32_t off = cs.nb_public;
+    for (uint32_t i = 0; i < off; i++) ql[i] = Fr::one().neg();
+    std::vector<int64_t> lro(3 * n, 0), perm(3 * n, -1);
+    for (uint32_t i = 0; i < off; i++) lro[i] = i;
+    for (size_t j = 0; j < cs.constraints.size(); j++) {
+        const auto& c = cs.constraints[j];
+        ql[off + j] = c.ql; qr[off + j] = c.qr; qm[off + j] = c.qm; qo[off + j] = c.qo; qk[off + j] = c.qk;
+        lro[off + j] = c.xa; lro[n + off + j] = c.xb; lro[2 * n + off + j] = c.xc;
+    }
+    std::vector<int64_t> cycle(cs.values.empty() ? 1 : cs.values.size(), -1);
+    for (uint64_t i = 0; i < 3 * n; i++) {
+        const int64_t v = lro[i];
+        if (cycle[v] != -1) perm[i] = cycle[v];
+        cycle[v] = (int64_t)i;
+    }
+    for (uint64_t i = 0; i < 3 * n; i++)
+        if (perm[i] == -1) perm[i] = cycle[lro[i]];
+    check(b2p_circuit_load(cc->srs_, n, cs.nb_public, ql.data(), qr.data(), qm.data(), qo.data(), qk.data(), perm.data(), 0,
+                           nullptr, nullptr, nullptr, 0, &cc->circuit_), "plonk.Setup");
+    return cc;
+}
+
+// algoplonk.go:37-59.  TestOnly setups: `test_tau` (unsafekzg draws a random one); trusted setups: the bytes of
+// the embedded setup/<name>/pk.bin.
+template <int CURVE>
+inline void Compile(CompiledCircuit<CURVE>& out, const SparseR1CS<typename ScalarField<CURVE>::Fr>& cs, setup::Name name,
+                    const typename ScalarField<CURVE>::Fr* test_tau = nullptr, const void* pk_bin = nullptr, uint64_t pk_len = 0) {
+    CompileInto<CURVE>(&out, cs, name, test_tau, pk_bin, pk_len);
+}
+
+}  // namespace algoplonk

@@ -115,6 +115,25 @@ def test_msm_properties_at_benchmark_size(gpu):
     srs.free()
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_msm_repeated_and_opposite_points(gpu, curve):
+    """Collisions: an SRS made of few distinct points, their negatives and infinity, with equal scalars, so
+    buckets add P + P (doubling branch), P + (-P) (back to infinity) and infinity itself, in the accumulation
+    and in every level of the bucket reduction."""
+    cv = po.CURVES[curve]
+    g2, g3 = po.g1_mul(cv, cv.g1, 2), po.g1_mul(cv, cv.g1, 3)
+    pts = ([cv.g1] * 70 + [po.g1_neg(cv, cv.g1)] * 50 + [g2] * 33 + [po.g1_neg(cv, g2)] * 33 + [None] * 9 + [g3] * 5)
+    rng = random.Random(9)
+    rng.shuffle(pts)
+    srs = api.SRS.from_points(curve, pts)
+    n = len(pts)
+    cases = [[7] * n, [1] * n, [cv.r - 1] * n, [rng.choice((1, 2, 3, cv.r - 2)) for _ in range(n)],
+             H.scalars_uniform(cv.r, n, 6), [5 if P == cv.g1 else 0 for P in pts]]
+    for sc in cases:
+        assert srs.msm(sc) == po.msm_naive(cv, pts, sc)
+    srs.free()
+
+
 def test_msm_errors(gpu):
     srs = api.SRS.unsafe("BN254", 8, H.TAU)
     with pytest.raises(gpu.B200PlonkError, match="more scalars"):
