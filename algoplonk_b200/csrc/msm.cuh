@@ -24,6 +24,10 @@ namespace b2p {
 constexpr int MSM_CAP = 128;       // max entries accumulated by one thread (the partial top window puts
                                    // ~n / 2^(bits - (W-1)c) entries into each of its buckets: ~90 at n = 2^20, c = 20)
 constexpr int MSM_THREADS = 128;
+// resident accumulation blocks per SM: 4 x 128 registers for 8-limb base fields (BN254); a 12-limb field
+// (BLS12-381) spills at 128 or 168 registers and loses more than the extra warps give (measured: 46.5 / 45.0 /
+// 44.2 ms of accumulation per 2^20 proof at 4 / 3 / 2 blocks)
+constexpr int MSM_ACC_BLOCKS_WIDE = 2;
 constexpr int MSM_SLOTS = 16;      // MSMs that can be queued before their results are fetched
 
 struct MsmPlan {
@@ -183,7 +187,7 @@ __device__ __forceinline__ Affine<Fp> ldg_point(const Affine<Fp>* src) {
 }
 
 template <class Fp>
-__global__ void __launch_bounds__(MSM_THREADS, 4)
+__global__ void __launch_bounds__(MSM_THREADS, (Fp::N <= 8 ? 4 : MSM_ACC_BLOCKS_WIDE))
 k_msm_accumulate(const Affine<Fp>* __restrict__ table, const uint32_t* __restrict__ entries,
                  const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                  const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ total_items,
