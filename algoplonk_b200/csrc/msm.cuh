@@ -10,10 +10,15 @@
 //     combination, and the window width can grow to c = 20 at n = 2^20.
 //   * digits -> buckets is a counting sort written here: histogram whose
 //     fetch-adds also rank every digit inside its bucket, exclusive scan, scatter.
-//   * bucket accumulation: one thread per <=CAP-entry slice of a bucket, XYZZ
-//     accumulator in registers, mixed additions (8M+2S), points gathered as
-//     full 64 B / 96 B sectors.
-//   * bucket reduction sum_b (b+1) * B_b: a radix-SEG tree of running sums.
+//   * bucket accumulation: one thread per <=CAP-entry slice of a bucket (slices sorted
+//     by length so a warp's lanes run equally long), XYZZ accumulator in registers,
+//     mixed additions (8M+2S), points gathered as full 64 B / 96 B sectors one
+//     addition ahead; bucket sums land in a dense array.
+//   * bucket reduction sum_b (b+1) * B_b: bucket index split b = h * 2^s + l, plain
+//     row / column sums (level 1: one wave of long per-thread chains; level 2: a
+//     shared-memory tree), then a bit-decomposed weighted sum of the ~1.5 k row and
+//     column sums.  Levels 2 and 3 are latency-bound and therefore deferred: they run
+//     once per fetch for all MSMs queued since (result slots).
 #pragma once
 #include <vector>
 #include "common.cuh"
