@@ -73,6 +73,17 @@ def real_srs_points(name: str):
     return [po.g1_decompress(cv, raw[i * cv.fp_bytes:(i + 1) * cv.fp_bytes]) for i in range(ent["count"])]
 
 
+@functools.lru_cache(maxsize=None)
+def real_srs_g2(name: str):
+    """(G2[0], G2[1]) = ([1]_2, [tau]_2) of a reference setup, from its committed vk.bin bytes."""
+    from oracle import pairing
+    ent = srs_kat()[name]
+    cv = po.CURVES[ent["curve"]]
+    g2, g1 = pairing.parse_vk_bin(cv, bytes.fromhex(ent["vk_bin"]))
+    assert g1 == cv.g1
+    return g2
+
+
 def case_id(case) -> str:
     return f"{case['curve']}-{case['name']}-{case['srs'][:4]}"
 

@@ -33,7 +33,9 @@ def test_golden_proofs_byte_identical(gpu, case):
     assert api.MarshalPublicInputs(case["curve"], vp.Witness).hex() == case["public_inputs"]
     if c["tau"] is not None:
         vk = H.vk_from_points(c["tc"], vk_pts, c["cv"].g1, tau=c["tau"])
-        assert po.verify_proof(vk, blob, bytes.fromhex(case["public_inputs"]))
+    else:       # real ceremony SRS: the verifier's pairing check against the G2 points of the setup's vk.bin
+        vk = H.vk_from_points(c["tc"], vk_pts, c["srs"][0], tau=None, g2=H.real_srs_g2(case["srs"]))
+    assert po.verify_proof(vk, blob, bytes.fromhex(case["public_inputs"]))
     cc.free()
 
 

@@ -154,6 +154,71 @@ def test_cpp_ntt(curve):
         assert co.ntt(cv.cid, fc, inverse=True, coset=True) == a
 
 
+# ---- pairing (oracle/pairing.py: the ec_pairing_check of the generated verifiers) ---------
+# setup/trusted_setup_test.go:93-95: the compressed G2 points of the Dusk verifying key
+DUSK_G2_HEX = (
+    "93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+    "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8",
+    "8fd840491fe66a0cc60f45930d88a9b562136137f78260648ce6a4bf5d31849f18de090e2644780d2bf6b42e20842276"
+    "0fabe7238383b48bd61f25125a0d093306ef5511550312e2c1a9fb985e21ce1bf71b1fb0565c3b54836463eb1f043d48",
+)
+
+
+def test_dusk_vk_bin_matches_the_reference_known_answers():
+    from oracle import pairing
+    ent = H.srs_kat()["DuskBLS12_381"]
+    vk_bin = bytes.fromhex(ent["vk_bin"])
+    assert vk_bin[:96].hex() == DUSK_G2_HEX[0] and vk_bin[96:192].hex() == DUSK_G2_HEX[1]
+    assert vk_bin[192:].hex() == ent["first"][:96]                    # Vk.G1 == Pk.G1[0] (:118-120)
+    cv = po.BLS12_381
+    for i, hx in enumerate(DUSK_G2_HEX):
+        Q = pairing.g2_decompress(cv, bytes.fromhex(hx))
+        assert pairing.g2_on_curve(cv, Q) and Q == H.real_srs_g2("DuskBLS12_381")[i]
+        # the X the test rebuilds from the hex: A1 = first half with the 3 flag bits cleared, A0 = second half
+        raw = bytes.fromhex(hx)
+        assert Q[0] == (int.from_bytes(raw[48:], "big"), int.from_bytes(bytes([raw[0] & 0x1F]) + raw[1:48], "big"))
+
+
+@pytest.mark.parametrize("name", sorted(H.srs_kat()))
+def test_pairing_on_the_ceremony_files(name):
+    """e([tau]_1, [1]_2) == e([1]_1, [tau]_2) with every operand read from the reference's pk.bin / vk.bin:
+    pins the pairing (and the G2 decoder) on data this repo did not produce; plus bilinearity."""
+    from oracle import pairing
+    ent = H.srs_kat()[name]
+    cv = po.CURVES[ent["curve"]]
+    g2_one, g2_tau = H.real_srs_g2(name)
+    g1 = H.real_srs_points(name)
+    assert pairing.pairing_product_is_one(cv, [(g1[1], g2_one), (po.g1_neg(cv, g1[0]), g2_tau)])
+    assert pairing.pairing_product_is_one(cv, [(g1[2], g2_one), (po.g1_neg(cv, g1[1]), g2_tau)])
+    assert not pairing.pairing_product_is_one(cv, [(g1[1], g2_one), (g1[0], g2_tau)])
+    assert not pairing.pairing_product_is_one(cv, [(g1[2], g2_one), (po.g1_neg(cv, g1[0]), g2_tau)])
+    # e(a P, Q) e(-P, Q)^a == 1, as e(aP, Q) * e(-a P, Q)
+    a = 0xC0FFEE
+    aP = po.g1_mul(cv, g1[0], a)
+    assert pairing.pairing_product_is_one(cv, [(aP, g2_tau), (po.g1_neg(cv, po.g1_mul(cv, g1[1], a)), g2_one)])
+
+
+@pytest.mark.parametrize("case", [c for c in H.golden_proofs() if c["srs"] != "tau"], ids=H.case_id)
+def test_real_srs_golden_proofs_pass_the_pairing_check(case):
+    """The proofs over the reference's REAL trusted setups (tau unknown) are accepted by the restated verifier
+    with an actual pairing against the G2 points of the setup's vk.bin, and rejected when tampered with."""
+    c = H.build_case(case)
+    cv = c["cv"]
+    def vk_point(raw):                          # G1Affine.Marshal(): infinity carries gnark's 0x40 flag on BLS12-381
+        return None if raw == bytes([0x40]) + bytes(len(raw) - 1) or not any(raw) else po.g1_from_raw_bytes(cv, raw)
+    vkb, nb2 = bytes.fromhex(case["vk"]), 2 * cv.fp_bytes
+    vk_pts = [vk_point(vkb[i * nb2:(i + 1) * nb2]) for i in range(8)]
+    vk = H.vk_from_points(c["tc"], vk_pts, c["srs"][0], tau=None, g2=H.real_srs_g2(case["srs"]))
+    blob, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
+    assert po.verify_proof(vk, blob, pub)
+    bad = bytearray(pub)
+    bad[31] ^= 1
+    assert not po.verify_proof(vk, blob, bytes(bad))
+    nb = 2 * cv.fp_bytes
+    swapped = blob[nb:2 * nb] + blob[nb:]                 # first G1 point overwritten with the second
+    assert not po.verify_proof(vk, swapped, pub)
+
+
 # ---- proofs -----------------------------------------------------------------------------
 @pytest.mark.parametrize("case", H.golden_proofs(), ids=H.case_id)
 def test_golden_proof_python_oracle(case):

@@ -7,7 +7,8 @@ the embedded SRS files); the outputs are committed so the tests never read
                  (/root/reference/setup/*/pk.bin, format: setup/setup.go:196-228): the
                  first points of each file (+ index 32767, the one
                  setup/trusted_setup_test.go:132,256 pins), and the slices used as real-SRS
-                 MSM bases by the parity tests (PPoT-BN254: 259 points, Dusk: 67 points).
+                 MSM bases by the parity tests (PPoT-BN254: 259 points, Dusk: 67 points),
+                 and each setup's vk.bin (160 / 240 bytes: the two G2 points of the pairing check).
   proofs.json    proofs produced by the big-integer oracle (oracle/plonk_oracle.py) on the
                  reference's own circuits (examples/basic, bsb22_test.go) and on small
                  squaring chains over the real SRS slices, with fixed blinding scalars.
@@ -44,12 +45,15 @@ def gen_srs():
             first = f.read(count * cv.fp_bytes)
             f.seek(4 + 32767 * cv.fp_bytes)
             p32767 = f.read(cv.fp_bytes)
+        with open(os.path.join(REF, name, "vk.bin"), "rb") as f:
+            vk_bin = f.read()       # 2 compressed G2 + 1 compressed G1 (setup/setup.go:216-225)
         out[name] = {
             "curve": curve,
             "declared_count": int.from_bytes(header, "big"),
             "first": first.hex(),
             "count": count,
             "index_32767": p32767.hex(),
+            "vk_bin": vk_bin.hex(),
         }
     return out
 
