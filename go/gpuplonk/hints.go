@@ -1,4 +1,4 @@
-// BSB22 commitment hint and curve dispatch helpers for prove_bn254.go.  NOT COMPILED here (no Go).
+// BSB22 commitment hint for prove_bn254.go (the BLS12-381 twin lives in prove_bls12381.go).  NOT COMPILED here (no Go).
 package gpuplonk
 
 /*
@@ -13,20 +13,10 @@ import (
 	"github.com/consensys/gnark-crypto/ecc/bn254"
 	"github.com/consensys/gnark-crypto/ecc/bn254/fr"
 	"github.com/consensys/gnark-crypto/ecc/bn254/fr/hash_to_field"
-	"github.com/consensys/gnark/backend"
-	"github.com/consensys/gnark/backend/plonk"
-	"github.com/consensys/gnark/backend/witness"
 	"github.com/consensys/gnark/constraint"
 	cs_bn254 "github.com/consensys/gnark/constraint/bn254"
 	"github.com/consensys/gnark/constraint/solver"
 )
-
-// proveOtherCurves: BLS12-381 goes to the twin of proveBN254 (prove_bls12381.go); anything else is not
-// an AlgoPlonk curve (algoplonk.go:39-41) and stays on gnark.
-func proveOtherCurves(ccs constraint.ConstraintSystem, pk plonk.ProvingKey, w witness.Witness,
-	opts ...backend.ProverOption) (plonk.Proof, error) {
-	return plonk.Prove(ccs, pk, w, opts...)
-}
 
 // bsb22Hints mirrors gnark's bsb22ComputeCommitmentHint (backend/plonk/bn254/prove.go): for commitment
 // i the solver hands over the committed wire values; they are written into a Lagrange column that is
