@@ -98,7 +98,8 @@ def build_case(case):
     elif case["name"].startswith("bsb22"):
         k = case["k"]
         n_dry = fe.bsb22_circuit(curve, k, lambda a, b, c: 1).build().domain_size
-        srs_o = po.srs_from_tau(cv, TAU, n_dry + 3)
+        srs_o = (po.srs_from_tau(cv, TAU, n_dry + 3) if case["srs"] == "tau"
+                 else real_srs_points(case["srs"])[: n_dry + 3])
         trd = type("T", (), {"curve": cv, "n": n_dry})
         cs, values, pi2s, coms = build_bsb22(curve, k, lambda col: po.bsb22_commit(trd, srs_o, col))
         assert [po.g1_raw_bytes(cv, P).hex() for P in coms] == case["bsb22"]

@@ -207,7 +207,7 @@ def test_real_srs_golden_proofs_pass_the_pairing_check(case):
     def vk_point(raw):                          # G1Affine.Marshal(): infinity carries gnark's 0x40 flag on BLS12-381
         return None if raw == bytes([0x40]) + bytes(len(raw) - 1) or not any(raw) else po.g1_from_raw_bytes(cv, raw)
     vkb, nb2 = bytes.fromhex(case["vk"]), 2 * cv.fp_bytes
-    vk_pts = [vk_point(vkb[i * nb2:(i + 1) * nb2]) for i in range(8)]
+    vk_pts = [vk_point(vkb[i * nb2:(i + 1) * nb2]) for i in range(8 + case["k"])]
     vk = H.vk_from_points(c["tc"], vk_pts, c["srs"][0], tau=None, g2=H.real_srs_g2(case["srs"]))
     blob, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
     assert po.verify_proof(vk, blob, pub)

@@ -113,6 +113,35 @@ def gen_proofs(srs_kat):
             "proof": po.marshal_proof(cv, pf).hex(),
             "public_inputs": po.marshal_public_inputs(L[: tc.nb_public]).hex(),
         })
+    # BASELINE config 4's substitute: bsb22Circuit (bsb22_test.go:18-39) with ONE commitment on the
+    # real Dusk BLS12-381 setup, and its BN254 / PPoT counterpart; the generated verifier's pairing check is
+    # evaluated with the setups' own G2 points (oracle/pairing.py)
+    from oracle import pairing
+    for fname in ("PerpetualPowersOfTauBN254", "DuskBLS12_381"):
+        ent = srs_kat[fname]
+        curve = ent["curve"]
+        cv = po.CURVES[curve]
+        raw = bytes.fromhex(ent["first"])
+        pts = [po.g1_decompress(cv, raw[i * cv.fp_bytes:(i + 1) * cv.fp_bytes]) for i in range(ent["count"])]
+        n_dry = fe.bsb22_circuit(curve, 1, lambda a, b, c: 1).build().domain_size
+        trd = type("T", (), {"curve": cv, "n": n_dry})
+        cs, values, pi2s, coms = H.build_bsb22(curve, 1, lambda col: po.bsb22_commit(trd, pts[: n_dry + 3], col))
+        tc = fe.build_trace(cs)
+        L, R, O = fe.solve_lro(cs, values, tc.n)
+        srs = pts[: tc.n + 3]
+        g2, _ = pairing.parse_vk_bin(cv, bytes.fromhex(ent["vk_bin"]))
+        tr = H.oracle_trace(tc)
+        vk = po.setup(tr, srs, g2=g2)
+        pf = po.prove(tr, vk, srs, L, R, O, blinding, pi2s, coms)
+        blob = po.marshal_proof(cv, pf)
+        pub = po.marshal_public_inputs(L[: tc.nb_public])
+        assert po.verify_proof(vk, blob, pub)
+        cases.append({
+            "name": "bsb22_k1", "curve": curve, "k": 1, "srs": fname, "n": tc.n, "blinding": blinding,
+            "pi2": [[hex(v) for v in col] for col in pi2s],
+            "bsb22": [po.g1_raw_bytes(cv, P).hex() for P in coms],
+            "vk": po.vk_transcript_bytes(vk).hex(), "proof": blob.hex(), "public_inputs": pub.hex(),
+        })
     return cases
 
 
