@@ -18,7 +18,10 @@
  * All functions return 0 on success and a negative code on failure; the message
  * is available from b2p_last_error() (thread local).  Nothing aborts, nothing
  * throws across the boundary, no caller pointer is retained after a call returns
- * (cgo rule).  Handles may be used from any thread, one call at a time per handle.
+ * (cgo rule).  Handles may be used from any thread, one call at a time per handle; a handle is bound to the
+ * CUDA device that was current when it was created and every entry point switches to that device for the
+ * duration of the call (goroutines migrate between OS threads).  The library is re-entrant across handles:
+ * several proofs can be in flight on one GPU, one proving key (SRS + circuit handle) each.
  */
 #ifndef B200PLONK_H
 #define B200PLONK_H
