@@ -275,7 +275,8 @@ class CompiledCircuit:
             self.handle = None
 
 
-def Compile(cs: fe.SparseR1CS, curve: str, setup_name: int, srs: Optional[SRS] = None) -> CompiledCircuit:
+def Compile(cs: fe.SparseR1CS, curve: str, setup_name: int, srs: Optional[SRS] = None,
+            vk_transcript: Optional[bytes] = None) -> CompiledCircuit:
     """algoplonk.go:37-59.  `cs` is the already-built constraint system (gnark's frontend.Compile
     stays on the CPU); a trusted setup needs its SRS passed in (the embedded pk.bin files of the
     reference are loaded by the caller, setup/setup.go:196-228)."""
@@ -305,5 +306,9 @@ def Compile(cs: fe.SparseR1CS, curve: str, setup_name: int, srs: Optional[SRS] =
     qcp_arr = (C.c_void_p * max(k, 1))(*[C.cast(b, C.c_void_p) for b in qcp_bufs]) if k else None
     cidx = (C.c_uint64 * max(k, 1))(*tc.commitment_constraint_indexes) if k else None
     h = C.c_void_p()
-    _lib.check(lib.b2p_circuit_load(srs.handle, n, tc.nb_public, *cols, perm, k, qcp_arr, cidx, None, 0, C.byref(h)))
+    # vk_transcript: the verifying key's commitments as gnark binds them into the transcript (S1 S2 S3 Ql Qr Qm Qo
+    # Qk Qcp*, G1Affine.Marshal() each) -- what the Go shim passes from pk.Vk; None: the library commits itself
+    vkb = _buf(vk_transcript) if vk_transcript is not None else None
+    _lib.check(lib.b2p_circuit_load(srs.handle, n, tc.nb_public, *cols, perm, k, qcp_arr, cidx, vkb,
+                                    len(vk_transcript) if vk_transcript is not None else 0, C.byref(h)))
     return CompiledCircuit(cs, tc, srs, h.value)

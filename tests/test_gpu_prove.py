@@ -257,6 +257,29 @@ def test_prove_from_pinned_host_buffers(gpu):
     cc.free()
 
 
+@pytest.mark.parametrize("case", [c for c in H.golden_proofs() if c["name"] in ("basic", "bsb22_k1", "squaring_2p6")],
+                         ids=H.case_id)
+def test_circuit_load_with_the_callers_vk_transcript(gpu, case):
+    """The Go shim hands b2p_circuit_load the verifying key's commitments as gnark marshals them (pk.Vk.*,
+    G1Affine.Marshal(), infinity = 0x40 flag on BLS12-381) instead of letting the library commit: same proofs,
+    and [Lin] is then built from the points decoded out of those bytes."""
+    c = H.build_case(case)
+    curve = case["curve"]
+    vkb = bytes.fromhex(case["vk"])
+    if case["srs"] == "tau":
+        cc = api.Compile(c["cs"], curve, SETUP[curve], vk_transcript=vkb)
+    else:
+        real = {"PerpetualPowersOfTauBN254": api.SetupName.PerpetualPowersOfTauBN254,
+                "DuskBLS12_381": api.SetupName.DuskBLS12381}[case["srs"]]
+        cc = api.Compile(c["cs"], curve, real, srs=api.SRS.from_points(curve, c["srs"]), vk_transcript=vkb)
+    blob = api.MarshalProof(cc.Prove(c["L"], c["R"], c["O"], c["blinding"], c["pi2"], c["coms"]))
+    assert blob.hex() == case["proof"]
+    with pytest.raises(_lib.B200PlonkError, match="wrong length"):
+        api.Compile(c["cs"], curve, SETUP[curve] if case["srs"] == "tau" else real,
+                    srs=None if case["srs"] == "tau" else api.SRS.from_points(curve, c["srs"]), vk_transcript=vkb[:-1])
+    cc.free()
+
+
 def test_prove_errors(gpu):
     B = fe.basic_circuit("BN254")
     cs = B.build()
