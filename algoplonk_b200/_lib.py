@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libb200plonk.so")
 B2P_BN254, B2P_BLS12_381 = 0, 1
 BASIS_CANONICAL, BASIS_LAGRANGE = 0, 1
 NTT_INVERSE, NTT_COSET = 1, 2
+IPC_HANDLE_BYTES = 64
 STAT_NAMES = ["total_ms", "msm_ms", "msm_accum_ms", "ntt_ms", "quotient_ms", "msm_calls", "msm_accum_adds",
               "h2d_bytes", "d2h_bytes", "launches"]
 STAT_COUNT = 16
@@ -41,6 +42,18 @@ SYMBOLS = [
     ("b2p_g1_sum", _int, [_int, _vp, _u64, _vp]),
     ("b2p_srs_stream", _vp, [_vp]),
     ("b2p_ntt", _int, [_int, _vp, _u64, _int]),
+    ("b2p_ntt_shard_create", _int, [_int, _u64, _u32, _u32, C.POINTER(_vp)]),
+    ("b2p_ntt_shard_free", None, [_vp]),
+    ("b2p_ntt_shard_local_size", _u64, [_vp]),
+    ("b2p_ntt_shard_chunk_size", _u64, [_vp]),
+    ("b2p_ntt_shard_forward_local", _int, [_vp, _vp, _u64, _int, _vp, _vp]),
+    ("b2p_ntt_shard_forward_combine", _int, [_vp, C.POINTER(_vp), _vp, _vp]),
+    ("b2p_ntt_shard_inverse_split", _int, [_vp, _vp, C.POINTER(_vp), _vp]),
+    ("b2p_ntt_shard_inverse_local", _int, [_vp, _vp, _int, _vp, _vp]),
+    ("b2p_peer_alloc", _int, [_u64, C.POINTER(_vp), _vp]),
+    ("b2p_peer_open", _int, [_vp, C.POINTER(_vp)]),
+    ("b2p_peer_close", _int, [_vp]),
+    ("b2p_peer_free", _int, [_vp]),
     ("b2p_circuit_load", _int, [_vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _u64,
                                 C.POINTER(_vp)]),
     ("b2p_circuit_vk_commitments", _int, [_vp, _vp]),

@@ -201,6 +201,100 @@ API int b2p_ntt(int curve, void* data, uint64_t n, int flags) {
     });
 }
 
+// ---- domain-sharded NTT (ntt_shard.cuh) and the peer memory its exchange runs over -------------------------
+API int b2p_ntt_shard_create(int curve, uint64_t n, uint32_t world, uint32_t rank, b2p_ntt_shard** out) {
+    return guarded([&] {
+        require(out, "null argument");
+        ops_for(curve);
+        const int dev = current_device();
+        NttShardBase* s = new_ntt_shard(curve, n, world, rank);
+        s->device = dev;
+        *out = reinterpret_cast<b2p_ntt_shard*>(s);
+    });
+}
+API void b2p_ntt_shard_free(b2p_ntt_shard* s) {
+    if (!s) return;
+    guarded([&] {
+        DeviceGuard g(reinterpret_cast<NttShardBase*>(s)->device);
+        delete reinterpret_cast<NttShardBase*>(s);
+    });
+}
+API uint64_t b2p_ntt_shard_local_size(const b2p_ntt_shard* s) {
+    return s ? reinterpret_cast<const NttShardBase*>(s)->local_size() : 0;
+}
+API uint64_t b2p_ntt_shard_chunk_size(const b2p_ntt_shard* s) {
+    return s ? reinterpret_cast<const NttShardBase*>(s)->chunk_size() : 0;
+}
+API int b2p_ntt_shard_forward_local(b2p_ntt_shard* s, const void* d_coeffs, uint64_t local_len, int flags, void* d_x,
+                                    void* stream) {
+    return guarded([&] {
+        require(s && d_x && (d_coeffs || local_len == 0), "null argument");
+        require((flags & ~B2P_NTT_COSET) == 0, "forward transform: only B2P_NTT_COSET is a valid flag");
+        DeviceGuard g(reinterpret_cast<NttShardBase*>(s)->device);
+        reinterpret_cast<NttShardBase*>(s)->forward_local(d_coeffs, local_len, flags, d_x, stream);
+    });
+}
+API int b2p_ntt_shard_forward_combine(b2p_ntt_shard* s, const void* const* d_chunks, void* d_out, void* stream) {
+    return guarded([&] {
+        require(s && d_chunks && d_out, "null argument");
+        DeviceGuard g(reinterpret_cast<NttShardBase*>(s)->device);
+        reinterpret_cast<NttShardBase*>(s)->forward_combine(d_chunks, d_out, stream);
+    });
+}
+API int b2p_ntt_shard_inverse_split(b2p_ntt_shard* s, const void* d_evals, void* const* d_chunks, void* stream) {
+    return guarded([&] {
+        require(s && d_chunks && d_evals, "null argument");
+        DeviceGuard g(reinterpret_cast<NttShardBase*>(s)->device);
+        reinterpret_cast<NttShardBase*>(s)->inverse_split(d_evals, d_chunks, stream);
+    });
+}
+API int b2p_ntt_shard_inverse_local(b2p_ntt_shard* s, void* d_x, int flags, void* d_out, void* stream) {
+    return guarded([&] {
+        require(s && d_x, "null argument");
+        require((flags & ~(B2P_NTT_COSET | B2P_NTT_INVERSE)) == 0, "unknown NTT flag");
+        DeviceGuard g(reinterpret_cast<NttShardBase*>(s)->device);
+        reinterpret_cast<NttShardBase*>(s)->inverse_local(d_x, flags, d_out, stream);
+    });
+}
+
+static void cuda_ok(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw Error(B2P_ERR_CUDA, std::string("CUDA error: ") + what + ": " + cudaGetErrorString(e));
+}
+static_assert(sizeof(cudaIpcMemHandle_t) == B2P_IPC_HANDLE_BYTES, "IPC handle size");
+API int b2p_peer_alloc(uint64_t bytes, void** d_ptr, void* ipc_handle) {
+    return guarded([&] {
+        require(d_ptr && bytes > 0, "null argument");
+        void* p = nullptr;
+        cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc");
+        if (ipc_handle) {
+            cudaIpcMemHandle_t h;
+            cudaError_t e = cudaIpcGetMemHandle(&h, p);
+            if (e != cudaSuccess) { cudaFree(p); cuda_ok(e, "cudaIpcGetMemHandle"); }
+            memcpy(ipc_handle, &h, sizeof h);
+        }
+        *d_ptr = p;
+    });
+}
+API int b2p_peer_open(const void* ipc_handle, void** d_ptr) {
+    return guarded([&] {
+        require(ipc_handle && d_ptr, "null argument");
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handle, sizeof h);
+        cuda_ok(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    });
+}
+API int b2p_peer_close(void* d_ptr) {
+    return guarded([&] {
+        require(d_ptr, "null argument");
+        cuda_ok(cudaIpcCloseMemHandle(d_ptr), "cudaIpcCloseMemHandle");
+    });
+}
+API int b2p_peer_free(void* d_ptr) {
+    return guarded([&] {
+        if (d_ptr) cuda_ok(cudaFree(d_ptr), "cudaFree");
+    });
+}
+
 API int b2p_circuit_load(b2p_srs* srs, uint64_t n, uint32_t nb_public, const void* ql, const void* qr, const void* qm,
                          const void* qo, const void* qk, const int64_t* perm, uint32_t k, const void* const* qcp,
                          const uint64_t* cidx, const void* vkb, uint64_t vkb_len, b2p_circuit** out) {

@@ -43,6 +43,20 @@ struct CircuitBase {
     virtual void set_profiling(bool on) = 0;
 };
 
+// One rank's part of an NTT whose domain is sharded over the GPUs of a box (ntt_shard.cuh).
+struct NttShardBase {
+    int curve = -1;
+    int device = -1;
+    virtual ~NttShardBase() {}
+    virtual uint64_t local_size() const = 0;    // n / world
+    virtual uint64_t chunk_size() const = 0;    // n / world^2
+    virtual void forward_local(const void* d_coeffs, uint64_t local_len, int flags, void* d_x, void* stream) const = 0;
+    virtual void forward_combine(const void* const* d_chunks, void* d_out, void* stream) const = 0;
+    virtual void inverse_split(const void* d_evals, void* const* d_chunks, void* stream) const = 0;
+    virtual void inverse_local(void* d_x, int flags, void* d_out, void* stream) const = 0;
+};
+NttShardBase* new_ntt_shard(int curve, uint64_t n, uint32_t world, uint32_t rank);   // inst_ntt.cu
+
 struct CurveOps {
     virtual ~CurveOps() {}
     virtual SrsBase* new_srs() const = 0;

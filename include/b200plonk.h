@@ -115,6 +115,50 @@ void* b2p_srs_stream(b2p_srs* srs);
 /* In-place, natural order in and out (gnark: FFT(DIF)+BitReverse / BitReverse+FFTInverse(DIT)). */
 int b2p_ntt(int curve, void* data, uint64_t n, int flags);
 
+/* ---- NTT with the domain sharded over the GPUs of one box ------------------------------------------
+ * The multi-GPU form of fft.Domain.FFT / FFTInverse (BASELINE config 5).  The reference
+ * is single-process and has no counterpart; single-GPU semantics are b2p_ntt's.  world = 1, 2, 4 or 8 ranks,
+ * one process per GPU, n >= world^2.  Distribution:
+ *   coefficients : cyclic      -- rank r holds a[j*world + r] at local index j            (n/world Fr)
+ *   evaluations  : bit-reversed order cut in world blocks -- rank r holds A(omega^brev(p)) for
+ *                  p in [r*n/world, (r+1)*n/world), i.e. b2p_ntt's DIF output before its bit reversal.
+ * A transform is two launches around ONE exchange of world chunks of n/world^2 Fr per rank:
+ *   forward :  forward_local (DIF passes on the shard -> d_x)   | exchange |  forward_combine (-> d_out)
+ *   inverse :  inverse_split (d_evals -> chunks)                | exchange |  inverse_local (DIT passes in place)
+ * d_chunks[r] is where the chunk exchanged with rank r lives: rank r's own buffer + my_rank*chunk when peer
+ * memory is mapped (b2p_peer_*: the combine / split kernel then IS the exchange, loads / stores over NVLink,
+ * and the caller only orders the ranks with a barrier), or slot r of the receive / send buffer of an
+ * all_to_all.  All pointers are device pointers; launches go to `stream` (a cudaStream_t, NULL = default). */
+typedef struct b2p_ntt_shard b2p_ntt_shard;
+int b2p_ntt_shard_create(int curve, uint64_t n, uint32_t world, uint32_t rank, b2p_ntt_shard** out);
+void b2p_ntt_shard_free(b2p_ntt_shard* s);
+uint64_t b2p_ntt_shard_local_size(const b2p_ntt_shard* s);   /* n / world   */
+uint64_t b2p_ntt_shard_chunk_size(const b2p_ntt_shard* s);   /* n / world^2 */
+/* d_x (n/world Fr) <- DIF(local_len <= n/world coefficients of this rank, zero padded); flags: 0 or
+ * B2P_NTT_COSET.  Chunk d of d_x (Fr [d*chunk, (d+1)*chunk)) is the part rank d combines. */
+int b2p_ntt_shard_forward_local(b2p_ntt_shard* s, const void* d_coeffs, uint64_t local_len, int flags, void* d_x,
+                                void* stream);
+/* d_out (n/world Fr) <- this rank's block of evaluations from the world chunks d_chunks[r] (chunk my_rank of
+ * rank r's d_x). */
+int b2p_ntt_shard_forward_combine(b2p_ntt_shard* s, const void* const* d_chunks, void* d_out, void* stream);
+/* d_chunks[r] (n/world^2 Fr each) <- the part of rank r's coefficients that this rank's block of
+ * evaluations d_evals determines; it belongs at Fr [my_rank*chunk, (my_rank+1)*chunk) of rank r's d_x. */
+int b2p_ntt_shard_inverse_split(b2p_ntt_shard* s, const void* d_evals, void* const* d_chunks, void* stream);
+/* d_x (n/world Fr, transformed in place): the exchanged chunks -> this rank's coefficients; the 1/n
+ * (B2P_NTT_COSET: g^-i / n) of the whole transform is applied here.  flags: B2P_NTT_INVERSE, optionally
+ * | B2P_NTT_COSET.  d_out: NULL or d_x leaves the result in d_x; otherwise it is also copied to d_out (d_x is
+ * exchange memory the next transform overwrites). */
+int b2p_ntt_shard_inverse_local(b2p_ntt_shard* s, void* d_x, int flags, void* d_out, void* stream);
+
+/* Device memory other processes on the box can map (CUDA IPC): the exchange buffers of the sharded NTT.
+ * b2p_peer_alloc returns the pointer and, when ipc_handle != NULL, the B2P_IPC_HANDLE_BYTES-byte handle to
+ * send to the other ranks; they map it with b2p_peer_open (not valid in the allocating process itself). */
+#define B2P_IPC_HANDLE_BYTES 64
+int b2p_peer_alloc(uint64_t bytes, void** d_ptr, void* ipc_handle);
+int b2p_peer_open(const void* ipc_handle, void** d_ptr);
+int b2p_peer_close(void* d_ptr);
+int b2p_peer_free(void* d_ptr);
+
 /* ---- circuit (replaces: the trace + domains inside gnark's plonk.ProvingKey) */
 
 /* ql..qk: Lagrange-form selector columns, n Fr each (pk trace; qk WITHOUT public inputs).
