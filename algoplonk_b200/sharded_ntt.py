@@ -175,20 +175,33 @@ class ShardedNtt:
         import torch.distributed as dist
         lib = _lib.load()
         ptr, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
-        _lib.check(lib.b2p_peer_alloc(2 * self.local_n * FR_BYTES, C.byref(ptr), handle))
-        self._own = ptr.value
+        failure = ""
+        if lib.b2p_peer_alloc(2 * self.local_n * FR_BYTES, C.byref(ptr), handle) != 0:
+            failure = f"rank {self.rank} cannot allocate exchange memory: " + lib.b2p_last_error().decode()
+            if self.world == 1:
+                raise RuntimeError(failure)
+        self._own = ptr.value or 0
         self._peer = [0] * self.world
         self._peer[self.rank] = self._own
         if self.world > 1:
             handles: list = [None] * self.world
             dist.all_gather_object(handles, handle.raw, group=self.group)
             for r, raw in enumerate(handles):
-                if r == self.rank:
+                if r == self.rank or failure:
                     continue
                 p = C.c_void_p()
-                _lib.check(lib.b2p_peer_open(C.create_string_buffer(raw, _lib.IPC_HANDLE_BYTES), C.byref(p)))
+                if lib.b2p_peer_open(C.create_string_buffer(raw, _lib.IPC_HANDLE_BYTES), C.byref(p)) != 0:
+                    failure = f"rank {self.rank} cannot map rank {r}'s exchange buffer: " + \
+                        lib.b2p_last_error().decode()
+                    break
                 self._peer[r] = p.value
                 self._opened.append(p.value)
+            # a rank that failed must not leave the others waiting in the barrier: agree on the outcome first
+            failures: list = [None] * self.world
+            dist.all_gather_object(failures, failure, group=self.group)
+            if any(failures):
+                self.free()
+                raise RuntimeError("; ".join(f for f in failures if f))
             self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._barrier()
 
@@ -264,8 +277,9 @@ class ShardedNtt:
 
     def free(self) -> None:
         lib = _lib.load()
-        if self.world > 1 and self._opened:
+        if self.world > 1 and self._flag is not None:
             self._barrier()               # nobody still reads a buffer that is about to be unmapped
+            self._flag = None
         for p in self._opened:
             lib.b2p_peer_close(p)
         self._opened = []

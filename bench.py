@@ -333,6 +333,10 @@ def run_b200(args):
     tot_ms, units = reduce_over_ranks(ms, args.steps, world, device)
     tot_ms_e2e, _ = reduce_over_ranks(ms_e2e, args.steps, world, device)
     tot_ms_single, _ = reduce_over_ranks(ms_single, args.steps, world, device)
+    # last, after every number of the line above is final: the domain-sharded NTT (both exchange modes)
+    ntt_sharded_line = None
+    if world in (2, 4, 8) and not args.no_ntt_sharded:
+        ntt_sharded_line = measure_sharded_ntt(args, rank, world, device)
     if rank != 0:
         return
     value = units / (tot_ms / 1e3)
@@ -373,6 +377,8 @@ def run_b200(args):
     }
     if sharded_line is not None:
         line["msm_sharded"] = sharded_line
+    if ntt_sharded_line is not None:
+        line["ntt_sharded"] = ntt_sharded_line
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(curve, args.log2)
     else:
@@ -437,6 +443,96 @@ def measure_sharded_msm(args, rank, world, device, iters: int = 10):
             "scalars": "uniform, resident in HBM"}
 
 
+def measure_sharded_ntt(args, rank, world, device, iters: int = 10):
+    """The largest transform of a proof -- the coset NTT of size 4n of the quotient step -- with its domain
+    sharded over the ranks (algoplonk_b200/sharded_ntt.py): cyclic coefficients in, block bit-reversed
+    evaluations out, and back.  Both exchange modes: "staged" (one NCCL all_to_all_single between the two
+    launches) and "p2p" (the combine / split kernel loads / stores the peers' memory over NVLink; the only
+    collective is a one-element all_reduce that orders the ranks).  CUDA events on torch's current stream (the
+    library launches there and NCCL orders itself on it), max over ranks.  Checked in the run: the inverse of
+    the forward is the input bit for bit, and both modes produce the same evaluations.
+    Every failure is reported in the line instead of raised: this leg must never cost the headline numbers."""
+    import torch
+    import torch.distributed as dist
+    from algoplonk_b200 import sharded_ntt as sn
+    curve, n = args.curve, 1 << (args.log2 + 2)
+    ln = n // world
+    res = {"elements": n, "elements_per_gpu": ln, "transform": "coset NTT / coset iNTT of size 4n",
+           "exchange_bytes_per_gpu": 32 * ln * (world - 1) // world}
+
+    def agree(ok: bool) -> bool:
+        t = torch.tensor([0 if ok else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(t)
+        return int(t.item()) == 0
+
+    gen = torch.Generator(device="cpu").manual_seed(0xB200 + rank)
+    coeffs = torch.randint(0, 1 << 60, (ln, 4), generator=gen, dtype=torch.int64).to(device)   # < r: canonical
+    evals = {}
+    for mode in ("staged", "p2p"):
+        nt, err = None, ""
+        try:
+            nt = sn.ShardedNtt(curve, n, rank=rank, world=world, mode=mode, device=device)
+        except Exception as e:  # noqa: BLE001 -- reported, see the docstring
+            err = f"{type(e).__name__}: {e}"
+        if not agree(nt is not None):
+            res[mode] = {"error": err or "setup failed on another rank"}
+            if nt is not None:
+                try:
+                    nt.free()
+                except Exception:  # noqa: BLE001
+                    pass
+            continue
+        try:
+            ev = nt.forward(coeffs, coset=True)
+            back = nt.inverse(ev, coset=True)
+            ok = bool(torch.equal(back, coeffs))
+            for _ in range(2):
+                nt.inverse(nt.forward(coeffs, coset=True), coset=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                nt.inverse(nt.forward(coeffs, coset=True), coset=True)
+            e1.record()
+            e1.synchronize()
+            dist.barrier()
+            ms, _ = reduce_over_ranks(e0.elapsed_time(e1) / (2 * iters), 0, world, device)
+            evals[mode] = ev
+            res[mode] = {"ms_per_transform": ms, "transforms_per_sec": 1e3 / ms, "round_trip_exact": ok,
+                         "exchange_GBps_per_gpu_if_exchange_only": res["exchange_bytes_per_gpu"] / (ms * 1e-3) / 1e9}
+        except Exception as e:  # noqa: BLE001
+            res[mode] = {"error": f"{type(e).__name__}: {e}"}
+        finally:
+            try:
+                nt.free()
+            except Exception:  # noqa: BLE001
+                pass
+    both = agree(len(evals) == 2)            # collectively, so that every rank takes the same branch
+    same = agree(both and bool(torch.equal(evals["staged"], evals["p2p"])))
+    if both:
+        res["modes_agree"] = same
+    # the same transform on one GPU (local passes only), for the speed-up figure
+    try:
+        one = sn.CudaSteps(curve, n, 1, 0)
+        full = torch.randint(0, 1 << 60, (n, 4), generator=gen, dtype=torch.int64).to(device)
+        x = torch.empty_like(full)
+        for _ in range(3):
+            one.forward_local(full, n, True, x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            one.forward_local(full, n, True, x)
+        e1.record()
+        e1.synchronize()
+        res["single_gpu_ms_per_transform"] = e0.elapsed_time(e1) / iters
+        one.free()
+    except Exception as e:  # noqa: BLE001
+        res["single_gpu_error"] = f"{type(e).__name__}: {e}"
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -446,6 +542,8 @@ def main():
     ap.add_argument("--log2", type=int, default=20, help="log2 of the constraint count (BASELINE: 20)")
     ap.add_argument("--curve", default="BN254", choices=["BN254", "BLS12_381"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ntt-sharded", action="store_true",
+                    help="skip the domain-sharded NTT leg of a multi-GPU run")
     ap.add_argument("--inflight", type=int, default=3,
                     help="proofs in flight per GPU (one proving key + stream each; SURVEY 8d timing protocol)")
     args = ap.parse_args()
