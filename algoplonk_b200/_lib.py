@@ -33,6 +33,7 @@ SYMBOLS = [
     ("b2p_srs_load_compressed", _int, [_int, _vp, _u64, _u64, C.POINTER(_vp)]),
     ("b2p_srs_generate_unsafe", _int, [_int, _vp, _u64, C.POINTER(_vp)]),
     ("b2p_srs_generate_unsafe_range", _int, [_int, _vp, _u64, _u64, C.POINTER(_vp)]),
+    ("b2p_srs_generate_unsafe_strided", _int, [_int, _vp, _u64, _u64, _u64, C.POINTER(_vp)]),
     ("b2p_srs_get_points", _int, [_vp, _u64, _u64, _vp]),
     ("b2p_srs_size", _u64, [_vp]),
     ("b2p_srs_msm_params", _int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_u64)]),

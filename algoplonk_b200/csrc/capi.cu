@@ -135,7 +135,7 @@ API int b2p_srs_generate_unsafe(int curve, const void* tau, uint64_t n_can, b2p_
         require(tau && out, "null argument");
         SrsBase* s = ops_for(curve)->new_srs();
         s->device = current_device();
-        try { s->generate_unsafe(tau, 0, n_can); } catch (...) { delete s; throw; }
+        try { s->generate_unsafe(tau, 0, 1, n_can); } catch (...) { delete s; throw; }
         *out = reinterpret_cast<b2p_srs*>(s);
     });
 }
@@ -145,7 +145,19 @@ API int b2p_srs_generate_unsafe_range(int curve, const void* tau, uint64_t first
         require(tau && out, "null argument");
         SrsBase* s = ops_for(curve)->new_srs();
         s->device = current_device();
-        try { s->generate_unsafe(tau, first, count); } catch (...) { delete s; throw; }
+        try { s->generate_unsafe(tau, first, 1, count); } catch (...) { delete s; throw; }
+        *out = reinterpret_cast<b2p_srs*>(s);
+    });
+}
+
+API int b2p_srs_generate_unsafe_strided(int curve, const void* tau, uint64_t first, uint64_t stride, uint64_t count,
+                                        b2p_srs** out) {
+    return guarded([&] {
+        require(tau && out, "null argument");
+        require(stride >= 1, "stride must be at least 1");
+        SrsBase* s = ops_for(curve)->new_srs();
+        s->device = current_device();
+        try { s->generate_unsafe(tau, first, stride, count); } catch (...) { delete s; throw; }
         *out = reinterpret_cast<b2p_srs*>(s);
     });
 }

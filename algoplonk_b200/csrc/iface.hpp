@@ -20,7 +20,7 @@ struct SrsBase {
     virtual ~SrsBase() {}
     virtual void load(const void* points, uint64_t n) = 0;
     virtual void load_compressed(const uint8_t* bytes, uint64_t n) = 0;
-    virtual void generate_unsafe(const void* tau, uint64_t first, uint64_t n) = 0;
+    virtual void generate_unsafe(const void* tau, uint64_t first, uint64_t stride, uint64_t n) = 0;
     virtual void get_points(uint64_t first, uint64_t count, void* out) const = 0;
     virtual uint64_t size() const = 0;
     virtual void msm_params(int* c, int* windows, uint64_t* buckets) const = 0;

@@ -123,13 +123,13 @@ inline typename C::Fr hash_fr(const uint8_t* point_bytes, size_t len) {
 
 // [tau^(first+j)] G1 for j < n  (unsafekzg.NewSRS; first > 0: one rank's shard of it)
 template <class C>
-__global__ void k_srs_from_tau(Affine<typename C::Fp>* __restrict__ out, uint64_t first, uint64_t n,
+__global__ void k_srs_from_tau(Affine<typename C::Fp>* __restrict__ out, uint64_t first, uint64_t stride, uint64_t n,
                                typename C::Fr tau, Affine<typename C::Fp> g) {
     using Fr = typename C::Fr;
     using Fp = typename C::Fp;
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    Fr s = tau.pow_u64(first + j).from_mont();
+    Fr s = tau.pow_u64(first + j * stride).from_mont();
     XYZZ<Fp> acc = XYZZ<Fp>::inf();
     for (int b = Fr::Params::BITS - 1; b >= 0; b--) {
         acc = acc.dbl();
@@ -321,14 +321,17 @@ struct Srs : SrsBase {
         fetch(0, 1, &a);
         memcpy(out, &a, sizeof a);
     }
-    void generate_unsafe(const void* tau_p, uint64_t first, uint64_t n) override {
+    // [tau^(first + j*stride)]_1, j < n: the whole SRS (first 0, stride 1), a block of it, or a cyclic shard
+    void generate_unsafe(const void* tau_p, uint64_t first, uint64_t stride, uint64_t n) override {
         Fr tau;
         memcpy(&tau, tau_p, sizeof tau);
         B2P_REQUIRE(n >= 1, "empty SRS");
         MsmPlan pl = msm_plan(n, Fr::Params::BITS, env_force_c());
         B2P_REQUIRE((uint64_t)pl.W * n < (1ull << 31), "SRS too large for 31-bit table indices");
         DevBuf<Aff> tbl((size_t)pl.W * n);
-        B2P_LAUNCH((k_srs_from_tau<C>), div_up(n, 128), 128, 0, stream, tbl.p, first, n, tau, CurveConsts<C>::generator());
+        B2P_REQUIRE(stride >= 1 && stride <= (1ull << 20) && first < (1ull << 40) && n < (1ull << 40), "SRS range too large");
+        B2P_LAUNCH((k_srs_from_tau<C>), div_up(n, 128), 128, 0, stream, tbl.p, first, stride, n, tau,
+                   CurveConsts<C>::generator());
         msm.load_device(std::move(tbl), n, pl, stream);
         finish_init();
     }

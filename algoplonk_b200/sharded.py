@@ -1,7 +1,9 @@
 """MSM sharded over the point set across the GPUs of one box (BASELINE config 3).
 
-An MSM is a sum, so rank g of G permanently owns the SRS slice [first_g, first_g + count_g) -- its own
-windowed table in its own HBM -- and, per MSM, the matching slice of the scalar vector.  Every rank runs
+An MSM is a sum, so rank g of G permanently owns a slice of the SRS -- the contiguous block [first_g, first_g +
+count_g) (layout "blocks"), or the indices g, g + G, ... (layout "cyclic": the coefficient distribution of the
+domain-sharded NTT, sharded_ntt.py, so a polynomial leaves a sharded inverse transform already placed for its
+commitment) -- as its own windowed table in its own HBM and, per MSM, the matching slice of the scalar vector.  Every rank runs
 the same kernels on its slice and produces ONE point; the G partial sums are exchanged with a single
 `all_gather` (64 B / 96 B per rank: NCCL over NVLink on the GPU box, gloo in the CPU tests) and added
 locally.  NCCL has no reduction over group elements, hence gather + local add instead of all_reduce.
@@ -26,6 +28,19 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(total, world)
     first = rank * base + min(rank, rem)
     return first, base + (1 if rank < rem else 0)
+
+
+def shard_indices(total: int, rank: int, world: int, layout: str = "blocks") -> range:
+    """Indices of [0, total) that `rank` owns: "blocks" = the contiguous range of shard_range, "cyclic" =
+    rank, rank + world, ... -- the coefficient distribution of the domain-sharded NTT (sharded_ntt.py)."""
+    if layout == "blocks":
+        first, count = shard_range(total, rank, world)
+        return range(first, first + count)
+    if layout == "cyclic":
+        if world < 1 or not 0 <= rank < world:
+            raise ValueError(f"bad rank {rank} of {world}")
+        return range(rank, total, world)
+    raise ValueError("layout must be 'blocks' or 'cyclic'")
 
 
 def g1_sum(curve: str, points_raw: bytes) -> bytes:
@@ -55,31 +70,40 @@ def all_gather_points(curve: str, local_point_raw: bytes, group=None, device=Non
 class ShardedSRS:
     """Rank-local shard of a canonical-basis SRS of `total` points."""
 
-    def __init__(self, curve: str, total: int, rank: int, world: int, handle: int, first: int, count: int):
+    def __init__(self, curve: str, total: int, rank: int, world: int, handle: int, first: int, count: int,
+                 layout: str = "blocks"):
         self.curve, self.total, self.rank, self.world = curve, total, rank, world
-        self.handle, self.first, self.count = handle, first, count
+        self.handle, self.first, self.count, self.layout = handle, first, count, layout
 
     @classmethod
-    def unsafe(cls, curve: str, total: int, rank: int, world: int, tau: int = api.TEST_TAU) -> "ShardedSRS":
-        """[tau^j]_1 for j in this rank's slice, generated on this rank's GPU."""
+    def unsafe(cls, curve: str, total: int, rank: int, world: int, tau: int = api.TEST_TAU,
+               layout: str = "blocks") -> "ShardedSRS":
+        """[tau^j]_1 for j in this rank's slice (shard_indices), generated on this rank's GPU."""
         _lib.init()
-        first, count = shard_range(total, rank, world)
+        idx = shard_indices(total, rank, world, layout)
         h = C.c_void_p()
         t = C.create_string_buffer(api.fr_to_mont_bytes(curve, [tau]))
-        _lib.check(_lib.load().b2p_srs_generate_unsafe_range(api.CURVE_ID[curve], t, first, count, C.byref(h)))
-        return cls(curve, total, rank, world, h.value, first, count)
+        if layout == "cyclic":
+            _lib.check(_lib.load().b2p_srs_generate_unsafe_strided(api.CURVE_ID[curve], t, idx.start, idx.step,
+                                                                   len(idx), C.byref(h)))
+        else:
+            _lib.check(_lib.load().b2p_srs_generate_unsafe_range(api.CURVE_ID[curve], t, idx.start, len(idx),
+                                                                 C.byref(h)))
+        return cls(curve, total, rank, world, h.value, idx.start, len(idx), layout)
 
     @classmethod
-    def from_points(cls, curve: str, points_raw: bytes, rank: int, world: int) -> "ShardedSRS":
+    def from_points(cls, curve: str, points_raw: bytes, rank: int, world: int, layout: str = "blocks") -> "ShardedSRS":
         """points_raw: the WHOLE SRS in G1Affine layout (e.g. pk.Kzg.G1); only this rank's slice is uploaded."""
         _lib.init()
         nb = 2 * api.FP_BYTES[curve]
         total = len(points_raw) // nb
-        first, count = shard_range(total, rank, world)
+        idx = shard_indices(total, rank, world, layout)
         h = C.c_void_p()
-        buf = C.create_string_buffer(points_raw[first * nb:(first + count) * nb], count * nb)
-        _lib.check(_lib.load().b2p_srs_load(api.CURVE_ID[curve], buf, count, None, 0, C.byref(h)))
-        return cls(curve, total, rank, world, h.value, first, count)
+        mine = b"".join(points_raw[i * nb:(i + 1) * nb] for i in idx) if layout == "cyclic" else \
+            points_raw[idx.start * nb:idx.stop * nb]
+        buf = C.create_string_buffer(mine, len(idx) * nb)
+        _lib.check(_lib.load().b2p_srs_load(api.CURVE_ID[curve], buf, len(idx), None, 0, C.byref(h)))
+        return cls(curve, total, rank, world, h.value, idx.start, len(idx), layout)
 
     def local_msm_raw(self, scalars_mont: bytes) -> bytes:
         """This rank's partial sum over its slice; `scalars_mont`: the slice's scalars (host, Montgomery)."""

@@ -288,3 +288,25 @@ class ShardedNtt:
             self._own = 0
         if hasattr(self.steps, "free"):
             self.steps.free()
+
+
+def commit_lagrange(nt: ShardedNtt, srs, evals, coset: bool = False, group=None) -> bytes:
+    """kzg.Commit of a polynomial given by its evaluations, both primitives sharded: the multi-GPU form of what
+    the prover does for every wire column (Lagrange values -> iNTT -> canonical-basis MSM).
+
+    evals : this rank's block of evaluations (ShardedNtt's evaluation distribution)
+    srs   : sharded.ShardedSRS with layout="cyclic" over the same world, >= n points in total
+    Returns the commitment (G1Affine memory layout), identical on every rank.  One exchange for the transform,
+    one all_gather of a point per rank for the sum; the coefficients never leave the GPU that holds them."""
+    import torch
+    from . import sharded
+    if srs.layout != "cyclic" or srs.world != nt.world or srs.rank != nt.rank or srs.curve != nt.curve:
+        raise ValueError("the SRS must be this rank's cyclic shard over the same world and curve")
+    if srs.count < nt.local_n:
+        raise ValueError("SRS shard smaller than the local domain")
+    stream = torch.cuda.ExternalStream(_lib.load().b2p_srs_stream(srs.handle), device=nt.device)
+    with torch.cuda.stream(stream):          # transform and MSM on the one stream the MSM launches on
+        coeffs = nt.inverse(evals, coset=coset)
+        local = srs.local_msm_dev_raw(coeffs.data_ptr(), nt.local_n)
+        return sharded.g1_sum(nt.curve, sharded.all_gather_points(nt.curve, local, group, nt.device)) \
+            if nt.world > 1 else local

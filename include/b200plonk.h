@@ -89,6 +89,12 @@ int b2p_srs_generate_unsafe(int curve, const void* tau, uint64_t n_can, b2p_srs*
  * split across the GPUs of a box). */
 int b2p_srs_generate_unsafe_range(int curve, const void* tau, uint64_t first, uint64_t count, b2p_srs** out);
 
+/* A cyclic shard: [tau^(first + j*stride)]_1 for j < count.  With first = rank and stride = world this is the
+ * SRS shard that matches the cyclic coefficient distribution of the domain-sharded NTT (b2p_ntt_shard_*), so a
+ * polynomial that leaves a sharded inverse transform is committed with no redistribution. */
+int b2p_srs_generate_unsafe_strided(int curve, const void* tau, uint64_t first, uint64_t stride, uint64_t count,
+                                    b2p_srs** out);
+
 /* Copies canonical points [first, first+count) back to the host (G1Affine layout). */
 int b2p_srs_get_points(const b2p_srs* srs, uint64_t first, uint64_t count, void* out);
 uint64_t b2p_srs_size(const b2p_srs* srs);

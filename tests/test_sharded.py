@@ -31,6 +31,21 @@ def test_shard_range_partitions_exactly():
         sharded.shard_range(8, 2, 2)
 
 
+def test_shard_indices_both_layouts():
+    for total in (0, 1, 7, 64, 1003):
+        for world in (1, 2, 4, 8):
+            for layout in ("blocks", "cyclic"):
+                idx = [sharded.shard_indices(total, r, world, layout) for r in range(world)]
+                assert sorted(i for rng_ in idx for i in rng_) == list(range(total))
+                assert max(len(r) for r in idx) - min(len(r) for r in idx) <= 1
+            # cyclic = the coefficient distribution of the domain-sharded NTT
+            assert list(sharded.shard_indices(total, world - 1, world, "cyclic")) == list(range(world - 1, total, world))
+    with pytest.raises(ValueError):
+        sharded.shard_indices(8, 0, 2, "striped")
+    with pytest.raises(ValueError):
+        sharded.shard_indices(8, 2, 2, "cyclic")
+
+
 @pytest.mark.parametrize("curve", CURVES)
 def test_g1_sum_matches_oracle(curve):
     cv = po.CURVES[curve]
@@ -61,10 +76,12 @@ tau = rng.randrange(cv.r)
 srs = [po.g1_mul(cv, cv.g1, pow(tau, j, cv.r)) for j in range(n)]
 scalars = [rng.randrange(cv.r) for _ in range(n)]
 first, count = sharded.shard_range(n, rank, world)
+layout = {layout!r}
+mine = sharded.shard_indices(n, rank, world, layout)
 # this rank's partial sum (oracle here; the CUDA MSM in the GPU test) ...
 local = None
-for P, s in zip(srs[first:first + count], scalars[first:first + count]):
-    local = po.g1_add(cv, local, po.g1_mul(cv, P, s))
+for i in mine:
+    local = po.g1_add(cv, local, po.g1_mul(cv, srs[i], scalars[i]))
 # ... then the product's collective + local add
 gathered = sharded.all_gather_points(curve, api.points_to_mont_bytes(curve, [local]))
 assert len(gathered) == world * 2 * api.FP_BYTES[curve]
@@ -80,10 +97,11 @@ dist.destroy_process_group()
 """
 
 
-@pytest.mark.parametrize("curve,port", [("BN254", 29551), ("BLS12_381", 29552)])
-def test_sharded_msm_collective_gloo_world2(tmp_path, curve, port):
+@pytest.mark.parametrize("curve,port,layout", [("BN254", 29551, "blocks"), ("BLS12_381", 29552, "blocks"),
+                                               ("BN254", 29553, "cyclic")])
+def test_sharded_msm_collective_gloo_world2(tmp_path, curve, port, layout):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, curve=curve))
+    script.write_text(WORKER.format(root=ROOT, curve=curve, layout=layout))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
@@ -121,4 +139,32 @@ def test_sharded_msm_on_one_gpu_equals_whole_msm(gpu, curve):
     for P, s in zip(srs_pts[:50], scalars[:50]):
         acc = po.g1_add(cv, acc, po.g1_mul(cv, P, s))
     assert whole.msm(scalars[:50]) == acc
+    whole.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("curve", CURVES)
+def test_cyclic_shards_on_one_gpu_equal_whole_msm(gpu, curve):
+    """layout="cyclic" (the coefficient distribution of the domain-sharded NTT): shards generated on the device
+    with b2p_srs_generate_unsafe_strided and shards cut from host points hold the whole SRS's points r, r+G, ...
+    and their partial sums add up to the whole MSM."""
+    n, world = 1003, 4
+    cv = po.CURVES[curve]
+    rng = random.Random(9)
+    scalars = [rng.randrange(cv.r) for _ in range(n)]
+    whole = api.SRS.unsafe(curve, n)
+    want = whole.msm(scalars)
+    all_pts = api.points_to_mont_bytes(curve, whole.points(0, n))
+    for make in ("unsafe", "from_points"):
+        parts = []
+        for r in range(world):
+            sh = sharded.ShardedSRS.unsafe(curve, n, r, world, layout="cyclic") if make == "unsafe" else \
+                sharded.ShardedSRS.from_points(curve, all_pts, r, world, layout="cyclic")
+            idx = sharded.shard_indices(n, r, world, "cyclic")
+            assert (sh.first, sh.count, sh.layout) == (r, len(idx), "cyclic")
+            assert api.SRS(curve, sh.handle).points(0, 3) == [whole.points(i, 1)[0] for i in idx[:3]]
+            assert api.SRS(curve, sh.handle).points(sh.count - 1, 1) == whole.points(idx[-1], 1)
+            parts.append(sh.local_msm_raw(api.fr_to_mont_bytes(curve, [scalars[i] for i in idx])))
+            sh.free()
+        assert api.points_from_mont_bytes(curve, sharded.g1_sum(curve, b"".join(parts)))[0] == want
     whole.free()
