@@ -305,6 +305,7 @@ def commit_lagrange(nt: ShardedNtt, srs, evals, coset: bool = False, group=None)
     if srs.count < nt.local_n:
         raise ValueError("SRS shard smaller than the local domain")
     stream = torch.cuda.ExternalStream(_lib.load().b2p_srs_stream(srs.handle), device=nt.device)
+    stream.wait_stream(torch.cuda.current_stream())     # whatever produced `evals` comes first
     with torch.cuda.stream(stream):          # transform and MSM on the one stream the MSM launches on
         coeffs = nt.inverse(evals, coset=coset)
         local = srs.local_msm_dev_raw(coeffs.data_ptr(), nt.local_n)

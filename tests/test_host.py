@@ -38,6 +38,24 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.b2p_version()
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (cgo parses it with a C compiler) and a C caller
+    must link against the library with nothing but the header."""
+    hdr = os.path.join(ROOT, "include", "b200plonk.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                   check=True)
+    src = tmp_path / "caller.c"
+    src.write_text('#include "b200plonk.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%s %d\\n", b2p_version(), (int)b2p_proof_marshal_size(B2P_BN254, 0)); '
+                   'return b2p_ntt(7, (void*)0, 1, 0) == B2P_ERR_ARG ? 0 : 1; }\n')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libb200plonk.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "sm_100a" in out.stdout and out.stdout.split()[-1] == "768"
+
+
 def test_sizes():
     lib = _lib.load()
     for k in (0, 1, 2):
