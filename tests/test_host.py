@@ -56,6 +56,49 @@ def test_header_is_plain_c(tmp_path):
     assert out.returncode == 0 and "sm_100a" in out.stdout and out.stdout.split()[-1] == "768"
 
 
+def _call_arities(src: str, prefix: str):
+    """(name, number of top-level arguments) of every `prefix name(...)` call in a source text."""
+    out = []
+    for m in re.finditer(re.escape(prefix) + r"(b2p_[a-z0-9_]+)\s*\(", src):
+        depth, args, i, seen = 1, 0, m.end(), False
+        while depth:
+            ch = src[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                args += 1
+            if depth and not ch.isspace():
+                seen = True
+            i += 1
+        if src[m.end():i - 1].strip() == "void":
+            seen = False
+        out.append((m.group(1), args + 1 if seen else 0))
+    return out
+
+
+def test_go_shim_calls_match_the_header():
+    """The cgo shim cannot be compiled here (no Go toolchain): at least every C.b2p_* call in go/gpuplonk must
+    name a function the header declares, with the declared number of arguments."""
+    with open(os.path.join(ROOT, "include", "b200plonk.h")) as f:
+        header = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = {}
+    for name, n in _call_arities(header, ""):
+        declared[name] = n
+    assert declared["b2p_prove"] == 8 and declared["b2p_last_error"] == 0 and declared["b2p_circuit_load"] == 15
+    godir = os.path.join(ROOT, "go", "gpuplonk")
+    calls = []
+    for fn in sorted(os.listdir(godir)):
+        if fn.endswith(".go"):
+            with open(os.path.join(godir, fn)) as f:
+                calls += [(fn, name, n) for name, n in _call_arities(f.read(), "C.")]
+    assert len(calls) >= 15
+    for fn, name, n in calls:
+        assert name in declared, f"{fn}: C.{name} is not declared in b200plonk.h"
+        assert declared[name] == n, f"{fn}: C.{name} called with {n} arguments, header declares {declared[name]}"
+
+
 def test_sizes():
     lib = _lib.load()
     for k in (0, 1, 2):
