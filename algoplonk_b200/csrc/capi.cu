@@ -4,6 +4,7 @@
 // per-curve instantiations (inst_*.cu).
 #include <atomic>
 #include <cuda_runtime.h>
+#include <mutex>
 #include <cstring>
 #include <new>
 #include <string>
@@ -187,6 +188,7 @@ API void b2p_srs_free(b2p_srs* srs) {
 API int b2p_msm_g1(b2p_srs* srs, int basis, const void* scalars, uint64_t n, void* out_affine) {
     return guarded([&] {
         require(srs && out_affine && (scalars || n == 0), "null argument");
+        std::lock_guard<std::mutex> lk(reinterpret_cast<SrsBase*>(srs)->mu);
         DeviceGuard g(reinterpret_cast<SrsBase*>(srs)->device);
         reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, scalars, n, out_affine, false);
     });
@@ -194,6 +196,7 @@ API int b2p_msm_g1(b2p_srs* srs, int basis, const void* scalars, uint64_t n, voi
 API int b2p_msm_g1_dev(b2p_srs* srs, int basis, const void* d_scalars, uint64_t n, void* out_affine) {
     return guarded([&] {
         require(srs && out_affine && (d_scalars || n == 0), "null argument");
+        std::lock_guard<std::mutex> lk(reinterpret_cast<SrsBase*>(srs)->mu);
         DeviceGuard g(reinterpret_cast<SrsBase*>(srs)->device);
         reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, d_scalars, n, out_affine, true);
     });
@@ -314,9 +317,11 @@ API int b2p_circuit_load(b2p_srs* srs, uint64_t n, uint32_t nb_public, const voi
         require(srs && ql && qr && qm && qo && qk && perm && out, "null argument");
         require(k == 0 || (qcp && cidx), "BSB22 columns missing");
         SrsBase* s = reinterpret_cast<SrsBase*>(srs);
+        std::lock_guard<std::mutex> lk(s->mu);
         DeviceGuard g(s->device);
         CircuitBase* c = ops_for(s->curve)->new_circuit();
         c->device = s->device;
+        c->owner = s;
         try { c->load(s, n, nb_public, ql, qr, qm, qo, qk, perm, k, qcp, cidx, vkb, vkb_len); }
         catch (...) { delete c; throw; }
         *out = reinterpret_cast<b2p_circuit*>(c);
@@ -325,6 +330,7 @@ API int b2p_circuit_load(b2p_srs* srs, uint64_t n, uint32_t nb_public, const voi
 API int b2p_circuit_vk_commitments(b2p_circuit* c, void* out_points) {
     return guarded([&] {
         require(c && out_points, "null argument");
+        std::lock_guard<std::mutex> lk(reinterpret_cast<CircuitBase*>(c)->owner->mu);
         DeviceGuard g(reinterpret_cast<CircuitBase*>(c)->device);
         reinterpret_cast<CircuitBase*>(c)->vk_commitments(out_points);
     });
@@ -346,6 +352,7 @@ API int b2p_prove(b2p_circuit* c, const void* L, const void* R, const void* O, c
                   const void* bsb22, const void* blinding, void* out_raw) {
     return guarded([&] {
         require(c && L && R && O && blinding && out_raw, "null argument");
+        std::lock_guard<std::mutex> lk(reinterpret_cast<CircuitBase*>(c)->owner->mu);
         DeviceGuard g(reinterpret_cast<CircuitBase*>(c)->device);
         reinterpret_cast<CircuitBase*>(c)->prove(L, R, O, pi2, bsb22, blinding, out_raw, false);
     });
@@ -354,6 +361,7 @@ API int b2p_prove_dev(b2p_circuit* c, const void* dL, const void* dR, const void
                       const void* bsb22, const void* blinding, void* out_raw) {
     return guarded([&] {
         require(c && dL && dR && dO && blinding && out_raw, "null argument");
+        std::lock_guard<std::mutex> lk(reinterpret_cast<CircuitBase*>(c)->owner->mu);
         DeviceGuard g(reinterpret_cast<CircuitBase*>(c)->device);
         reinterpret_cast<CircuitBase*>(c)->prove(dL, dR, dO, d_pi2, bsb22, blinding, out_raw, true);
     });

@@ -4,6 +4,7 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 
@@ -17,6 +18,10 @@ struct Error : std::runtime_error {
 struct SrsBase {
     int curve = -1;
     int device = -1;      // CUDA device the handle lives on; every entry point switches to it
+    // One stream, one MSM scratch area and one prover workspace per proving key: calls that use them are
+    // serialised here ("re-entrant across handles, serialise calls on the same handle"); a circuit
+    // handle locks the SRS handle it was loaded on.
+    std::mutex mu;
     virtual ~SrsBase() {}
     virtual void load(const void* points, uint64_t n) = 0;
     virtual void load_compressed(const uint8_t* bytes, uint64_t n) = 0;
@@ -31,6 +36,7 @@ struct SrsBase {
 struct CircuitBase {
     int curve = -1;
     int device = -1;
+    SrsBase* owner = nullptr;   // the SRS handle this circuit was loaded on (its lock serialises the calls)
     double stats[16] = {0};
     virtual ~CircuitBase() {}
     virtual void load(SrsBase* srs, uint64_t n, uint32_t nb_public, const void* ql, const void* qr, const void* qm,

@@ -18,10 +18,12 @@
  * All functions return 0 on success and a negative code on failure; the message
  * is available from b2p_last_error() (thread local).  Nothing aborts, nothing
  * throws across the boundary, no caller pointer is retained after a call returns
- * (cgo rule).  Handles may be used from any thread, one call at a time per handle; a handle is bound to the
- * CUDA device that was current when it was created and every entry point switches to that device for the
- * duration of the call (goroutines migrate between OS threads).  The library is re-entrant across handles:
- * several proofs can be in flight on one GPU, one proving key (SRS + circuit handle) each.
+ * (cgo rule).  Handles may be used from any thread; a handle is bound to the CUDA device that was current when
+ * it was created and every entry point switches to that device for the duration of the call (goroutines migrate
+ * between OS threads).  A proving key (an SRS handle and the circuit handles loaded on it) owns one stream and one
+ * workspace: concurrent b2p_prove / b2p_msm_g1 / b2p_circuit_load calls on the same key are serialised by the
+ * library (a lock per SRS handle), calls on different keys run concurrently -- several proofs can be in flight on
+ * one GPU, one proving key each.  Freeing a handle while another thread uses it is the caller's error.
  */
 #ifndef B200PLONK_H
 #define B200PLONK_H
