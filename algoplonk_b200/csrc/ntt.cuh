@@ -382,25 +382,25 @@ struct NttDomain {
     void launch_pass(const NttPassArgs<Fr>& a, cudaStream_t st) const {
         if (a.nst >= NTT_R8_MIN_STAGES && !force_radix2()) {
             auto kern = k_ntt_pass8<Fr, DIF, FUSE>;
-            static bool attr_set[64] = {};     // the attribute is per device
+            static std::atomic<bool> attr_set[64];     // the attribute is per device; any host thread may launch
             int dev = 0;
             B2P_CUDA(cudaGetDevice(&dev));
-            if (!attr_set[dev & 63]) {
+            if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
                 B2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)(sizeof(Fr) << NTT_MAX_STAGES)));
-                attr_set[dev & 63] = true;
+                attr_set[dev & 63].store(true, std::memory_order_release);
             }
             B2P_LAUNCH(kern, (unsigned)(n >> a.nst), 1 << (a.nst - 3), sizeof(Fr) << a.nst, st, a);
             return;
         }
         auto kern = k_ntt_pass<Fr, DIF, FUSE>;
-        static bool attr_set[64] = {};
+        static std::atomic<bool> attr_set[64];
         int dev = 0;
         B2P_CUDA(cudaGetDevice(&dev));
-        if (!attr_set[dev & 63]) {
+        if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
             B2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(sizeof(Fr) << NTT_MAX_STAGES)));
-            attr_set[dev & 63] = true;
+            attr_set[dev & 63].store(true, std::memory_order_release);
         }
         B2P_LAUNCH(kern, (unsigned)(n >> a.nst), 1 << (a.nst - 1), sizeof(Fr) << a.nst, st, a);
     }
