@@ -258,3 +258,33 @@ def squaring_chain(curve: str, log2_rows: int, x0: int = 2):
     constraints.append((one, neg1, 0, 0, 0, 0, 1 + m, 0))          # y == x_m
     cs = SparseR1CS(curve, 1, m + 2, constraints)
     return cs, values
+
+
+def random_dense_circuit(curve: str, log2_rows: int, seed: int = 0, nb_public: int = 3):
+    """SURVEY 8d "random-dense" shape: every selector column carries full-width random field elements and the
+    wires are reused at random, so the permutation has long, irregular cycles -- the squaring chain only ever
+    exercises qm = 1, qo = -1.  Gate i:  ql*a + qr*b + qm*a*b + qo*c + qk = 0  with a, b drawn from the
+    variables seen so far and c a fresh variable solved from the gate (one gate in eight reuses an existing
+    variable as c and solves qk instead).  nb_public + nb_constraints == 2^log2_rows exactly.
+    Returns (SparseR1CS, values)."""
+    import random
+    r = R_MOD[curve]
+    rng = random.Random(seed)
+    rows = 1 << log2_rows
+    assert rows > nb_public >= 1
+    values = [rng.randrange(r) for _ in range(nb_public)]
+    values.append(rng.randrange(r))                      # one secret input
+    constraints = []
+    for i in range(rows - nb_public):
+        a, b = rng.randrange(len(values)), rng.randrange(len(values))
+        ql, qr, qm = (0 if rng.random() < 0.1 else rng.randrange(r) for _ in range(3))
+        lin = (ql * values[a] + qr * values[b] + qm * values[a] * values[b]) % r
+        if i % 8 == 7:
+            c, qo = rng.randrange(len(values)), rng.randrange(r)
+            qk = (-(lin + qo * values[c])) % r
+        else:
+            qo, qk = rng.randrange(1, r), (0 if rng.random() < 0.5 else rng.randrange(r))
+            values.append((-(lin + qk)) * pow(qo, -1, r) % r)
+            c = len(values) - 1
+        constraints.append((ql, qr, qm, qo, qk, a, b, c))
+    return SparseR1CS(curve, nb_public, len(values), constraints), values

@@ -312,3 +312,46 @@ def test_cpp_oracle_mid_size_accepts():
     blob = circ.prove(L, R, O, H.scalars_uniform(cv.r, 9, 77))
     vk = H.vk_from_points(tc, circ.vk_points(), cv.g1, tau=H.TAU)
     assert po.verify_proof(vk, blob, po.marshal_public_inputs(L[: tc.nb_public]))
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("logn,seed", [(3, 1), (5, 2), (6, 3)])
+def test_random_dense_circuits_both_oracles_agree(curve, logn, seed):
+    """Random-dense circuits (full-width random values in EVERY selector column, irregular copy
+    cycles, three public inputs): the big-integer prover and the C++ prover produce the same bytes, and the
+    restated reference verifier accepts them and rejects a wrong public input."""
+    from algoplonk_b200 import frontend as fe
+    cv = po.CURVES[curve]
+    cs, values = fe.random_dense_circuit(curve, logn, seed=seed)
+    tc = fe.build_trace(cs)
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    assert fe.check_gates(tc, L, R, O)
+    blinding = H.scalars_uniform(cv.r, 9, seed)
+    srs = po.srs_from_tau(cv, H.TAU, tc.n + 3)
+    tr = H.oracle_trace(tc)
+    vk = po.setup(tr, srs, tau=H.TAU)
+    blob = po.marshal_proof(cv, po.prove(tr, vk, srs, L, R, O, blinding, [], []))
+    circ = co.Circuit(cv.cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (),
+                      co.points_le(cv.cid, srs))
+    assert circ.prove(L, R, O, blinding) == blob
+    circ.free()
+    pub = po.marshal_public_inputs(L[: tc.nb_public])
+    assert po.verify_proof(vk, blob, pub)
+    bad = bytearray(pub)
+    bad[31] ^= 1
+    assert not po.verify_proof(vk, blob, bytes(bad))
+
+
+def test_random_dense_circuit_cpp_oracle_mid_size():
+    """2^11 rows, past the single-tile sizes: the C++ prover's proof is accepted by the restated verifier."""
+    from algoplonk_b200 import frontend as fe
+    cv = po.BLS12_381
+    cs, values = fe.random_dense_circuit("BLS12_381", 11, seed=4)
+    tc = fe.build_trace(cs)
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    srs_le = co.srs_from_tau_bytes(cv.cid, H.TAU, tc.n + 3)
+    circ = co.Circuit(cv.cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
+    blob = circ.prove(L, R, O, H.scalars_uniform(cv.r, 9, 5))
+    vk = H.vk_from_points(tc, circ.vk_points(), cv.g1, tau=H.TAU)
+    circ.free()
+    assert po.verify_proof(vk, blob, po.marshal_public_inputs(L[: tc.nb_public]))
