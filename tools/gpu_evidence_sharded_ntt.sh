@@ -11,7 +11,7 @@ mkdir -p gpurun_out
 case "${1:-one}" in
   one)
     # the four GPU tests added after round 1's last GPU call, then the whole sharded files
-    timeout 300 python -m pytest tests/test_sharded.py tests/test_sharded_ntt.py -m gpu -x -q 2>&1 | tail -5
+    timeout 400 python -m pytest tests/test_sharded.py tests/test_sharded_ntt.py tests/test_gpu_prove.py -m gpu -x -q 2>&1 | tail -5
     # launch list + full capture of one rank's four steps (world 8, 2^21: BASELINE config 5's per-rank work)
     timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
         --log-file gpurun_out/launches_ntt_shard.csv python tools/ntt_shard_time.py --logn 21 --worlds 8 \
