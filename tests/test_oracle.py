@@ -355,3 +355,34 @@ def test_random_dense_circuit_cpp_oracle_mid_size():
     vk = H.vk_from_points(tc, circ.vk_points(), cv.g1, tau=H.TAU)
     circ.free()
     assert po.verify_proof(vk, blob, po.marshal_public_inputs(L[: tc.nb_public]))
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_no_public_inputs_and_zero_blinding(curve):
+    """Edge of the input space: a circuit without public inputs (empty public-input bytes, PI(zeta) = 0) proved
+    with all-zero blinding scalars: both oracles agree, the restated verifier accepts, and a flipped byte of
+    a claimed value is rejected."""
+    from algoplonk_b200 import frontend as fe
+    cv = po.CURVES[curve]
+    B = fe.Builder(curve)
+    x = B.secret(3)
+    z = B.add(B.mul(x, x), x)
+    B.assert_is_equal(z, B.secret(12))
+    B.assert_is_different_from_zero(z)
+    cs = B.build()
+    tc = fe.build_trace(cs)
+    assert tc.nb_public == 0 and tc.n == 4
+    L, R, O = fe.solve_lro(cs, B.values, tc.n)
+    assert fe.check_gates(tc, L, R, O)
+    srs = po.srs_from_tau(cv, H.TAU, tc.n + 3)
+    tr = H.oracle_trace(tc)
+    vk = po.setup(tr, srs, tau=H.TAU)
+    for blinding in ([0] * 9, list(range(1, 10))):
+        blob = po.marshal_proof(cv, po.prove(tr, vk, srs, L, R, O, blinding, [], []))
+        circ = co.Circuit(cv.cid, tc.n, 0, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), co.points_le(cv.cid, srs))
+        assert circ.prove(L, R, O, blinding) == blob
+        circ.free()
+        assert po.verify_proof(vk, blob, b"")
+        bad = bytearray(blob)
+        bad[6 * 2 * cv.fp_bytes + 5] ^= 1          # inside l(zeta), the first claimed value (Appendix B)
+        assert not po.verify_proof(vk, bytes(bad), b"")
