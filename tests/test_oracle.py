@@ -360,8 +360,9 @@ def test_random_dense_circuit_cpp_oracle_mid_size():
 @pytest.mark.parametrize("curve", CURVES)
 def test_no_public_inputs_and_zero_blinding(curve):
     """Edge of the input space: a circuit without public inputs (empty public-input bytes, PI(zeta) = 0) proved
-    with all-zero blinding scalars: both oracles agree, the restated verifier accepts, and a flipped byte of
-    a claimed value is rejected."""
+    with all-zero blinding scalars (which puts a proof commitment at infinity): both oracles agree, the restated
+    verifier accepts (except where the reference BLS12-381 template itself cannot, see below) and a flipped
+    byte of a claimed value is rejected."""
     from algoplonk_b200 import frontend as fe
     cv = po.CURVES[curve]
     B = fe.Builder(curve)
@@ -382,7 +383,13 @@ def test_no_public_inputs_and_zero_blinding(curve):
         circ = co.Circuit(cv.cid, tc.n, 0, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), co.points_le(cv.cid, srs))
         assert circ.prove(L, R, O, blinding) == blob
         circ.free()
-        assert po.verify_proof(vk, blob, b"")
+        # Without blinding the quotient is short here and one of the three H commitments is the point at infinity.  The
+        # BLS12-381 template hashes an all-zero point with flag 0x80 (templateLogicSigBLS12_381.go:401-407) where
+        # gnark's own transcript uses 0x40 (verifier/verifier.go:95-99): the generated AVM verifier then derives
+        # other challenges than the prover and rejects -- a quirk of the reference that blinded proofs never
+        # meet (footnote), restated faithfully.  BN254 has no flag byte and accepts.
+        infinity_in_proof = blinding[0] == 0
+        assert po.verify_proof(vk, blob, b"") == (not (infinity_in_proof and curve == "BLS12_381"))
         bad = bytearray(blob)
         bad[6 * 2 * cv.fp_bytes + 5] ^= 1          # inside l(zeta), the first claimed value (Appendix B)
         assert not po.verify_proof(vk, bytes(bad), b"")
