@@ -82,27 +82,6 @@ def test_mid_size_byte_identical_to_cpp_oracle(gpu, curve, logn):
     cc.free()
 
 
-@pytest.mark.parametrize("curve,logn", [("BN254", 10), ("BN254", 13), ("BLS12_381", 12)])
-def test_random_dense_circuit_byte_identical_to_cpp_oracle(gpu, curve, logn):
-    """SURVEY 8d "random-dense" shape: full-width random values in every selector column (the squaring chain
-    only has qm = 1, qo = -1), irregular copy cycles, three public inputs, past the single-tile NTT sizes."""
-    cv = po.CURVES[curve]
-    cs, values = fe.random_dense_circuit(curve, logn, seed=logn)
-    cc = api.Compile(cs, curve, SETUP[curve])
-    tc = cc.trace
-    L, R, O = fe.solve_lro(cs, values, tc.n)
-    blinding = H.scalars_uniform(cv.r, 9, logn)
-    blob = api.MarshalProof(cc.Prove(L, R, O, blinding))
-    srs_le = co.srs_from_tau_bytes(cv.cid, api.TEST_TAU, tc.n + 3)
-    circ = co.Circuit(cv.cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
-    assert cc.vk_commitments() == circ.vk_points()
-    assert blob == circ.prove(L, R, O, blinding)
-    vk = H.vk_from_points(tc, cc.vk_commitments(), cv.g1, tau=api.TEST_TAU)
-    assert po.verify_proof(vk, blob, api.MarshalPublicInputs(curve, L[: tc.nb_public]))
-    circ.free()
-    cc.free()
-
-
 def _many_public_circuit(curve, nb_public):
     """sum of nb_public public inputs == a secret, padded with a few multiplications."""
     B = fe.Builder(curve)

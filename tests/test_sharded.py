@@ -142,29 +142,3 @@ def test_sharded_msm_on_one_gpu_equals_whole_msm(gpu, curve):
     whole.free()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("curve", CURVES)
-def test_cyclic_shards_on_one_gpu_equal_whole_msm(gpu, curve):
-    """layout="cyclic" (the coefficient distribution of the domain-sharded NTT): shards generated on the device
-    with b2p_srs_generate_unsafe_strided and shards cut from host points hold the whole SRS's points r, r+G, ...
-    and their partial sums add up to the whole MSM."""
-    n, world = 1003, 4
-    cv = po.CURVES[curve]
-    rng = random.Random(9)
-    scalars = [rng.randrange(cv.r) for _ in range(n)]
-    whole = api.SRS.unsafe(curve, n)
-    want = whole.msm(scalars)
-    all_pts = api.points_to_mont_bytes(curve, whole.points(0, n))
-    for make in ("unsafe", "from_points"):
-        parts = []
-        for r in range(world):
-            sh = sharded.ShardedSRS.unsafe(curve, n, r, world, layout="cyclic") if make == "unsafe" else \
-                sharded.ShardedSRS.from_points(curve, all_pts, r, world, layout="cyclic")
-            idx = sharded.shard_indices(n, r, world, "cyclic")
-            assert (sh.first, sh.count, sh.layout) == (r, len(idx), "cyclic")
-            assert api.SRS(curve, sh.handle).points(0, 3) == [whole.points(i, 1)[0] for i in idx[:3]]
-            assert api.SRS(curve, sh.handle).points(sh.count - 1, 1) == whole.points(idx[-1], 1)
-            parts.append(sh.local_msm_raw(api.fr_to_mont_bytes(curve, [scalars[i] for i in idx])))
-            sh.free()
-        assert api.points_from_mont_bytes(curve, sharded.g1_sum(curve, b"".join(parts)))[0] == want
-    whole.free()

@@ -346,34 +346,6 @@ def test_gpu_class_world_one(gpu, mode):
         nt.free()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("curve", CURVES)
-def test_gpu_commit_lagrange_world_one(gpu, curve):
-    """Sharded iNTT + cyclic-sharded MSM composed (sharded_ntt.commit_lagrange) == the single-GPU Lagrange-basis
-    commitment b2p_msm_g1(B2P_BASIS_LAGRANGE) == the oracle's MSM over the Lagrange SRS, at world 1."""
-    import torch
-    from algoplonk_b200 import sharded
-    cv = po.CURVES[curve]
-    n = 256
-    vals = H.scalars_uniform(cv.r, n, 17)                     # evaluations in natural order
-    whole = api.SRS.unsafe(curve, n + 3)
-    want = whole.msm(vals, basis=_lib.BASIS_LAGRANGE)
-    block = [vals[k] for k in sn.local_eval_exponents(n, 0, 1)]
-    for mode in ("staged", "p2p"):
-        nt = sn.ShardedNtt(curve, n, rank=0, world=1, mode=mode)
-        srs = sharded.ShardedSRS.unsafe(curve, n + 3, 0, 1, layout="cyclic")
-        got = sn.commit_lagrange(nt, srs, to_tensor(curve, block, "cuda"))
-        assert api.points_from_mont_bytes(curve, got)[0] == want
-        with pytest.raises(ValueError):
-            sn.commit_lagrange(nt, sharded.ShardedSRS.unsafe(curve, n + 3, 0, 1), to_tensor(curve, block, "cuda"))
-        nt.free()
-        srs.free()
-    # the oracle's view of the same commitment: coefficients by inverse NTT, then the canonical-basis sum
-    coeffs = po.intt(cv, vals, po.domain_generator(cv, n))
-    assert want == po.commit(cv, whole.points(0, n), coeffs)
-    whole.free()
-
-
 IPC_WORKER = r"""
 import json, os, sys
 sys.path.insert(0, {root!r})
