@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200plonk.so")
 
 B2P_BN254, B2P_BLS12_381 = 0, 1
+ERR_ARG, ERR_CUDA, ERR_INTERNAL, ERR_VERIFY = -1, -2, -3, -4
 BASIS_CANONICAL, BASIS_LAGRANGE = 0, 1
 NTT_INVERSE, NTT_COSET = 1, 2
 IPC_HANDLE_BYTES = 64
@@ -66,6 +67,9 @@ SYMBOLS = [
     ("b2p_proof_marshal_size", _u64, [_int, _u32]),
     ("b2p_marshal_proof", _int, [_int, _u32, _vp, _vp, _vp]),
     ("b2p_marshal_public_inputs", _int, [_int, _vp, _u32, _vp]),
+    ("b2p_verify", _int, [_int, _u64, _u32, _u32, C.POINTER(_u64), _vp, _vp, _vp, _vp, _u64, _vp, _u64]),
+    ("b2p_pairing_check", _int, [_int, _vp, _vp, _u64, C.POINTER(_int)]),
+    ("b2p_g2_generate_unsafe", _int, [_int, _vp, _vp]),
     ("b2p_circuit_set_profiling", _int, [_vp, _int]),
     ("b2p_circuit_stats", _int, [_vp, C.POINTER(C.c_double)]),
 ]

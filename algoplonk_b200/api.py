@@ -90,23 +90,82 @@ def _buf(data: bytes):
     return C.create_string_buffer(data, len(data))
 
 
+def g2_to_mont_bytes(curve: str, points) -> bytes:
+    """affine ((x.A0, x.A1), (y.A0, y.A1)) ints or None -> G2Affine memory layout (X.A0 X.A1 Y.A0 Y.A1)."""
+    p, nb = P_MOD[curve], FP_BYTES[curve]
+    R = 1 << (8 * nb)
+    out = bytearray()
+    for Q in points:
+        if Q is None:
+            out += bytes(4 * nb)
+        else:
+            for c in (Q[0][0], Q[0][1], Q[1][0], Q[1][1]):
+                out += (c * R % p).to_bytes(nb, "little")
+    return bytes(out)
+
+
+def g2_from_mont_bytes(curve: str, data: bytes):
+    p, nb = P_MOD[curve], FP_BYTES[curve]
+    Rinv = pow(1 << (8 * nb), -1, p)
+    out = []
+    for i in range(0, len(data), 4 * nb):
+        c = [int.from_bytes(data[i + j * nb:i + (j + 1) * nb], "little") * Rinv % p for j in range(4)]
+        out.append(None if not any(c) else ((c[0], c[1]), (c[2], c[3])))
+    return out
+
+
+# ---- verification: plonk.Verify and its pairing check, host arithmetic of the library (no GPU) --------------
+def g2_unsafe(curve: str, tau: int = TEST_TAU) -> bytes:
+    """[1]_2, [tau]_2 in G2Affine layout: the G2 half of unsafekzg.NewSRS (setup/setup.go:124)."""
+    out = C.create_string_buffer(8 * FP_BYTES[curve])
+    _lib.check(_lib.load().b2p_g2_generate_unsafe(CURVE_ID[curve], _buf(fr_to_mont_bytes(curve, [tau])), out))
+    return out.raw
+
+
+def pairing_check(curve: str, g1_raw: bytes, g2_raw: bytes) -> bool:
+    """prod e(P_i, Q_i) == 1 for points in G1Affine / G2Affine memory layout."""
+    n = len(g1_raw) // (2 * FP_BYTES[curve])
+    if len(g1_raw) != n * 2 * FP_BYTES[curve] or len(g2_raw) != n * 4 * FP_BYTES[curve]:
+        raise ValueError("point buffers have the wrong length")
+    ok = C.c_int(0)
+    _lib.check(_lib.load().b2p_pairing_check(CURVE_ID[curve], _buf(g1_raw) if n else None, _buf(g2_raw) if n else None,
+                                             n, C.byref(ok)))
+    return bool(ok.value)
+
+
+def verify(curve: str, n: int, nb_public: int, commitment_indexes: Sequence[int], vk_points_raw: bytes,
+           kzg_g1_raw: bytes, kzg_g2_raw: bytes, proof: bytes, public_inputs: bytes) -> None:
+    """plonk.Verify (algoplonk.go:93) on the marshalled proof / public inputs; raises ValueError("error verifying
+    proof: ...") when the proof is rejected, as the reference returns an error."""
+    k = len(commitment_indexes)
+    cidx = (C.c_uint64 * max(k, 1))(*commitment_indexes) if k else None
+    rc = _lib.load().b2p_verify(CURVE_ID[curve], n, nb_public, k, cidx, _buf(vk_points_raw), _buf(kzg_g1_raw),
+                                _buf(kzg_g2_raw), _buf(proof), len(proof),
+                                _buf(public_inputs) if public_inputs else None, len(public_inputs))
+    if rc == _lib.ERR_VERIFY:
+        raise ValueError(_lib.load().b2p_last_error().decode())
+    _lib.check(rc)
+
+
 # ---- SRS ------------------------------------------------------------------------
 class SRS:
     """kzg.SRS resident on the GPU (canonical basis + windowed multiples)."""
 
-    def __init__(self, curve: str, handle: int, tau: Optional[int] = None):
+    def __init__(self, curve: str, handle: int, tau: Optional[int] = None, g2: Optional[bytes] = None):
+        self._g2 = g2            # Kzg.G2[0], Kzg.G2[1] in G2Affine layout (a trusted setup's vk.bin, decoded)
         self.curve, self.handle, self.tau = curve, handle, tau
 
     @classmethod
-    def from_points(cls, curve: str, points) -> "SRS":
-        """points: affine int pairs, or bytes already in G1Affine layout."""
+    def from_points(cls, curve: str, points, g2: Optional[bytes] = None) -> "SRS":
+        """points: affine int pairs, or bytes already in G1Affine layout; g2: the setup's two G2 points
+        (G2Affine layout), needed only to verify proofs made on this SRS."""
         _lib.init()
         data = points if isinstance(points, (bytes, bytearray)) else points_to_mont_bytes(curve, points)
         n = len(data) // (2 * FP_BYTES[curve])
         h = C.c_void_p()
         buf = _buf(bytes(data))
         _lib.check(_lib.load().b2p_srs_load(CURVE_ID[curve], buf, n, None, 0, C.byref(h)))
-        return cls(curve, h.value)
+        return cls(curve, h.value, g2=g2)
 
     @classmethod
     def from_pk_bin(cls, curve: str, pk_bin: bytes, count: int) -> "SRS":
@@ -126,6 +185,13 @@ class SRS:
         t = _buf(fr_to_mont_bytes(curve, [tau]))
         _lib.check(_lib.load().b2p_srs_generate_unsafe(CURVE_ID[curve], t, size, C.byref(h)))
         return cls(curve, h.value, tau % R_MOD[curve])
+
+    @property
+    def g2(self) -> Optional[bytes]:
+        """vk.Kzg.G2 (two G2Affine): derived from tau for a TestOnly SRS, else what the caller supplied."""
+        if self._g2 is None and self.tau is not None:
+            self._g2 = g2_unsafe(self.curve, self.tau)
+        return self._g2
 
     @property
     def size(self) -> int:
@@ -219,6 +285,7 @@ class CompiledCircuit:
         self.Ccs, self.trace, self.srs, self.handle = cs, trace, srs, handle
         self.Curve = cs.curve
         self._vk_points = None
+        self._vk_raw = self._g1_raw = None
 
     # verifying-key commitments S1 S2 S3 Ql Qr Qm Qo Qk Qcp* (affine ints)
     def vk_commitments(self):
@@ -260,14 +327,35 @@ class CompiledCircuit:
                               points_to_mont_bytes(cv, bsb22_points))
 
     def Verify(self, L, R, O, blinding, pi2=(), bsb22_points=(), verifier: Optional[Callable] = None) -> VerifiedProof:
-        """algoplonk.go:79-98: prove, then check the proof with `verifier(proof_bytes, public_bytes)`
-        (plonk.Verify in the reference; tests inject the oracle's restatement of the AVM verifier)."""
+        """algoplonk.go:79-98: prove, then plonk.Verify (algoplonk.go:93) -- the library's host verifier
+        b2p_verify against this circuit's verifying key whenever the SRS's G2 points are known (always for the
+        TestOnly setups; a trusted setup's when the caller passed them to SRS.from_points).  `verifier(proof_bytes,
+        public_bytes)`, if given, runs as well (tests inject the oracle's restatement of the AVM verifier)."""
         proof = self.Prove(L, R, O, blinding, pi2, bsb22_points)
         public = [v % R_MOD[self.Curve] for v in L[: self.trace.nb_public]]
+        blob = pub = None
+        if self.srs.g2 is not None:
+            blob, pub = MarshalProof(proof), MarshalPublicInputs(self.Curve, public)
+            self.VerifyProof(blob, pub)
         if verifier is not None:
-            if not verifier(MarshalProof(proof), MarshalPublicInputs(self.Curve, public)):
+            if blob is None:
+                blob, pub = MarshalProof(proof), MarshalPublicInputs(self.Curve, public)
+            if not verifier(blob, pub):
                 raise ValueError("error verifying proof")
         return VerifiedProof(proof, public)
+
+    def VerifyProof(self, proof_bytes: bytes, public_bytes: bytes) -> None:
+        """plonk.Verify(proof, cc.Vk, publicWitness) on marshalled bytes; raises ValueError when rejected."""
+        if self.srs.g2 is None:
+            raise ValueError("the SRS's G2 points are unknown: pass g2= to SRS.from_points")
+        if self._vk_raw is None:
+            k = len(self.trace.qcp)
+            out = C.create_string_buffer((8 + k) * 2 * FP_BYTES[self.Curve])
+            _lib.check(_lib.load().b2p_circuit_vk_commitments(self.handle, out))
+            self._vk_raw = out.raw
+            self._g1_raw = points_to_mont_bytes(self.Curve, self.srs.points(0, 1))
+        verify(self.Curve, self.trace.n, self.trace.nb_public, self.trace.commitment_constraint_indexes,
+               self._vk_raw, self._g1_raw, self.srs.g2, proof_bytes, public_bytes)
 
     def free(self):
         if self.handle:

@@ -396,3 +396,41 @@ API int b2p_circuit_stats(const b2p_circuit* c, double* out) {
         memcpy(out, reinterpret_cast<const CircuitBase*>(c)->stats, sizeof(double) * B2P_STAT_COUNT);
     });
 }
+
+// ---- plonk.Verify on the host (verify.cu) ---------------------------------------------------------------
+static void require_curve(int curve) {
+    require(curve == B2P_BN254 || curve == B2P_BLS12_381, "unsupported curve id (B2P_BN254 = 0, B2P_BLS12_381 = 1)");
+}
+API int b2p_verify(int curve, uint64_t n, uint32_t nb_public, uint32_t k, const uint64_t* commitment_indexes,
+                   const void* vk_points, const void* kzg_g1, const void* kzg_g2, const void* proof_bytes,
+                   uint64_t proof_len, const void* public_inputs, uint64_t public_len) {
+    return guarded([&] {
+        require_curve(curve);
+        require(vk_points && kzg_g1 && kzg_g2 && proof_bytes && (k == 0 || commitment_indexes) &&
+                    (public_len == 0 || public_inputs), "null argument");
+        require(k <= 64, "too many BSB22 commitments");
+        HostVerifyKey vk{n, nb_public, k, commitment_indexes, vk_points, kzg_g1, kzg_g2};
+        std::string why;
+        static const uint8_t none = 0;
+        if (!host_verify(curve, vk, proof_bytes, proof_len, public_inputs ? public_inputs : &none, public_len, &why))
+            throw Error(B2P_ERR_VERIFY, "error verifying proof: " + why);
+    });
+}
+API int b2p_pairing_check(int curve, const void* g1_points, const void* g2_points, uint64_t n, int* is_one) {
+    return guarded([&] {
+        require_curve(curve);
+        require(is_one && (n == 0 || (g1_points && g2_points)), "null argument");
+        require(n <= 1024, "too many pairs");
+        std::string why;
+        const bool ok = host_pairing_check(curve, g1_points, g2_points, n, &why);
+        if (!ok && !why.empty()) throw Error(B2P_ERR_ARG, why);
+        *is_one = ok ? 1 : 0;
+    });
+}
+API int b2p_g2_generate_unsafe(int curve, const void* tau, void* out_g2) {
+    return guarded([&] {
+        require_curve(curve);
+        require(tau && out_g2, "null argument");
+        host_g2_unsafe(curve, tau, out_g2);
+    });
+}

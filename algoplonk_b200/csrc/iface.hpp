@@ -77,4 +77,18 @@ const CurveOps* curve_ops_bls12381();
 
 extern std::atomic<unsigned long long> g_launch_count;
 
+// Host-side plonk.Verify (verify.cu): no device involved.
+struct HostVerifyKey {
+    uint64_t n;
+    uint32_t nb_public, k;
+    const uint64_t* commit_idx;   // k entries
+    const void* vk_points;        // S1 S2 S3 Ql Qr Qm Qo Qk Qcp*, G1Affine memory
+    const void* g1;               // Kzg.G1
+    const void* g2;               // Kzg.G2[0], Kzg.G2[1], G2Affine memory
+};
+bool host_verify(int curve, const HostVerifyKey& vk, const void* proof, uint64_t proof_len, const void* pub,
+                 uint64_t pub_len, std::string* why);
+bool host_pairing_check(int curve, const void* g1s, const void* g2s, uint64_t n, std::string* why);
+void host_g2_unsafe(int curve, const void* tau_mont, void* out_two_g2);
+
 }  // namespace b2p

@@ -1,0 +1,49 @@
+// Host-only translation unit: plonk.Verify, the pairing-product check and the G2 half of a known-tau SRS,
+// per curve (verify_host.hpp, pairing_host.hpp).  No device code and no CUDA calls: these entry points also
+// work on a box without a GPU, exactly like gnark's verifier which they stand in for.
+#include "iface.hpp"
+#include "verify_host.hpp"
+
+namespace b2p {
+
+template <class PC>
+static bool verify_t(const HostVerifyKey& vk, const uint8_t* proof, uint64_t proof_len, const uint8_t* pub,
+                     uint64_t pub_len, std::string* why) {
+    using V = hp::HostVerifier<PC>;
+    typename V::Key k{vk.n, vk.nb_public, vk.k, vk.commit_idx, static_cast<const uint8_t*>(vk.vk_points),
+                      static_cast<const uint8_t*>(vk.g1), static_cast<const uint8_t*>(vk.g2)};
+    return V::verify(k, proof, proof_len, pub, pub_len, why);
+}
+
+bool host_verify(int curve, const HostVerifyKey& vk, const void* proof, uint64_t proof_len, const void* pub,
+                 uint64_t pub_len, std::string* why) {
+    const uint8_t* p = static_cast<const uint8_t*>(proof);
+    const uint8_t* q = static_cast<const uint8_t*>(pub);
+    return curve == 0 ? verify_t<hp::Bn254Pairing>(vk, p, proof_len, q, pub_len, why)
+                      : verify_t<hp::Bls12381Pairing>(vk, p, proof_len, q, pub_len, why);
+}
+
+bool host_pairing_check(int curve, const void* g1s, const void* g2s, uint64_t n, std::string* why) {
+    const uint8_t* a = static_cast<const uint8_t*>(g1s);
+    const uint8_t* b = static_cast<const uint8_t*>(g2s);
+    return curve == 0 ? hp::Pairing<hp::Bn254Pairing>::product_is_one(a, b, n, why)
+                      : hp::Pairing<hp::Bls12381Pairing>::product_is_one(a, b, n, why);
+}
+
+template <class PC>
+static void g2_unsafe_t(const void* tau_mont, uint8_t* out) {
+    using PR = hp::Pairing<PC>;
+    using Fr = typename PC::Fr;
+    const Fr tau = Fr::load(tau_mont).from_mont();
+    const typename PR::G2 g = PR::g2_generator();
+    PR::store_g2(g, out);
+    PR::store_g2(PR::g2_mul(g, tau.v, Fr::N), out + 4 * PR::FPB);
+}
+
+// [1]_2, [tau]_2: the G2 half of unsafekzg.NewSRS (setup/setup.go:124), for the TestOnly setups
+void host_g2_unsafe(int curve, const void* tau_mont, void* out) {
+    if (curve == 0) g2_unsafe_t<hp::Bn254Pairing>(tau_mont, static_cast<uint8_t*>(out));
+    else g2_unsafe_t<hp::Bls12381Pairing>(tau_mont, static_cast<uint8_t*>(out));
+}
+
+}  // namespace b2p

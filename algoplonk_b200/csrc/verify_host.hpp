@@ -1,0 +1,342 @@
+// plonk.Verify on the host: the self-check (*CompiledCircuit).Verify runs right after plonk.Prove
+// (/root/reference/algoplonk.go:93; testutils/testutils.go:51 runs the same call).  gnark's verifier is
+// third-party code that is not in /root/reference; the acceptance condition restated here is the one the
+// reference's own generated verifiers implement (verifier/templateLogicSigBN254.go:126-397,
+// templateLogicSigBLS12_381.go:144-420), on the marshalled proof of helper.go:27-88:
+//   1. challenges gamma, beta, alpha, zeta from the SHA-256 transcript (vk commitments, public inputs, L R O,
+//      BSB22 commitments, Z, H0 H1 H2)
+//   2. PI(zeta) from the public inputs and the BSB22 commitment hashes; alpha^2 L_1(zeta)
+//   3. the constant term of the linearised polynomial and its commitment [Lin]
+//   4. fold challenge v, folded digest / claimed value of the batch opening at zeta
+//   5. batching of the two openings (zeta and omega zeta) with u = H(digest, W_zeta, Z, W_{omega zeta}, zeta, v)
+//   6. e(digest, [1]_2) e(-(W_zeta + u W_{omega zeta}), [tau]_2) == 1           (pairing_host.hpp)
+// Everything runs in 64-bit-limb host arithmetic; the handful of scalar multiplications share one Straus pass
+// per linear combination.  Infinity commitments are hashed the way the prover hashes them (prover.cuh
+// point_marshal: gnark's 0x40 flag on BLS12-381, zero bytes on BN254).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "pairing_host.hpp"
+#include "sha256.hpp"
+
+namespace b2p {
+namespace hp {
+
+template <class PC>
+struct HostVerifier {
+    using Fp = typename PC::Fp;
+    using Fr = typename PC::Fr;
+    using PR = Pairing<PC>;
+    static constexpr int NB = Fp::N * 8;    // bytes per coordinate
+    static constexpr int PB = 2 * NB;       // marshalled point
+    static constexpr bool BLS = !PC::D_TWIST;
+
+    struct Aff { Fp x, y; bool inf; };
+    struct Ext {                            // extended Jacobian: x = X/ZZ, y = Y/ZZZ
+        Fp X, Y, ZZ, ZZZ;
+        static Ext inf() { return {Fp::zero(), Fp::zero(), Fp::zero(), Fp::zero()}; }
+        bool is_inf() const { return ZZ.is_zero(); }
+        static Ext from(const Aff& a) { return a.inf ? inf() : Ext{a.x, a.y, Fp::one(), Fp::one()}; }
+        Ext dbl() const {
+            if (is_inf() || Y.is_zero()) return inf();
+            Fp U = Y.dbl(), V = U.sqr(), W = U * V, S = X * V, X2 = X.sqr(), M = X2.dbl() + X2;
+            Fp X3 = M.sqr() - S.dbl();
+            return {X3, M * (S - X3) - W * Y, V * ZZ, W * ZZZ};
+        }
+        Ext add(const Ext& o) const {
+            if (is_inf()) return o;
+            if (o.is_inf()) return *this;
+            Fp U1 = X * o.ZZ, U2 = o.X * ZZ, S1 = Y * o.ZZZ, S2 = o.Y * ZZZ, P = U2 - U1, R = S2 - S1;
+            if (P.is_zero()) return R.is_zero() ? dbl() : inf();
+            Fp PP = P.sqr(), PPP = P * PP, Q = U1 * PP;
+            Fp X3 = R.sqr() - PPP - Q.dbl();
+            return {X3, R * (Q - X3) - S1 * PPP, ZZ * o.ZZ * PP, ZZZ * o.ZZZ * PPP};
+        }
+        Aff to_affine() const {
+            if (is_inf()) return {Fp::zero(), Fp::zero(), true};
+            // ZZ = Z^2, ZZZ = Z^3:  1/ZZ = Z^4 / Z^6 = ZZ^2 / ZZZ^2
+            Fp zi = ZZZ.inverse();
+            Fp zzi = zi.sqr() * ZZ.sqr();
+            return {X * zzi, Y * zi, false};
+        }
+    };
+    static Aff neg(const Aff& a) { return a.inf ? a : Aff{a.x, a.y.neg(), false}; }
+
+    // sum_i s_i P_i, scalars in Montgomery form; Straus with 4-bit windows and shared doublings
+    static Aff lincomb(const std::vector<Aff>& pts, const std::vector<Fr>& sc_mont) {
+        const size_t cnt = pts.size();
+        std::vector<Ext> tbl(cnt * 16);
+        std::vector<Fr> sc(cnt);
+        for (size_t i = 0; i < cnt; i++) {
+            sc[i] = sc_mont[i].from_mont();
+            Ext* t = &tbl[i * 16];
+            t[0] = Ext::inf();
+            t[1] = Ext::from(pts[i]);
+            for (int j = 2; j < 16; j++) t[j] = t[j - 1].add(t[1]);
+        }
+        Ext acc = Ext::inf();
+        for (int w = Fr::N * 16 - 1; w >= 0; w--) {
+            for (int k = 0; k < 4; k++) acc = acc.dbl();
+            for (size_t i = 0; i < cnt; i++) {
+                const unsigned d = (unsigned)(sc[i].v[w >> 4] >> (4 * (w & 15))) & 15u;
+                if (d) acc = acc.add(tbl[i * 16 + d]);
+            }
+        }
+        return acc.to_affine();
+    }
+
+    // ---- encodings --------------------------------------------------------------------------------------
+    template <class F>
+    static bool from_be(const uint8_t* in, int nbytes, F* out, bool reduce) {   // canonical big-endian -> Montgomery
+        F raw = F::zero();
+        for (int b = 0; b < nbytes; b++) raw.v[b >> 3] |= (uint64_t)in[nbytes - 1 - b] << (8 * (b & 7));
+        if (!reduce && F::geq_mod(raw.v)) return false;
+        *out = F::mul(raw, F::r2());
+        return true;
+    }
+    template <class F>
+    static void to_be(const F& mont, uint8_t* out) {
+        F c = mont.from_mont();
+        constexpr int nbytes = F::N * 8;
+        for (int b = 0; b < nbytes; b++) out[nbytes - 1 - b] = (uint8_t)(c.v[b >> 3] >> (8 * (b & 7)));
+    }
+    static Fr fr_mod(const uint8_t* be32) { Fr r; from_be(be32, 32, &r, true); return r; }
+    // X || Y big-endian, all-zero = infinity (helper.go:35 RawBytes); false: not reduced or not on the curve
+    static bool parse_point(const uint8_t* in, Aff* out) {
+        bool zero = true;
+        for (int i = 0; i < PB; i++) zero &= in[i] == 0;
+        if (zero) { *out = {Fp::zero(), Fp::zero(), true}; return true; }
+        Aff a{Fp::zero(), Fp::zero(), false};
+        if (!from_be(in, NB, &a.x, false) || !from_be(in + NB, NB, &a.y, false)) return false;
+        if (!(a.y.sqr() == a.x.sqr() * a.x + Fp::from_u64(PC::B))) return false;
+        *out = a;
+        return true;
+    }
+    static void marshal(const Aff& a, uint8_t* out, bool transcript_flag) {
+        if (a.inf) {
+            memset(out, 0, PB);
+            if (transcript_flag && BLS) out[0] = 0x40;
+            return;
+        }
+        to_be(a.x, out);
+        to_be(a.y, out + NB);
+    }
+    static Aff load_aff(const uint8_t* mem) {   // gnark G1Affine memory
+        Aff a{Fp::load(mem), Fp::load(mem + NB), false};
+        a.inf = a.x.is_zero() && a.y.is_zero();
+        return a;
+    }
+    static void store_aff(const Aff& a, uint8_t* mem) {
+        if (a.inf) { memset(mem, 0, PB); return; }
+        a.x.store(mem); a.y.store(mem + NB);
+    }
+
+    // hash_to_field, DST "BSB22-Plonk" (templateLogicSigBN254.go:386-397)
+    static Fr hash_fr(const uint8_t* point_bytes, size_t len) {
+        static const uint8_t dst_prime[12] = {'B', 'S', 'B', '2', '2', '-', 'P', 'l', 'o', 'n', 'k', 0x0b};
+        uint8_t b0[32], b1[32], b2[32], z[64] = {0};
+        Sha256 h;
+        h.update(z, 64); h.update(point_bytes, len);
+        const uint8_t lib[3] = {0x00, 0x30, 0x00};
+        h.update(lib, 3); h.update(dst_prime, 12); h.final(b0);
+        h.reset(); h.update(b0, 32); uint8_t one = 1; h.update(&one, 1); h.update(dst_prime, 12); h.final(b1);
+        uint8_t x[32];
+        for (int i = 0; i < 32; i++) x[i] = b0[i] ^ b1[i];
+        h.reset(); h.update(x, 32); uint8_t two = 2; h.update(&two, 1); h.update(dst_prime, 12); h.final(b2);
+        uint8_t lo[32] = {0};
+        memcpy(lo + 16, b2, 16);
+        uint64_t e128[1] = {128};
+        return fr_mod(b1) * Fr::from_u64(2).pow(e128, 1) + fr_mod(lo);
+    }
+
+    static Fr pow_u64(const Fr& b, uint64_t e) { return b.pow(&e, 1); }
+    static Fr root_of_unity(uint64_t n) {   // generator of the size-n subgroup (gnark fft.NewDomain)
+        Fr w;
+        for (int i = 0; i < Fr::N; i++)
+            w.v[i] = (uint64_t)PC::FrP::root_[2 * i] | ((uint64_t)PC::FrP::root_[2 * i + 1] << 32);
+        int logn = 0;
+        while ((1ull << logn) < n) logn++;
+        for (int i = logn; i < PC::FrP::TWO_ADICITY; i++) w = w.sqr();
+        return w;
+    }
+
+    struct Key {
+        uint64_t n;
+        uint32_t nb_public, k;
+        const uint64_t* commit_idx;   // CommitmentConstraintIndexes
+        const uint8_t* vk_points;     // S1 S2 S3 Ql Qr Qm Qo Qk Qcp*  (G1Affine memory)
+        const uint8_t* g1;            // Kzg.G1
+        const uint8_t* g2;            // Kzg.G2[0], Kzg.G2[1]  (G2Affine memory)
+    };
+    static uint64_t proof_size(uint32_t k) { return 9ull * PB + 6 * 32 + (uint64_t)k * (32 + PB); }
+
+    // true = accepted; false = rejected, *why says at which check
+    static bool verify(const Key& vk, const uint8_t* proof, uint64_t proof_len, const uint8_t* pub, uint64_t pub_len,
+                       std::string* why) {
+        auto fail = [&](const char* m) { if (why) *why = m; return false; };
+        const uint32_t k = vk.k;
+        if (vk.n < 2 || (vk.n & (vk.n - 1))) return fail("domain size is not a power of two");
+        if (proof_len != proof_size(k)) return fail("proof has the wrong length");
+        if (pub_len != 32ull * vk.nb_public) return fail("public inputs have the wrong length");
+
+        // -- proof fields (helper.go:27-88) -------------------------------------------------------------
+        const uint8_t* p = proof;
+        Aff LRO[3], H[3], Z, Wz, Wzw;
+        Fr l_z, r_z, o_z, s1_z, s2_z, z_zw;
+        std::vector<Fr> qcp_z(k);
+        std::vector<Aff> bsb(k);
+        auto point = [&](Aff* a) { bool ok = parse_point(p, a); p += PB; return ok; };
+        auto scalar = [&](Fr* f) { bool ok = from_be(p, 32, f, false); p += 32; return ok; };
+        bool ok = true;
+        for (int i = 0; i < 3; i++) ok &= point(&LRO[i]);
+        for (int i = 0; i < 3; i++) ok &= point(&H[i]);
+        if (!ok) return fail("a wire or quotient commitment is not a point of the curve");
+        ok &= scalar(&l_z); ok &= scalar(&r_z); ok &= scalar(&o_z); ok &= scalar(&s1_z); ok &= scalar(&s2_z);
+        if (!ok) return fail("an evaluation is not reduced mod r");
+        if (!point(&Z)) return fail("[Z] is not a point of the curve");
+        if (!scalar(&z_zw)) return fail("z(omega zeta) is not reduced mod r");
+        if (!point(&Wz) || !point(&Wzw)) return fail("an opening proof is not a point of the curve");
+        for (uint32_t c = 0; c < k; c++) if (!scalar(&qcp_z[c])) return fail("qcp(zeta) is not reduced mod r");
+        for (uint32_t c = 0; c < k; c++) if (!point(&bsb[c])) return fail("a BSB22 commitment is not a point of the curve");
+        std::vector<Fr> pubv(vk.nb_public);
+        for (uint32_t i = 0; i < vk.nb_public; i++)
+            if (!from_be(pub + 32 * i, 32, &pubv[i], false)) return fail("a public input is not reduced mod r");
+
+        // -- verifying key ----------------------------------------------------------------------------------
+        std::vector<Aff> vkp(8 + k);
+        std::vector<uint8_t> vk_fs((size_t)(8 + k) * PB);
+        for (uint32_t i = 0; i < 8 + k; i++) {
+            vkp[i] = load_aff(vk.vk_points + (size_t)i * PB);
+            marshal(vkp[i], &vk_fs[(size_t)i * PB], true);
+        }
+        const Aff &S1 = vkp[0], &S2 = vkp[1], &S3 = vkp[2], &Ql = vkp[3], &Qr = vkp[4], &Qm = vkp[5], &Qo = vkp[6],
+                  &Qk = vkp[7];
+        const Aff G1 = load_aff(vk.g1);
+
+        // -- challenges (templateLogicSigBN254.go:131-140) ---------------------------------------------------
+        uint8_t gamma_pre[32], beta_pre[32], alpha_pre[32], zeta_pre[32], pb[PB], b32[32];
+        std::vector<uint8_t> lro_fs(3 * PB), bsb_fs((size_t)k * PB);
+        for (int j = 0; j < 3; j++) marshal(LRO[j], &lro_fs[j * PB], true);
+        for (uint32_t c = 0; c < k; c++) marshal(bsb[c], &bsb_fs[(size_t)c * PB], true);
+        Sha256 hs;
+        hs.update("gamma"); hs.update(vk_fs); hs.update(pub, pub_len); hs.update(lro_fs); hs.final(gamma_pre);
+        hs.reset(); hs.update("beta"); hs.update(gamma_pre, 32); hs.final(beta_pre);
+        hs.reset(); hs.update("alpha"); hs.update(beta_pre, 32); hs.update(bsb_fs);
+        marshal(Z, pb, true); hs.update(pb, PB); hs.final(alpha_pre);
+        hs.reset(); hs.update("zeta"); hs.update(alpha_pre, 32);
+        for (int j = 0; j < 3; j++) { marshal(H[j], pb, true); hs.update(pb, PB); }
+        hs.final(zeta_pre);
+        const Fr gamma = fr_mod(gamma_pre), beta = fr_mod(beta_pre), alpha = fr_mod(alpha_pre), zeta = fr_mod(zeta_pre);
+
+        // -- PI(zeta), alpha^2 L_1(zeta) (:142-201) ----------------------------------------------------------
+        const Fr one = Fr::one();
+        const Fr omega = root_of_unity(vk.n);
+        const Fr zn = pow_u64(zeta, vk.n);
+        const Fr zh = zn - one;
+        const Fr zh_n = zh * Fr::from_u64(vk.n).inverse();
+        Fr PI = Fr::zero();
+        {
+            // L_i(zeta) = omega^i (zeta^n - 1) / (n (zeta - omega^i)), one inversion for all public inputs
+            std::vector<Fr> den(vk.nb_public), pre(vk.nb_public + 1);
+            Fr w = one;
+            pre[0] = one;
+            for (uint32_t i = 0; i < vk.nb_public; i++) {
+                den[i] = zeta - w;
+                pre[i + 1] = pre[i] * den[i];
+                w = w * omega;
+            }
+            Fr inv = pre[vk.nb_public].inverse();
+            std::vector<Fr> li(vk.nb_public);
+            for (uint32_t i = vk.nb_public; i > 0; i--) {
+                li[i - 1] = inv * pre[i - 1];
+                inv = inv * den[i - 1];
+            }
+            w = one;
+            for (uint32_t i = 0; i < vk.nb_public; i++) {
+                PI = PI + li[i] * zh_n * w * pubv[i];
+                w = w * omega;
+            }
+            for (uint32_t c = 0; c < k; c++) {
+                const Fr wp = pow_u64(omega, vk.nb_public + vk.commit_idx[c]);
+                const Fr lag = (zeta - wp).inverse() * wp * zh_n;
+                PI = PI + hash_fr(&bsb_fs[(size_t)c * PB], PB) * lag;
+            }
+        }
+        const Fr a2l = (zeta - one).inverse() * zh_n * alpha * alpha;
+
+        // -- constant term of the linearised polynomial (:203-218) --------------------------------------------
+        const Fr t1 = l_z + beta * s1_z + gamma, t2 = r_z + beta * s2_z + gamma;
+        const Fr lin_z = (t1 * t2 * (o_z + gamma) * alpha * z_zw + PI - a2l).neg();
+
+        // -- [Lin] (:220-278) ---------------------------------------------------------------------------------
+        const Fr u = Fr::from_u64(PC::FrP::SHIFT_SMALL), u2 = u * u;
+        const Fr s1p = alpha * beta * z_zw * t1 * t2;
+        const Fr bz = beta * zeta;
+        const Fr s2p = a2l - alpha * (l_z + bz + gamma) * (r_z + bz * u + gamma) * (o_z + bz * u2 + gamma);
+        const Fr zn2 = pow_u64(zeta, vk.n + 2);
+        const Fr mzh = zh.neg();
+        std::vector<Aff> pts = {Ql, Qr, Qm, Qo, Qk};
+        std::vector<Fr> sc = {l_z, r_z, l_z * r_z, o_z, one};
+        for (uint32_t c = 0; c < k; c++) { pts.push_back(bsb[c]); sc.push_back(qcp_z[c]); }
+        pts.push_back(S3); sc.push_back(s1p);
+        pts.push_back(Z); sc.push_back(s2p);
+        pts.push_back(H[0]); sc.push_back(mzh);
+        pts.push_back(H[1]); sc.push_back(mzh * zn2);
+        pts.push_back(H[2]); sc.push_back(mzh * zn2 * zn2);
+        const Aff lin = lincomb(pts, sc);
+
+        // -- fold challenge and folded opening at zeta (:280-321) ----------------------------------------------
+        uint8_t v_pre[32];
+        hs.reset();
+        hs.update("gamma");
+        to_be(zeta, b32); hs.update(b32, 32);
+        marshal(lin, pb, false); hs.update(pb, PB);
+        hs.update(lro_fs);
+        hs.update(vk_fs.data(), 2 * PB);
+        hs.update(vk_fs.data() + 8 * PB, (size_t)k * PB);
+        to_be(lin_z, b32); hs.update(b32, 32);
+        const Fr evs[5] = {l_z, r_z, o_z, s1_z, s2_z};
+        for (int i = 0; i < 5; i++) { to_be(evs[i], b32); hs.update(b32, 32); }
+        for (uint32_t c = 0; c < k; c++) { to_be(qcp_z[c], b32); hs.update(b32, 32); }
+        to_be(z_zw, b32); hs.update(b32, 32);
+        hs.final(v_pre);
+        const Fr v = fr_mod(v_pre);
+        pts = {lin, LRO[0], LRO[1], LRO[2], S1, S2};
+        std::vector<Fr> vals = {lin_z, l_z, r_z, o_z, s1_z, s2_z};
+        for (uint32_t c = 0; c < k; c++) { pts.push_back(vkp[8 + c]); vals.push_back(qcp_z[c]); }
+        sc.clear();
+        Fr claims = Fr::zero(), acc = one;
+        for (size_t i = 0; i < pts.size(); i++) {
+            sc.push_back(acc);
+            claims = claims + vals[i] * acc;
+            acc = acc * v;
+        }
+        const Aff digest = lincomb(pts, sc);
+
+        // -- both openings in one pairing check (:323-356) ------------------------------------------------------
+        uint8_t u_pre[32];
+        hs.reset();
+        marshal(digest, pb, false); hs.update(pb, PB);
+        marshal(Wz, pb, false); hs.update(pb, PB);
+        marshal(Z, pb, true); hs.update(pb, PB);
+        marshal(Wzw, pb, false); hs.update(pb, PB);
+        to_be(zeta, b32); hs.update(b32, 32);
+        to_be(v, b32); hs.update(b32, 32);
+        hs.final(u_pre);
+        const Fr ub = fr_mod(u_pre);
+        claims = claims + z_zw * ub;
+        const Aff lhs = lincomb({digest, Z, G1, Wz, Wzw}, {one, ub, claims.neg(), zeta, ub * zeta * omega});
+        const Aff rhs = neg(lincomb({Wz, Wzw}, {one, ub}));
+
+        uint8_t g1s[2 * PB];
+        store_aff(lhs, g1s);
+        store_aff(rhs, g1s + PB);
+        std::string pwhy;
+        if (!PR::product_is_one(g1s, vk.g2, 2, &pwhy)) return fail(pwhy.empty() ? "pairing check failed" : pwhy.c_str());
+        return true;
+    }
+};
+
+}  // namespace hp
+}  // namespace b2p

@@ -41,6 +41,7 @@ extern "C" {
 #define B2P_ERR_ARG       -1   /* bad argument / unsupported size */
 #define B2P_ERR_CUDA      -2   /* CUDA runtime failure (no device, OOM, launch error) */
 #define B2P_ERR_INTERNAL  -3
+#define B2P_ERR_VERIFY    -4   /* b2p_verify: the proof was rejected (plonk.Verify's error) */
 
 #define B2P_BASIS_CANONICAL 0  /* pk.Kzg          : [tau^j]_1            */
 #define B2P_BASIS_LAGRANGE  1  /* pk.KzgLagrange  : [L_j(tau)]_1, size n */
@@ -221,6 +222,33 @@ uint64_t b2p_proof_marshal_size(int curve, uint32_t k);      /* (24+3k)*32 / (33
 int b2p_marshal_proof(int curve, uint32_t k, const void* proof_raw, const void* bsb22, void* out_bytes);
 /* public inputs: nb_public Fr (Montgomery) -> nb_public * 32 bytes big-endian */
 int b2p_marshal_public_inputs(int curve, const void* values, uint32_t nb_public, void* out_bytes);
+
+/* ---- verification (replaces: plonk.Verify, algoplonk.go:93; testutils/testutils.go:51) ----
+ *
+ * The self-check (*CompiledCircuit).Verify runs right after plonk.Prove, on the marshalled proof
+ * (b2p_marshal_proof) and public inputs (b2p_marshal_public_inputs).  Host arithmetic only -- gnark verifies
+ * on the CPU too; these three calls need no GPU and no b2p_init.  The acceptance condition is the one the
+ * reference's generated verifiers implement (verifier/templateLogicSigBN254.go:126-397,
+ * templateLogicSigBLS12_381.go:144-420) with a real pairing check against the setup's G2 points.
+ *
+ *   n, nb_public        vk.Size, vk.NbPublicVariables
+ *   k, commitment_indexes   len(vk.Qcp), vk.CommitmentConstraintIndexes
+ *   vk_points           8+k G1Affine: S[0] S[1] S[2] Ql Qr Qm Qo Qk Qcp[0..k)   (what b2p_circuit_vk_commitments writes)
+ *   kzg_g1              vk.Kzg.G1                    (1 G1Affine, = SRS point 0)
+ *   kzg_g2              vk.Kzg.G2[0], vk.Kzg.G2[1]   (2 G2Affine: X.A0 X.A1 Y.A0 Y.A1, Montgomery limbs)
+ * Returns B2P_OK when the proof is accepted, B2P_ERR_VERIFY when it is rejected (b2p_last_error says at which
+ * check: wrong length, value not reduced, point off the curve, pairing), B2P_ERR_ARG for null arguments. */
+int b2p_verify(int curve, uint64_t n, uint32_t nb_public, uint32_t k, const uint64_t* commitment_indexes,
+               const void* vk_points, const void* kzg_g1, const void* kzg_g2,
+               const void* proof_bytes, uint64_t proof_len,
+               const void* public_inputs, uint64_t public_len);
+/* prod_i e(g1_points[i], g2_points[i]) == 1 ?  (replaces the curve package's PairingCheck, the last line of
+ * kzg.BatchVerifyMultiPoints; setup/trusted_setup_test.go checks its setups with the same equation).
+ * Points off their curve give B2P_ERR_ARG. */
+int b2p_pairing_check(int curve, const void* g1_points, const void* g2_points, uint64_t n, int* is_one);
+/* [1]_2, [tau]_2 : the G2 half of the TestOnly setups' unsafekzg.NewSRS (setup/setup.go:124);
+ * tau as in b2p_srs_generate_unsafe; writes 2 G2Affine. */
+int b2p_g2_generate_unsafe(int curve, const void* tau, void* out_g2);
 
 /* ---- instrumentation -------------------------------------------------------- */
 

@@ -1,0 +1,225 @@
+"""plonk.Verify and its pairing check in the library's host arithmetic (csrc/verify_host.hpp, pairing_host.hpp;
+b2p_verify / b2p_pairing_check / b2p_g2_generate_unsafe) -- the step right after plonk.Prove in
+(*CompiledCircuit).Verify (/root/reference/algoplonk.go:93).  No GPU on this path, so all of it runs here.
+
+Pinned on data this repo did not produce: the ceremony files' own points (e([tau]_1,[1]_2) = e([1]_1,[tau]_2) with
+every operand from setup/<name>/pk.bin / vk.bin), whose G2[0] must be the generator the library hard-codes; and on
+the golden proofs, which the oracle's line-by-line restatement of the reference's AVM verifier accepts.
+"""
+import random
+from math import gcd
+
+import pytest
+
+import helpers as H
+from algoplonk_b200 import _lib, api
+from oracle import pairing as opair
+from oracle import plonk_oracle as po
+
+CURVES = ("BN254", "BLS12_381")
+REAL = {"BN254": "PerpetualPowersOfTauBN254", "BLS12_381": "DuskBLS12_381"}
+
+
+def test_final_exponentiation_chains_are_integer_identities():
+    """The two x-chains pairing_host.hpp evaluates equal (p^4 - p^2 + 1)/r (BN254) / 3 times it (BLS12-381, 3 prime to r)."""
+    x = 4965661367192848881
+    p = 36 * x**4 + 36 * x**3 + 24 * x**2 + 6 * x + 1
+    r = 36 * x**4 + 36 * x**3 + 18 * x**2 + 6 * x + 1
+    assert (p, r) == (po.CURVES["BN254"].p, po.CURVES["BN254"].r)
+    d, rem = divmod(p**4 - p**2 + 1, r)
+    assert rem == 0
+    e = (-2 - 18 * x - 30 * x**2 - 36 * x**3) + (1 - 12 * x - 18 * x**2 - 36 * x**3) * p + (1 + 6 * x**2) * p**2 + p**3
+    assert e == d                                                           # the BN hard part, exactly
+    assert (6 * x * x - p) % r == 0 and (6 * x * x).bit_length() == 127        # the Miller loop length t - 1
+    x = -0xD201000000010000
+    p = (x - 1) ** 2 * (x**4 - x**2 + 1) // 3 + x
+    r = x**4 - x**2 + 1
+    assert (p, r) == (po.CURVES["BLS12_381"].p, po.CURVES["BLS12_381"].r)
+    d, rem = divmod(p**4 - p**2 + 1, r)
+    assert rem == 0
+    assert (x - 1) ** 2 * (x + p) * (x**2 + p**2 - 1) + 3 == 3 * d and gcd(3, r) == 1
+    assert (x - p) % r == 0
+
+
+def _g1(curve, k):
+    cv = po.CURVES[curve]
+    return po.g1_mul(cv, cv.g1, k % cv.r) if k % cv.r else None
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_g2_generator_is_the_ceremonys_and_on_the_twist(curve):
+    cv = po.CURVES[curve]
+    gen, tau_g2 = api.g2_from_mont_bytes(curve, api.g2_unsafe(curve, 12345))
+    assert opair.g2_on_curve(cv, gen) and opair.g2_on_curve(cv, tau_g2)
+    assert gen == H.real_srs_g2(REAL[curve])[0]          # vk.bin of the reference's setup: G2[0] = [1]_2
+    # tau = 1 gives the generator twice, tau = 0 infinity
+    assert api.g2_from_mont_bytes(curve, api.g2_unsafe(curve, 1)) == [gen, gen]
+    assert api.g2_from_mont_bytes(curve, api.g2_unsafe(curve, 0)) == [gen, None]
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_pairing_is_bilinear_and_non_degenerate(curve):
+    cv = po.CURVES[curve]
+    rng = random.Random(11)
+    for _ in range(2):
+        a, b = rng.randrange(1, cv.r), rng.randrange(1, cv.r)
+        g2 = api.g2_unsafe(curve, b)                      # [1]_2, [b]_2
+        q_one, q_b = g2[: len(g2) // 2], g2[len(g2) // 2:]
+        P = lambda k: api.points_to_mont_bytes(curve, [_g1(curve, k)])
+        # e(a G1, b G2) e(-ab G1, G2) == 1
+        assert api.pairing_check(curve, P(a) + P(-a * b), q_b + q_one)
+        # e(G1, b G2) e(-b G1, G2) == 1  (the KZG setup equation)
+        assert api.pairing_check(curve, P(1) + P(-b), q_b + q_one)
+        # three pairs: e(a G1, G2) e(b G1, G2) e(-(a+b) G1, G2) == 1
+        assert api.pairing_check(curve, P(a) + P(b) + P(-(a + b)), q_one * 3)
+        # not degenerate / not always true
+        assert not api.pairing_check(curve, P(1), q_one)
+        assert not api.pairing_check(curve, P(a) + P(-a * b + 1), q_b + q_one)
+        assert not api.pairing_check(curve, P(a) + P(-a), q_b + q_one)
+    # infinity on either side contributes 1; the empty product is 1
+    inf1, inf2 = api.points_to_mont_bytes(curve, [None]), api.g2_to_mont_bytes(curve, [None])
+    assert api.pairing_check(curve, inf1, q_one) and api.pairing_check(curve, P(5), inf2)
+    assert api.pairing_check(curve, b"", b"")
+    # points off their curve are an argument error, not "false"
+    bad = api.points_to_mont_bytes(curve, [(1, 1)])
+    with pytest.raises(_lib.B200PlonkError):
+        api.pairing_check(curve, bad, q_one)
+    with pytest.raises(_lib.B200PlonkError):
+        api.pairing_check(curve, P(1), api.g2_to_mont_bytes(curve, [((1, 2), (3, 4))]))
+
+
+@pytest.mark.parametrize("name", ["PerpetualPowersOfTauBN254", "DuskBLS12_381", "EthereumKzgCeremonyBLS12_381"])
+def test_pairing_on_the_reference_setups_own_points(name):
+    """e([tau]_1, [1]_2) == e([1]_1, [tau]_2), every operand read from the ceremony files
+    (setup/trusted_setup_test.go checks its setups with the same equation)."""
+    if name not in H.srs_kat():
+        pytest.skip("setup not in the committed fixture")
+    ent = H.srs_kat()[name]
+    curve = ent["curve"]
+    cv = po.CURVES[curve]
+    pts = H.real_srs_points(name)
+    g2 = api.g2_to_mont_bytes(curve, H.real_srs_g2(name))
+    half = len(g2) // 2
+    g1s = api.points_to_mont_bytes(curve, [pts[1], po.g1_neg(cv, pts[0])])
+    assert api.pairing_check(curve, g1s, g2[:half] + g2[half:])
+    # consecutive powers too: e([tau^3]_1, [1]_2) == e([tau^2]_1, [tau]_2); and a wrong pairing of them fails
+    assert api.pairing_check(curve, api.points_to_mont_bytes(curve, [pts[3], po.g1_neg(cv, pts[2])]), g2)
+    assert not api.pairing_check(curve, api.points_to_mont_bytes(curve, [pts[3], po.g1_neg(cv, pts[1])]), g2)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_library_pairing_agrees_with_the_oracles_pairing(curve):
+    """Same yes/no as oracle/pairing.py (an unrelated construction: Fp12 as plain polynomials, E(Fp12), plain
+    final exponentiation) on a true and a false product."""
+    cv = po.CURVES[curve]
+    a = 0xC0FFEE
+    g2 = api.g2_unsafe(curve, a)
+    Q = api.g2_from_mont_bytes(curve, g2)
+    for k, want in ((-a, True), (-a + 1, False)):
+        pairs = [(cv.g1, Q[1]), (_g1(curve, k), Q[0])]
+        assert opair.pairing_product_is_one(cv, pairs) is want
+        assert api.pairing_check(curve, api.points_to_mont_bytes(curve, [p for p, _ in pairs]),
+                                 api.g2_to_mont_bytes(curve, [q for _, q in pairs])) is want
+
+
+# ---- plonk.Verify ----------------------------------------------------------------------------------------------
+def _verify_args(case):
+    """(curve, n, nb_public, commitment indexes, vk points raw, g1 raw, g2 raw) of a golden case."""
+    c = H.build_case(case)
+    cv, tc, curve = c["cv"], c["tc"], case["curve"]
+    nb = 2 * cv.fp_bytes
+    vkb = bytes.fromhex(case["vk"])
+    vk_pts = []
+    for i in range(0, len(vkb), nb):
+        chunk = bytearray(vkb[i:i + nb])
+        chunk[0] &= 0x1F if curve == "BLS12_381" else 0x3F          # gnark's infinity flag
+        vk_pts.append(po.g1_from_raw_bytes(cv, bytes(chunk)))
+    if c["tau"] is not None:
+        g1, g2 = cv.g1, api.g2_unsafe(curve, c["tau"])
+    else:
+        g1, g2 = c["srs"][0], api.g2_to_mont_bytes(curve, H.real_srs_g2(case["srs"]))
+    return (curve, tc.n, tc.nb_public, list(tc.commitment_constraint_indexes),
+            api.points_to_mont_bytes(curve, vk_pts), api.points_to_mont_bytes(curve, [g1]), g2), c, vk_pts
+
+
+@pytest.mark.parametrize("case", H.golden_proofs(), ids=H.case_id)
+def test_golden_proofs_are_accepted_and_tampered_ones_rejected(case):
+    args, c, vk_pts = _verify_args(case)
+    proof, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
+    api.verify(*args, proof, pub)                                     # accepted: no exception
+    cv = c["cv"]
+    pb = 2 * cv.fp_bytes
+    k = case.get("k", 0)
+    # one flipped bit in every field of the proof (testutils/verifier_integration_test.go:188-228 tampers the same way)
+    fields, off = [], 0
+    for size in [pb] * 6 + [32] * 5 + [pb, 32, pb, pb] + [32] * k + [pb] * k:
+        fields.append((off, size))
+        off += size
+    assert off == len(proof)
+    for off, size in fields:
+        bad = bytearray(proof)
+        bad[off + size - 1] ^= 1
+        with pytest.raises(ValueError, match="error verifying proof"):
+            api.verify(*args, bytes(bad), pub)
+    # wrong public input, wrong lengths
+    if pub:
+        bad = bytearray(pub)
+        bad[-1] ^= 1
+        with pytest.raises(ValueError, match="pairing"):
+            api.verify(*args, proof, bytes(bad))
+        with pytest.raises(ValueError, match="public inputs have the wrong length"):
+            api.verify(*args, proof, pub[:-32])
+    with pytest.raises(ValueError, match="wrong length"):
+        api.verify(*args, proof + b"\0", pub)
+    # an evaluation that is not reduced mod r, a coordinate that is not reduced mod p
+    bad = bytearray(proof)
+    bad[6 * pb:6 * pb + 32] = (int.from_bytes(proof[6 * pb:6 * pb + 32], "big") + cv.r).to_bytes(32, "big")
+    with pytest.raises(ValueError, match="not reduced"):
+        api.verify(*args, bytes(bad), pub)
+    bad = bytearray(proof)
+    bad[: cv.fp_bytes] = b"\xff" * cv.fp_bytes
+    with pytest.raises(ValueError, match="not a point"):
+        api.verify(*args, bytes(bad), pub)
+    # another key: a different Ql commitment, or the wrong G2 pair
+    other = list(vk_pts)
+    other[3] = po.g1_add(cv, other[3], cv.g1)
+    with pytest.raises(ValueError, match="pairing"):
+        api.verify(*args[:4], api.points_to_mont_bytes(case["curve"], other), *args[5:], proof, pub)
+    with pytest.raises(ValueError, match="pairing"):
+        api.verify(*args[:6], api.g2_unsafe(case["curve"], 777), proof, pub)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_verdicts_match_the_restated_reference_verifier(curve):
+    """Random single-byte corruptions anywhere in proof or public inputs: b2p_verify and the oracle's restatement
+    of the generated AVM verifier give the same verdict (exceptions of the oracle = reject)."""
+    case = next(c for c in H.golden_proofs() if c["curve"] == curve and c["name"].startswith("bsb22") and c["srs"] == "tau")
+    args, c, vk_pts = _verify_args(case)
+    vk = H.vk_from_points(c["tc"], vk_pts, c["cv"].g1, tau=c["tau"])
+    proof, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
+    rng = random.Random(5)
+    outcomes = set()
+    for trial in range(12):
+        p2, q2 = bytearray(proof), bytearray(pub)
+        if trial:                                                     # trial 0: untouched
+            tgt = p2 if trial % 3 else q2
+            tgt[rng.randrange(len(tgt))] ^= 1 << rng.randrange(8)
+        try:
+            want = bool(po.verify_proof(vk, bytes(p2), bytes(q2)))
+        except Exception:
+            want = False
+        try:
+            api.verify(*args, bytes(p2), bytes(q2))
+            got = True
+        except ValueError:
+            got = False
+        assert got is want, trial
+        outcomes.add(got)
+    assert outcomes == {True, False}
+
+
+def test_verify_argument_errors():
+    lib = _lib.load()
+    assert lib.b2p_verify(7, 8, 0, 0, None, None, None, None, None, 0, None, 0) == _lib.ERR_ARG
+    assert lib.b2p_verify(0, 8, 0, 0, None, None, None, None, None, 0, None, 0) == _lib.ERR_ARG
+    assert b"null" in lib.b2p_last_error()
