@@ -375,6 +375,20 @@ def run_b200(args):
                       "quotient": stats["quotient_ms"], "total_host_wall": stats["total_ms"]},
         "circuit_load_s": load_s,
     }
+    # plonk.Verify (algoplonk.go:93) on a proof of the timed region: outside every timed region, host arithmetic
+    # of the library (b2p_verify); reported so the line says its proofs are valid, never raised
+    try:
+        blob = api.MarshalProof(api.Proof(curve, 0, proof_resident))
+        pub = api.MarshalPublicInputs(curve, L[: tc.nb_public])
+        ccs[0].VerifyProof(blob, pub)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ccs[0].VerifyProof(blob, pub)
+        line["verify"] = {"accepted": True, "ms_per_proof": (time.perf_counter() - t0) / 5 * 1e3,
+                          "where": "host thread, b2p_verify; not part of value / e2e (the reference arm times "
+                                   "plonk.Prove only)"}
+    except Exception as e:  # noqa: BLE001 -- reported in the line
+        line["verify"] = {"accepted": False, "error": f"{type(e).__name__}: {e}"[:300]}
     if sharded_line is not None:
         line["msm_sharded"] = sharded_line
     if ntt_sharded_line is not None:
