@@ -68,6 +68,8 @@ SYMBOLS = [
     ("b2p_marshal_proof", _int, [_int, _u32, _vp, _vp, _vp]),
     ("b2p_marshal_public_inputs", _int, [_int, _vp, _u32, _vp]),
     ("b2p_verify", _int, [_int, _u64, _u32, _u32, C.POINTER(_u64), _vp, _vp, _vp, _vp, _u64, _vp, _u64]),
+    ("b2p_verify_batch", _int, [_int, _u64, _u32, _u32, C.POINTER(_u64), _vp, _vp, _vp, _vp, _u64, _vp, _u64, _u64,
+                          C.POINTER(_u64)]),
     ("b2p_pairing_check", _int, [_int, _vp, _vp, _u64, C.POINTER(_int)]),
     ("b2p_g2_generate_unsafe", _int, [_int, _vp, _vp]),
     ("b2p_circuit_set_profiling", _int, [_vp, _int]),

@@ -147,6 +147,28 @@ def verify(curve: str, n: int, nb_public: int, commitment_indexes: Sequence[int]
     _lib.check(rc)
 
 
+def verify_batch(curve: str, n: int, nb_public: int, commitment_indexes: Sequence[int], vk_points_raw: bytes,
+                 kzg_g1_raw: bytes, kzg_g2_raw: bytes, proofs: Sequence[bytes], public_inputs: Sequence[bytes]) -> None:
+    """Many proofs of one circuit, one pairing check (b2p_verify_batch).  Raises ValueError naming the first proof
+    rejected before the pairing, or "batch" when only the folded pairing check failed."""
+    if len(proofs) != len(public_inputs):
+        raise ValueError("one public-input blob per proof")
+    if len({len(p) for p in proofs}) > 1 or len({len(p) for p in public_inputs}) > 1:
+        raise ValueError("proofs of one circuit have one length")
+    k = len(commitment_indexes)
+    cidx = (C.c_uint64 * max(k, 1))(*commitment_indexes) if k else None
+    pl = len(proofs[0]) if proofs else 0
+    ql = len(public_inputs[0]) if public_inputs else 0
+    pj, qj = b"".join(proofs), b"".join(public_inputs)
+    bad = C.c_uint64(0)
+    rc = _lib.load().b2p_verify_batch(CURVE_ID[curve], n, nb_public, k, cidx, _buf(vk_points_raw), _buf(kzg_g1_raw),
+                                      _buf(kzg_g2_raw), _buf(pj) if pj else None, pl, _buf(qj) if qj else None, ql,
+                                      len(proofs), C.byref(bad))
+    if rc == _lib.ERR_VERIFY:
+        raise ValueError(_lib.load().b2p_last_error().decode())
+    _lib.check(rc)
+
+
 # ---- SRS ------------------------------------------------------------------------
 class SRS:
     """kzg.SRS resident on the GPU (canonical basis + windowed multiples)."""

@@ -23,6 +23,23 @@ bool host_verify(int curve, const HostVerifyKey& vk, const void* proof, uint64_t
                       : verify_t<hp::Bls12381Pairing>(vk, p, proof_len, q, pub_len, why);
 }
 
+template <class PC>
+static bool verify_batch_t(const HostVerifyKey& vk, const uint8_t* proofs, uint64_t proof_len, const uint8_t* pubs,
+                           uint64_t pub_len, uint64_t count, uint64_t* bad, std::string* why) {
+    using V = hp::HostVerifier<PC>;
+    typename V::Key k{vk.n, vk.nb_public, vk.k, vk.commit_idx, static_cast<const uint8_t*>(vk.vk_points),
+                      static_cast<const uint8_t*>(vk.g1), static_cast<const uint8_t*>(vk.g2)};
+    return V::verify_batch(k, proofs, proof_len, pubs, pub_len, count, bad, why);
+}
+
+bool host_verify_batch(int curve, const HostVerifyKey& vk, const void* proofs, uint64_t proof_len, const void* pubs,
+                       uint64_t pub_len, uint64_t count, uint64_t* bad, std::string* why) {
+    const uint8_t* p = static_cast<const uint8_t*>(proofs);
+    const uint8_t* q = static_cast<const uint8_t*>(pubs);
+    return curve == 0 ? verify_batch_t<hp::Bn254Pairing>(vk, p, proof_len, q, pub_len, count, bad, why)
+                      : verify_batch_t<hp::Bls12381Pairing>(vk, p, proof_len, q, pub_len, count, bad, why);
+}
+
 bool host_pairing_check(int curve, const void* g1s, const void* g2s, uint64_t n, std::string* why) {
     const uint8_t* a = static_cast<const uint8_t*>(g1s);
     const uint8_t* b = static_cast<const uint8_t*>(g2s);

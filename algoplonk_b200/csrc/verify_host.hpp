@@ -171,9 +171,10 @@ struct HostVerifier {
     };
     static uint64_t proof_size(uint32_t k) { return 9ull * PB + 6 * 32 + (uint64_t)k * (32 + PB); }
 
-    // true = accepted; false = rejected, *why says at which check
-    static bool verify(const Key& vk, const uint8_t* proof, uint64_t proof_len, const uint8_t* pub, uint64_t pub_len,
-                       std::string* why) {
+    // Steps 1-5: everything but the pairing.  On success the proof is valid iff e(lhs, G2[0]) e(rhs, G2[1]) == 1.
+    // false = rejected before the pairing, *why says at which check
+    static bool reduce(const Key& vk, const uint8_t* proof, uint64_t proof_len, const uint8_t* pub, uint64_t pub_len,
+                       Aff* lhs_out, Aff* rhs_out, std::string* why) {
         auto fail = [&](const char* m) { if (why) *why = m; return false; };
         const uint32_t k = vk.k;
         if (vk.n < 2 || (vk.n & (vk.n - 1))) return fail("domain size is not a power of two");
@@ -326,15 +327,61 @@ struct HostVerifier {
         hs.final(u_pre);
         const Fr ub = fr_mod(u_pre);
         claims = claims + z_zw * ub;
-        const Aff lhs = lincomb({digest, Z, G1, Wz, Wzw}, {one, ub, claims.neg(), zeta, ub * zeta * omega});
-        const Aff rhs = neg(lincomb({Wz, Wzw}, {one, ub}));
+        *lhs_out = lincomb({digest, Z, G1, Wz, Wzw}, {one, ub, claims.neg(), zeta, ub * zeta * omega});
+        *rhs_out = neg(lincomb({Wz, Wzw}, {one, ub}));
+        return true;
+    }
 
+    static bool pair_is_one(const Key& vk, const Aff& lhs, const Aff& rhs, std::string* why) {
         uint8_t g1s[2 * PB];
         store_aff(lhs, g1s);
         store_aff(rhs, g1s + PB);
         std::string pwhy;
-        if (!PR::product_is_one(g1s, vk.g2, 2, &pwhy)) return fail(pwhy.empty() ? "pairing check failed" : pwhy.c_str());
-        return true;
+        if (PR::product_is_one(g1s, vk.g2, 2, &pwhy)) return true;
+        if (why) *why = pwhy.empty() ? "pairing check failed" : pwhy;
+        return false;
+    }
+
+    // true = accepted; false = rejected, *why says at which check
+    static bool verify(const Key& vk, const uint8_t* proof, uint64_t proof_len, const uint8_t* pub, uint64_t pub_len,
+                       std::string* why) {
+        Aff lhs, rhs;
+        return reduce(vk, proof, proof_len, pub, pub_len, &lhs, &rhs, why) && pair_is_one(vk, lhs, rhs, why);
+    }
+
+    // `count` proofs of ONE circuit (same key), proof i at proofs + i*proof_len, its public inputs at pubs + i*pub_len.
+    // Each proof is reduced to its pair (lhs_i, rhs_i); the pairs are folded with 128-bit coefficients rho_i drawn
+    // from a hash of the whole batch (rho_0 = 1), and ONE pairing check decides
+    //     e(sum rho_i lhs_i, G2[0]) e(sum rho_i rhs_i, G2[1]) == 1,
+    // which holds for an invalid batch with probability 2^-128 (the same folding kzg.BatchVerifyMultiPoints
+    // applies to the two openings of one proof).  *bad: index of the first proof rejected before the pairing, or
+    // `count` when only the folded check failed (some proof is invalid: verify them one by one to find it).
+    static bool verify_batch(const Key& vk, const uint8_t* proofs, uint64_t proof_len, const uint8_t* pubs,
+                             uint64_t pub_len, uint64_t count, uint64_t* bad, std::string* why) {
+        if (bad) *bad = count;
+        if (count == 0) return true;
+        std::vector<Aff> lhs(count), rhs(count);
+        for (uint64_t i = 0; i < count; i++)
+            if (!reduce(vk, proofs + i * proof_len, proof_len, pubs + i * pub_len, pub_len, &lhs[i], &rhs[i], why)) {
+                if (bad) *bad = i;
+                return false;
+            }
+        uint8_t seed[32];
+        Sha256 hs;
+        hs.update("b2p-batch-verify");
+        hs.update(proofs, count * proof_len);
+        hs.update(pubs, count * pub_len);
+        hs.final(seed);
+        std::vector<Fr> rho(count);
+        rho[0] = Fr::one();
+        for (uint64_t i = 1; i < count; i++) {
+            uint8_t d[32], ctr[8], lo[32] = {0};
+            for (int b = 0; b < 8; b++) ctr[b] = (uint8_t)(i >> (8 * b));
+            hs.reset(); hs.update(seed, 32); hs.update(ctr, 8); hs.final(d);
+            memcpy(lo + 16, d, 16);
+            rho[i] = fr_mod(lo);
+        }
+        return pair_is_one(vk, lincomb(lhs, rho), lincomb(rhs, rho), why);
     }
 };
 

@@ -169,10 +169,28 @@ public:
         vp.raw.resize(b2p_proof_raw_size(CURVE, 0));
         check(b2p_prove(circuit_, L.data(), R.data(), O.data(), nullptr, nullptr, blinding.data(), vp.raw.data()), "plonk.Prove");
         vp.witness.assign(ccs.values.begin(), ccs.values.begin() + ccs.nb_public);
+        if (!kzg_g2_.empty()) VerifyProof(vp.MarshalProof(), vp.MarshalPublicInputs());   // plonk.Verify, algoplonk.go:93
         if constexpr (!std::is_same<Verifier, std::nullptr_t>::value) {
             if (!verifier(vp.MarshalProof(), vp.MarshalPublicInputs())) throw Error("error verifying proof");
         }
         return vp;
+    }
+    // plonk.Verify(proof, cc.Vk, publicWitness) on marshalled bytes (b2p_verify: host arithmetic of the library);
+    // throws "error verifying proof: <failed check>" when the proof is rejected
+    void VerifyProof(const std::vector<uint8_t>& proof, const std::vector<uint8_t>& public_inputs) const {
+        if (kzg_g2_.empty()) throw Error("the setup's G2 points are unknown (SetKzgG2)");
+        const auto vk = VkCommitments();
+        std::vector<uint8_t> g1(CURVE == B2P_BN254 ? 64 : 96);
+        check(b2p_srs_get_points(srs_, 0, 1, g1.data()), "vk.Kzg.G1");
+        check(b2p_verify(CURVE, n, ccs.nb_public, 0, nullptr, vk.data(), g1.data(), kzg_g2_.data(), proof.data(),
+                         proof.size(), public_inputs.empty() ? nullptr : public_inputs.data(), public_inputs.size()),
+              "plonk.Verify");
+    }
+    // vk.Kzg.G2[0], vk.Kzg.G2[1] of a trusted setup (two G2Affine in gnark memory layout, from its vk.bin);
+    // the TestOnly setups derive theirs from tau in Compile
+    void SetKzgG2(const void* two_g2_affine) {
+        const auto* p = static_cast<const uint8_t*>(two_g2_affine);
+        kzg_g2_.assign(p, p + 8 * (CURVE == B2P_BN254 ? 32 : 48));
     }
     // S1 S2 S3 Ql Qr Qm Qo Qk commitments of the verifying key (G1Affine memory layout)
     std::vector<uint8_t> VkCommitments() const {
@@ -186,6 +204,7 @@ public:
 private:
     b2p_srs* srs_ = nullptr;
     b2p_circuit* circuit_ = nullptr;
+    std::vector<uint8_t> kzg_g2_;
 };
 
 template <int CURVE>
@@ -204,6 +223,8 @@ inline CompiledCircuit<CURVE>* CompileInto(CompiledCircuit<CURVE>* cc, const Spa
     } else {
         if (!test_tau) throw Error("TestOnly setups need a tau");
         check(b2p_srs_generate_unsafe(CURVE, test_tau, n + 3, &cc->srs_), "unsafekzg.NewSRS");         // setup.go:102-108
+        cc->kzg_g2_.resize(8 * (CURVE == B2P_BN254 ? 32 : 48));
+        check(b2p_g2_generate_unsafe(CURVE, test_tau, cc->kzg_g2_.data()), "unsafekzg.NewSRS (G2)");
     }
     // trace: Lagrange columns + permutation (gnark NewTrace / buildPermutation)
     std::vector<Fr> ql(n, Fr::zero()), qr = ql, qm = ql, qo = ql, qk = ql;

@@ -242,6 +242,17 @@ int b2p_verify(int curve, uint64_t n, uint32_t nb_public, uint32_t k, const uint
                const void* vk_points, const void* kzg_g1, const void* kzg_g2,
                const void* proof_bytes, uint64_t proof_len,
                const void* public_inputs, uint64_t public_len);
+/* `count` proofs of the SAME circuit in one call (a prover service checking what it emitted): proof i at
+ * proofs + i*proof_len, its public inputs at public_inputs + i*public_len.  Every proof goes through all the
+ * checks of b2p_verify up to the pairing; the `count` pairing equations are then folded with 128-bit
+ * coefficients hashed from the whole batch into ONE pairing check (soundness error 2^-128; the folding
+ * kzg.BatchVerifyMultiPoints applies to the two openings of a single proof).  B2P_OK: all accepted.
+ * B2P_ERR_VERIFY: *first_bad = index of the first proof rejected before the pairing, or `count` when only the
+ * folded pairing check failed (at least one proof is invalid; b2p_verify one by one finds it). */
+int b2p_verify_batch(int curve, uint64_t n, uint32_t nb_public, uint32_t k, const uint64_t* commitment_indexes,
+                     const void* vk_points, const void* kzg_g1, const void* kzg_g2,
+                     const void* proofs, uint64_t proof_len,
+                     const void* public_inputs, uint64_t public_len, uint64_t count, uint64_t* first_bad);
 /* prod_i e(g1_points[i], g2_points[i]) == 1 ?  (replaces the curve package's PairingCheck, the last line of
  * kzg.BatchVerifyMultiPoints; setup/trusted_setup_test.go checks its setups with the same equation).
  * Points off their curve give B2P_ERR_ARG. */

@@ -223,3 +223,55 @@ def test_verify_argument_errors():
     assert lib.b2p_verify(7, 8, 0, 0, None, None, None, None, None, 0, None, 0) == _lib.ERR_ARG
     assert lib.b2p_verify(0, 8, 0, 0, None, None, None, None, None, 0, None, 0) == _lib.ERR_ARG
     assert b"null" in lib.b2p_last_error()
+
+
+# ---- many proofs, one pairing check ---------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", CURVES)
+def test_batch_verification_folds_many_proofs_into_one_pairing(curve):
+    """b2p_verify_batch: proofs of one circuit with different witnesses / blinding (made by the C++ oracle here --
+    the GPU makes the same bytes) are accepted together; one bad proof anywhere in the batch is caught, either
+    by its own pre-pairing checks (index reported) or by the folded pairing check ("batch")."""
+    from algoplonk_b200 import frontend as fe
+    from oracle import cpu_oracle as co
+    cv = po.CURVES[curve]
+    proofs, pubs, args = [], [], None
+    for i in range(5):
+        cs, values = fe.squaring_chain(curve, 6, x0=3 + i)
+        tc = fe.build_trace(cs)
+        L, R, O = fe.solve_lro(cs, values, tc.n)
+        if args is None:
+            srs_le = co.srs_from_tau_bytes(cv.cid, api.TEST_TAU, tc.n + 3)
+            circ = co.Circuit(cv.cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
+            args = (curve, tc.n, tc.nb_public, [], api.points_to_mont_bytes(curve, circ.vk_points()),
+                    api.points_to_mont_bytes(curve, [cv.g1]), api.g2_unsafe(curve, api.TEST_TAU))
+        proofs.append(circ.prove(L, R, O, H.scalars_uniform(cv.r, 9, 100 + i)))
+        pubs.append(b"".join((v % cv.r).to_bytes(32, "big") for v in L[: tc.nb_public]))   # helper.go:91-110
+    circ.free()
+    assert len(set(proofs)) == 5
+    for p, q in zip(proofs, pubs):
+        api.verify(*args, p, q)
+    api.verify_batch(*args, proofs, pubs)
+    api.verify_batch(*args, [], [])
+    api.verify_batch(*args, proofs[:1], pubs[:1])
+    # a proof point moved to another point of the curve passes every pre-pairing check: only the fold sees it
+    pb = 2 * cv.fp_bytes
+    other = po.g1_raw_bytes(cv, po.g1_mul(cv, cv.g1, 99))
+    for victim in (0, 3, 4):
+        bad = list(proofs)
+        bad[victim] = other + proofs[victim][pb:]
+        with pytest.raises(ValueError, match="batch: pairing"):
+            api.verify_batch(*args, bad, pubs)
+        with pytest.raises(ValueError, match="pairing"):
+            api.verify(*args, bad[victim], pubs[victim])
+    # two invalid proofs whose errors would cancel under equal weights still fail: proof 1 and 2 swapped
+    with pytest.raises(ValueError, match="batch"):
+        api.verify_batch(*args, [proofs[0], proofs[2], proofs[1]], pubs[:3])
+    # a malformed proof is reported by index
+    bad = list(proofs)
+    bad[2] = b"\xff" * cv.fp_bytes + proofs[2][cv.fp_bytes:]
+    with pytest.raises(ValueError, match="error verifying proof 2: "):
+        api.verify_batch(*args, bad, pubs)
+    # public inputs belong to their proof
+    if pubs[0] != pubs[1]:
+        with pytest.raises(ValueError, match="batch"):
+            api.verify_batch(*args, proofs, [pubs[1], pubs[0]] + pubs[2:])
