@@ -43,6 +43,7 @@ SYMBOLS = [
     ("b2p_msm_g1_dev", _int, [_vp, _int, _vp, _u64, _vp]),
     ("b2p_g1_sum", _int, [_int, _vp, _u64, _vp]),
     ("b2p_srs_stream", _vp, [_vp]),
+    ("b2p_srs_set_commit_hook", _int, [_vp, _vp, _vp]),
     ("b2p_ntt", _int, [_int, _vp, _u64, _int]),
     ("b2p_ntt_shard_create", _int, [_int, _u64, _u32, _u32, C.POINTER(_vp)]),
     ("b2p_ntt_shard_free", None, [_vp]),
@@ -75,6 +76,10 @@ SYMBOLS = [
     ("b2p_circuit_set_profiling", _int, [_vp, _int]),
     ("b2p_circuit_stats", _int, [_vp, C.POINTER(C.c_double)]),
 ]
+
+
+# b2p_commit_fn: int fn(void* ctx, const void* d_scalars, uint64_t n, void* out_affine)
+COMMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
 
 
 class B200PlonkError(RuntimeError):

@@ -207,6 +207,14 @@ API int b2p_g1_sum(int curve, const void* points, uint64_t n, void* out_affine) 
         ops_for(curve)->g1_sum(points, n, out_affine);
     });
 }
+API int b2p_srs_set_commit_hook(b2p_srs* srs, b2p_commit_fn fn, void* ctx) {
+    return guarded([&] {
+        require(srs, "null argument");
+        SrsBase* s = reinterpret_cast<SrsBase*>(srs);
+        std::lock_guard<std::mutex> g(s->mu);
+        s->set_commit_hook(fn, ctx);
+    });
+}
 API void* b2p_srs_stream(b2p_srs* srs) { return srs ? reinterpret_cast<SrsBase*>(srs)->stream_handle() : nullptr; }
 
 API int b2p_ntt(int curve, void* data, uint64_t n, int flags) {

@@ -30,6 +30,7 @@ struct SrsBase {
     virtual uint64_t size() const = 0;
     virtual void msm_params(int* c, int* windows, uint64_t* buckets) const = 0;
     virtual void* stream_handle() = 0;
+    virtual void set_commit_hook(int (*fn)(void*, const void*, uint64_t, void*), void* ctx) = 0;
     virtual void msm_g1(int basis, const void* scalars, uint64_t n, void* out_affine, bool device_scalars) = 0;
 };
 

@@ -244,6 +244,12 @@ struct Srs : SrsBase {
     DevBuf<Fr> scratch;         // scalar staging for b2p_msm_g1
     Profiler* prof = nullptr;
     static constexpr int OUT_SLOTS = MSM_SLOTS;
+    // b2p_srs_set_commit_hook: every commitment on this handle is delegated (a point-set-sharded MSM over
+    // several GPUs, algoplonk_b200/sharded_prover.py); results wait in hook_out until fetch()
+    b2p_commit_fn hook = nullptr;
+    void* hook_ctx = nullptr;
+    Aff hook_out[MSM_SLOTS];
+    void set_commit_hook(b2p_commit_fn fn, void* ctx) override { hook = fn; hook_ctx = ctx; }
 
     Srs() { curve = C::ID; B2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); }
     ~Srs() override { if (stream) cudaStreamDestroy(stream); }
@@ -341,6 +347,13 @@ struct Srs : SrsBase {
     }
     // queue an MSM of n device scalars (Montgomery form); result lands in slot
     void commit_async(const Fr* d_scalars, uint64_t n, int slot) {
+        if (hook) {
+            B2P_REQUIRE(slot >= 0 && slot < OUT_SLOTS, "result slot out of range");
+            B2P_CUDA(cudaStreamSynchronize(stream));      // the scalars are final before the hook reads them
+            if (hook(hook_ctx, d_scalars, n, &hook_out[slot]) != 0)
+                throw Error(B2P_ERR_INTERNAL, "the commit hook reported a failure");
+            return;
+        }
         int id = prof ? prof->begin(B2P_STAT_MSM_MS, stream) : -1;
         msm.prof = prof;
         msm.run_async(d_scalars, n, true, stream, slot);
@@ -352,6 +365,10 @@ struct Srs : SrsBase {
     void fetch(int first, int cnt, Aff* host_out) {
         Ext h[OUT_SLOTS];
         B2P_REQUIRE(first >= 0 && cnt >= 0 && first + cnt <= OUT_SLOTS, "result slot out of range");
+        if (hook) {
+            for (int i = 0; i < cnt; i++) host_out[i] = hook_out[first + i];
+            return;
+        }
         int id = prof ? prof->begin(B2P_STAT_MSM_MS, stream) : -1;
         msm.finish_async(first, cnt, stream);          // the latency-bound end of the reductions, once for all slots
         if (prof) prof->end(id, stream);

@@ -118,6 +118,16 @@ int b2p_msm_g1_dev(b2p_srs* srs, int basis, const void* d_scalars, uint64_t n, v
 int b2p_g1_sum(int curve, const void* points, uint64_t n, void* out_affine);
 /* The cudaStream_t every launch of this SRS handle is issued on. */
 void* b2p_srs_stream(b2p_srs* srs);
+/* Commit hook -- how one proof is spread over several GPUs (point-set-sharded MSMs).  While a hook
+ * is set, every kzg.Commit made on this handle (the 9 MSMs of b2p_prove on its circuits, b2p_msm_g1) is
+ * delegated: the handle's stream is synchronised, then fn(ctx, d_scalars, n, out) is called on the calling
+ * thread with the DEVICE pointer of the n scalars (Fr, Montgomery; valid until fn returns) and must write the
+ * commitment sum_j scalars[j] [tau^j]_1 as one G1Affine (Montgomery) to the HOST buffer `out`; non-zero return
+ * aborts the call with B2P_ERR_INTERNAL.  fn must not call into THIS handle (its lock is held); it typically
+ * broadcasts the scalars to the other ranks, runs b2p_msm_g1_dev on each rank's own SRS shard and adds the
+ * partial sums (b2p_g1_sum): algoplonk_b200/sharded_prover.py.  fn = NULL removes the hook. */
+typedef int (*b2p_commit_fn)(void* ctx, const void* d_scalars, uint64_t n, void* out_affine);
+int b2p_srs_set_commit_hook(b2p_srs* srs, b2p_commit_fn fn, void* ctx);
 
 #define B2P_NTT_INVERSE   1   /* FFTInverse (includes the 1/n scaling) */
 #define B2P_NTT_COSET     2   /* on the coset FrMultiplicativeGen * <omega> */

@@ -91,3 +91,48 @@ def test_gpu_commit_lagrange_world_one(gpu, curve):
     coeffs = po.intt(cv, vals, po.domain_generator(cv, n))
     assert want == po.commit(cv, whole.points(0, n), coeffs)
     whole.free()
+
+
+# ---- one proof over several GPUs: the commit hook (algoplonk_b200/sharded_prover.py) --------------------------
+@pytest.mark.parametrize("curve", CURVES)
+def test_whole_proof_through_the_commit_hook(gpu, curve):
+    """b2p_prove with every kzg.Commit delegated through b2p_srs_set_commit_hook gives the plain prover's bytes:
+    (1) ShardedProver at world 1 (one shard = the whole SRS, no process group); (2) a world of 3 simulated on one
+    device -- three ragged SRS blocks, the committer's own slicing, partial sums added with b2p_g1_sum."""
+    import torch
+    from algoplonk_b200 import sharded_prover as sp
+    cv = po.CURVES[curve]
+    cs, values = fe.squaring_chain(curve, 10)
+    plain = api.Compile(cs, curve, SETUP[curve])
+    tc = plain.trace
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    blinding = H.scalars_uniform(cv.r, 9, 3)
+    want = api.MarshalProof(plain.Prove(L, R, O, blinding))
+
+    prover = sp.ShardedProver(cs, curve, SETUP[curve])
+    assert api.MarshalProof(prover.Prove(L, R, O, blinding)) == want
+    assert prover.committer.commits == 9                      # L R O Z H0 H1 H2 W_zeta W_{omega zeta}
+    prover.close()
+
+    world, total = 3, tc.n + 3
+    shards = [sharded.ShardedSRS.unsafe(curve, total, r, world) for r in range(world)]
+    seen = []
+
+    def all_ranks(scalars, offset, count):                    # what ranks 0..2 would each do, one after the other
+        assert (offset, count) == (0, len(scalars) // 32)     # world 1 from the committer's point of view
+        n, parts = count, []
+        for r in range(world):
+            off, cnt = sp.slice_for(total, r, world, n)
+            parts.append(shards[r].local_msm_dev_raw(scalars.data_ptr() + 32 * off, cnt) if cnt
+                         else bytes(2 * cv.fp_bytes))
+        seen.append(n)
+        return sharded.g1_sum(curve, b"".join(parts))
+    device = torch.device("cuda", torch.cuda.current_device())
+    hook = sp.CommitHook(plain.srs, sp.ShardedCommitter(curve, total, device=device, local_msm=all_ranks), device)
+    assert api.MarshalProof(plain.Prove(L, R, O, blinding)) == want
+    assert seen == [tc.n + 2] * 3 + [tc.n + 3] + [tc.n + 2] * 5
+    hook.remove()
+    assert api.MarshalProof(plain.Prove(L, R, O, blinding)) == want      # and the handle commits by itself again
+    for s in shards:
+        s.free()
+    plain.free()
