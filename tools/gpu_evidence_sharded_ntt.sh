@@ -1,5 +1,6 @@
 #!/usr/bin/env bash
-# Evidence still owed for the domain-sharded NTT, one gpurun call each:
+# Evidence still owed for the domain-sharded NTT and the MSM-sharded proof (DESIGN.md sections 7 and 8), one gpurun
+# call each:
 #
 #   gpurun --timeout 600 -- 'bash tools/gpu_evidence_sharded_ntt.sh one'
 #   gpurun --gpus 2 --timeout 300 -- 'bash tools/gpu_evidence_sharded_ntt.sh two'
@@ -11,7 +12,7 @@ mkdir -p gpurun_out
 case "${1:-one}" in
   one)
     # the four GPU tests added after round 1's last GPU call, then the whole sharded files
-    timeout 400 python -m pytest tests/test_sharded.py tests/test_sharded_ntt.py tests/test_gpu_prove.py -m gpu -x -q 2>&1 | tail -5
+    timeout 400 python -m pytest tests/test_zz_gpu_unconfirmed.py tests/test_sharded.py tests/test_sharded_ntt.py tests/test_gpu_prove.py tests/test_gpu_host_mirror.py -m gpu -q 2>&1 | tail -8
     # launch list + full capture of one rank's four steps (world 8, 2^21: BASELINE config 5's per-rank work)
     timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
         --log-file gpurun_out/launches_ntt_shard.csv python tools/ntt_shard_time.py --logn 21 --worlds 8 \
@@ -37,11 +38,20 @@ case "${1:-one}" in
     timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29556 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
     tail -c 1500 gpurun_out/bench_2gpu.json
+    # ... and one proof over both GPUs (commit hook, MSMs sharded over the point set)
+    timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29557 tools/sharded_proof_bench.py BN254:20 BLS12_381:20 \
+        > gpurun_out/sharded_proof_2gpu.jsonl 2> gpurun_out/sharded_proof_2gpu.err
+    cat gpurun_out/sharded_proof_2gpu.jsonl
     ;;
   eight)
     timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         --master-port 29555 tools/ntt_shard_bench.py BN254:20 BLS12_381:21 \
         > gpurun_out/ntt_shard_bench_8gpu.jsonl 2> gpurun_out/ntt_shard_bench_8gpu.err
     cat gpurun_out/ntt_shard_bench_8gpu.jsonl
+    timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29557 tools/sharded_proof_bench.py BN254:20 BLS12_381:20 \
+        > gpurun_out/sharded_proof_8gpu.jsonl 2> gpurun_out/sharded_proof_8gpu.err
+    cat gpurun_out/sharded_proof_8gpu.jsonl
     ;;
 esac
