@@ -122,6 +122,14 @@ def g2_unsafe(curve: str, tau: int = TEST_TAU) -> bytes:
     return out.raw
 
 
+def kzg_vk_load(curve: str, vk_bin: bytes):
+    """srs.Vk.ReadFrom on a setup's vk.bin (setup/setup.go:174,190): (Kzg.G2 as 2 G2Affine raw, Kzg.G1 raw)."""
+    nb = FP_BYTES[curve]
+    g2, g1 = C.create_string_buffer(8 * nb), C.create_string_buffer(2 * nb)
+    _lib.check(_lib.load().b2p_kzg_vk_load(CURVE_ID[curve], _buf(bytes(vk_bin)), len(vk_bin), g2, g1))
+    return g2.raw, g1.raw
+
+
 def pairing_check(curve: str, g1_raw: bytes, g2_raw: bytes) -> bool:
     """prod e(P_i, Q_i) == 1 for points in G1Affine / G2Affine memory layout."""
     n = len(g1_raw) // (2 * FP_BYTES[curve])
@@ -190,14 +198,14 @@ class SRS:
         return cls(curve, h.value, g2=g2)
 
     @classmethod
-    def from_pk_bin(cls, curve: str, pk_bin: bytes, count: int) -> "SRS":
+    def from_pk_bin(cls, curve: str, pk_bin: bytes, count: int, vk_bin: Optional[bytes] = None) -> "SRS":
         """setup/setup.go:165-228: the first `count` points of an embedded pk.bin (u32 BE count + compressed
-        G1), decompressed on the GPU."""
+        G1), decompressed on the GPU; vk_bin: the setup's vk.bin (its G2 points, for plonk.Verify)."""
         _lib.init()
         h = C.c_void_p()
         _lib.check(_lib.load().b2p_srs_load_compressed(CURVE_ID[curve], _buf(bytes(pk_bin)), len(pk_bin), count,
                                                        C.byref(h)))
-        return cls(curve, h.value)
+        return cls(curve, h.value, g2=kzg_vk_load(curve, vk_bin)[0] if vk_bin is not None else None)
 
     @classmethod
     def unsafe(cls, curve: str, size: int, tau: int = TEST_TAU) -> "SRS":

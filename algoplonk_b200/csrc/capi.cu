@@ -457,6 +457,13 @@ API int b2p_pairing_check(int curve, const void* g1_points, const void* g2_point
         *is_one = ok ? 1 : 0;
     });
 }
+API int b2p_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g2, void* out_g1) {
+    return guarded([&] {
+        require_curve(curve);
+        require(vk_bin && out_g2 && out_g1, "null argument");
+        if (const char* e = host_kzg_vk_load(curve, vk_bin, len, out_g2, out_g1)) throw Error(B2P_ERR_ARG, e);
+    });
+}
 API int b2p_g2_generate_unsafe(int curve, const void* tau, void* out_g2) {
     return guarded([&] {
         require_curve(curve);

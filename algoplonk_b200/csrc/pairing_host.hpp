@@ -463,6 +463,94 @@ struct Pairing {
         return acc;
     }
 
+    // ---- gnark's compressed encodings (kzg.VerifyingKey.ReadFrom on setup/<name>/vk.bin, setup/setup.go:174,190) ----
+    // Both base fields are 3 mod 4: sqrt(a) = a^((p+1)/4) when it exists.
+    static bool fp_sqrt(const Fp& a, Fp* out) {
+        uint64_t e[Fp::N];
+        uint64_t carry = 1;
+        for (int i = 0; i < Fp::N; i++) {           // p + 1
+            u128 s = (u128)Fp::M(i) + carry;
+            e[i] = (uint64_t)s;
+            carry = (uint64_t)(s >> 64);
+        }
+        for (int i = 0; i < Fp::N; i++) e[i] = (e[i] >> 2) | (i + 1 < Fp::N ? e[i + 1] << 62 : 0);
+        Fp s = a.pow(e, Fp::N);
+        if (!(s.sqr() == a)) return false;
+        *out = s;
+        return true;
+    }
+    // through the norm: x0^2 = (a0 +- sqrt(a0^2 + a1^2)) / 2, x1 = a1 / (2 x0)
+    static bool e2_sqrt(const E2& a, E2* out) {
+        if (a.b.is_zero()) {
+            Fp s;
+            if (fp_sqrt(a.a, &s)) { *out = {s, Fp::zero()}; return true; }
+            if (fp_sqrt(a.a.neg(), &s)) { *out = {Fp::zero(), s}; return true; }   // -1 is a non-residue
+            return false;
+        }
+        Fp n;
+        if (!fp_sqrt(a.a.sqr() + a.b.sqr(), &n)) return false;
+        const Fp half = Fp::from_u64(2).inverse();
+        const Fp cands[2] = {(a.a + n) * half, (a.a - n) * half};
+        for (const Fp& cand : cands) {
+            Fp x0;
+            if (!fp_sqrt(cand, &x0) || x0.is_zero()) continue;
+            E2 x = {x0, a.b * x0.dbl().inverse()};
+            if (x.sqr() == a) { *out = x; return true; }
+        }
+        return false;
+    }
+    static bool lex_largest(const Fp& mont) {       // canonical value > (p - 1) / 2
+        const Fp c = mont.from_mont();
+        for (int i = Fp::N - 1; i >= 0; i--) {
+            const uint64_t h = (Fp::M(i) >> 1) | (i + 1 < Fp::N ? Fp::M(i + 1) << 63 : 0);   // (p - 1) / 2, p odd
+            if (c.v[i] > h) return true;
+            if (c.v[i] < h) return false;
+        }
+        return false;
+    }
+    static bool be_to_fp(const uint8_t* in, uint8_t first_mask, Fp* out) {   // big-endian, canonical
+        Fp raw = Fp::zero();
+        for (int b = 0; b < FPB; b++) {
+            uint8_t byte = in[FPB - 1 - b];
+            if (b == FPB - 1) byte &= first_mask;
+            raw.v[b >> 3] |= (uint64_t)byte << (8 * (b & 7));
+        }
+        if (Fp::geq_mod(raw.v)) return false;
+        *out = Fp::mul(raw, Fp::r2());
+        return true;
+    }
+    struct Flags { uint8_t mask, small, large, inf; int shift; };
+    static Flags flags() {   // BN254: 2 flag bits (10 smallest y, 11 largest, 01 infinity); BLS12-381: 3 (100 / 101 / 110)
+        return PC::D_TWIST ? Flags{0x3F, 2, 3, 1, 6} : Flags{0x1F, 4, 5, 6, 5};
+    }
+    // X.A1 || X.A0 with the flags on the first byte; y is "largest" by A1, or by A0 when A1 = 0.  nullptr = ok
+    static const char* g2_decompress(const uint8_t* in, G2* out) {
+        const Flags f = flags();
+        const uint8_t flag = in[0] >> f.shift;
+        if (flag == f.inf) { *out = {E2::zero(), E2::zero(), true}; return nullptr; }
+        if (flag != f.small && flag != f.large) return "compressed G2: invalid flag";
+        E2 x;
+        if (!be_to_fp(in, f.mask, &x.b) || !be_to_fp(in + FPB, 0xFF, &x.a)) return "compressed G2: coordinate not reduced";
+        E2 y;
+        if (!e2_sqrt(x.sqr() * x + twist_b(), &y)) return "compressed G2: x is not on the twist";
+        const bool largest = y.b.is_zero() ? lex_largest(y.a) : lex_largest(y.b);
+        if (largest != (flag == f.large)) y = y.neg();
+        *out = {x, y, false};
+        return nullptr;
+    }
+    static const char* g1_decompress(const uint8_t* in, G1* out) {
+        const Flags f = flags();
+        const uint8_t flag = in[0] >> f.shift;
+        if (flag == f.inf) { *out = {Fp::zero(), Fp::zero(), true}; return nullptr; }
+        if (flag != f.small && flag != f.large) return "compressed G1: invalid flag";
+        Fp x, y;
+        if (!be_to_fp(in, f.mask, &x)) return "compressed G1: coordinate not reduced";
+        if (!fp_sqrt(x.sqr() * x + Fp::from_u64(PC::B), &y)) return "compressed G1: x is not on the curve";
+        if (lex_largest(y) != (flag == f.large)) y = y.neg();
+        *out = {x, y, false};
+        return nullptr;
+    }
+
     // line coefficients of the Miller loop of Q, in the order the loop consumes them
     static Prepared prepare(const G2& q) {
         Prepared pr;

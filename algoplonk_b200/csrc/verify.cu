@@ -48,6 +48,29 @@ bool host_pairing_check(int curve, const void* g1s, const void* g2s, uint64_t n,
 }
 
 template <class PC>
+static const char* kzg_vk_load_t(const uint8_t* in, uint64_t len, uint8_t* out_g2, uint8_t* out_g1) {
+    using PR = hp::Pairing<PC>;
+    if (len != 5ull * PR::FPB) return "vk.bin has the wrong length (2 compressed G2 + 1 compressed G1)";
+    typename PR::G2 q[2];
+    typename PR::G1 g;
+    for (int i = 0; i < 2; i++)
+        if (const char* e = PR::g2_decompress(in + 2 * i * PR::FPB, &q[i])) return e;
+    if (const char* e = PR::g1_decompress(in + 4 * PR::FPB, &g)) return e;
+    PR::store_g2(q[0], out_g2);
+    PR::store_g2(q[1], out_g2 + 4 * PR::FPB);
+    if (g.inf) memset(out_g1, 0, 2 * PR::FPB);
+    else { g.x.store(out_g1); g.y.store(out_g1 + PR::FPB); }
+    return nullptr;
+}
+
+// kzg.VerifyingKey.ReadFrom on an embedded setup/<name>/vk.bin (setup/setup.go:174,190): nullptr = ok
+const char* host_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g2, void* out_g1) {
+    const uint8_t* in = static_cast<const uint8_t*>(vk_bin);
+    return curve == 0 ? kzg_vk_load_t<hp::Bn254Pairing>(in, len, static_cast<uint8_t*>(out_g2), static_cast<uint8_t*>(out_g1))
+                      : kzg_vk_load_t<hp::Bls12381Pairing>(in, len, static_cast<uint8_t*>(out_g2), static_cast<uint8_t*>(out_g1));
+}
+
+template <class PC>
 static void g2_unsafe_t(const void* tau_mont, uint8_t* out) {
     using PR = hp::Pairing<PC>;
     using Fr = typename PC::Fr;

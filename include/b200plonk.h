@@ -267,6 +267,11 @@ int b2p_verify_batch(int curve, uint64_t n, uint32_t nb_public, uint32_t k, cons
  * kzg.BatchVerifyMultiPoints; setup/trusted_setup_test.go checks its setups with the same equation).
  * Points off their curve give B2P_ERR_ARG. */
 int b2p_pairing_check(int curve, const void* g1_points, const void* g2_points, uint64_t n, int* is_one);
+/* srs.Vk.ReadFrom on an embedded setup/<name>/vk.bin (setup/setup.go:174,190,204-211): 2 compressed G2 + 1
+ * compressed G1 (gnark's flag bits: BN254 10/11/01, BLS12-381 100/101/110 on the first byte; G2 as X.A1 || X.A0)
+ * -> vk.Kzg.G2 as 2 G2Affine and vk.Kzg.G1 as 1 G1Affine (Montgomery): the kzg_g2 / kzg_g1 arguments of b2p_verify.
+ * B2P_ERR_ARG: wrong length, bad flag, coordinate not reduced, x not on the curve / twist. */
+int b2p_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g2, void* out_g1);
 /* [1]_2, [tau]_2 : the G2 half of the TestOnly setups' unsafekzg.NewSRS (setup/setup.go:124);
  * tau as in b2p_srs_generate_unsafe; writes 2 G2Affine. */
 int b2p_g2_generate_unsafe(int curve, const void* tau, void* out_g2);

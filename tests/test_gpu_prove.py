@@ -18,7 +18,7 @@ def _compile(c, case):
         return api.Compile(c["cs"], curve, SETUP[curve])
     real = {"PerpetualPowersOfTauBN254": api.SetupName.PerpetualPowersOfTauBN254,
             "DuskBLS12_381": api.SetupName.DuskBLS12381}[case["srs"]]
-    g2 = api.g2_to_mont_bytes(curve, H.real_srs_g2(case["srs"]))     # the setup's vk.bin: cc.Verify runs b2p_verify
+    g2, _ = api.kzg_vk_load(curve, bytes.fromhex(H.srs_kat()[case["srs"]]["vk_bin"]))   # the setup's vk.bin: cc.Verify runs b2p_verify
     return api.Compile(c["cs"], curve, real, srs=api.SRS.from_points(curve, c["srs"], g2=g2))
 
 

@@ -275,3 +275,45 @@ def test_batch_verification_folds_many_proofs_into_one_pairing(curve):
     if pubs[0] != pubs[1]:
         with pytest.raises(ValueError, match="batch"):
             api.verify_batch(*args, proofs, [pubs[1], pubs[0]] + pubs[2:])
+
+
+# ---- setup/<name>/vk.bin ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["PerpetualPowersOfTauBN254", "DuskBLS12_381"])
+def test_vk_bin_of_the_reference_setups_decodes_like_the_oracle(name):
+    """b2p_kzg_vk_load (srs.Vk.ReadFrom, setup/setup.go:174,190) on the committed bytes of the reference's vk.bin:
+    same points as oracle/pairing.py (itself pinned on the Dusk known answers of setup/trusted_setup_test.go:93-95),
+    G1 = the curve generator; damaged files are refused with the reason."""
+    ent = H.srs_kat()[name]
+    curve = ent["curve"]
+    cv = po.CURVES[curve]
+    vk_bin = bytes.fromhex(ent["vk_bin"])
+    g2_raw, g1_raw = api.kzg_vk_load(curve, vk_bin)
+    assert tuple(api.g2_from_mont_bytes(curve, g2_raw)) == tuple(H.real_srs_g2(name))
+    assert api.points_from_mont_bytes(curve, g1_raw) == [cv.g1]
+    nb = cv.fp_bytes
+    # the other sign of y: flip the "largest" flag bit of G2[1] -> the negated point
+    flipped = bytearray(vk_bin)
+    flipped[2 * nb] ^= 0x40 if curve == "BN254" else 0x20
+    q = api.g2_from_mont_bytes(curve, api.kzg_vk_load(curve, bytes(flipped))[0])[1]
+    want = H.real_srs_g2(name)[1]
+    assert q == (want[0], ((-want[1][0]) % cv.p, (-want[1][1]) % cv.p))
+    for damage, why in ((lambda b: b[:-1], "wrong length"),
+                        (lambda b: bytes([b[0] & (0x3F if curve == "BN254" else 0x1F)]) + b[1:], "invalid flag"),
+                        (lambda b: bytes([b[0] | (0x3F if curve == "BN254" else 0x1F)]) + b[1:], "not reduced")):
+        with pytest.raises(_lib.B200PlonkError, match=why):
+            api.kzg_vk_load(curve, damage(vk_bin))
+    # an x that is not on the twist (search a few)
+    for delta in range(1, 40):
+        bad = bytearray(vk_bin)
+        bad[2 * nb - 1] = (bad[2 * nb - 1] + delta) & 0xFF
+        try:
+            api.kzg_vk_load(curve, bytes(bad))
+        except _lib.B200PlonkError as e:
+            assert "not on the twist" in str(e)
+            break
+    else:
+        raise AssertionError("every perturbed x was on the twist")
+    # infinity encodings
+    inf = bytes([0x40 if curve == "BN254" else 0xC0]) + bytes(2 * nb - 1)
+    g2i, _ = api.kzg_vk_load(curve, inf + inf + vk_bin[4 * nb:])
+    assert api.g2_from_mont_bytes(curve, g2i) == [None, None]
