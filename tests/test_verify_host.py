@@ -317,3 +317,27 @@ def test_vk_bin_of_the_reference_setups_decodes_like_the_oracle(name):
     inf = bytes([0x40 if curve == "BN254" else 0xC0]) + bytes(2 * nb - 1)
     g2i, _ = api.kzg_vk_load(curve, inf + inf + vk_bin[4 * nb:])
     assert api.g2_from_mont_bytes(curve, g2i) == [None, None]
+
+
+@pytest.mark.parametrize("case", [c for c in H.golden_proofs() if c["name"] in ("basic", "bsb22_k1")], ids=H.case_id)
+def test_compiled_circuit_verifyproof_glue_without_a_gpu(case):
+    """api.CompiledCircuit.VerifyProof with the key material it would otherwise fetch from the device already in
+    place: the Python glue between the circuit object and b2p_verify (argument order, commitment indexes, G2 of
+    the SRS object) -- the part of cc.Verify the CPU suite can reach."""
+    args, c, vk_pts = _verify_args(case)
+    curve = case["curve"]
+
+    class _Srs:
+        g2 = args[6]
+    cc = api.CompiledCircuit.__new__(api.CompiledCircuit)
+    cc.Ccs, cc.trace, cc.srs, cc.handle, cc.Curve = c["cs"], c["tc"], _Srs(), None, curve
+    cc._vk_points, cc._vk_raw, cc._g1_raw = None, args[4], args[5]
+    proof, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
+    cc.VerifyProof(proof, pub)
+    bad = bytearray(proof)
+    bad[-1] ^= 1
+    with pytest.raises(ValueError, match="error verifying proof"):
+        cc.VerifyProof(bytes(bad), pub)
+    cc.srs.g2 = None
+    with pytest.raises(ValueError, match="G2 points are unknown"):
+        cc.VerifyProof(proof, pub)
