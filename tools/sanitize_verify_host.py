@@ -1,0 +1,114 @@
+"""AddressSanitizer + UndefinedBehaviorSanitizer over the host verifier (csrc/verify_host.hpp, pairing_host.hpp,
+verify.cu): the translation unit is rebuilt with g++ -fsanitize=address,undefined next to a few extern "C" wrappers,
+and every golden proof, a tampered copy of each, the pairing on the ceremony files and the vk.bin decoder (good and
+damaged input) go through it.  CPU only.
+
+    python tools/sanitize_verify_host.py          # prints "sanitizers: 0 reports" and exits 0 when clean
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "algoplonk_b200", "csrc")
+SHIM = r"""
+#include "iface.hpp"
+using namespace b2p;
+extern "C" {
+int s_verify(int curve, uint64_t n, uint32_t nbp, uint32_t k, const uint64_t* cidx, const void* vk, const void* g1,
+             const void* g2, const void* proof, uint64_t plen, const void* pub, uint64_t publen) {
+    HostVerifyKey key{n, nbp, k, cidx, vk, g1, g2};
+    std::string why;
+    static const unsigned char none = 0;
+    return host_verify(curve, key, proof, plen, pub ? pub : &none, publen, &why) ? 1 : 0;
+}
+int s_verify_batch(int curve, uint64_t n, uint32_t nbp, uint32_t k, const uint64_t* cidx, const void* vk, const void* g1,
+                   const void* g2, const void* proofs, uint64_t plen, const void* pubs, uint64_t publen, uint64_t count) {
+    HostVerifyKey key{n, nbp, k, cidx, vk, g1, g2};
+    std::string why;
+    uint64_t bad = 0;
+    static const unsigned char none = 0;
+    return host_verify_batch(curve, key, proofs, plen, pubs ? pubs : &none, publen, count, &bad, &why) ? 1 : 0;
+}
+int s_pairing(int curve, const void* g1s, const void* g2s, uint64_t n) {
+    std::string why;
+    return host_pairing_check(curve, g1s, g2s, n, &why) ? 1 : 0;
+}
+int s_vk_load(int curve, const void* in, uint64_t len, void* g2, void* g1) { return host_kzg_vk_load(curve, in, len, g2, g1) ? 1 : 0; }
+void s_g2_unsafe(int curve, const void* tau, void* out) { host_g2_unsafe(curve, tau, out); }
+}
+"""
+
+
+def build(tmp):
+    shim = os.path.join(tmp, "shim.cpp")
+    with open(shim, "w") as f:
+        f.write(SHIM)
+    lib = os.path.join(tmp, "libverify_san.so")
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address,undefined",
+                    "-fno-sanitize-recover=undefined", "-DHD=inline", "-I", CSRC, "-x", "c++",
+                    os.path.join(CSRC, "verify.cu"), shim, "-o", lib], check=True)
+    return lib
+
+
+def workload(lib_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    import test_verify_host as T
+    from algoplonk_b200 import api
+    from oracle import plonk_oracle as po
+    lib = C.CDLL(lib_path)
+    buf = lambda b: C.create_string_buffer(bytes(b), len(b))
+    n_ok = n_bad = 0
+    for case in H.golden_proofs():
+        (curve, n, nbp, cidx, vk, g1, g2), c, _ = T._verify_args(case)
+        cid = api.CURVE_ID[curve]
+        proof, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
+        ci = (C.c_uint64 * max(len(cidx), 1))(*cidx)
+        call = lambda p, q: lib.s_verify(cid, C.c_uint64(n), nbp, len(cidx), ci, buf(vk), buf(g1), buf(g2), buf(p),
+                                         C.c_uint64(len(p)), buf(q) if q else None, C.c_uint64(len(q)))
+        assert call(proof, pub) == 1
+        n_ok += 1
+        for pos in range(0, len(proof), 37):
+            bad = bytearray(proof)
+            bad[pos] ^= 0x10
+            assert call(bytes(bad), pub) == 0
+            n_bad += 1
+        assert lib.s_verify_batch(cid, C.c_uint64(n), nbp, len(cidx), ci, buf(vk), buf(g1), buf(g2), buf(proof * 3),
+                                  C.c_uint64(len(proof)), buf(pub * 3) if pub else None, C.c_uint64(len(pub)),
+                                  C.c_uint64(3)) == 1
+    for name in ("PerpetualPowersOfTauBN254", "DuskBLS12_381"):
+        ent = H.srs_kat()[name]
+        curve = ent["curve"]
+        cv, cid, nb = po.CURVES[curve], api.CURVE_ID[curve], po.CURVES[curve].fp_bytes
+        vk_bin = bytes.fromhex(ent["vk_bin"])
+        g2, g1 = C.create_string_buffer(8 * nb), C.create_string_buffer(2 * nb)
+        assert lib.s_vk_load(cid, buf(vk_bin), C.c_uint64(len(vk_bin)), g2, g1) == 0
+        for pos in range(0, len(vk_bin), 7):
+            bad = bytearray(vk_bin)
+            bad[pos] ^= 0xA5
+            lib.s_vk_load(cid, buf(bad), C.c_uint64(len(bad)), g2, g1)       # any verdict, no report
+        assert lib.s_vk_load(cid, buf(vk_bin), C.c_uint64(len(vk_bin)), g2, g1) == 0
+        pts = H.real_srs_points(name)
+        g1s = api.points_to_mont_bytes(curve, [pts[1], po.g1_neg(cv, pts[0])])
+        assert lib.s_pairing(cid, buf(g1s), g2, C.c_uint64(2)) == 1
+        out = C.create_string_buffer(8 * nb)
+        lib.s_g2_unsafe(cid, buf(api.fr_to_mont_bytes(curve, [cv.r - 1])), out)
+    print(f"sanitizers: 0 reports ({n_ok} proofs accepted, {n_bad} tampered proofs rejected, vk.bin fuzzed, "
+          f"ceremony pairings checked)")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        workload(sys.argv[1])
+        sys.exit(0)
+    with tempfile.TemporaryDirectory() as tmp:
+        lib = build(tmp)
+        pre = [subprocess.run(["gcc", f"-print-file-name={n}"], capture_output=True, text=True).stdout.strip()
+               for n in ("libasan.so", "libubsan.so")]
+        env = dict(os.environ, LD_PRELOAD=":".join(pre), ASAN_OPTIONS="detect_leaks=0:abort_on_error=1",
+                   UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+        sys.exit(subprocess.run([sys.executable, os.path.abspath(__file__), lib], env=env).returncode)
