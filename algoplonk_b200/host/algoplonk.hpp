@@ -192,6 +192,12 @@ public:
         const auto* p = static_cast<const uint8_t*>(two_g2_affine);
         kzg_g2_.assign(p, p + 8 * (CURVE == B2P_BN254 ? 32 : 48));
     }
+    // the same from the bytes of the embedded setup/<name>/vk.bin (srs.Vk.ReadFrom, setup/setup.go:174,190)
+    void LoadKzgVk(const void* vk_bin, uint64_t vk_len) {
+        std::vector<uint8_t> g2(8 * (CURVE == B2P_BN254 ? 32 : 48)), g1(2 * (CURVE == B2P_BN254 ? 32 : 48));
+        check(b2p_kzg_vk_load(CURVE, vk_bin, vk_len, g2.data(), g1.data()), "srs.Vk.ReadFrom");
+        kzg_g2_ = g2;
+    }
     // S1 S2 S3 Ql Qr Qm Qo Qk commitments of the verifying key (G1Affine memory layout)
     std::vector<uint8_t> VkCommitments() const {
         std::vector<uint8_t> out(8 * (CURVE == B2P_BN254 ? 64 : 96));
