@@ -8,8 +8,9 @@
 //   Fp      Montgomery CIOS multiplication; the radix 2^(32 N32) of the device fields equals 2^(64 N64), so
 //           gnark's in-memory elements are read with a memcpy
 //   Fp2     Fp[u]/(u^2+1)            (both curves)
-//   Fp12    Fp2[w]/(w^6 - xi), flat, xi = 9+u (BN254) / 1+u (BLS12-381); Fp6 = Fp2[v]/(v^3 - xi), v = w^2, only
-//           for the one inversion of the final exponentiation
+//   Fp12    Fp2[w]/(w^6 - xi), stored flat (coefficients of w^0..w^5), xi = 9+u (BN254) / 1+u (BLS12-381);
+//           products, squarings and the inversion go through the tower view Fp6[w]/(w^2 - v), Fp6 = Fp2[v]/(v^3 - xi),
+//           v = w^2 (Karatsuba: 18 / 12 products in Fp2); line functions multiply in sparsely on the flat form
 //   Miller  ate pairing f_{T,Q}(P) with T = t-1: 6x^2 (BN254, 127 bits; no Frobenius correction lines needed
 //           with this loop length) and |x| (BLS12-381); affine doubling/addition on the twist, line
 //           coefficients (slope, slope*x_T - y_T) computed once per G2 point and cached (a verifying key has two)
@@ -31,6 +32,10 @@
 #include <string>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <x86intrin.h>
+#endif
+
 #include "field_params.cuh"
 
 namespace b2p {
@@ -40,7 +45,6 @@ typedef unsigned __int128 u128;
 
 // add / subtract with carry: the x86-64 intrinsics keep the chain in the flags register
 #if defined(__x86_64__)
-#include <x86intrin.h>
 #define B2P_ADC(c, a, b, out) _addcarry_u64((c), (a), (b), reinterpret_cast<unsigned long long*>(out))
 #define B2P_SBB(c, a, b, out) _subborrow_u64((c), (a), (b), reinterpret_cast<unsigned long long*>(out))
 #else
@@ -96,14 +100,6 @@ struct Fe {
             if (a[i] < M(i)) return false;
         }
         return true;
-    }
-    static void sub_mod(uint64_t* a) {
-        uint64_t br = 0;
-        for (int i = 0; i < N; i++) {
-            u128 d = (u128)a[i] - M(i) - br;
-            a[i] = (uint64_t)d;
-            br = (uint64_t)(d >> 64) & 1;
-        }
     }
     // r = t - p if t >= p (or `force`), else t
     static inline void cond_sub(uint64_t* t, uint64_t force) {
@@ -226,7 +222,7 @@ struct Fp2T {
     }
 };
 
-// Fp6 = Fp2[v]/(v^3 - xi): only what the Fp12 inversion needs
+// Fp6 = Fp2[v]/(v^3 - xi): what the tower view of Fp12 needs
 template <class E2>
 struct Fp6T {
     E2 c[3];
