@@ -341,3 +341,31 @@ def test_compiled_circuit_verifyproof_glue_without_a_gpu(case):
     cc.srs.g2 = None
     with pytest.raises(ValueError, match="G2 points are unknown"):
         cc.VerifyProof(proof, pub)
+
+
+def test_verifier_is_reentrant_across_host_threads():
+    """b2p_verify from 6 host threads at once (ctypes drops the GIL), both curves interleaved, good and tampered
+    proofs: the shared state -- the per-G2 line cache and the Frobenius constants -- is built once under a lock."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = []
+    for case in H.golden_proofs():
+        if case["name"] != "basic":
+            continue
+        args, _, _ = _verify_args(case)
+        proof, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
+        bad = bytearray(proof)
+        bad[100] ^= 4
+        # a G2 pair nobody has prepared yet, so that the first calls race on the cache
+        fresh = api.g2_unsafe(case["curve"], 424242)
+        jobs += [(args, proof, pub, True), (args, bytes(bad), pub, False),
+                 (args[:6] + (fresh,), proof, pub, False)] * 6
+
+    def run(job):
+        args, proof, pub, want = job
+        try:
+            api.verify(*args, proof, pub)
+            return want is True
+        except ValueError:
+            return want is False
+    with ThreadPoolExecutor(6) as ex:
+        assert all(ex.map(run, jobs))
