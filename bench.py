@@ -354,6 +354,15 @@ def run_b200(args):
                 "note": "254-bit modular arithmetic makes this kernel INT32-multiplier-bound, not HBM-bound: ncu shows "
                         "sm__pipe_fmaheavy_cycles_active at 91 % (DESIGN.md section 4); the honest roofline is "
                         "msm.msm_g1_adds_per_sec against msm.madd_roofline_per_sec"}
+    # the roof that binds this kernel (SURVEY 8d asks for both fractions): G1 mixed additions / s against the rate at
+    # which the INT32 multiplier pipe saturates (MADD_ROOFLINE above, from the measured field-multiplication peak)
+    adds_per_sec = stats["msm_accum_adds"] / (stats["msm_accum_ms"] * 1e-3)
+    if MADD_ROOFLINE.get(curve):
+        roofline["binding_roof"] = {"bound": "int32-multiplier", "achieved": adds_per_sec,
+                                    "peak": MADD_ROOFLINE[curve], "unit": "G1 mixed additions/s",
+                                    "frac": adds_per_sec / MADD_ROOFLINE[curve],
+                                    "peak_source": "profiles/microbench_r1.json (field multiplications/s on all SMs) "
+                                                   "/ 9.4 multiplication-equivalents per XYZZ mixed addition"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
