@@ -40,3 +40,28 @@ extern "C" void ht_field_op(int field, int op, const uint32_t* a, const uint32_t
         case 3: binop<FpBls12381>(op, a, b, o); break;
     }
 }
+
+// ---- the curve formulas of ec.cuh (what k_msm_accumulate and the bucket reductions execute) -----------------
+#include "../../algoplonk_b200/csrc/ec.cuh"
+template <class Fp> static void ecop(int op, const uint32_t* p1, const uint32_t* p2, uint64_t k, uint32_t* o) {
+    Affine<Fp> a, b;
+    memcpy(&a, p1, sizeof a); memcpy(&b, p2, sizeof b);     // Montgomery coordinates, (0,0) = infinity
+    XYZZ<Fp> acc = XYZZ<Fp>::from_affine(a);
+    switch (op) {
+        case 0: acc.add(XYZZ<Fp>::from_affine(b)); break;                       // general addition
+        case 1: if (!b.is_inf()) acc.add_affine(b.x, b.y); break;              // mixed addition (the hot formula)
+        case 2: acc = acc.dbl(); break;
+        case 3: acc.add_affine_signed(b, true); break;                          // a - b
+        case 4: acc.add_affine_signed(b, false); break;                         // a + b, infinity-aware
+        case 5: acc = acc.mul_small(k); break;
+        case 6: acc = XYZZ<Fp>::dbl_affine(a.x, a.y); break;
+        case 7: acc = acc.dbl(); acc.add(XYZZ<Fp>::from_affine(a)); acc.add(acc.neg()); break;   // 3a - 3a
+        case 8: { XYZZ<Fp> t = acc.dbl(); t.add(acc); acc = t; acc.add(XYZZ<Fp>::from_affine(b).dbl()); break; }  // 3a + 2b
+    }
+    Affine<Fp> r = acc.to_affine();
+    memcpy(o, &r, sizeof r);
+}
+extern "C" void ht_ec_op(int curve, int op, const uint32_t* p1, const uint32_t* p2, uint64_t k, uint32_t* o) {
+    if (curve == 0) ecop<FpBn254>(op, p1, p2, k, o);
+    else ecop<FpBls12381>(op, p1, p2, k, o);
+}

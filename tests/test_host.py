@@ -283,3 +283,42 @@ def test_conversions_roundtrip():
         assert api.fr_from_mont_bytes(curve, api.fr_to_mont_bytes(curve, vals)) == vals
         pts = po.srs_from_tau(cv, 5, 3) + [None]
         assert api.points_from_mont_bytes(curve, api.points_to_mont_bytes(curve, pts)) == pts
+
+
+@pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
+def test_device_curve_formulas_on_host(hostfield, curve):
+    """ec.cuh -- the XYZZ mixed addition, doubling and general addition the MSM kernels execute -- through the same
+    host emulation, against the big-int oracle, including the cases a bucket sees rarely: P + P, P - P, infinity
+    on either side, small multiples."""
+    from algoplonk_b200 import api
+    cv = po.CURVES[curve]
+    cid = 0 if curve == "BN254" else 1
+    nw = 2 * (8 if curve == "BN254" else 12)
+    rng = random.Random(41 + cid)
+
+    def call(op, P, Q=None, k=0):
+        a = (C.c_uint32 * nw).from_buffer_copy(api.points_to_mont_bytes(curve, [P]))
+        b = (C.c_uint32 * nw).from_buffer_copy(api.points_to_mont_bytes(curve, [Q]))
+        o = (C.c_uint32 * nw)()
+        hostfield.ht_ec_op(cid, op, a, b, C.c_uint64(k), o)
+        return api.points_from_mont_bytes(curve, bytes(o))[0]
+
+    pts = [po.g1_mul(cv, cv.g1, rng.randrange(1, cv.r)) for _ in range(6)] + [cv.g1]
+    for P in pts:
+        Q = rng.choice(pts)
+        want = po.g1_add(cv, P, Q)
+        assert call(0, P, Q) == want
+        assert call(1, P, Q) == want                       # includes P == Q for some draws: the doubling branch
+        assert call(4, P, Q) == want
+        assert call(3, P, Q) == po.g1_add(cv, P, po.g1_neg(cv, Q))
+        assert call(2, P) == po.g1_add(cv, P, P) == call(6, P)
+        assert call(7, P) is None
+        assert call(8, P, Q) == po.g1_add(cv, po.g1_mul(cv, P, 3), po.g1_mul(cv, Q, 2))
+        for k in (0, 1, 2, 3, 7, 255, 65537):
+            assert call(5, P, None, k) == (po.g1_mul(cv, P, k) if k else None)
+    P = pts[0]
+    assert call(1, P, P) == po.g1_add(cv, P, P) == call(0, P, P) == call(4, P, P)
+    assert call(1, P, po.g1_neg(cv, P)) is None and call(0, P, po.g1_neg(cv, P)) is None and call(3, P, P) is None
+    assert call(0, None, P) == P and call(0, P, None) == P and call(4, None, P) == P and call(4, P, None) == P
+    assert call(1, None, P) == P and call(3, None, P) == po.g1_neg(cv, P)
+    assert call(2, None) is None and call(0, None, None) is None and call(5, None, None, 5) is None
