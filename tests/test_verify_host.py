@@ -88,7 +88,7 @@ def test_pairing_is_bilinear_and_non_degenerate(curve):
         api.pairing_check(curve, P(1), api.g2_to_mont_bytes(curve, [((1, 2), (3, 4))]))
 
 
-@pytest.mark.parametrize("name", ["PerpetualPowersOfTauBN254", "DuskBLS12_381", "EthereumKzgCeremonyBLS12_381"])
+@pytest.mark.parametrize("name", ["PerpetualPowersOfTauBN254", "DuskBLS12_381", "EethereumKzgCeremonyBLS12_381"])
 def test_pairing_on_the_reference_setups_own_points(name):
     """e([tau]_1, [1]_2) == e([1]_1, [tau]_2), every operand read from the ceremony files
     (setup/trusted_setup_test.go checks its setups with the same equation)."""
@@ -278,7 +278,7 @@ def test_batch_verification_folds_many_proofs_into_one_pairing(curve):
 
 
 # ---- setup/<name>/vk.bin ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["PerpetualPowersOfTauBN254", "DuskBLS12_381"])
+@pytest.mark.parametrize("name", ["PerpetualPowersOfTauBN254", "DuskBLS12_381", "EethereumKzgCeremonyBLS12_381"])
 def test_vk_bin_of_the_reference_setups_decodes_like_the_oracle(name):
     """b2p_kzg_vk_load (srs.Vk.ReadFrom, setup/setup.go:174,190) on the committed bytes of the reference's vk.bin:
     same points as oracle/pairing.py (itself pinned on the Dusk known answers of setup/trusted_setup_test.go:93-95),
