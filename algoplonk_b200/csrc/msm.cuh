@@ -23,6 +23,7 @@
 #include <vector>
 #include "common.cuh"
 #include "scan.cuh"
+#include "msm_digits.cuh"
 
 namespace b2p {
 
@@ -34,24 +35,6 @@ constexpr int MSM_THREADS = 128;
 // 44.2 ms of accumulation per 2^20 proof at 4 / 3 / 2 blocks)
 constexpr int MSM_ACC_BLOCKS_WIDE = 2;
 constexpr int MSM_SLOTS = 16;      // MSMs that can be queued before their results are fetched
-
-struct MsmPlan {
-    int c = 0;        // window bits
-    int W = 0;        // windows
-    uint32_t nbuckets = 0;   // 2^(c-1)
-};
-
-inline MsmPlan msm_plan(uint64_t npoints, int scalar_bits, int force_c = 0) {
-    MsmPlan best;
-    double best_cost = 1e300;
-    for (int c = 2; c <= 22; c++) {
-        if (force_c && c != force_c) continue;
-        int W = (scalar_bits + 1 + c - 1) / c;
-        double cost = (double)npoints * W + 3.0 * (double)(1u << (c - 1));
-        if (cost < best_cost) { best_cost = cost; best.c = c; best.W = W; best.nbuckets = 1u << (c - 1); }
-    }
-    return best;
-}
 
 // ---------------------------------------------------------------------------
 // SRS table:  T[w * npoints + i] = 2^(c*w) * P_i
@@ -71,32 +54,6 @@ __global__ void k_msm_build_table(Affine<Fp>* __restrict__ table, uint64_t npoin
         st_field(&table[(uint64_t)w * npoints + i].y, a.y);
         // continue from the affine form: keeps ZZ = ZZZ = 1 so later doublings stay cheap
         acc = XYZZ<Fp>::from_affine(a);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// digit extraction
-// ---------------------------------------------------------------------------
-template <class Fr>
-__device__ __forceinline__ uint32_t window_bits(const Fr& s, int off, int c) {
-    const int limb = off >> 5, sh = off & 31;
-    uint64_t lo = limb < Fr::N ? s.v[limb] : 0u;
-    uint64_t hi = limb + 1 < Fr::N ? s.v[limb + 1] : 0u;
-    uint64_t t = (lo | (hi << 32)) >> sh;
-    return (uint32_t)(t & ((1u << c) - 1));
-}
-
-// Calls f(w, bucket, neg) for every non-zero signed digit of s (canonical form).
-template <class Fr, class Fn>
-__device__ __forceinline__ void for_each_digit(const Fr& s, int c, int W, Fn f) {
-    uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1);
-    for (int w = 0; w < W; w++) {
-        uint32_t d = window_bits(s, w * c, c) + carry;
-        carry = 0;
-        bool neg = false;
-        if (d > half) { d = (1u << c) - d; neg = true; carry = 1; }
-        if (d) f(w, d - 1, neg);
     }
 }
 

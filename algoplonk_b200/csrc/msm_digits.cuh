@@ -1,0 +1,53 @@
+// Window plan and signed-digit recoding of the MSM (split out of msm.cuh so that the host tests can run the very
+// code the kernels execute: tests/csrc/msm_digits_shim.cpp, tests/test_host.py).
+#pragma once
+#include <cstdint>
+#include "ptx.cuh"
+
+namespace b2p {
+
+struct MsmPlan {
+    int c = 0;        // window bits
+    int W = 0;        // windows
+    uint32_t nbuckets = 0;   // 2^(c-1)
+};
+
+inline MsmPlan msm_plan(uint64_t npoints, int scalar_bits, int force_c = 0) {
+    MsmPlan best;
+    double best_cost = 1e300;
+    for (int c = 2; c <= 22; c++) {
+        if (force_c && c != force_c) continue;
+        int W = (scalar_bits + 1 + c - 1) / c;
+        double cost = (double)npoints * W + 3.0 * (double)(1u << (c - 1));
+        if (cost < best_cost) { best_cost = cost; best.c = c; best.W = W; best.nbuckets = 1u << (c - 1); }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------
+// digit extraction
+// ---------------------------------------------------------------------------
+template <class Fr>
+HD uint32_t window_bits(const Fr& s, int off, int c) {
+    const int limb = off >> 5, sh = off & 31;
+    uint64_t lo = limb < Fr::N ? s.v[limb] : 0u;
+    uint64_t hi = limb + 1 < Fr::N ? s.v[limb + 1] : 0u;
+    uint64_t t = (lo | (hi << 32)) >> sh;
+    return (uint32_t)(t & ((1u << c) - 1));
+}
+
+// Calls f(w, bucket, neg) for every non-zero signed digit of s (canonical form).
+template <class Fr, class Fn>
+HD void for_each_digit(const Fr& s, int c, int W, Fn f) {
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    for (int w = 0; w < W; w++) {
+        uint32_t d = window_bits(s, w * c, c) + carry;
+        carry = 0;
+        bool neg = false;
+        if (d > half) { d = (1u << c) - d; neg = true; carry = 1; }
+        if (d) f(w, d - 1, neg);
+    }
+}
+
+}  // namespace b2p

@@ -322,3 +322,44 @@ def test_device_curve_formulas_on_host(hostfield, curve):
     assert call(0, None, P) == P and call(0, P, None) == P and call(4, None, P) == P and call(4, P, None) == P
     assert call(1, None, P) == P and call(3, None, P) == po.g1_neg(cv, P)
     assert call(2, None) is None and call(0, None, None) is None and call(5, None, None, 5) is None
+
+
+def test_msm_signed_digits_recompose_the_scalar(tmp_path_factory):
+    """msm_digits.cuh on the host: for every window size the plan can choose and scalars built to stress the carry
+    chain (all windows at / just above half, all ones, r - 1, powers of two around window edges), the signed digits
+    sum back to the scalar, every bucket index is inside [0, 2^(c-1)), and the last window absorbs the final carry."""
+    out = tmp_path_factory.mktemp("md") / "msm_digits.so"
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O1", "-std=c++17", "-shared", "-fPIC",
+                    "-x", "c++", os.path.join(ROOT, "tests", "csrc", "msm_digits_shim.cpp"), "-o", str(out)], check=True)
+    lib = C.CDLL(str(out))
+    rng = random.Random(77)
+    for curve, bits in (("BN254", 254), ("BLS12_381", 255)):
+        r = po.CURVES[curve].r
+        assert r.bit_length() == bits
+        for c in range(2, 23):
+            cc, W, nb = C.c_int(), C.c_int(), C.c_uint32()
+            lib.ht_msm_plan(C.c_uint64(1 << 20), bits, c, C.byref(cc), C.byref(W), C.byref(nb))
+            assert (cc.value, nb.value) == (c, 1 << (c - 1)) and W.value * c >= bits + 1 > (W.value - 1) * c
+            half = 1 << (c - 1)
+            pattern = lambda d: sum(d << (c * w) for w in range(W.value)) % r
+            scalars = [0, 1, r - 1, r - 2, (1 << (bits - 1)) - 1, (1 << (bits - 1)), pattern(half), pattern(half + 1),
+                       pattern(half - 1), pattern((1 << c) - 1), (1 << c) - 1, 1 << c, (1 << (c * (W.value - 1))) - 1]
+            scalars += [rng.randrange(r) for _ in range(6)]
+            for s in scalars:
+                words = (C.c_uint32 * 8)(*[(s >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+                win, bucket, neg = (C.c_int * 64)(), (C.c_uint32 * 64)(), (C.c_int * 64)()
+                assert W.value <= 64 or c < 4
+                if W.value > 64:
+                    win, bucket, neg = (C.c_int * 128)(), (C.c_uint32 * 128)(), (C.c_int * 128)()
+                cnt = lib.ht_msm_digits(words, c, W.value, win, bucket, neg)
+                assert 0 <= cnt <= W.value
+                total = 0
+                for i in range(cnt):
+                    assert 0 <= bucket[i] < half and 0 <= win[i] < W.value
+                    assert i == 0 or win[i] > win[i - 1]
+                    total += (-1 if neg[i] else 1) * (bucket[i] + 1) << (c * win[i])
+                assert total == s, (curve, c, hex(s))
+    # the plan picks the window the cost model says: 2^20 points -> c = 20, 13 windows for BN254 (DESIGN.md 4.2)
+    cc, W, nb = C.c_int(), C.c_int(), C.c_uint32()
+    lib.ht_msm_plan(C.c_uint64((1 << 20) + 3), 254, 0, C.byref(cc), C.byref(W), C.byref(nb))
+    assert (cc.value, W.value, nb.value) == (20, 13, 1 << 19)
