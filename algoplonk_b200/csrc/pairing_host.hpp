@@ -312,13 +312,39 @@ struct Fp12T {
         E6 d = (A * A - (B * B).mul_v()).inverse();
         return from_tower(A * d, (B * d).neg());
     }
-    Fp12T pow_u64(uint64_t e) const {
+    // Squaring of an element of the cyclotomic subgroup (norm 1 over Fp6: everything after the easy part of the
+    // final exponentiation).  Granger-Scott: with Fp12 = Fp4[.]^3 the square costs three squarings in
+    // Fp4 = Fp2[y]/(y^2 - xi), i.e. 6 products in Fp2 instead of 12.  In the tower view (g0 g1 g2) + (g3 g4 g5) w
+    // the three Fp4 elements are (g0, g4), (g3, g2), (g1, g5).
+    Fp12T cyclotomic_sqr() const {
+        const E2 &g0 = c[0], &g1 = c[2], &g2 = c[4], &g3 = c[1], &g4 = c[3], &g5 = c[5];
+        auto fp4_sqr = [](const E2& a, const E2& b, E2* r0, E2* r1) {   // (a + b y)^2 = (a^2 + xi b^2) + 2ab y
+            E2 ab = a * b;
+            *r0 = (a + b) * (a + b.mul_xi()) - ab - ab.mul_xi();
+            *r1 = ab.dbl();
+        };
+        E2 t0, t1, t2, t3, t4, t5;
+        fp4_sqr(g0, g4, &t0, &t1);
+        fp4_sqr(g3, g2, &t2, &t3);
+        fp4_sqr(g1, g5, &t4, &t5);
+        auto three_minus_two = [](const E2& t, const E2& z) { E2 d = t - z; return d.dbl() + t; };   // 3t - 2z
+        auto three_plus_two = [](const E2& t, const E2& z) { E2 d = t + z; return d.dbl() + t; };    // 3t + 2z
+        Fp12T r;
+        r.c[0] = three_minus_two(t0, g0);             // g0'
+        r.c[3] = three_plus_two(t1, g4);              // g4'
+        r.c[1] = three_plus_two(t5.mul_xi(), g3);     // g3'
+        r.c[4] = three_minus_two(t4, g2);             // g2'
+        r.c[2] = three_minus_two(t2, g1);             // g1'
+        r.c[5] = three_plus_two(t3, g5);              // g5'
+        return r;
+    }
+    Fp12T pow_u64(uint64_t e, bool cyclotomic = false) const {
         if (e == 0) return one();
         int top = 63;
         while (!((e >> top) & 1)) top--;
         Fp12T acc = *this;
         for (int i = top - 1; i >= 0; i--) {
-            acc = acc.sqr();
+            acc = cyclotomic ? acc.cyclotomic_sqr() : acc.sqr();
             if ((e >> i) & 1) acc = acc * *this;
         }
         return acc;
@@ -654,10 +680,10 @@ struct Pairing {
     }
     // f^x for f in the cyclotomic subgroup (inverse = conjugate)
     static E12 exp_x(const E12& f) {
-        E12 r = f.pow_u64(PC::X);
+        E12 r = f.pow_u64(PC::X, true);
         return PC::X_NEG ? r.conj() : r;
     }
-    static E12 pow_small(const E12& f, unsigned e) { return f.pow_u64(e); }
+    static E12 pow_small(const E12& f, unsigned e) { return f.pow_u64(e, true); }   // cyclotomic inputs only
 
     static E12 final_exponentiation(const E12& f0) {
         // easy part: f^((p^6 - 1)(p^2 + 1))

@@ -369,3 +369,15 @@ def test_verifier_is_reentrant_across_host_threads():
             return want is False
     with ThreadPoolExecutor(6) as ex:
         assert all(ex.map(run, jobs))
+
+
+def test_pairing_internal_identities(tmp_path):
+    """tests/csrc/pairing_selfcheck.cpp: cyclotomic squaring == squaring on the cyclotomic subgroup, != off it."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "selfcheck"
+    subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "csrc", "pairing_selfcheck.cpp"), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["bad=0", "bad=0"], out.stdout
