@@ -73,3 +73,28 @@ func TestByteIdenticalToGnark(t *testing.T) {
 		t.Fatal(err)
 	}
 }
+
+// The library's verifier gives gnark's verdicts: gnark's own proof is accepted, the same proof with another public
+// witness or a moved commitment is rejected by both.
+func TestVerifyMatchesGnark(t *testing.T) {
+	for _, curve := range []ecc.ID{ecc.BN254, ecc.BLS12_381} {
+		cc, err := ap.Compile(&basicCircuit{}, curve, setup.TestOnlySetup(curve))
+		if err != nil {
+			t.Fatal(err)
+		}
+		w, _ := frontend.NewWitness(&basicCircuit{A: 3, B: 4, C: 5}, curve.ScalarField())
+		proof, err := plonk.Prove(cc.Ccs, cc.Pk, w)
+		if err != nil {
+			t.Fatal(err)
+		}
+		pub, _ := w.Public()
+		if err := Verify(proof, cc.Vk, pub); err != nil {
+			t.Fatalf("%v: gnark's proof rejected: %v", curve, err)
+		}
+		other, _ := frontend.NewWitness(&basicCircuit{A: 4, B: 3, C: 5}, curve.ScalarField())
+		otherPub, _ := other.Public()
+		if plonk.Verify(proof, cc.Vk, otherPub) == nil || Verify(proof, cc.Vk, otherPub) == nil {
+			t.Fatalf("%v: proof accepted for another public witness", curve)
+		}
+	}
+}
