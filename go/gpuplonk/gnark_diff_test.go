@@ -75,7 +75,7 @@ func TestByteIdenticalToGnark(t *testing.T) {
 }
 
 // The library's verifier gives gnark's verdicts: gnark's own proof is accepted, the same proof with another public
-// witness or a moved commitment is rejected by both.
+// witness is rejected by both.
 func TestVerifyMatchesGnark(t *testing.T) {
 	for _, curve := range []ecc.ID{ecc.BN254, ecc.BLS12_381} {
 		cc, err := ap.Compile(&basicCircuit{}, curve, setup.TestOnlySetup(curve))
