@@ -374,8 +374,19 @@ class CompiledCircuit:
                 raise ValueError("error verifying proof")
         return VerifiedProof(proof, public)
 
+    def VerifyProofs(self, proofs: Sequence[bytes], publics: Sequence[bytes]) -> None:
+        """Many proofs of this circuit, one folded pairing check (b2p_verify_batch); raises ValueError when rejected."""
+        self._key_material()
+        verify_batch(self.Curve, self.trace.n, self.trace.nb_public, self.trace.commitment_constraint_indexes,
+                     self._vk_raw, self._g1_raw, self.srs.g2, proofs, publics)
+
     def VerifyProof(self, proof_bytes: bytes, public_bytes: bytes) -> None:
         """plonk.Verify(proof, cc.Vk, publicWitness) on marshalled bytes; raises ValueError when rejected."""
+        self._key_material()
+        verify(self.Curve, self.trace.n, self.trace.nb_public, self.trace.commitment_constraint_indexes,
+               self._vk_raw, self._g1_raw, self.srs.g2, proof_bytes, public_bytes)
+
+    def _key_material(self) -> None:
         if self.srs.g2 is None:
             raise ValueError("the SRS's G2 points are unknown: pass g2= to SRS.from_points")
         if self._vk_raw is None:
@@ -384,8 +395,6 @@ class CompiledCircuit:
             _lib.check(_lib.load().b2p_circuit_vk_commitments(self.handle, out))
             self._vk_raw = out.raw
             self._g1_raw = points_to_mont_bytes(self.Curve, self.srs.points(0, 1))
-        verify(self.Curve, self.trace.n, self.trace.nb_public, self.trace.commitment_constraint_indexes,
-               self._vk_raw, self._g1_raw, self.srs.g2, proof_bytes, public_bytes)
 
     def free(self):
         if self.handle:

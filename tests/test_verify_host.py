@@ -334,10 +334,13 @@ def test_compiled_circuit_verifyproof_glue_without_a_gpu(case):
     cc._vk_points, cc._vk_raw, cc._g1_raw = None, args[4], args[5]
     proof, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
     cc.VerifyProof(proof, pub)
+    cc.VerifyProofs([proof] * 3, [pub] * 3)
     bad = bytearray(proof)
     bad[-1] ^= 1
     with pytest.raises(ValueError, match="error verifying proof"):
         cc.VerifyProof(bytes(bad), pub)
+    with pytest.raises(ValueError, match="error verifying proof"):
+        cc.VerifyProofs([proof, bytes(bad)], [pub] * 2)
     cc.srs.g2 = None
     with pytest.raises(ValueError, match="G2 points are unknown"):
         cc.VerifyProof(proof, pub)
