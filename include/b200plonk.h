@@ -24,6 +24,10 @@
  * workspace: concurrent b2p_prove / b2p_msm_g1 / b2p_circuit_load calls on the same key are serialised by the
  * library (a lock per SRS handle), calls on different keys run concurrently -- several proofs can be in flight on
  * one GPU, one proving key each.  Freeing a handle while another thread uses it is the caller's error.
+ *
+ * The verification entry points (b2p_verify, b2p_verify_batch, b2p_pairing_check, b2p_kzg_vk_load,
+ * b2p_g2_generate_unsafe: plonk.Verify, algoplonk.go:93) take no handle and touch no device: host arithmetic, as in
+ * gnark, re-entrant from any number of threads.  G2Affine = X.A0 X.A1 Y.A0 Y.A1, each an Fp as above.
  */
 #ifndef B200PLONK_H
 #define B200PLONK_H
