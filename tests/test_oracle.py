@@ -393,3 +393,28 @@ def test_no_public_inputs_and_zero_blinding(curve):
         bad = bytearray(blob)
         bad[6 * 2 * cv.fp_bytes + 5] ^= 1          # inside l(zeta), the first claimed value (Appendix B)
         assert not po.verify_proof(vk, bytes(bad), b"")
+
+
+def test_hash_to_field_is_rfc9380_expand_message_xmd():
+    """The BSB22 challenge hash (templateLogicSigBN254.go:386-397, gnark's fr.Hash with DST "BSB22-Plonk") as
+    restated in the oracle is RFC 9380 expand_message_xmd(SHA-256) with 48 output bytes, reduced mod r.  The generic
+    expander written here is pinned on the RFC's own known answers (Appendix K.1), so the restatement is anchored on
+    a published vector, not only on itself."""
+    import hashlib
+
+    def xmd(msg: bytes, dst: bytes, n: int) -> bytes:
+        ell = (n + 31) // 32
+        dst_prime = dst + bytes([len(dst)])
+        b0 = hashlib.sha256(bytes(64) + msg + n.to_bytes(2, "big") + b"\x00" + dst_prime).digest()
+        blocks = [hashlib.sha256(b0 + b"\x01" + dst_prime).digest()]
+        for i in range(2, ell + 1):
+            blocks.append(hashlib.sha256(bytes(x ^ y for x, y in zip(b0, blocks[-1])) + bytes([i]) + dst_prime).digest())
+        return b"".join(blocks)[:n]
+
+    quux = b"QUUX-V01-CS02-with-expander-SHA256-128"
+    assert xmd(b"", quux, 32).hex() == "68a985b87eb6b46952128911f2a4412bbc302a9d759667f87f7a21d803f07235"
+    assert xmd(b"abc", quux, 32).hex() == "d8ccab23b5985ccea865c6c97b6e5b8350e794e603b4b97902f53a8a0d605615"
+    assert xmd(b"", quux, 128).hex().startswith("af84c27ccfd45d41914fdff5df25293e221afc53d8ad2ac06d5e3e29485dadbe")
+    for cv in (po.BN254, po.BLS12_381):
+        for msg in (bytes(2 * cv.fp_bytes), po.g1_raw_bytes(cv, cv.g1), b"\x40" + bytes(95)):
+            assert po.hash_fr(cv, msg) == int.from_bytes(xmd(msg, b"BSB22-Plonk", 48), "big") % cv.r
