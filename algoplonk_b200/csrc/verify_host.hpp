@@ -178,6 +178,7 @@ struct HostVerifier {
         auto fail = [&](const char* m) { if (why) *why = m; return false; };
         const uint32_t k = vk.k;
         if (vk.n < 2 || (vk.n & (vk.n - 1))) return fail("domain size is not a power of two");
+        if (vk.n > (1ull << PC::FrP::TWO_ADICITY)) return fail("domain size exceeds the scalar field's 2-adicity");
         if (proof_len != proof_size(k)) return fail("proof has the wrong length");
         if (pub_len != 32ull * vk.nb_public) return fail("public inputs have the wrong length");
 

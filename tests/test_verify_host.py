@@ -218,6 +218,16 @@ def test_verdicts_match_the_restated_reference_verifier(curve):
     assert outcomes == {True, False}
 
 
+def test_verify_rejects_impossible_domains():
+    case = H.golden_proofs()[0]
+    args, _, _ = _verify_args(case)
+    proof, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
+    for n, why in ((12, "power of two"), (0, "power of two"), (1, "power of two"), (1 << 40, "2-adicity"),
+                   (2 * args[1], "pairing")):
+        with pytest.raises(ValueError, match=why):
+            api.verify(args[0], n, *args[2:], proof, pub)
+
+
 def test_verify_argument_errors():
     lib = _lib.load()
     assert lib.b2p_verify(7, 8, 0, 0, None, None, None, None, None, 0, None, 0) == _lib.ERR_ARG
