@@ -77,6 +77,14 @@ def workload(lib_path):
             bad[pos] ^= 0x10
             assert call(bytes(bad), pub) == 0
             n_bad += 1
+        import random
+        rng = random.Random(len(proof))
+        for _ in range(8):                                  # garbage proof / public inputs / key: any verdict, no report
+            call(bytes(rng.randrange(256) for _ in range(len(proof))), pub)
+            call(proof, bytes(rng.randrange(256) for _ in range(len(pub))))
+            junk_vk = bytes(rng.randrange(256) for _ in range(len(vk)))
+            assert lib.s_verify(cid, C.c_uint64(n), nbp, len(cidx), ci, buf(junk_vk), buf(g1), buf(g2), buf(proof),
+                                C.c_uint64(len(proof)), buf(pub) if pub else None, C.c_uint64(len(pub))) == 0
         assert lib.s_verify_batch(cid, C.c_uint64(n), nbp, len(cidx), ci, buf(vk), buf(g1), buf(g2), buf(proof * 3),
                                   C.c_uint64(len(proof)), buf(pub * 3) if pub else None, C.c_uint64(len(pub)),
                                   C.c_uint64(3)) == 1
