@@ -124,6 +124,10 @@ def test_argument_errors_do_not_need_a_gpu():
     assert b"unsupported curve" in lib.b2p_last_error()
     assert lib.b2p_marshal_proof(0, 0, None, None, None) == -1
     assert lib.b2p_srs_size(None) == 0
+    assert lib.b2p_srs_set_commit_hook(None, None, None) == -1 and b"null" in lib.b2p_last_error()
+    assert lib.b2p_kzg_vk_load(0, None, 0, None, None) == -1
+    assert lib.b2p_verify_batch(5, 8, 0, 0, None, None, None, None, None, 0, None, 0, 0, None) == -1
+    assert lib.b2p_g2_generate_unsafe(0, None, None) == -1
 
 
 @pytest.mark.parametrize("case", H.golden_proofs(), ids=H.case_id)
