@@ -3,7 +3,10 @@ CUDA library through the C ABI.
 
 Reference surface mirrored (same names, argument meaning and error behaviour):
   Compile(circuit, curve, setup)            /root/reference/algoplonk.go:37-59
-  (*CompiledCircuit).Verify(assignment)     /root/reference/algoplonk.go:79-98  (witness -> Prove -> verify)
+  (*CompiledCircuit).Verify(assignment)     /root/reference/algoplonk.go:79-98  (witness -> Prove -> plonk.Verify)
+  plonk.Verify                              /root/reference/algoplonk.go:93     (verify / verify_batch / VerifyProof:
+                                            b2p_verify, host arithmetic of the library, no GPU)
+  srs.Vk.ReadFrom(vk.bin)                   /root/reference/setup/setup.go:174,190  (kzg_vk_load)
   MarshalProof / MarshalPublicInputs        /root/reference/helper.go:13-24,91-110
   setup names                                /root/reference/setup/setup.go:23-36
 In the real integration these stay Go (go/gpuplonk); this module
