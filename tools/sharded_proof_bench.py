@@ -37,27 +37,35 @@ def main():
             prover.serve()
             prover.close()
             continue
-        plain = api.Compile(cs, curve, setup)
-        cols = [api.fr_to_mont_bytes(curve, c) for c in (L, R, O)]
-        bl = api.fr_to_mont_bytes(curve, blinding)
+        plain = None
+        try:
+            plain = api.Compile(cs, curve, setup)
+            cols = [api.fr_to_mont_bytes(curve, c) for c in (L, R, O)]
+            bl = api.fr_to_mont_bytes(curve, blinding)
 
-        def timed(cc):
-            cc.prove_raw(*cols, bl)                       # warm-up
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(steps):
-                proof = cc.prove_raw(*cols, bl)           # blocking: returns with the proof on the host
-            return (time.perf_counter() - t0) / steps * 1e3, proof.raw
-        ms_plain, want = timed(plain)
-        ms_sharded, got = timed(prover.cc)
-        line = {"curve": curve, "log2_constraints": int(log2), "n_gpus": world, "steps": steps,
-                "ms_per_proof_one_gpu": ms_plain, "ms_per_proof_msm_sharded": ms_sharded,
-                "speedup": ms_plain / ms_sharded, "byte_identical": got == want,
-                "commits_per_proof": prover.committer.commits // (steps + 1),
-                "timing": "host wall clock around blocking b2p_prove calls on rank 0 (a proof ends with its D2H)"}
-        print(json.dumps(line), flush=True)
-        plain.free()
-        prover.close()
+            def timed(cc):
+                cc.prove_raw(*cols, bl)                       # warm-up
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    proof = cc.prove_raw(*cols, bl)           # blocking: returns with the proof on the host
+                return (time.perf_counter() - t0) / steps * 1e3, proof.raw
+            ms_plain, want = timed(plain)
+            ms_sharded, got = timed(prover.cc)
+            line = {"curve": curve, "log2_constraints": int(log2), "n_gpus": world, "steps": steps,
+                    "ms_per_proof_one_gpu": ms_plain, "ms_per_proof_msm_sharded": ms_sharded,
+                    "speedup": ms_plain / ms_sharded, "byte_identical": got == want,
+                    "commits_per_proof": prover.committer.commits // (steps + 1),
+                    "timing": "host wall clock around blocking b2p_prove calls on rank 0 (a proof ends with its D2H)"}
+        except Exception as e:  # noqa: BLE001 -- reported; the other ranks must still be released
+            hook_err = getattr(getattr(prover, "_hook", None), "error", None)
+            line = {"curve": curve, "log2_constraints": int(log2), "n_gpus": world,
+                    "error": f"{type(e).__name__}: {e}"[:300], "hook_error": repr(hook_err)[:300] if hook_err else None}
+        finally:
+            print(json.dumps(line), flush=True)
+            if plain is not None:
+                plain.free()
+            prover.close()                                    # sends STOP: ranks > 0 leave serve()
     dist.barrier()
     dist.destroy_process_group()
 
