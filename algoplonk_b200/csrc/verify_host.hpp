@@ -14,7 +14,10 @@
 // per linear combination.  Infinity commitments are hashed the way the prover hashes them (prover.cuh
 // point_marshal: gnark's 0x40 flag on BLS12-381, zero bytes on BN254).
 #pragma once
+#include <algorithm>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pairing_host.hpp"
@@ -362,11 +365,39 @@ struct HostVerifier {
         if (bad) *bad = count;
         if (count == 0) return true;
         std::vector<Aff> lhs(count), rhs(count);
-        for (uint64_t i = 0; i < count; i++)
-            if (!reduce(vk, proofs + i * proof_len, proof_len, pubs + i * pub_len, pub_len, &lhs[i], &rhs[i], why)) {
-                if (bad) *bad = i;
-                return false;
-            }
+        // the per-proof reductions are independent: spread them over host threads (B2P_VERIFY_THREADS, default
+        // min(cores, 8); small batches stay on the calling thread)
+        unsigned T = 1;
+        if (count >= 4) {
+            const char* e = getenv("B2P_VERIFY_THREADS");
+            unsigned want = e ? (unsigned)atoi(e) : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+            T = (unsigned)std::min<uint64_t>(std::max(1u, want), count);
+        }
+        std::vector<uint64_t> first_bad(T, count);
+        std::vector<std::string> whys(T);
+        auto work = [&](unsigned t) {
+            for (uint64_t i = t; i < count; i += T)
+                if (!reduce(vk, proofs + i * proof_len, proof_len, pubs + i * pub_len, pub_len, &lhs[i], &rhs[i], &whys[t])) {
+                    first_bad[t] = i;
+                    return;
+                }
+        };
+        if (T == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < T; t++) pool.emplace_back(work, t);
+            work(0);
+            for (auto& th : pool) th.join();
+        }
+        unsigned best = 0;                        // every thread stops at its own first failure: the smallest wins
+        for (unsigned t = 1; t < T; t++)
+            if (first_bad[t] < first_bad[best]) best = t;
+        if (first_bad[best] < count) {
+            if (bad) *bad = first_bad[best];
+            if (why) *why = whys[best];
+            return false;
+        }
         uint8_t seed[32];
         Sha256 hs;
         hs.update("b2p-batch-verify");

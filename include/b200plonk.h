@@ -262,7 +262,8 @@ int b2p_verify(int curve, uint64_t n, uint32_t nb_public, uint32_t k, const uint
  * coefficients hashed from the whole batch into ONE pairing check (soundness error 2^-128; the folding
  * kzg.BatchVerifyMultiPoints applies to the two openings of a single proof).  B2P_OK: all accepted.
  * B2P_ERR_VERIFY: *first_bad = index of the first proof rejected before the pairing, or `count` when only the
- * folded pairing check failed (at least one proof is invalid; b2p_verify one by one finds it). */
+ * folded pairing check failed (at least one proof is invalid; b2p_verify one by one finds it).  Batches of 4 or
+ * more spread their per-proof work over host threads: env B2P_VERIFY_THREADS, default min(cores, 8). */
 int b2p_verify_batch(int curve, uint64_t n, uint32_t nb_public, uint32_t k, const uint64_t* commitment_indexes,
                      const void* vk_points, const void* kzg_g1, const void* kzg_g2,
                      const void* proofs, uint64_t proof_len,

@@ -1,4 +1,4 @@
-"""AddressSanitizer + UndefinedBehaviorSanitizer over the host verifier (csrc/verify_host.hpp, pairing_host.hpp,
+"""AddressSanitizer + UndefinedBehaviorSanitizer, then ThreadSanitizer, over the host verifier (csrc/verify_host.hpp, pairing_host.hpp,
 verify.cu): the translation unit is rebuilt with g++ -fsanitize=address,undefined next to a few extern "C" wrappers,
 and every golden proof, a tampered copy of each, the pairing on the ceremony files and the vk.bin decoder (good and
 damaged input) go through it.  CPU only.
@@ -42,13 +42,13 @@ void s_g2_unsafe(int curve, const void* tau, void* out) { host_g2_unsafe(curve, 
 """
 
 
-def build(tmp):
+def build(tmp, sanitize="address,undefined"):
     shim = os.path.join(tmp, "shim.cpp")
     with open(shim, "w") as f:
         f.write(SHIM)
     lib = os.path.join(tmp, "libverify_san.so")
-    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address,undefined",
-                    "-fno-sanitize-recover=undefined", "-DHD=inline", "-I", CSRC, "-x", "c++",
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", f"-fsanitize={sanitize}",
+                    *(["-fno-sanitize-recover=undefined"] if "undefined" in sanitize else []), "-DHD=inline", "-I", CSRC, "-x", "c++",
                     os.path.join(CSRC, "verify.cu"), shim, "-o", lib], check=True)
     return lib
 
@@ -85,9 +85,9 @@ def workload(lib_path):
             junk_vk = bytes(rng.randrange(256) for _ in range(len(vk)))
             assert lib.s_verify(cid, C.c_uint64(n), nbp, len(cidx), ci, buf(junk_vk), buf(g1), buf(g2), buf(proof),
                                 C.c_uint64(len(proof)), buf(pub) if pub else None, C.c_uint64(len(pub))) == 0
-        assert lib.s_verify_batch(cid, C.c_uint64(n), nbp, len(cidx), ci, buf(vk), buf(g1), buf(g2), buf(proof * 3),
-                                  C.c_uint64(len(proof)), buf(pub * 3) if pub else None, C.c_uint64(len(pub)),
-                                  C.c_uint64(3)) == 1
+        assert lib.s_verify_batch(cid, C.c_uint64(n), nbp, len(cidx), ci, buf(vk), buf(g1), buf(g2), buf(proof * 6),
+                                  C.c_uint64(len(proof)), buf(pub * 6) if pub else None, C.c_uint64(len(pub)),
+                                  C.c_uint64(6)) == 1      # >= 4 proofs: the threaded path
     for name in ("PerpetualPowersOfTauBN254", "DuskBLS12_381"):
         ent = H.srs_kat()[name]
         curve = ent["curve"]
@@ -113,10 +113,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         workload(sys.argv[1])
         sys.exit(0)
-    with tempfile.TemporaryDirectory() as tmp:
-        lib = build(tmp)
-        pre = [subprocess.run(["gcc", f"-print-file-name={n}"], capture_output=True, text=True).stdout.strip()
-               for n in ("libasan.so", "libubsan.so")]
-        env = dict(os.environ, LD_PRELOAD=":".join(pre), ASAN_OPTIONS="detect_leaks=0:abort_on_error=1",
-                   UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
-        sys.exit(subprocess.run([sys.executable, os.path.abspath(__file__), lib], env=env).returncode)
+    rc = 0
+    for sanitize, libs in (("address,undefined", ("libasan.so", "libubsan.so")), ("thread", ("libtsan.so",))):
+        with tempfile.TemporaryDirectory() as tmp:
+            lib = build(tmp, sanitize)
+            pre = [subprocess.run(["gcc", f"-print-file-name={n}"], capture_output=True, text=True).stdout.strip()
+                   for n in libs]
+            env = dict(os.environ, LD_PRELOAD=":".join(pre), ASAN_OPTIONS="detect_leaks=0:abort_on_error=1",
+                       UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1", TSAN_OPTIONS="halt_on_error=1",
+                       B2P_VERIFY_THREADS="4")
+            print(f"-fsanitize={sanitize}:", flush=True)
+            rc |= subprocess.run([sys.executable, os.path.abspath(__file__), lib], env=env).returncode
+    sys.exit(rc)
