@@ -1,7 +1,9 @@
 """ctypes binding of libb200plonk.so (include/b200plonk.h).
 
-There is no CPU fallback: if the shared library is missing or no CUDA device is
-usable, every entry point raises.  Build with `python -c "import
+There is no CPU fallback: if the shared library is missing every call raises, and without a usable CUDA device
+every proving / MSM / NTT entry point does (b2p_init fails).  The verification entry points (b2p_verify,
+b2p_verify_batch, b2p_pairing_check, b2p_kzg_vk_load, b2p_g2_generate_unsafe) and the marshalling helpers are host
+arithmetic by design -- plonk.Verify runs on the CPU in the reference too -- and need no device.  Build with `python -c "import
 __graft_entry__ as g; g.build()"` or `make -C algoplonk_b200/csrc -j8`.
 """
 from __future__ import annotations
