@@ -56,6 +56,15 @@ struct HostVerifier {
             Fp X3 = R.sqr() - PPP - Q.dbl();
             return {X3, R * (Q - X3) - S1 * PPP, ZZ * o.ZZ * PP, ZZZ * o.ZZZ * PPP};
         }
+        Ext add_affine(const Aff& o) const {   // mixed addition: o has ZZ = ZZZ = 1
+            if (o.inf) return *this;
+            if (is_inf()) return from(o);
+            Fp U2 = o.x * ZZ, S2 = o.y * ZZZ, P = U2 - X, R = S2 - Y;
+            if (P.is_zero()) return R.is_zero() ? from(o).dbl() : inf();
+            Fp PP = P.sqr(), PPP = P * PP, Q = X * PP;
+            Fp X3 = R.sqr() - PPP - Q.dbl();
+            return {X3, R * (Q - X3) - Y * PPP, ZZ * PP, ZZZ * PPP};
+        }
         Aff to_affine() const {
             if (is_inf()) return {Fp::zero(), Fp::zero(), true};
             // ZZ = Z^2, ZZZ = Z^3:  1/ZZ = Z^4 / Z^6 = ZZ^2 / ZZZ^2
@@ -67,7 +76,8 @@ struct HostVerifier {
     static Aff neg(const Aff& a) { return a.inf ? a : Aff{a.x, a.y.neg(), false}; }
 
     // sum_i s_i P_i, scalars in Montgomery form; Straus with 4-bit windows and shared doublings
-    static Aff lincomb(const std::vector<Aff>& pts, const std::vector<Fr>& sc_mont) {
+    // `plus`: points with coefficient one, added at the end (no table, no window digits)
+    static Aff lincomb(const std::vector<Aff>& pts, const std::vector<Fr>& sc_mont, const std::vector<Aff>& plus = {}) {
         const size_t cnt = pts.size();
         std::vector<Ext> tbl(cnt * 16);
         std::vector<Fr> sc(cnt);
@@ -76,7 +86,7 @@ struct HostVerifier {
             Ext* t = &tbl[i * 16];
             t[0] = Ext::inf();
             t[1] = Ext::from(pts[i]);
-            for (int j = 2; j < 16; j++) t[j] = t[j - 1].add(t[1]);
+            for (int j = 2; j < 16; j++) t[j] = t[j - 1].add_affine(pts[i]);
         }
         Ext acc = Ext::inf();
         for (int w = Fr::N * 16 - 1; w >= 0; w--) {
@@ -86,6 +96,7 @@ struct HostVerifier {
                 if (d) acc = acc.add(tbl[i * 16 + d]);
             }
         }
+        for (const Aff& p : plus) acc = acc.add_affine(p);
         return acc.to_affine();
     }
 
@@ -281,15 +292,15 @@ struct HostVerifier {
         const Fr s2p = a2l - alpha * (l_z + bz + gamma) * (r_z + bz * u + gamma) * (o_z + bz * u2 + gamma);
         const Fr zn2 = pow_u64(zeta, vk.n + 2);
         const Fr mzh = zh.neg();
-        std::vector<Aff> pts = {Ql, Qr, Qm, Qo, Qk};
-        std::vector<Fr> sc = {l_z, r_z, l_z * r_z, o_z, one};
+        std::vector<Aff> pts = {Ql, Qr, Qm, Qo};               // Qk enters with coefficient one
+        std::vector<Fr> sc = {l_z, r_z, l_z * r_z, o_z};
         for (uint32_t c = 0; c < k; c++) { pts.push_back(bsb[c]); sc.push_back(qcp_z[c]); }
         pts.push_back(S3); sc.push_back(s1p);
         pts.push_back(Z); sc.push_back(s2p);
         pts.push_back(H[0]); sc.push_back(mzh);
         pts.push_back(H[1]); sc.push_back(mzh * zn2);
         pts.push_back(H[2]); sc.push_back(mzh * zn2 * zn2);
-        const Aff lin = lincomb(pts, sc);
+        const Aff lin = lincomb(pts, sc, {Qk});
 
         // -- fold challenge and folded opening at zeta (:280-321) ----------------------------------------------
         uint8_t v_pre[32];
@@ -317,7 +328,8 @@ struct HostVerifier {
             claims = claims + vals[i] * acc;
             acc = acc * v;
         }
-        const Aff digest = lincomb(pts, sc);
+        const Aff digest = lincomb(std::vector<Aff>(pts.begin() + 1, pts.end()), std::vector<Fr>(sc.begin() + 1, sc.end()),
+                                   {lin});                     // [Lin] enters with coefficient v^0 = 1
 
         // -- both openings in one pairing check (:323-356) ------------------------------------------------------
         uint8_t u_pre[32];
@@ -331,8 +343,8 @@ struct HostVerifier {
         hs.final(u_pre);
         const Fr ub = fr_mod(u_pre);
         claims = claims + z_zw * ub;
-        *lhs_out = lincomb({digest, Z, G1, Wz, Wzw}, {one, ub, claims.neg(), zeta, ub * zeta * omega});
-        *rhs_out = neg(lincomb({Wz, Wzw}, {one, ub}));
+        *lhs_out = lincomb({Z, G1, Wz, Wzw}, {ub, claims.neg(), zeta, ub * zeta * omega}, {digest});
+        *rhs_out = neg(lincomb({Wzw}, {ub}, {Wz}));
         return true;
     }
 
