@@ -36,7 +36,14 @@ class _DevicePtr:
     """A raw device allocation as something torch.as_tensor understands."""
 
     def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+        self.ptr, self.nbytes = int(ptr or 0), nbytes
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def data_ptr(self) -> int:       # the two tensor methods the single-rank path uses
+        return self.ptr
+
+    def __len__(self) -> int:
+        return self.nbytes
 
 
 def slice_for(total_points: int, rank: int, world: int, n_scalars: int):
@@ -144,8 +151,11 @@ class CommitHook:
 
         def hook(_ctx, d_scalars, n, out):
             try:
-                t = torch.as_tensor(_DevicePtr(d_scalars, 32 * n), device=device) if n else \
-                    torch.empty(0, dtype=torch.uint8, device=device)
+                if committer.world == 1:                             # nothing to broadcast: the pointer is enough
+                    t = _DevicePtr(d_scalars, 32 * n)
+                else:
+                    t = torch.as_tensor(_DevicePtr(d_scalars, 32 * n), device=device) if n else \
+                        torch.empty(0, dtype=torch.uint8, device=device)
                 C.memmove(out, committer.commit(t, n), nb)
                 return 0
             except BaseException as e:  # noqa: BLE001 -- must not unwind into C; the caller re-raises it
