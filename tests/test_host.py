@@ -367,3 +367,23 @@ def test_msm_signed_digits_recompose_the_scalar(tmp_path_factory):
     cc, W, nb = C.c_int(), C.c_int(), C.c_uint32()
     lib.ht_msm_plan(C.c_uint64((1 << 20) + 3), 254, 0, C.byref(cc), C.byref(W), C.byref(nb))
     assert (cc.value, W.value, nb.value) == (20, 13, 1 << 19)
+
+
+def test_transcript_sha256_against_hashlib(tmp_path_factory):
+    """csrc/sha256.hpp (every Fiat-Shamir challenge of prover and verifier goes through it) against hashlib at the
+    padding boundaries (55, 56, 63, 64, 119, 120 bytes ...), long messages, and with the message split across two
+    update() calls at every kind of offset."""
+    import hashlib
+    out = tmp_path_factory.mktemp("sha") / "sha256.so"
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O1", "-std=c++17", "-shared", "-fPIC",
+                    os.path.join(ROOT, "tests", "csrc", "sha256_shim.cpp"), "-o", str(out)], check=True)
+    lib = C.CDLL(str(out))
+    rng = random.Random(256)
+    lengths = list(range(0, 70)) + [111, 112, 119, 120, 127, 128, 129, 191, 192, 1000, 4096, 65537]
+    for n in lengths:
+        msg = bytes(rng.randrange(256) for _ in range(n))
+        want = hashlib.sha256(msg).digest()
+        for split in sorted({0, 1, n // 2, max(n - 1, 0), n, min(n, 55), min(n, 56), min(n, 64), min(n, 65)}):
+            got = C.create_string_buffer(32)
+            lib.ht_sha256(msg, C.c_uint64(n), C.c_uint64(split), got)
+            assert got.raw == want, (n, split)
