@@ -46,6 +46,7 @@ SYMBOLS = [
     ("b2p_g1_sum", _int, [_int, _vp, _u64, _vp]),
     ("b2p_srs_stream", _vp, [_vp]),
     ("b2p_srs_set_commit_hook", _int, [_vp, _vp, _vp]),
+    ("b2p_device_copy", _int, [_vp, _vp, _u64]),
     ("b2p_ntt", _int, [_int, _vp, _u64, _int]),
     ("b2p_ntt_shard_create", _int, [_int, _u64, _u32, _u32, C.POINTER(_vp)]),
     ("b2p_ntt_shard_free", None, [_vp]),

@@ -215,6 +215,15 @@ API int b2p_srs_set_commit_hook(b2p_srs* srs, b2p_commit_fn fn, void* ctx) {
         s->set_commit_hook(fn, ctx);
     });
 }
+API int b2p_device_copy(void* d_dst, const void* d_src, uint64_t bytes) {
+    return guarded([&] {
+        require((d_dst && d_src) || bytes == 0, "null argument");
+        if (bytes) {
+            cudaError_t e = cudaMemcpy(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice);
+            if (e != cudaSuccess) throw Error(B2P_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+        }
+    });
+}
 API void* b2p_srs_stream(b2p_srs* srs) { return srs ? reinterpret_cast<SrsBase*>(srs)->stream_handle() : nullptr; }
 
 API int b2p_ntt(int curve, void* data, uint64_t n, int flags) {

@@ -33,13 +33,13 @@ OP_COMMIT, OP_STOP = 1, 2
 
 
 class _DevicePtr:
-    """A raw device allocation as something torch.as_tensor understands."""
+    """The scalars a commit hook is handed: a raw device pointer with the two tensor methods the single-rank path
+    uses (data_ptr, len in bytes)."""
 
     def __init__(self, ptr: int, nbytes: int):
         self.ptr, self.nbytes = int(ptr or 0), nbytes
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
 
-    def data_ptr(self) -> int:       # the two tensor methods the single-rank path uses
+    def data_ptr(self) -> int:
         return self.ptr
 
     def __len__(self) -> int:
@@ -148,14 +148,15 @@ class CommitHook:
         import torch
         self.srs, self.error = srs, None
         nb = 2 * api.FP_BYTES[srs.curve]
+        stage = torch.empty(32 * committer.total, dtype=torch.uint8, device=device) if committer.world > 1 else None
 
         def hook(_ctx, d_scalars, n, out):
             try:
                 if committer.world == 1:                             # nothing to broadcast: the pointer is enough
                     t = _DevicePtr(d_scalars, 32 * n)
-                else:
-                    t = torch.as_tensor(_DevicePtr(d_scalars, 32 * n), device=device) if n else \
-                        torch.empty(0, dtype=torch.uint8, device=device)
+                else:                                                # stage into the tensor that is broadcast
+                    t = stage[: 32 * n]
+                    _lib.check(_lib.load().b2p_device_copy(t.data_ptr(), d_scalars, 32 * n))
                 C.memmove(out, committer.commit(t, n), nb)
                 return 0
             except BaseException as e:  # noqa: BLE001 -- must not unwind into C; the caller re-raises it

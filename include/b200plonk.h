@@ -132,6 +132,9 @@ void* b2p_srs_stream(b2p_srs* srs);
  * partial sums (b2p_g1_sum): algoplonk_b200/sharded_prover.py.  fn = NULL removes the hook. */
 typedef int (*b2p_commit_fn)(void* ctx, const void* d_scalars, uint64_t n, void* out_affine);
 int b2p_srs_set_commit_hook(b2p_srs* srs, b2p_commit_fn fn, void* ctx);
+/* Device-to-device copy on the current device, complete on return: lets a commit hook written in a language without
+ * CUDA bindings stage the scalars it was handed into a buffer of its own (e.g. the tensor it broadcasts). */
+int b2p_device_copy(void* d_dst, const void* d_src, uint64_t bytes);
 
 #define B2P_NTT_INVERSE   1   /* FFTInverse (includes the 1/n scaling) */
 #define B2P_NTT_COSET     2   /* on the coset FrMultiplicativeGen * <omega> */

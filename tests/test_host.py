@@ -128,6 +128,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.b2p_kzg_vk_load(0, None, 0, None, None) == -1
     assert lib.b2p_verify_batch(5, 8, 0, 0, None, None, None, None, None, 0, None, 0, 0, None) == -1
     assert lib.b2p_g2_generate_unsafe(0, None, None) == -1
+    assert lib.b2p_device_copy(None, None, 16) == -1 and lib.b2p_device_copy(None, None, 0) == 0
 
 
 @pytest.mark.parametrize("case", H.golden_proofs(), ids=H.case_id)
