@@ -219,7 +219,9 @@ API int b2p_device_copy(void* d_dst, const void* d_src, uint64_t bytes) {
     return guarded([&] {
         require((d_dst && d_src) || bytes == 0, "null argument");
         if (bytes) {
-            cudaError_t e = cudaMemcpy(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice);
+            // cudaMemcpy does not wait for device-to-device copies: issue on the thread's stream and wait for it
+            cudaError_t e = cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, cudaStreamPerThread);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
             if (e != cudaSuccess) throw Error(B2P_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
         }
     });
