@@ -359,22 +359,26 @@ class CompiledCircuit:
                               fr_to_mont_bytes(cv, blinding), [fr_to_mont_bytes(cv, v) for v in pi2],
                               points_to_mont_bytes(cv, bsb22_points))
 
-    def Verify(self, L, R, O, blinding, pi2=(), bsb22_points=(), verifier: Optional[Callable] = None) -> VerifiedProof:
+    def Verify(self, L, R, O, blinding, pi2=(), bsb22_points=(), verifier: Optional[Callable] = None,
+               verify: bool = True) -> VerifiedProof:
         """algoplonk.go:79-98: prove, then plonk.Verify (algoplonk.go:93) -- the library's host verifier
-        b2p_verify against this circuit's verifying key whenever the SRS's G2 points are known (always for the
-        TestOnly setups; a trusted setup's when the caller passed them to SRS.from_points).  `verifier(proof_bytes,
-        public_bytes)`, if given, runs as well (tests inject the oracle's restatement of the AVM verifier)."""
+        b2p_verify against this circuit's verifying key.  The reference ALWAYS verifies and returns an error when
+        that fails, so an SRS whose G2 points are unknown (a trusted setup loaded without its vk.bin / g2=) is an
+        error here too, unless a `verifier` callback does the checking or the caller opts out with verify=False
+        (then this is plonk.Prove only).  `verifier(proof_bytes, public_bytes)`, if given, runs in addition to
+        b2p_verify when the G2 points are known (tests inject the oracle's restatement of the AVM verifier)."""
+        if verify and verifier is None and self.srs.g2 is None:
+            raise ValueError("error verifying proof: the SRS's G2 points are unknown (load the setup's vk.bin: "
+                             "SRS.from_pk_bin(vk_bin=...) / SRS.from_points(g2=...)), or pass verify=False")
         proof = self.Prove(L, R, O, blinding, pi2, bsb22_points)
         public = [v % R_MOD[self.Curve] for v in L[: self.trace.nb_public]]
-        blob = pub = None
+        if not verify:
+            return VerifiedProof(proof, public)
+        blob, pub = MarshalProof(proof), MarshalPublicInputs(self.Curve, public)
         if self.srs.g2 is not None:
-            blob, pub = MarshalProof(proof), MarshalPublicInputs(self.Curve, public)
             self.VerifyProof(blob, pub)
-        if verifier is not None:
-            if blob is None:
-                blob, pub = MarshalProof(proof), MarshalPublicInputs(self.Curve, public)
-            if not verifier(blob, pub):
-                raise ValueError("error verifying proof")
+        if verifier is not None and not verifier(blob, pub):
+            raise ValueError("error verifying proof")
         return VerifiedProof(proof, public)
 
     def VerifyProofs(self, proofs: Sequence[bytes], publics: Sequence[bytes]) -> None:

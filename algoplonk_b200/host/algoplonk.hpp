@@ -152,10 +152,16 @@ public:
         if (srs_) b2p_srs_free(srs_);
     }
 
-    // algoplonk.go:79-98: witness -> Prove -> (verify with `verifier`, if given)
+    // plonk.Prove alone (algoplonk.go:89 without :93): the explicit opt-out of the self-check below
+    VerifiedProof<CURVE> ProveOnly(const std::vector<Fr>& blinding) const {
+        return Verify(blinding, [](const std::vector<uint8_t>&, const std::vector<uint8_t>&) { return true; }, false);
+    }
+    // algoplonk.go:79-98: witness -> Prove -> plonk.Verify (+ `verifier`, if given).
+    // This mirror covers circuits WITHOUT BSB22 commitments (k = 0 in b2p_prove / b2p_verify / MarshalProof below):
+    // its Builder has no Commit; circuits with commitments go through the C ABI directly (or the Python / Go hosts).
     // `blinding`: the 9 scalars gnark draws with fr.SetRandom (an input, so proofs are reproducible).
     template <class Verifier = std::nullptr_t>
-    VerifiedProof<CURVE> Verify(const std::vector<Fr>& blinding, Verifier verifier = nullptr) const {
+    VerifiedProof<CURVE> Verify(const std::vector<Fr>& blinding, Verifier verifier = nullptr, bool self_check = true) const {
         if (blinding.size() != 9) throw Error("9 blinding scalars expected");
         std::vector<Fr> L(n, ccs.values.empty() ? Fr::zero() : ccs.values[0]), R = L, O = L;   // padding rows: variable 0
         for (uint32_t i = 0; i < ccs.nb_public; i++) L[i] = ccs.values[i];
@@ -169,7 +175,13 @@ public:
         vp.raw.resize(b2p_proof_raw_size(CURVE, 0));
         check(b2p_prove(circuit_, L.data(), R.data(), O.data(), nullptr, nullptr, blinding.data(), vp.raw.data()), "plonk.Prove");
         vp.witness.assign(ccs.values.begin(), ccs.values.begin() + ccs.nb_public);
-        if (!kzg_g2_.empty()) VerifyProof(vp.MarshalProof(), vp.MarshalPublicInputs());   // plonk.Verify, algoplonk.go:93
+        // plonk.Verify, algoplonk.go:93: the reference always verifies.  Without the setup's G2 points and without
+        // a verifier callback nothing could check the proof: that is an error, not a silent pass (ProveOnly() is
+        // the explicit opt-out).
+        if (self_check && kzg_g2_.empty() && std::is_same<Verifier, std::nullptr_t>::value)
+            throw Error("error verifying proof: the setup's G2 points are unknown (LoadKzgVk / SetKzgG2), "
+                        "or call ProveOnly()");
+        if (self_check && !kzg_g2_.empty()) VerifyProof(vp.MarshalProof(), vp.MarshalPublicInputs());
         if constexpr (!std::is_same<Verifier, std::nullptr_t>::value) {
             if (!verifier(vp.MarshalProof(), vp.MarshalPublicInputs())) throw Error("error verifying proof");
         }

@@ -139,70 +139,101 @@ def build_workload(curve: str, log2_rows: int):
 # ---------------------------------------------------------------------------------------
 # CPU oracle timing (cpu_baseline leg and --impl reference)
 # ---------------------------------------------------------------------------------------
-def cpu_prove_seconds(curve: str, log2_rows: int, repeats: int = 1, warmup: int = 0):
-    """Times oracle proofs of a 2^log2_rows circuit; returns the list of timed step durations."""
-    from oracle import cpu_oracle as co
-    cid = co.CURVE_ID[curve]
-    cs, tc, L, R, O = build_workload(curve, log2_rows)
-    srs = co.srs_from_tau_bytes(cid, TAU, tc.n + 3)
-    circ = co.Circuit(cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs)
-    Lb, Rb, Ob = co.scalars_le(L), co.scalars_le(R), co.scalars_le(O)
-    bl = co.scalars_le(range(1, 10))
-    out = []
-    for i in range(warmup + repeats):
+def host_cores() -> int:
+    """The cores this process may run on (cgroup / affinity aware), NOT what OMP_NUM_THREADS says:
+    torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, which is right for ranks that drive a GPU
+    and wrong for the CPU arm, whose whole point is to use the box's host cores."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+class CpuProver:
+    """The CPU arm: oracle/cpu_plonk.cpp (kind "port": gnark itself needs Go, absent here) proving the SAME
+    full-size workload as the GPU arm, on all host cores.  Nothing is ever extrapolated from a smaller circuit."""
+
+    def __init__(self, curve: str, log2_rows: int):
+        from oracle import cpu_oracle as co
+        self.co = co
+        self.cores = host_cores()
+        co.set_threads(self.cores)
+        cid = co.CURVE_ID[curve]
+        cs, tc, L, R, O = build_workload(curve, log2_rows)
+        srs = co.srs_from_tau_bytes(cid, TAU, tc.n + 3)
+        self.circ = co.Circuit(cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs)
+        self.cols = [co.scalars_le(c) for c in (L, R, O)]
+        self.bl = co.scalars_le(range(1, 10))
+        self.threads = co.threads()
+
+    def prove_seconds(self) -> float:
         t0 = time.perf_counter()
-        circ.prove(Lb, Rb, Ob, bl)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            out.append(dt)
-    circ.free()
-    return out
+        self.circ.prove(*self.cols, self.bl)
+        return time.perf_counter() - t0
+
+    def free(self):
+        self.circ.free()
 
 
-def choose_sample_log2(curve: str, target_log2: int, seconds_per_step: float):
-    """Largest sample size <= target whose predicted proof time fits the per-step budget
-    (prediction: linear in n from a 2^12 calibration proof)."""
-    cal_log2 = min(12, target_log2)
-    t_cal = min(cpu_prove_seconds(curve, cal_log2, repeats=2))
-    s = cal_log2
-    while s < target_log2 and t_cal * (1 << (s + 1 - cal_log2)) <= seconds_per_step:
-        s += 1
-    return s
+def cpu_baseline(curve: str, target_log2: int, budget_s: float = 30.0):
+    """cpu_baseline leg of the GPU arm's line (rank 0, N = 1): full-size proofs on all host cores, as many as
+    fit ~budget_s (at least one)."""
+    cp = CpuProver(curve, target_log2)
+    times = [cp.prove_seconds()]
+    while sum(times) + times[-1] <= budget_s:
+        times.append(cp.prove_seconds())
+    cp.free()
+    t = min(times)
+    return {"value": 1.0 / t, "unit": UNIT, "cores": cp.threads, "kind": "port",
+            "sample": f"{len(times)} full 2^{target_log2}-row {curve} proof(s) (the bench workload itself, nothing "
+                      f"scaled), best {t:.2f} s, OpenMP over {cp.threads} host threads"}
 
 
-def cpu_baseline(curve: str, target_log2: int, seconds_per_step: float = 25.0):
-    from oracle import cpu_oracle as co
-    s = choose_sample_log2(curve, target_log2, seconds_per_step)
-    t = min(cpu_prove_seconds(curve, s, repeats=1))
-    scale = 1 << (target_log2 - s)
-    sample = f"one 2^{s}-row {curve} proof in {t:.2f} s"
-    if scale > 1:
-        sample += f", scaled x{scale} linearly in n to 2^{target_log2} rows (favours the CPU: the work grows n log n)"
-    return {"value": 1.0 / (t * scale), "unit": UNIT, "cores": co.threads(), "kind": "port", "sample": sample}
+REFERENCE_BUDGET_S = 240.0      # wall-clock bound of the timed + warm-up proofs of --impl reference
+
+
+def plan_reference_steps(step_s: float, steps: int, warmup: int, budget_s: float = REFERENCE_BUDGET_S):
+    """(warm-up proofs, timed proofs) the CPU arm actually runs: the requested counts when they fit the
+    budget, else fewer -- reported as run, never scaled up."""
+    if (steps + warmup) * step_s <= budget_s:
+        return warmup, steps
+    w = 1 if warmup else 0              # the first proof (page faults, thread start-up) is the warm-up that matters
+    k = int((budget_s - w * step_s) // step_s)
+    return w, max(1, min(steps, k))
 
 
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    from oracle import cpu_oracle as co
-    budget = max(2.0, 150.0 / max(1, args.steps + args.warmup))
-    s = choose_sample_log2(args.curve, args.log2, budget)
-    times = cpu_prove_seconds(args.curve, s, repeats=args.steps, warmup=args.warmup)
-    scale = 1 << (args.log2 - s)
-    per_step = sum(times) / len(times) * scale
+    cp = CpuProver(args.curve, args.log2)
+    first = cp.prove_seconds()                   # full-size proof: calibrates the plan and is the first warm-up
+    w, k = plan_reference_steps(first, args.steps, args.warmup)
+    for _ in range(max(0, w - 1)):
+        cp.prove_seconds()
+    if w == 0:
+        times = [first] + [cp.prove_seconds() for _ in range(k - 1)]
+    else:
+        times = [cp.prove_seconds() for _ in range(k)]
+    cp.free()
+    per_step = sum(times) / len(times)
     value = 1.0 / per_step
-    sample = (f"each step = one 2^{s}-row {args.curve} proof on the host cores"
-              + (f", scaled x{scale} linearly in n" if scale > 1 else ""))
+    sample = (f"each step = one FULL 2^{args.log2}-row {args.curve} proof (the GPU arm's workload, nothing scaled) on "
+              f"{cp.threads} host threads; {k} timed + {w} warm-up proofs run"
+              + ("" if (w, k) == (args.warmup, args.steps) else
+                 f" (requested {args.steps} + {args.warmup}: reduced to fit {REFERENCE_BUDGET_S:.0f} s of CPU time)"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "steps": k, "warmup": w, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": co.threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cp.threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU restatement of gnark's prover (oracle/cpu_plonk.cpp, OpenMP); gnark itself needs Go, absent here",
+        "step_seconds": {"min": min(times), "max": max(times)},
+        "note": "CPU restatement of gnark's prover (oracle/cpu_plonk.cpp, OpenMP); gnark itself needs Go, absent here. "
+                "One CPU prover on the whole host at every --gpus N (the GPU arm's value is the N-replica aggregate).",
     }
     print(json.dumps(line), flush=True)
 

@@ -40,6 +40,8 @@ def load() -> C.CDLL:
         lib.ora_field_mul.argtypes = [i, vp, vp, vp]
         lib.ora_srs_from_tau.argtypes = [i, vp, u64, vp]
         lib.ora_msm.argtypes = [i, vp, vp, u64, vp]
+        lib.ora_g1_decompress.restype = C.c_int64
+        lib.ora_g1_decompress.argtypes = [i, vp, u64, vp]
         lib.ora_ntt.argtypes = [i, vp, u64, i]
         lib.ora_circuit_load.restype = vp
         lib.ora_circuit_load.argtypes = [i, u64, u32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, u64]
@@ -96,6 +98,17 @@ def srs_from_tau_bytes(cid: int, tau: int, n: int) -> bytes:
 
 def srs_from_tau(cid: int, tau: int, n: int):
     return points_from_le(cid, srs_from_tau_bytes(cid, tau, n))
+
+
+def g1_decompress_bytes(cid: int, compressed: bytes) -> bytes:
+    """gnark compressed G1 stream (a pk.bin payload, setup/setup.go:196-228) -> x || y little-endian points."""
+    nb = FP_BYTES[cid]
+    n = len(compressed) // nb
+    out = C.create_string_buffer(n * 2 * nb)
+    rc = load().ora_g1_decompress(cid, compressed, n, out)
+    if rc != 0:
+        raise ValueError(f"compressed point {rc - 1} is invalid")
+    return out.raw
 
 
 def msm_bytes(cid: int, points: bytes, scalars: bytes):

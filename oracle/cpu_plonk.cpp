@@ -1074,6 +1074,67 @@ API int ora_srs_from_tau(int curve, const uint8_t* tau_le, uint64_t n, uint8_t* 
     return 0;
 }
 
+// Compressed G1 stream (payload of setup/<name>/pk.bin after its 4-byte count) -> affine points: what
+// srs.Pk.ReadFrom does in /root/reference/setup/setup.go:173,189,196-228.  Format (pinned by
+// /root/reference/setup/trusted_setup_test.go:53-59,132,290-303 and by oracle/plonk_oracle.py:g1_decompress,
+// which tests/test_oracle.py checks against those known answers): big-endian x under the flag bits of byte 0 --
+// BN254 top 2 bits 10 smallest y / 11 largest y / 01 infinity; BLS12-381 top 3 bits 100 / 101 / 110.
+// y = (x^3 + b)^((p+1)/4) (both p are 3 mod 4).  Returns 0, or 1 + index of the first bad point.
+template <class C>
+static uint64_t g1_decompress_all(const uint8_t* in, uint64_t n, uint8_t* out_points) {
+    typedef typename C::Fp Fp;
+    const int NB = (int)sizeof(Fp);
+    const bool bls = C::ID == 1;
+    u64 e[sizeof(Fp) / 8];   // (p + 1) / 4
+    {
+        u64 carry = 1;
+        for (size_t i = 0; i < sizeof(Fp) / 8; i++) { u128 s = (u128)Fp::M.p[i] + carry; e[i] = (u64)s; carry = (u64)(s >> 64); }
+        for (size_t i = 0; i < sizeof(Fp) / 8; i++) e[i] = (e[i] >> 2) | (i + 1 < sizeof(Fp) / 8 ? e[i + 1] << 62 : 0);
+    }
+    const Fp bcoef = Fp::from_u64(bls ? 4 : 3);
+    std::vector<Aff<Fp>> pts(n);
+    uint64_t bad = 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const uint8_t* b = in + (size_t)i * NB;
+        const unsigned flag = bls ? (b[0] >> 5) : (b[0] >> 6);
+        const uint8_t mask = bls ? 0x1F : 0x3F;
+        if (flag == (bls ? 6u : 1u)) { pts[i] = Aff<Fp>{Fp::zero(), Fp::zero()}; continue; }
+        bool ok = flag == (bls ? 4u : 2u) || flag == (bls ? 5u : 3u);
+        uint8_t le[sizeof(Fp)];
+        for (int k = 0; k < NB; k++) le[k] = b[NB - 1 - k];
+        le[NB - 1] &= mask;
+        u64 raw[sizeof(Fp) / 8];
+        memcpy(raw, le, sizeof raw);
+        ok = ok && !geq<sizeof(Fp) / 8>(raw, Fp::M.p);
+        Fp x = Fp::from_le(le), rhs = x.sqr() * x + bcoef, y = Fp::one();
+        for (int bit = Fp::M.bits - 1; bit >= 0; bit--) {
+            y = y.sqr();
+            if ((e[bit / 64] >> (bit % 64)) & 1) y = y * rhs;
+        }
+        ok = ok && y.sqr() == rhs;
+        if (!ok) {
+#pragma omp critical
+            if (!bad || (uint64_t)i + 1 < bad) bad = (uint64_t)i + 1;
+            continue;
+        }
+        const Fp yc = y.from_mont(), nyc = y.neg().from_mont();
+        bool larger = false;
+        for (int l = (int)sizeof(Fp) / 8 - 1; l >= 0; l--)
+            if (yc.v[l] != nyc.v[l]) { larger = yc.v[l] > nyc.v[l]; break; }
+        if (larger != (flag == (bls ? 5u : 3u))) y = y.neg();
+        pts[i] = Aff<Fp>{x, y};
+    }
+    if (!bad) store_points(pts.data(), n, out_points);
+    return bad;
+}
+API int64_t ora_g1_decompress(int curve, const uint8_t* in, uint64_t n, uint8_t* out_points) {
+    init_fields();
+    if (curve == 0) return (int64_t)g1_decompress_all<Bn254>(in, n, out_points);
+    if (curve == 1) return (int64_t)g1_decompress_all<Bls12381>(in, n, out_points);
+    return -1;
+}
+
 API int ora_msm(int curve, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out_point) {
     init_fields();
     if (curve == 0) {

@@ -69,6 +69,36 @@ def test_reference_arm_prints_contract_line():
     assert line["steps"] == 2 and line["warmup"] == 1 and line["higher_is_better"] is True
 
 
+def test_reference_arm_uses_all_host_cores_under_torchrun_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU arm must ignore it (round 1's N > 1
+    reference lines ran on ONE core), prove the workload it names at full size and never scale a smaller one."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", LOCAL_RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--log2", "9",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["cores"] == bench.host_cores()
+    assert "scaled x" not in line["cpu_baseline"]["sample"] and "FULL 2^9-row" in line["cpu_baseline"]["sample"]
+    assert abs(line["ms_per_step"] * line["value"] - 1e3) < 1e-6
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--log2", "8", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=600, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_step_plan_never_extrapolates():
+    # fits: run exactly what was asked
+    assert bench.plan_reference_steps(8.5, 20, 5, 240.0) == (5, 20)
+    # does not fit: one warm-up proof, as many timed proofs as the budget holds, at least one
+    assert bench.plan_reference_steps(40.0, 20, 5, 240.0) == (1, 5)
+    assert bench.plan_reference_steps(400.0, 20, 5, 240.0) == (1, 1)
+    assert bench.plan_reference_steps(40.0, 3, 0, 240.0) == (0, 3)
+
+
 def test_b200_arm_fails_loudly_without_gpu():
     try:
         import torch

@@ -89,6 +89,24 @@ def test_msm_mid_size_vs_cpp_oracle(gpu, curve, logn):
     srs.free()
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_msm_benchmark_size_vs_cpp_oracle(gpu, curve):
+    """2^20 + 3 points (the SRS of the 2^20-row configs), uniform and witness-like scalars, against the C++ oracle's
+    Pippenger -- bit-exact affine result; the generated SRS itself is compared point by point as well."""
+    cv = po.CURVES[curve]
+    n = (1 << 20) + 3
+    srs = api.SRS.unsafe(curve, n, H.TAU)
+    pts_le = co.srs_from_tau_bytes(cv.cid, H.TAU, n)
+    out = bytearray()
+    for first in range(0, n, 1 << 18):
+        out += co.points_le(cv.cid, srs.points(first, min(1 << 18, n - first)))
+    assert bytes(out) == pts_le
+    for dist, seed in ((H.scalars_uniform, 31), (H.scalars_witness_like, 32)):
+        sc = dist(cv.r, n, seed)
+        assert srs.msm(sc) == co.msm_bytes(cv.cid, pts_le, co.scalars_le(sc))
+    srs.free()
+
+
 def test_msm_properties_at_benchmark_size(gpu):
     """2^20 + 3 points (the north-star size): linearity and unit vectors, no oracle run needed."""
     curve = "BN254"

@@ -37,10 +37,13 @@ def test_ntt_small_vs_bigint_oracle(gpu, curve, logn):
 
 
 @pytest.mark.parametrize("curve", CURVES)
-@pytest.mark.parametrize("logn", [16, 17, 19, 20])
+@pytest.mark.parametrize("logn", [16, 17, 19, 20, 22, 23])
 def test_ntt_large_vs_cpp_oracle(gpu, curve, logn):
-    """Config sizes (2^17 / 2^20-row circuits use domains 2^17..2^22): multi-pass path."""
+    """Config sizes (2^17 / 2^20-row circuits use domains 2^17..2^22, the 2^21-row BLS12-381 config 2^23):
+    multi-pass path, bit-exact against the C++ oracle."""
     cv = po.CURVES[curve]
+    if logn == 23 and curve == "BN254":
+        pytest.skip("4n = 2^23 only occurs for the 2^21-row BLS12-381 config")
     n = 1 << logn
     rng = random.Random(logn)
     raw = b"".join(rng.randrange(cv.r).to_bytes(32, "little") for _ in range(n))

@@ -162,6 +162,76 @@ def test_config_sizes_accepted_by_reference_verifier(gpu, curve, logn):
     cc.free()
 
 
+@pytest.mark.parametrize("curve,logn", [("BN254", 20), ("BLS12_381", 20), ("BLS12_381", 21)])
+def test_benchmark_sizes_byte_identical_to_cpp_oracle(gpu, curve, logn):
+    """The sizes bench.py reports on -- 2^20 BN254 (BASELINE configs[2], the headline), 2^20 BLS12-381 and 2^21
+    BLS12-381 (configs[4]'s size) -- compared BYTE FOR BYTE with the C++ CPU oracle, verifying-key commitments
+    included, with full-width random blinding scalars; then accepted by the restated AVM verifier."""
+    cv = po.CURVES[curve]
+    cs, values = fe.squaring_chain(curve, logn, x0=13)
+    cc = api.Compile(cs, curve, SETUP[curve])
+    tc = cc.trace
+    assert tc.n == 1 << logn
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    blinding = H.scalars_uniform(cv.r, 9, 1000 + logn)
+    blob = api.MarshalProof(cc.Prove(L, R, O, blinding))
+    vk_pts = cc.vk_commitments()
+    cc.free()
+    cc.srs.free()
+    srs_le = co.srs_from_tau_bytes(cv.cid, api.TEST_TAU, tc.n + 3)
+    circ = co.Circuit(cv.cid, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
+    assert vk_pts == circ.vk_points()
+    want = circ.prove(L, R, O, blinding)
+    circ.free()
+    assert blob == want
+    vk = H.vk_from_points(tc, vk_pts, cv.g1, tau=api.TEST_TAU)
+    assert po.verify_proof(vk, blob, api.MarshalPublicInputs(curve, L[: tc.nb_public]))
+
+
+def test_config2_real_ppot_srs_at_2p17(gpu):
+    """BASELINE configs[1]: the 2^17-row circuit on the REAL PerpetualPowersOfTau bytes (the first 2^17 + 3
+    compressed points of setup/PerpetualPowersOfTauBN254/pk.bin, committed as a fixture by tools/gen_ppot_slice.py):
+    b2p_srs_load_compressed (setup/setup.go:196-228) -> Compile -> cc.Verify, whose plonk.Verify runs the pairing
+    check against the G2 points of the setup's own vk.bin; every decompressed point, the verifying key and the
+    proof bytes equal the C++ oracle's (live and the committed golden); the restated AVM verifier accepts with
+    the ceremony's G2 points."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(H.GOLDEN, "config2_ppot_2p17.json")) as f:
+        gold = json.load(f)
+    with open(os.path.join(H.GOLDEN, "ppot_bn254_first_131075.bin"), "rb") as f:
+        pk_bin = f.read()
+    assert hashlib.sha256(pk_bin).hexdigest() == gold["srs_sha256"]
+    count = gold["srs_points"]
+    name = "PerpetualPowersOfTauBN254"
+    srs = api.SRS.from_pk_bin("BN254", pk_bin, count, vk_bin=bytes.fromhex(H.srs_kat()[name]["vk_bin"]))
+    assert srs.size == count
+    pts_le = co.g1_decompress_bytes(0, pk_bin[4:])
+    assert co.points_le(0, srs.points(0, count)) == pts_le
+    cs, values = fe.squaring_chain("BN254", gold["log2"], x0=gold["x0"])
+    cc = api.Compile(cs, "BN254", api.SetupName.PerpetualPowersOfTauBN254, srs=srs)
+    tc = cc.trace
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    vp = cc.Verify(L, R, O, gold["blinding"])                # raises if b2p_verify (real pairing) rejects
+    blob = api.MarshalProof(vp.Proof)
+    assert co.points_le(0, cc.vk_commitments()) == bytes.fromhex(gold["vk_points_le"])
+    assert blob.hex() == gold["proof"]
+    circ = co.Circuit(0, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), pts_le)
+    assert blob == circ.prove(L, R, O, gold["blinding"])
+    circ.free()
+    pub = api.MarshalPublicInputs("BN254", vp.Witness)
+    assert pub.hex() == gold["public_inputs"]
+    vk = H.vk_from_points(tc, cc.vk_commitments(), H.real_srs_points(name)[0], tau=None, g2=H.real_srs_g2(name))
+    assert po.verify_proof(vk, blob, pub)
+    bad = bytearray(blob)
+    bad[700] ^= 1
+    with pytest.raises(ValueError):
+        cc.VerifyProof(bytes(bad), pub)
+    cc.free()
+    srs.free()
+
+
 def test_two_proofs_in_flight_on_two_handles(gpu):
     """The library is re-entrant across handles and calls may come from any host thread (fresh threads start
     on CUDA device 0; every entry point switches to its handle's device): two keys, two threads, the same

@@ -418,3 +418,64 @@ def test_hash_to_field_is_rfc9380_expand_message_xmd():
     for cv in (po.BN254, po.BLS12_381):
         for msg in (bytes(2 * cv.fp_bytes), po.g1_raw_bytes(cv, cv.g1), b"\x40" + bytes(95)):
             assert po.hash_fr(cv, msg) == int.from_bytes(xmd(msg, b"BSB22-Plonk", 48), "big") % cv.r
+
+
+@pytest.mark.parametrize("name", ["PerpetualPowersOfTauBN254", "DuskBLS12_381", "EethereumKzgCeremonyBLS12_381"])
+def test_cpp_decompress_equals_the_pinned_python_decoder(name):
+    """ora_g1_decompress (the checker of b2p_srs_load_compressed at config sizes) against plonk_oracle.g1_decompress,
+    which test_srs_known_answers pins on setup/trusted_setup_test.go's vectors; bad streams are reported by index."""
+    ent = H.srs_kat()[name]
+    cv = po.CURVES[ent["curve"]]
+    raw = bytes.fromhex(ent["first"]) + bytes.fromhex(ent["index_32767"])
+    want = [po.g1_decompress(cv, raw[i:i + cv.fp_bytes]) for i in range(0, len(raw), cv.fp_bytes)]
+    assert co.points_from_le(cv.cid, co.g1_decompress_bytes(cv.cid, raw)) == want
+    inf = po.g1_compress(cv, None)
+    assert co.points_from_le(cv.cid, co.g1_decompress_bytes(cv.cid, inf + raw[:cv.fp_bytes])) == [None, want[0]]
+    bad = bytearray(raw[: 3 * cv.fp_bytes])
+    bad[2 * cv.fp_bytes] &= 0x1F                       # flag bits cleared: not a compressed point
+    with pytest.raises(ValueError, match="point 2"):
+        co.g1_decompress_bytes(cv.cid, bytes(bad))
+    # an x that is not on the curve
+    for x in range(2, 50):
+        if po.fp_sqrt(cv, (x ** 3 + cv.b) % cv.p) is None:
+            break
+    off = bytearray(x.to_bytes(cv.fp_bytes, "big"))
+    off[0] |= 0x80
+    with pytest.raises(ValueError, match="point 1"):
+        co.g1_decompress_bytes(cv.cid, raw[:cv.fp_bytes] + bytes(off))
+
+
+def test_config2_golden_on_the_real_ppot_bytes():
+    """tests/golden/ppot_bn254_first_131075.bin + config2_ppot_2p17.json (tools/gen_ppot_slice.py): the fixture's
+    first points are the ones srs_kat.json copied from the reference file, the C++ oracle reproduces the committed
+    proof, and the library's plonk.Verify accepts it with the G2 points of the setup's own vk.bin (host code, no GPU)."""
+    import hashlib
+    import json
+    import os
+    from algoplonk_b200 import api, frontend as fe
+    with open(os.path.join(H.GOLDEN, "config2_ppot_2p17.json")) as f:
+        gold = json.load(f)
+    with open(os.path.join(H.GOLDEN, "ppot_bn254_first_131075.bin"), "rb") as f:
+        pk_bin = f.read()
+    assert hashlib.sha256(pk_bin).hexdigest() == gold["srs_sha256"]
+    count = gold["srs_points"]
+    assert int.from_bytes(pk_bin[:4], "big") == count == (1 << 17) + 3 and len(pk_bin) == 4 + 32 * count
+    ent = H.srs_kat()["PerpetualPowersOfTauBN254"]
+    assert pk_bin[4:4 + 32 * ent["count"]].hex() == ent["first"]
+    assert pk_bin[4 + 32 * 32767:4 + 32 * 32768].hex() == ent["index_32767"]
+    pts_le = co.g1_decompress_bytes(0, pk_bin[4:])
+    cs, values = fe.squaring_chain("BN254", gold["log2"], x0=gold["x0"])
+    tc = fe.build_trace(cs)
+    L, R, O = fe.solve_lro(cs, values, tc.n)
+    circ = co.Circuit(0, tc.n, tc.nb_public, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), pts_le)
+    vk_pts = circ.vk_points()
+    assert co.points_le(0, vk_pts).hex() == gold["vk_points_le"]
+    proof = circ.prove(L, R, O, gold["blinding"])
+    circ.free()
+    assert proof.hex() == gold["proof"]
+    g2, g1 = api.kzg_vk_load("BN254", bytes.fromhex(ent["vk_bin"]))
+    pub = bytes.fromhex(gold["public_inputs"])
+    api.verify("BN254", tc.n, tc.nb_public, [], api.points_to_mont_bytes("BN254", vk_pts), g1, g2, proof, pub)
+    with pytest.raises(ValueError):
+        api.verify("BN254", tc.n, tc.nb_public, [], api.points_to_mont_bytes("BN254", vk_pts), g1, g2,
+                   proof[:100] + bytes([proof[100] ^ 1]) + proof[101:], pub)
