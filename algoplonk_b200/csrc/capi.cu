@@ -329,6 +329,73 @@ API int b2p_peer_free(void* d_ptr) {
     });
 }
 
+// ---- one proof over the GPUs of a box: commitments sharded over the point set (shard_group.cuh) -------------
+API int b2p_shard_group_create(int curve, uint32_t world, uint32_t rank, uint64_t total_points, b2p_srs* shard,
+                               void* ipc_handles_out, b2p_shard_group** out) {
+    return guarded([&] {
+        require(shard && out, "null argument");
+        SrsBase* s = reinterpret_cast<SrsBase*>(shard);
+        DeviceGuard g(s->device);
+        ShardGroupBase* grp = ops_for(curve)->new_shard_group(world, rank, total_points, s);
+        grp->device = s->device;
+        try { if (ipc_handles_out) grp->ipc_handles(ipc_handles_out); } catch (...) { delete grp; throw; }
+        *out = reinterpret_cast<b2p_shard_group*>(grp);
+    });
+}
+API int b2p_shard_group_connect(b2p_shard_group* g, const void* all_handles) {
+    return guarded([&] {
+        require(g && all_handles, "null argument");
+        DeviceGuard dg(reinterpret_cast<ShardGroupBase*>(g)->device);
+        reinterpret_cast<ShardGroupBase*>(g)->connect(all_handles);
+    });
+}
+API int b2p_shard_group_connect_local(b2p_shard_group* const* groups, uint32_t world) {
+    return guarded([&] {
+        require(groups && world >= 1 && world <= 8, "null argument");
+        void* mails[8] = {nullptr};
+        for (uint32_t i = 0; i < world; i++) {
+            require(groups[i] != nullptr, "null group");
+            const ShardGroupBase* gi = reinterpret_cast<const ShardGroupBase*>(groups[i]);
+            require(gi->world == world && gi->rank == i, "groups must be listed by rank, all of the same world");
+            mails[i] = gi->mail_ptr();
+        }
+        void* staging0 = reinterpret_cast<const ShardGroupBase*>(groups[0])->staging_ptr();
+        for (uint32_t i = 0; i < world; i++) {
+            ShardGroupBase* gi = reinterpret_cast<ShardGroupBase*>(groups[i]);
+            DeviceGuard dg(gi->device);
+            gi->connect_local(mails, staging0);
+        }
+    });
+}
+API int b2p_shard_group_attach(b2p_shard_group* g, b2p_srs* prover_srs) {
+    return guarded([&] {
+        require(g, "null argument");
+        ShardGroupBase* grp = reinterpret_cast<ShardGroupBase*>(g);
+        DeviceGuard dg(grp->device);
+        if (prover_srs) {
+            SrsBase* s = reinterpret_cast<SrsBase*>(prover_srs);
+            std::lock_guard<std::mutex> lk(s->mu);
+            grp->attach(s);
+        } else {
+            grp->attach(nullptr);
+        }
+    });
+}
+API int b2p_shard_group_serve_proof(b2p_shard_group* g, uint64_t n) {
+    return guarded([&] {
+        require(g, "null argument");
+        DeviceGuard dg(reinterpret_cast<ShardGroupBase*>(g)->device);
+        reinterpret_cast<ShardGroupBase*>(g)->serve_proof(n);
+    });
+}
+API void b2p_shard_group_free(b2p_shard_group* g) {
+    if (!g) return;
+    guarded([&] {
+        DeviceGuard dg(reinterpret_cast<ShardGroupBase*>(g)->device);
+        delete reinterpret_cast<ShardGroupBase*>(g);
+    });
+}
+
 API int b2p_circuit_load(b2p_srs* srs, uint64_t n, uint32_t nb_public, const void* ql, const void* qr, const void* qm,
                          const void* qo, const void* qk, const int64_t* perm, uint32_t k, const void* const* qcp,
                          const uint64_t* cidx, const void* vkb, uint64_t vkb_len, b2p_circuit** out) {

@@ -1,6 +1,6 @@
 // Explicit instantiation: SRS handle + circuit/prover + curve-erased ops, Bls12381.
 #define B2P_INSTANTIATE_PROVER
-#include "prover.cuh"
+#include "shard_group.cuh"
 namespace b2p {
 template struct Srs<Bls12381>;
 template struct Circuit<Bls12381>;

@@ -1,6 +1,6 @@
 // Explicit instantiation: SRS handle + circuit/prover + curve-erased ops, Bn254.
 #define B2P_INSTANTIATE_PROVER
-#include "prover.cuh"
+#include "shard_group.cuh"
 namespace b2p {
 template struct Srs<Bn254>;
 template struct Circuit<Bn254>;

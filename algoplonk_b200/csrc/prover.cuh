@@ -230,6 +230,15 @@ template <> struct CurveConsts<Bls12381> {
     }
 };
 
+// Where the commitments of a proving key go when they are not computed on its own table: a shard group
+// (shard_group.cuh) spreads every kzg.Commit over the GPUs of the box.
+struct CommitRouter {
+    virtual ~CommitRouter() {}
+    virtual void begin_proof() = 0;
+    virtual void commit(const void* d_scalars, uint64_t n, int slot, cudaStream_t st) = 0;
+    virtual void fetch(int first, int cnt, void* host_affine_out, cudaStream_t st) = 0;
+};
+
 // ---------------------------------------------------------------------------
 // SRS handle
 // ---------------------------------------------------------------------------
@@ -250,6 +259,8 @@ struct Srs : SrsBase {
     void* hook_ctx = nullptr;
     Aff hook_out[MSM_SLOTS];
     void set_commit_hook(b2p_commit_fn fn, void* ctx) override { hook = fn; hook_ctx = ctx; }
+    // b2p_shard_group_attach: the native multi-GPU route (peer memory + flags, no host hop per commitment)
+    CommitRouter* router = nullptr;
 
     Srs() { curve = C::ID; B2P_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); }
     ~Srs() override { if (stream) cudaStreamDestroy(stream); }
@@ -294,7 +305,7 @@ struct Srs : SrsBase {
         finish_init();
     }
     void get_points(uint64_t first, uint64_t count, void* out) const override {
-        B2P_REQUIRE(first + count <= msm.npoints, "range exceeds SRS size");
+        B2P_REQUIRE(count <= msm.npoints && first <= msm.npoints - count, "range exceeds SRS size");
         B2P_CUDA(cudaMemcpy(out, msm.table.p + first, count * sizeof(Aff), cudaMemcpyDeviceToHost));
     }
     uint64_t size() const override { return msm.npoints; }
@@ -306,6 +317,7 @@ struct Srs : SrsBase {
     }
     // b2p_msm_g1: host scalars (Montgomery) -> affine result on the host
     void msm_g1(int basis, const void* scalars, uint64_t n, void* out, bool device_scalars) override {
+        B2P_REQUIRE(!router, "this SRS handle's commitments are routed to a shard group: only b2p_prove may use it");
         B2P_REQUIRE(n <= msm.npoints, "more scalars than SRS points");
         if (scratch.n < n + 1) scratch.alloc(n + 1);
         if (n) B2P_CUDA(cudaMemcpyAsync(scratch.p, scalars, n * sizeof(Fr),
@@ -347,6 +359,12 @@ struct Srs : SrsBase {
     }
     // queue an MSM of n device scalars (Montgomery form); result lands in slot
     void commit_async(const Fr* d_scalars, uint64_t n, int slot) {
+        if (router) {
+            int id = prof ? prof->begin(B2P_STAT_MSM_MS, stream) : -1;
+            router->commit(d_scalars, n, slot, stream);
+            if (prof) prof->end(id, stream);
+            return;
+        }
         if (hook) {
             B2P_REQUIRE(slot >= 0 && slot < OUT_SLOTS, "result slot out of range");
             B2P_CUDA(cudaStreamSynchronize(stream));      // the scalars are final before the hook reads them
@@ -365,6 +383,10 @@ struct Srs : SrsBase {
     void fetch(int first, int cnt, Aff* host_out) {
         Ext h[OUT_SLOTS];
         B2P_REQUIRE(first >= 0 && cnt >= 0 && first + cnt <= OUT_SLOTS, "result slot out of range");
+        if (router) {
+            router->fetch(first, cnt, host_out, stream);
+            return;
+        }
         if (hook) {
             for (int i = 0; i < cnt; i++) host_out[i] = hook_out[first + i];
             return;
@@ -631,7 +653,13 @@ struct Circuit : CircuitBase {
         auto t0 = std::chrono::steady_clock::now();
         for (auto& s : stats) s = 0;
         const unsigned long long launches0 = g_launch_count;
+        // srs->prof points into this circuit: reset on EVERY exit (a throw below must not leave it dangling)
+        struct ProfGuard {
+            Srs<C>* s;
+            ~ProfGuard() { s->prof = nullptr; s->msm.prof = nullptr; }
+        } prof_guard{srs};
         srs->prof = prof.on ? &prof : nullptr;
+        if (srs->router) srs->router->begin_proof();
         B2P_CUDA(cudaMemsetAsync(srs->msm.adds_total.p, 0, sizeof(unsigned long long), st));
         // wire columns: host buffers (the cgo path) or buffers already resident in HBM
         const cudaMemcpyKind in_kind = device_inputs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -955,6 +983,7 @@ struct CurveOpsImpl : CurveOps {
     using Aff = Affine<typename C::Fp>;
     SrsBase* new_srs() const override { return new Srs<C>(); }
     CircuitBase* new_circuit() const override { return new Circuit<C>(); }
+    ShardGroupBase* new_shard_group(uint32_t world, uint32_t rank, uint64_t total, SrsBase* shard) const override;  // shard_group.cuh
 
     // b2p_ntt: natural order in and out
     void ntt(void* data, uint64_t n, int flags) const override {

@@ -1,0 +1,148 @@
+"""One proof over the GPUs of a box, native path: host plumbing of b2p_shard_group_* (csrc/shard_group.cuh).
+
+The 9 kzg.Commit calls of plonk.Prove (algoplonk.go:89) are sharded over the point set (BASELINE
+configs[2]).  Everything on the data path is in the library: the scalars are read by the other ranks'
+Pippenger kernels straight out of rank 0's HBM over NVLink, the partial sums come back as peer stores, flags in
+peer memory order the ranks.  What is left for the host language, and all this module does:
+
+  * once: every rank creates its block of the SRS and its group handle, the 2 x 64-byte CUDA IPC handles of all
+    ranks are all_gathered (torch.distributed: plumbing) and mapped (b2p_shard_group_connect);
+  * per proof: ONE small broadcast "a proof of n rows starts" (or STOP); the other ranks answer it with
+    b2p_shard_group_serve_proof(n), which queues their share of the proof's fixed commitment sequence and returns
+    when it is done.
+
+Round 1's Python commit hook (sharded_prover.py: a 32 n-byte broadcast and two host hops per commitment) stays as the
+reference implementation the tests compare against; this is the path the benchmarks time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+from . import _lib
+from . import api
+from . import sharded
+
+OP_PROVE, OP_STOP = 1, 2
+
+
+class ShardGroup:
+    """This rank's end of the group.  Collective constructor (every rank calls it with the same arguments)."""
+
+    def __init__(self, curve: str, total_points: int, group=None, tau: int = api.TEST_TAU,
+                 srs_points: Optional[bytes] = None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.curve, self.total, self.group = curve, total_points, group
+        self.dist = dist if dist.is_initialized() else None
+        self.rank = dist.get_rank(group) if self.dist else 0
+        self.world = dist.get_world_size(group) if self.dist else 1
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        _lib.init(self.device.index)
+        lib = _lib.load()
+        # this rank's block of the SRS: its own table, planned for its own size
+        self.shard = (sharded.ShardedSRS.from_points(curve, srs_points[: total_points * 2 * api.FP_BYTES[curve]],
+                                                     self.rank, self.world)
+                      if srs_points is not None else
+                      sharded.ShardedSRS.unsafe(curve, total_points, self.rank, self.world, tau))
+        handles = C.create_string_buffer(2 * _lib.IPC_HANDLE_BYTES)
+        h = C.c_void_p()
+        _lib.check(lib.b2p_shard_group_create(api.CURVE_ID[curve], self.world, self.rank, total_points,
+                                              self.shard.handle, handles, C.byref(h)))
+        self.handle = h.value
+        self._attached = None
+        if self.world > 1:
+            mine = torch.frombuffer(bytearray(handles.raw), dtype=torch.uint8).to(self.device)
+            allh = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            buf = C.create_string_buffer(bytes(allh.cpu().numpy().tobytes()))
+            _lib.check(lib.b2p_shard_group_connect(self.handle, buf))
+            dist.barrier(group=group)           # every rank has mapped its peers before the first flag is written
+
+    # ---- rank 0 ---------------------------------------------------------------------------------------------
+    def attach(self, srs: api.SRS) -> None:
+        """Route the commitments of the proving key loaded on `srs` through the group (after api.Compile)."""
+        _lib.check(_lib.load().b2p_shard_group_attach(self.handle, srs.handle))
+        self._attached = srs
+
+    def detach(self) -> None:
+        if self._attached is not None and self.handle:
+            _lib.check(_lib.load().b2p_shard_group_attach(self.handle, None))
+        self._attached = None
+
+    def _header(self, op: int, n: int):
+        import torch
+        h = torch.tensor([op, n], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            src = self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            self.dist.broadcast(h, src=src, group=self.group)
+        return int(h[0]), int(h[1])
+
+    def announce(self, n: int) -> None:
+        """Rank 0, before each b2p_prove on the attached key: the other ranks start serving a proof of n rows."""
+        if self.world > 1:
+            self._header(OP_PROVE, n)
+
+    def stop(self) -> None:
+        if self.rank == 0 and self.world > 1:
+            self._header(OP_STOP, 0)
+
+    # ---- ranks > 0 ----------------------------------------------------------------------------------------------
+    def serve(self) -> int:
+        """Take part in rank 0's proofs until it stops; returns how many proofs were served."""
+        if self.rank == 0:
+            raise RuntimeError("rank 0 proves; the other ranks serve")
+        served = 0
+        while True:
+            op, n = self._header(0, 0)
+            if op == OP_STOP:
+                return served
+            if op != OP_PROVE:
+                raise RuntimeError(f"bad header from rank 0: op={op} n={n}")
+            _lib.check(_lib.load().b2p_shard_group_serve_proof(self.handle, n))
+            served += 1
+
+    def free(self) -> None:
+        self.detach()
+        if self.handle:
+            _lib.load().b2p_shard_group_free(self.handle)
+            self.handle = None
+        self.shard.free()
+
+
+class ShardedProver:
+    """api.CompiledCircuit whose commitments run on every GPU of the process group (rank 0 proves), native path.
+
+    every rank:  sp = ShardedProver(cs, curve, setup)
+    rank 0:      proof = sp.prove_raw(L, R, O, blinding) ...; sp.close()
+    ranks > 0:   sp.serve(); sp.close()
+    """
+
+    def __init__(self, cs, curve: str, setup_name: int, group=None, tau: int = api.TEST_TAU):
+        from . import frontend as fe
+        n = fe.build_trace(cs).n if hasattr(cs, "constraints") else int(cs)
+        self.n = n
+        self.grp = ShardGroup(curve, n + 3, group, tau)
+        self.rank, self.world = self.grp.rank, self.grp.world
+        self.cc = None
+        if self.rank == 0:
+            self.cc = api.Compile(cs, curve, setup_name)          # full SRS on rank 0: setup commitments are local
+            self.grp.attach(self.cc.srs)
+
+    def prove_raw(self, L: bytes, R: bytes, O: bytes, blinding: bytes) -> api.Proof:
+        if self.rank != 0:
+            raise RuntimeError("rank 0 proves; the other ranks serve")
+        self.grp.announce(self.n)
+        return self.cc.prove_raw(L, R, O, blinding)
+
+    def serve(self) -> int:
+        return self.grp.serve()
+
+    def close(self) -> None:
+        self.grp.stop()
+        self.grp.free()
+        if self.cc is not None:
+            srs = self.cc.srs
+            self.cc.free()
+            srs.free()
+            self.cc = None

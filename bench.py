@@ -360,6 +360,11 @@ def run_b200(args):
         assert bytes(o.raw) == proof_resident, "host-buffer and resident-buffer proofs differ"
 
     sharded_line = measure_sharded_msm(args, rank, world, device) if world > 1 else None
+    # one proof over all the GPUs (commitments sharded over the point set, native peer-memory path)
+    proof_sharded_line = None
+    if world > 1 and not args.no_proof_sharded:
+        proof_sharded_line = measure_sharded_proof(args, rank, world, device, cs, (hL, hR, hO), blinding,
+                                                   proof_resident, ms_single / args.steps)
 
     tot_ms, units = reduce_over_ranks(ms, args.steps, world, device)
     tot_ms_e2e, _ = reduce_over_ranks(ms_e2e, args.steps, world, device)
@@ -435,6 +440,8 @@ def run_b200(args):
         line["verify"] = {"accepted": False, "error": f"{type(e).__name__}: {e}"[:300]}
     if sharded_line is not None:
         line["msm_sharded"] = sharded_line
+    if proof_sharded_line is not None:
+        line["proof_sharded"] = proof_sharded_line
     if ntt_sharded_line is not None:
         line["ntt_sharded"] = ntt_sharded_line
     if world == 1 and not args.no_cpu_baseline:
@@ -499,6 +506,89 @@ def measure_sharded_msm(args, rank, world, device, iters: int = 10):
             "g1_adds_per_sec": n * windows / (ms * 1e-3), "c": c_bits, "windows": windows,
             "collective": f"all_gather of one {nb}-byte point per rank (NCCL), then a local {world}-point add",
             "scalars": "uniform, resident in HBM"}
+
+
+def measure_sharded_proof(args, rank, world, device, cs, host_cols, blinding, want_raw: bytes, ms_one_gpu: float):
+    """ONE proof at a time with its 9 commitments spread over all the GPUs (algoplonk_b200/shard_group.py,
+    csrc/shard_group.cuh: peer loads of the scalars, peer stores of the partial sums, flags; BASELINE configs[2]).
+    Rank 0 proves through the reference-facing b2p_prove with pinned host columns, the other ranks serve.  CUDA
+    events on rank 0's proving stream (a proof ends with its D2H on that stream), and the host wall clock around the
+    same blocking calls.  The proof bytes must equal the single-GPU proof of the timed region above.
+    Every failure is reported in the line instead of raised."""
+    import torch
+    import torch.distributed as dist
+    from algoplonk_b200 import _lib, api, shard_group as sg
+    lib = _lib.load()
+    curve = args.curve
+    setup = api.SetupName.TestOnlyBN254 if curve == "BN254" else api.SetupName.TestOnlyBLS12381
+    res, sp = None, None
+    old_c = os.environ.get("B2P_MSM_C")
+    try:
+        if args.shard_c:
+            os.environ["B2P_MSM_C"] = str(args.shard_c)
+        sp = sg.ShardedProver(cs, curve, setup)
+    except Exception as e:  # noqa: BLE001
+        res = {"error": f"setup: {type(e).__name__}: {e}"[:300]}
+    finally:
+        if old_c is None:
+            os.environ.pop("B2P_MSM_C", None)
+        else:
+            os.environ["B2P_MSM_C"] = old_c
+    ok = torch.tensor([0 if sp is not None else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(ok)
+    if int(ok.item()) != 0:
+        if sp is not None:
+            try:
+                sp.grp.free()
+            except Exception:  # noqa: BLE001
+                pass
+        return res or {"error": "setup failed on another rank"}
+    if rank != 0:
+        try:
+            sp.serve()
+        finally:
+            sp.close()
+        return None
+    try:
+        hL, hR, hO = host_cols
+        cid = api.CURVE_ID[curve]
+        out = C.create_string_buffer(lib.b2p_proof_raw_size(cid, 0))
+        stream = torch.cuda.ExternalStream(lib.b2p_circuit_stream(sp.cc.handle), device=device)
+
+        def one():
+            sp.grp.announce(sp.n)
+            _lib.check(lib.b2p_prove(sp.cc.handle, hL.data_ptr(), hR.data_ptr(), hO.data_ptr(), None, None,
+                                     blinding, out))
+        for _ in range(max(2, args.warmup)):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        c_bits, windows, buckets = api.SRS(curve, sp.grp.shard.handle).msm_params()
+        res = {"ms_per_proof": ms, "proofs_per_sec": 1e3 / ms, "host_wall_ms_per_proof": wall_ms,
+               "byte_identical_to_one_gpu_proof": bytes(out.raw) == want_raw,
+               "one_gpu_ms_per_proof": ms_one_gpu, "speedup_vs_one_gpu": ms_one_gpu / ms, "n_gpus": world,
+               "points_per_gpu": sp.grp.shard.count, "shard_c": c_bits, "shard_windows": windows,
+               "exchange": "scalars: peer loads of 32 n/G bytes per rank and commitment out of rank 0's HBM; partial "
+                           "sums: one XYZZ point per rank and commitment stored into rank 0's mailbox; flags in peer "
+                           "memory, no collective library on the data path",
+               "timing": "CUDA events on rank 0's proving stream around `steps` blocking b2p_prove calls (pinned "
+                         "host columns, H2D and D2H inside)"}
+    except Exception as e:  # noqa: BLE001
+        res = {"error": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        try:
+            sp.close()                      # STOP: the other ranks leave serve()
+        except Exception as e:  # noqa: BLE001
+            res = dict(res or {}, close_error=f"{type(e).__name__}: {e}"[:200])
+    return res
 
 
 def measure_sharded_ntt(args, rank, world, device, iters: int = 10):
@@ -600,6 +690,10 @@ def main():
     ap.add_argument("--log2", type=int, default=20, help="log2 of the constraint count (BASELINE: 20)")
     ap.add_argument("--curve", default="BN254", choices=["BN254", "BLS12_381"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-proof-sharded", action="store_true",
+                    help="skip the one-proof-over-all-GPUs leg of a multi-GPU run")
+    ap.add_argument("--shard-c", type=int, default=0,
+                    help="window bits of the per-rank SRS blocks of the sharded proof (0: planned for the block size)")
     ap.add_argument("--no-ntt-sharded", action="store_true",
                     help="skip the domain-sharded NTT leg of a multi-GPU run")
     ap.add_argument("--inflight", type=int, default=3,

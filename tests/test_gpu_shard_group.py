@@ -1,0 +1,100 @@
+"""GPU: the native multi-GPU commitment path (b2p_shard_group_*, csrc/shard_group.cuh) with every rank of the group
+living on ONE device -- each rank a host thread with its own SRS block, stream and mailbox, wired with
+b2p_shard_group_connect_local (plain pointers instead of CUDA IPC handles; everything else -- staging, the peers'
+count / scatter kernels reading rank 0's scalars, partial sums stored into rank 0's mailbox, the flags, the device-side
+sum -- is the code the multi-process runs execute).  The proof must equal the single-GPU proof byte for byte.
+Real multi-GPU runs: tools/sharded_proof_bench.py (bench.py --gpus N reports them as `proof_sharded`)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import pytest
+
+import helpers as H
+from algoplonk_b200 import _lib, api, frontend as fe, sharded
+from oracle import plonk_oracle as po
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+ONE_DEVICE = r"""
+import ctypes as C, sys, threading
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import helpers as H
+from algoplonk_b200 import _lib, api, frontend as fe, sharded
+from oracle import plonk_oracle as po
+curve, logn, world = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+_lib.init(0)
+lib = _lib.load()
+cv = po.CURVES[curve]
+SETUP = {{"BN254": api.SetupName.TestOnlyBN254, "BLS12_381": api.SetupName.TestOnlyBLS12381}}
+cs, values = fe.squaring_chain(curve, logn, x0=5)
+cc = api.Compile(cs, curve, SETUP[curve])
+n = cc.trace.n
+L, R, O = fe.solve_lro(cs, values, n)
+cols = [api.fr_to_mont_bytes(curve, c) for c in (L, R, O)]
+blindings = [api.fr_to_mont_bytes(curve, H.scalars_uniform(cv.r, 9, s)) for s in (1, 2, 3)]
+want = [cc.prove_raw(*cols, bl).raw for bl in blindings]
+shards = [sharded.ShardedSRS.unsafe(curve, n + 3, r, world) for r in range(world)]
+groups = []
+for r in range(world):
+    h = C.c_void_p()
+    _lib.check(lib.b2p_shard_group_create(api.CURVE_ID[curve], world, r, n + 3, shards[r].handle, None, C.byref(h)))
+    groups.append(h.value)
+_lib.check(lib.b2p_shard_group_connect_local((C.c_void_p * world)(*groups), world))
+_lib.check(lib.b2p_shard_group_attach(groups[0], cc.srs.handle))
+errs = []
+def serve(r):
+    try:
+        for _ in blindings:
+            _lib.check(lib.b2p_shard_group_serve_proof(groups[r], n))
+    except Exception as e:
+        errs.append((r, repr(e)))
+ths = [threading.Thread(target=serve, args=(r,)) for r in range(1, world)]
+for t in ths: t.start()
+got = [cc.prove_raw(*cols, bl).raw for bl in blindings]
+for t in ths: t.join()
+assert not errs, errs
+assert got == want, "sharded proof differs from the single-GPU proof"
+# while attached the handle serves b2p_prove only; detached it is an ordinary proving key again
+try:
+    cc.srs.msm([1, 2, 3]); raise SystemExit("msm on an attached handle did not fail")
+except _lib.B200PlonkError as e:
+    assert "shard group" in str(e)
+_lib.check(lib.b2p_shard_group_attach(groups[0], None))
+assert cc.prove_raw(*cols, blindings[0]).raw == want[0]
+assert cc.srs.msm([1]) == cv.g1
+for g in groups: lib.b2p_shard_group_free(g)
+print("SHARD_GROUP_OK")
+"""
+
+
+@pytest.mark.parametrize("curve,logn,world", [("BN254", 10, 2), ("BN254", 13, 3), ("BN254", 12, 8), ("BLS12_381", 11, 4)])
+def test_sharded_commitments_on_one_device_equal_single_gpu_proof(gpu, curve, logn, world, tmp_path):
+    """Own process with CUDA_DEVICE_MAX_CONNECTIONS=32: every rank's stream needs its own hardware queue, or a
+    kernel that spins on a flag could sit in front of the kernel that will raise it (one process per GPU in the real
+    runs: the question does not arise there)."""
+    script = tmp_path / "one_device.py"
+    script.write_text(ONE_DEVICE.format(root=ROOT))
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    out = subprocess.run([sys.executable, str(script), curve, str(logn), str(world)], capture_output=True, text=True,
+                         env=env, timeout=600)
+    assert out.returncode == 0 and "SHARD_GROUP_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
+
+
+def test_shard_group_argument_errors(gpu):
+    lib = _lib.load()
+    whole = api.SRS.unsafe("BN254", 67, H.TAU)
+    h = C.c_void_p()
+    # the block handed in must be exactly this rank's share of the points
+    assert lib.b2p_shard_group_create(0, 2, 0, 67, whole.handle, None, C.byref(h)) == _lib.ERR_ARG
+    assert b"share" in lib.b2p_last_error()
+    assert lib.b2p_shard_group_create(0, 9, 0, 67, whole.handle, None, C.byref(h)) == _lib.ERR_ARG
+    assert lib.b2p_shard_group_create(1, 1, 0, 67, whole.handle, None, C.byref(h)) == _lib.ERR_ARG
+    # world 1: the group is the SRS itself
+    _lib.check(lib.b2p_shard_group_create(0, 1, 0, 67, whole.handle, None, C.byref(h)))
+    assert lib.b2p_shard_group_serve_proof(h, 64) == _lib.ERR_ARG            # rank 0 does not serve
+    lib.b2p_shard_group_free(h)
+    whole.free()
