@@ -143,6 +143,17 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         if (rank == 0) B2P_CUDA(cudaMalloc(&staging, (size_t)STAGE_SLOTS * total * sizeof(Fr)));
         B2P_CUDA(cudaMallocHost(&h_err, sizeof(uint32_t)));
         *h_err = 0;
+        // Load the four exchange kernels NOW (no-op launches).  CUDA loads a kernel at its first launch, and that
+        // load can wait for kernels that are running -- such as a k_shard_wait spinning on a flag which only a
+        // not-yet-loaded kernel would raise (seen with all ranks of a group in one process: a 20 s stall).
+        {
+            ShardPeerFlags none{};
+            ShardFlags* f = flags(mail);
+            B2P_LAUNCH(k_shard_signal, 1, 32, 0, 0, none, 0, 0u);
+            B2P_LAUNCH(k_shard_wait, 1, 32, 0, 0, &f->ready[0], 0, 1, 0u, &f->error);
+            B2P_LAUNCH((k_shard_post<Fp>), 1, 32, 0, 0, partials(mail), partials(mail), &f->done[0][0], 0, 0, 0u);
+            B2P_LAUNCH((k_shard_sum<Fp>), 1, 32, 0, 0, partials(mail), partials(mail), 1, 0, 0);
+        }
         B2P_CUDA(cudaDeviceSynchronize());
         peer_mail[rank] = mail;
     }

@@ -41,9 +41,11 @@ func bsb22Hints(spr *cs_bn254.SparseR1CS, key *gpuKey, pi2 [][]fr.Element, coms 
 				return err
 			}
 			pi2[i] = col
-			if rc := C.b2p_msm_g1(key.srs, C.B2P_BASIS_LAGRANGE, unsafe.Pointer(&col[0]), C.uint64_t(n),
-				unsafe.Pointer(&coms[i])); rc != 0 {
-				return lastErr(rc)
+			if err := call(func() C.int {
+				return C.b2p_msm_g1(key.srs, C.B2P_BASIS_LAGRANGE, unsafe.Pointer(&col[0]), C.uint64_t(n),
+					unsafe.Pointer(&coms[i]))
+			}); err != nil {
+				return err
 			}
 			h := hash_to_field.New([]byte("BSB22-Plonk"))
 			h.Write(coms[i].Marshal())

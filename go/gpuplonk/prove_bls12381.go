@@ -17,6 +17,7 @@ import (
 
 	bls12381 "github.com/consensys/gnark-crypto/ecc/bls12-381"
 	"github.com/consensys/gnark-crypto/ecc/bls12-381/fr"
+	fft_bls12381 "github.com/consensys/gnark-crypto/ecc/bls12-381/fr/fft"
 	"github.com/consensys/gnark-crypto/ecc/bls12-381/fr/hash_to_field"
 	"github.com/consensys/gnark/backend"
 	"github.com/consensys/gnark/backend/plonk"
@@ -29,8 +30,6 @@ import (
 
 // BlindingSourceBls: see BlindingSource (prove_bn254.go).
 var BlindingSourceBls func() [9]fr.Element
-
-var keysBls = map[*plonk_bls12381.ProvingKey]*gpuKey{}
 
 // proveOtherCurves: BLS12-381 runs on the GPU like BN254; anything else is not an AlgoPlonk curve and stays on
 // gnark, as does any failure of the GPU path other than an unsatisfied constraint system.
@@ -53,34 +52,34 @@ func proveOtherCurves(ccs constraint.ConstraintSystem, pk plonk.ProvingKey, w wi
 
 // upload builds the device-resident key once per proving key: SRS table + selector / permutation columns.
 func uploadBls(spr *cs_bls12381.SparseR1CS, pk *plonk_bls12381.ProvingKey) (*gpuKey, error) {
-	mu.Lock()
-	defer mu.Unlock()
-	if k, ok := keysBls[pk]; ok {
+	if k := lookup(pk); k != nil {
 		return k, nil
 	}
-	if rc := C.b2p_init(-1); rc != 0 {
-		return nil, lastErr(rc)
+	if err := call(func() C.int { return C.b2p_init(-1) }); err != nil {
+		return nil, err
 	}
 	k := &gpuKey{}
 	g1 := pk.Kzg.G1 // canonical SRS, n+3 points, gnark in-memory layout == library layout
-	if rc := C.b2p_srs_load(C.B2P_BLS12_381, unsafe.Pointer(&g1[0]), C.uint64_t(len(g1)), nil, 0, &k.srs); rc != 0 {
-		return nil, lastErr(rc)
+	if err := call(func() C.int {
+		return C.b2p_srs_load(C.B2P_BLS12_381, unsafe.Pointer(&g1[0]), C.uint64_t(len(g1)), nil, 0, &k.srs)
+	}); err != nil {
+		return nil, err
 	}
-	trace := plonk_bls12381.NewTrace(spr, pk.Vk.Size) // Lagrange-form ql qr qm qo qk, S, qcp
+	// gnark v0.15: NewTrace(spr *cs.SparseR1CS, domain *fft.Domain) -- Lagrange-form ql qr qm qo qk, S, qcp
+	trace := plonk_bls12381.NewTrace(spr, fft_bls12381.NewDomain(pk.Vk.Size))
 	n := C.uint64_t(pk.Vk.Size)
 	col := func(p interface{ Coefficients() []fr.Element }) unsafe.Pointer {
 		return unsafe.Pointer(&p.Coefficients()[0])
 	}
 	nq := len(trace.Qcp)
-	var qcp *unsafe.Pointer
+	qcpPtrs := make([]unsafe.Pointer, nq)
+	for i := range trace.Qcp {
+		qcpPtrs[i] = col(trace.Qcp[i])
+	}
+	qcp, unpin := pointerArray(qcpPtrs) // Go pointers inside an array handed to C: pinned for the call
+	defer unpin()
 	var cidx *C.uint64_t
 	if nq > 0 {
-		ptrs := (*[1 << 10]unsafe.Pointer)(C.malloc(C.size_t(nq) * C.size_t(unsafe.Sizeof(uintptr(0)))))
-		defer C.free(unsafe.Pointer(ptrs))
-		for i := range trace.Qcp {
-			ptrs[i] = col(trace.Qcp[i])
-		}
-		qcp = &ptrs[0]
 		cidx = (*C.uint64_t)(unsafe.Pointer(&pk.Vk.CommitmentConstraintIndexes[0]))
 	}
 	// the VK digests gnark binds into gamma: S1 S2 S3 Ql Qr Qm Qo Qk Qcp*, Marshal() each
@@ -91,15 +90,17 @@ func uploadBls(spr *cs_bls12381.SparseR1CS, pk *plonk_bls12381.ProvingKey) (*gpu
 	for _, p := range pk.Vk.Qcp {
 		vkb = append(vkb, p.Marshal()...)
 	}
-	rc := C.b2p_circuit_load(k.srs, n, C.uint32_t(pk.Vk.NbPublicVariables),
-		col(trace.Ql), col(trace.Qr), col(trace.Qm), col(trace.Qo), col(trace.Qk),
-		(*C.int64_t)(unsafe.Pointer(&trace.S[0])), C.uint32_t(nq), qcp, cidx,
-		unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)), &k.circuit)
-	if rc != 0 {
+	if err := call(func() C.int {
+		return C.b2p_circuit_load(k.srs, n, C.uint32_t(pk.Vk.NbPublicVariables),
+			col(trace.Ql), col(trace.Qr), col(trace.Qm), col(trace.Qo), col(trace.Qk),
+			(*C.int64_t)(unsafe.Pointer(&trace.S[0])), C.uint32_t(nq), (*unsafe.Pointer)(unsafe.Pointer(qcp)), cidx,
+			unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)), &k.circuit)
+	}); err != nil {
 		C.b2p_srs_free(k.srs)
-		return nil, lastErr(rc)
+		return nil, err
 	}
-	keysBls[pk] = k
+	k.allocColumns(int(pk.Vk.Size))
+	remember(pk, k) // may evict the least recently used key (MaxResidentKeys)
 	return k, nil
 }
 
@@ -142,8 +143,8 @@ func proveBLS12381(spr *cs_bls12381.SparseR1CS, pk *plonk_bls12381.ProvingKey, f
 		return nil, err
 	}
 	s := sol.(*cs_bls12381.SparseR1CSSolution)
-	L, R, O := padBls(s.L, n), padBls(s.R, n), padBls(s.O, n)
-	defer releaseBls(L, R, O)
+	// the key's own page-locked columns (allocated once at upload; key.mu is held): no per-proof allocation
+	L, R, O := padBls(key, 0, s.L, n), padBls(key, 1, s.R, n), padBls(key, 2, s.O, n)
 
 	var blinding [9]fr.Element
 	if BlindingSourceBls != nil {
@@ -157,21 +158,21 @@ func proveBLS12381(spr *cs_bls12381.SparseR1CS, pk *plonk_bls12381.ProvingKey, f
 	}
 
 	raw := make([]byte, int(C.b2p_proof_raw_size(C.B2P_BLS12_381, C.uint32_t(k))))
-	var pi2p *unsafe.Pointer
+	pi2Ptrs := make([]unsafe.Pointer, k)
+	for i := range pi2 {
+		pi2Ptrs[i] = unsafe.Pointer(&pi2[i][0])
+	}
+	pi2p, unpin := pointerArray(pi2Ptrs)
+	defer unpin()
 	var bsbp unsafe.Pointer
 	if k > 0 {
-		ptrs := (*[1 << 10]unsafe.Pointer)(C.malloc(C.size_t(k) * C.size_t(unsafe.Sizeof(uintptr(0)))))
-		defer C.free(unsafe.Pointer(ptrs))
-		for i := range pi2 {
-			ptrs[i] = unsafe.Pointer(&pi2[i][0])
-		}
-		pi2p = &ptrs[0]
 		bsbp = unsafe.Pointer(&proof.Bsb22Commitments[0])
 	}
-	rc := C.b2p_prove(key.circuit, unsafe.Pointer(&L[0]), unsafe.Pointer(&R[0]), unsafe.Pointer(&O[0]),
-		pi2p, bsbp, unsafe.Pointer(&blinding[0]), unsafe.Pointer(&raw[0]))
-	if rc != 0 {
-		return nil, lastErr(rc)
+	if err := call(func() C.int {
+		return C.b2p_prove(key.circuit, unsafe.Pointer(&L[0]), unsafe.Pointer(&R[0]), unsafe.Pointer(&O[0]),
+			(*unsafe.Pointer)(unsafe.Pointer(pi2p)), bsbp, unsafe.Pointer(&blinding[0]), unsafe.Pointer(&raw[0]))
+	}); err != nil {
+		return nil, err
 	}
 	// raw = 9 G1Affine then 7+k fr.Element, gnark memory layout: copy into the gnark struct
 	pts := unsafe.Slice((*bls12381.G1Affine)(unsafe.Pointer(&raw[0])), 9)
@@ -188,32 +189,20 @@ func proveBLS12381(spr *cs_bls12381.SparseR1CS, pk *plonk_bls12381.ProvingKey, f
 
 // pad copies a solver column into a page-locked buffer of n elements (zero padded): pinned memory uploads at
 // PCIe speed and overlaps with the first transforms; the buffer is returned to the pool after the proof.
-func padBls(v []fr.Element, n int) []fr.Element {
-	var p unsafe.Pointer
-	if rc := C.b2p_host_alloc(C.uint64_t(n)*C.uint64_t(unsafe.Sizeof(fr.Element{})), &p); rc != 0 {
-		out := make([]fr.Element, n) // pageable fallback: correct, slower upload
-		copy(out, v)
-		return out
+// padBls copies a solver column into column `which` of the key's page-locked set (zero padded to n elements);
+// without pinned memory (allocation failed at upload) it falls back to a pageable slice: correct, slower upload.
+func padBls(key *gpuKey, which int, v []fr.Element, n int) []fr.Element {
+	var out []fr.Element
+	if p := key.cols[which]; p != nil && key.n == n {
+		out = unsafe.Slice((*fr.Element)(p), n)
+	} else {
+		out = make([]fr.Element, n)
 	}
-	out := unsafe.Slice((*fr.Element)(p), n)
 	k := copy(out, v)
 	for i := k; i < n; i++ {
 		out[i] = fr.Element{}
 	}
-	pinned.Store(p, struct{}{})
 	return out
-}
-
-func releaseBls(cols ...[]fr.Element) {
-	for _, c := range cols {
-		if len(c) == 0 {
-			continue
-		}
-		p := unsafe.Pointer(&c[0])
-		if _, ok := pinned.LoadAndDelete(p); ok {
-			C.b2p_host_free(p)
-		}
-	}
 }
 
 // bsb22Hints mirrors gnark's bsb22ComputeCommitmentHint (backend/plonk/bls12-381/prove.go): for commitment
@@ -239,9 +228,11 @@ func bsb22HintsBls(spr *cs_bls12381.SparseR1CS, key *gpuKey, pi2 [][]fr.Element,
 				return err
 			}
 			pi2[i] = col
-			if rc := C.b2p_msm_g1(key.srs, C.B2P_BASIS_LAGRANGE, unsafe.Pointer(&col[0]), C.uint64_t(n),
-				unsafe.Pointer(&coms[i])); rc != 0 {
-				return lastErr(rc)
+			if err := call(func() C.int {
+				return C.b2p_msm_g1(key.srs, C.B2P_BASIS_LAGRANGE, unsafe.Pointer(&col[0]), C.uint64_t(n),
+					unsafe.Pointer(&coms[i]))
+			}); err != nil {
+				return err
 			}
 			h := hash_to_field.New([]byte("BSB22-Plonk"))
 			h.Write(coms[i].Marshal())

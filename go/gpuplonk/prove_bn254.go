@@ -24,15 +24,13 @@ package gpuplonk
 import "C"
 
 import (
-	"crypto/rand"
 	"errors"
-	"fmt"
 	"runtime"
-	"sync"
 	"unsafe"
 
 	"github.com/consensys/gnark-crypto/ecc/bn254"
 	"github.com/consensys/gnark-crypto/ecc/bn254/fr"
+	fft_bn254 "github.com/consensys/gnark-crypto/ecc/bn254/fr/fft"
 	"github.com/consensys/gnark/backend"
 	"github.com/consensys/gnark/backend/plonk"
 	plonk_bn254 "github.com/consensys/gnark/backend/plonk/bn254"
@@ -46,51 +44,36 @@ import (
 // nil = crypto/rand, like gnark's fr.SetRandom.
 var BlindingSource func() [9]fr.Element
 
-type gpuKey struct {
-	mu      sync.Mutex // a handle takes one call at a time (b200plonk.h); concurrent provers of one key queue here
-	srs     *C.b2p_srs
-	circuit *C.b2p_circuit
-}
-
-var (
-	mu   sync.Mutex
-	keys = map[*plonk_bn254.ProvingKey]*gpuKey{} // pk + trace live in HBM across proofs
-)
-
-func lastErr(rc C.int) error {
-	return fmt.Errorf("b200plonk error %d: %s", int(rc), C.GoString(C.b2p_last_error()))
-}
-
 // upload builds the device-resident key once per proving key: SRS table + selector / permutation columns.
 func upload(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey) (*gpuKey, error) {
-	mu.Lock()
-	defer mu.Unlock()
-	if k, ok := keys[pk]; ok {
+	if k := lookup(pk); k != nil {
 		return k, nil
 	}
-	if rc := C.b2p_init(-1); rc != 0 {
-		return nil, lastErr(rc)
+	if err := call(func() C.int { return C.b2p_init(-1) }); err != nil {
+		return nil, err
 	}
 	k := &gpuKey{}
 	g1 := pk.Kzg.G1 // canonical SRS, n+3 points, gnark in-memory layout == library layout
-	if rc := C.b2p_srs_load(C.B2P_BN254, unsafe.Pointer(&g1[0]), C.uint64_t(len(g1)), nil, 0, &k.srs); rc != 0 {
-		return nil, lastErr(rc)
+	if err := call(func() C.int {
+		return C.b2p_srs_load(C.B2P_BN254, unsafe.Pointer(&g1[0]), C.uint64_t(len(g1)), nil, 0, &k.srs)
+	}); err != nil {
+		return nil, err
 	}
-	trace := plonk_bn254.NewTrace(spr, pk.Vk.Size) // Lagrange-form ql qr qm qo qk, S, qcp
+	// gnark v0.15: NewTrace(spr *cs.SparseR1CS, domain *fft.Domain) -- Lagrange-form ql qr qm qo qk, S, qcp
+	trace := plonk_bn254.NewTrace(spr, fft_bn254.NewDomain(pk.Vk.Size))
 	n := C.uint64_t(pk.Vk.Size)
 	col := func(p interface{ Coefficients() []fr.Element }) unsafe.Pointer {
 		return unsafe.Pointer(&p.Coefficients()[0])
 	}
 	nq := len(trace.Qcp)
-	var qcp *unsafe.Pointer
+	qcpPtrs := make([]unsafe.Pointer, nq)
+	for i := range trace.Qcp {
+		qcpPtrs[i] = col(trace.Qcp[i])
+	}
+	qcp, unpin := pointerArray(qcpPtrs) // Go pointers inside an array handed to C: pinned for the call
+	defer unpin()
 	var cidx *C.uint64_t
 	if nq > 0 {
-		ptrs := (*[1 << 10]unsafe.Pointer)(C.malloc(C.size_t(nq) * C.size_t(unsafe.Sizeof(uintptr(0)))))
-		defer C.free(unsafe.Pointer(ptrs))
-		for i := range trace.Qcp {
-			ptrs[i] = col(trace.Qcp[i])
-		}
-		qcp = &ptrs[0]
 		cidx = (*C.uint64_t)(unsafe.Pointer(&pk.Vk.CommitmentConstraintIndexes[0]))
 	}
 	// the VK digests gnark binds into gamma: S1 S2 S3 Ql Qr Qm Qo Qk Qcp*, Marshal() each
@@ -101,15 +84,17 @@ func upload(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey) (*gpuKey, erro
 	for _, p := range pk.Vk.Qcp {
 		vkb = append(vkb, p.Marshal()...)
 	}
-	rc := C.b2p_circuit_load(k.srs, n, C.uint32_t(pk.Vk.NbPublicVariables),
-		col(trace.Ql), col(trace.Qr), col(trace.Qm), col(trace.Qo), col(trace.Qk),
-		(*C.int64_t)(unsafe.Pointer(&trace.S[0])), C.uint32_t(nq), qcp, cidx,
-		unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)), &k.circuit)
-	if rc != 0 {
+	if err := call(func() C.int {
+		return C.b2p_circuit_load(k.srs, n, C.uint32_t(pk.Vk.NbPublicVariables),
+			col(trace.Ql), col(trace.Qr), col(trace.Qm), col(trace.Qo), col(trace.Qk),
+			(*C.int64_t)(unsafe.Pointer(&trace.S[0])), C.uint32_t(nq), (*unsafe.Pointer)(unsafe.Pointer(qcp)), cidx,
+			unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)), &k.circuit)
+	}); err != nil {
 		C.b2p_srs_free(k.srs)
-		return nil, lastErr(rc)
+		return nil, err
 	}
-	keys[pk] = k
+	k.allocColumns(int(pk.Vk.Size))
+	remember(pk, k) // may evict the least recently used key (MaxResidentKeys)
 	return k, nil
 }
 
@@ -172,8 +157,8 @@ func proveBN254(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey, fullWitnes
 		return nil, err
 	}
 	s := sol.(*cs_bn254.SparseR1CSSolution)
-	L, R, O := pad(s.L, n), pad(s.R, n), pad(s.O, n)
-	defer release(L, R, O)
+	// the key's own page-locked columns (allocated once at upload; key.mu is held): no per-proof allocation
+	L, R, O := pad(key, 0, s.L, n), pad(key, 1, s.R, n), pad(key, 2, s.O, n)
 
 	var blinding [9]fr.Element
 	if BlindingSource != nil {
@@ -185,24 +170,23 @@ func proveBN254(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey, fullWitnes
 			}
 		}
 	}
-	_ = rand.Reader
 
 	raw := make([]byte, int(C.b2p_proof_raw_size(C.B2P_BN254, C.uint32_t(k))))
-	var pi2p *unsafe.Pointer
+	pi2Ptrs := make([]unsafe.Pointer, k)
+	for i := range pi2 {
+		pi2Ptrs[i] = unsafe.Pointer(&pi2[i][0])
+	}
+	pi2p, unpin := pointerArray(pi2Ptrs)
+	defer unpin()
 	var bsbp unsafe.Pointer
 	if k > 0 {
-		ptrs := (*[1 << 10]unsafe.Pointer)(C.malloc(C.size_t(k) * C.size_t(unsafe.Sizeof(uintptr(0)))))
-		defer C.free(unsafe.Pointer(ptrs))
-		for i := range pi2 {
-			ptrs[i] = unsafe.Pointer(&pi2[i][0])
-		}
-		pi2p = &ptrs[0]
 		bsbp = unsafe.Pointer(&proof.Bsb22Commitments[0])
 	}
-	rc := C.b2p_prove(key.circuit, unsafe.Pointer(&L[0]), unsafe.Pointer(&R[0]), unsafe.Pointer(&O[0]),
-		pi2p, bsbp, unsafe.Pointer(&blinding[0]), unsafe.Pointer(&raw[0]))
-	if rc != 0 {
-		return nil, lastErr(rc)
+	if err := call(func() C.int {
+		return C.b2p_prove(key.circuit, unsafe.Pointer(&L[0]), unsafe.Pointer(&R[0]), unsafe.Pointer(&O[0]),
+			(*unsafe.Pointer)(unsafe.Pointer(pi2p)), bsbp, unsafe.Pointer(&blinding[0]), unsafe.Pointer(&raw[0]))
+	}); err != nil {
+		return nil, err
 	}
 	// raw = 9 G1Affine then 7+k fr.Element, gnark memory layout: copy into the gnark struct
 	pts := unsafe.Slice((*bn254.G1Affine)(unsafe.Pointer(&raw[0])), 9)
@@ -217,35 +201,19 @@ func proveBN254(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey, fullWitnes
 	return proof, nil
 }
 
-// pad copies a solver column into a page-locked buffer of n elements (zero padded): pinned memory uploads at
-// PCIe speed and overlaps with the first transforms; the buffer is returned to the pool after the proof.
-func pad(v []fr.Element, n int) []fr.Element {
-	var p unsafe.Pointer
-	if rc := C.b2p_host_alloc(C.uint64_t(n)*C.uint64_t(unsafe.Sizeof(fr.Element{})), &p); rc != 0 {
-		out := make([]fr.Element, n) // pageable fallback: correct, slower upload
-		copy(out, v)
-		return out
+// pad copies a solver column into column `which` of the key's page-locked set (zero padded to n elements);
+// without pinned memory (allocation failed at upload) it falls back to a pageable slice: correct, slower upload.
+func pad(key *gpuKey, which int, v []fr.Element, n int) []fr.Element {
+	var out []fr.Element
+	if p := key.cols[which]; p != nil && key.n == n {
+		out = unsafe.Slice((*fr.Element)(p), n)
+	} else {
+		out = make([]fr.Element, n)
 	}
-	out := unsafe.Slice((*fr.Element)(p), n)
 	k := copy(out, v)
 	for i := k; i < n; i++ {
 		out[i] = fr.Element{}
 	}
-	pinned.Store(p, struct{}{})
 	return out
 }
 
-// pinned tracks the page-locked columns of proofs in progress; release frees them.
-var pinned sync.Map
-
-func release(cols ...[]fr.Element) {
-	for _, c := range cols {
-		if len(c) == 0 {
-			continue
-		}
-		p := unsafe.Pointer(&c[0])
-		if _, ok := pinned.LoadAndDelete(p); ok {
-			C.b2p_host_free(p)
-		}
-	}
-}

@@ -19,6 +19,8 @@ import "C"
 
 import (
 	"errors"
+	"fmt"
+	"runtime"
 	"unsafe"
 
 	bls12381 "github.com/consensys/gnark-crypto/ecc/bls12-381"
@@ -53,14 +55,18 @@ func Verify(proof plonk.Proof, vk plonk.VerifyingKey, publicWitness witness.Witn
 	return plonk.Verify(proof, vk, publicWitness)
 }
 
-func verdict(rc C.int) error {
-	switch rc {
+// verdict runs one verification call and reads its message on the same OS thread (b2p_last_error is thread local).
+func verdict(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	switch rc := f(); rc {
 	case C.B2P_OK:
 		return nil
 	case C.B2P_ERR_VERIFY:
 		return errors.Join(ErrInvalidProof, errors.New(C.GoString(C.b2p_last_error())))
+	default:
+		return fmt.Errorf("b200plonk error %d: %s", int(rc), C.GoString(C.b2p_last_error()))
 	}
-	return lastErr(rc)
 }
 
 func verifyBN254(p *plonk_bn254.Proof, vk *plonk_bn254.VerifyingKey, w witness.Witness) error {
@@ -83,9 +89,11 @@ func verifyBN254(p *plonk_bn254.Proof, vk *plonk_bn254.VerifyingKey, w witness.W
 	if len(pubBytes) > 0 {
 		pubPtr = unsafe.Pointer(&pubBytes[0])
 	}
-	return verdict(C.b2p_verify(C.B2P_BN254, C.uint64_t(vk.Size), C.uint32_t(vk.NbPublicVariables),
+	return verdict(func() C.int {
+		return C.b2p_verify(C.B2P_BN254, C.uint64_t(vk.Size), C.uint32_t(vk.NbPublicVariables),
 		C.uint32_t(len(vk.Qcp)), cidx, unsafe.Pointer(&points[0]), unsafe.Pointer(&vk.Kzg.G1),
-		unsafe.Pointer(&vk.Kzg.G2[0]), unsafe.Pointer(&blob[0]), C.uint64_t(len(blob)), pubPtr, C.uint64_t(len(pubBytes))))
+		unsafe.Pointer(&vk.Kzg.G2[0]), unsafe.Pointer(&blob[0]), C.uint64_t(len(blob)), pubPtr, C.uint64_t(len(pubBytes)))
+	})
 }
 
 func verifyBLS12381(p *plonk_bls12381.Proof, vk *plonk_bls12381.VerifyingKey, w witness.Witness) error {
@@ -131,7 +139,9 @@ func verifyBLS12381(p *plonk_bls12381.Proof, vk *plonk_bls12381.VerifyingKey, w 
 	if len(pubBytes) > 0 {
 		pubPtr = unsafe.Pointer(&pubBytes[0])
 	}
-	return verdict(C.b2p_verify(C.B2P_BLS12_381, C.uint64_t(vk.Size), C.uint32_t(vk.NbPublicVariables),
+	return verdict(func() C.int {
+		return C.b2p_verify(C.B2P_BLS12_381, C.uint64_t(vk.Size), C.uint32_t(vk.NbPublicVariables),
 		C.uint32_t(len(vk.Qcp)), cidx, unsafe.Pointer(&points[0]), unsafe.Pointer(&vk.Kzg.G1),
-		unsafe.Pointer(&vk.Kzg.G2[0]), unsafe.Pointer(&blob[0]), C.uint64_t(len(blob)), pubPtr, C.uint64_t(len(pubBytes))))
+		unsafe.Pointer(&vk.Kzg.G2[0]), unsafe.Pointer(&blob[0]), C.uint64_t(len(blob)), pubPtr, C.uint64_t(len(pubBytes)))
+	})
 }

@@ -73,12 +73,12 @@ print("SHARD_GROUP_OK")
 
 @pytest.mark.parametrize("curve,logn,world", [("BN254", 10, 2), ("BN254", 13, 3), ("BN254", 12, 8), ("BLS12_381", 11, 4)])
 def test_sharded_commitments_on_one_device_equal_single_gpu_proof(gpu, curve, logn, world, tmp_path):
-    """Own process with CUDA_DEVICE_MAX_CONNECTIONS=32: every rank's stream needs its own hardware queue, or a
-    kernel that spins on a flag could sit in front of the kernel that will raise it (one process per GPU in the real
-    runs: the question does not arise there)."""
+    """Own process with CUDA_DEVICE_MAX_CONNECTIONS=32 and eager module loading: with every rank in ONE process, a
+    kernel that spins on a flag must never sit in front of the kernel that will raise it -- neither in a shared
+    hardware queue nor behind a lazy kernel load (one process per GPU in the real runs: neither arises there)."""
     script = tmp_path / "one_device.py"
     script.write_text(ONE_DEVICE.format(root=ROOT))
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER")
     out = subprocess.run([sys.executable, str(script), curve, str(logn), str(world)], capture_output=True, text=True,
                          env=env, timeout=600)
     assert out.returncode == 0 and "SHARD_GROUP_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])

@@ -389,85 +389,3 @@ def test_transcript_sha256_against_hashlib(tmp_path_factory):
             lib.ht_sha256(msg, C.c_uint64(n), C.c_uint64(split), got)
             assert got.raw == want, (n, split)
 
-
-# ---- reduced-radix field (field29.cuh): the representation the MSM accumulation computes in ---------------------
-@pytest.fixture(scope="module")
-def field29(tmp_path_factory):
-    """field29.cuh is plain C++ on 32/64-bit integers: compiled for the host it is the code the device runs."""
-    out = tmp_path_factory.mktemp("f29") / "field29.so"
-    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O1", "-std=c++17", "-shared", "-fPIC",
-                    "-x", "c++", os.path.join(ROOT, "tests", "csrc", "field29_shim.cpp"), "-o", str(out)], check=True)
-    return C.CDLL(str(out))
-
-
-@pytest.mark.parametrize("fid,mod,nw,rbits", [(0, po.BN254.r, 8, 261), (1, po.BN254.p, 8, 261),
-                                             (2, po.BLS12_381.r, 8, 261), (3, po.BLS12_381.p, 12, 392)])
-def test_reduced_radix_field_against_python_ints(field29, fid, mod, nw, rbits):
-    """9 x 29-bit / 14 x 28-bit limbs, Montgomery constant 2^261 / 2^392, lazy reduction: products, squares, the fused
-    a b + c d, additions and subtractions with their K p offsets, chains of lazy values, the exact zero test on every
-    multiple of p that fits, the radix changes and the change of Montgomery constant to and from the memory format."""
-    p, Rp, R = mod, 1 << rbits, 1 << (32 * nw)
-    Ri = pow(Rp, -1, p)
-    rng = random.Random(fid)
-
-    def words(x):
-        return (C.c_uint32 * nw)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(nw)])
-
-    def op(o, a, b=0, c=0, d=0):
-        out = (C.c_uint32 * nw)()
-        field29.h29_field_op(fid, o, words(a), words(b), words(c), words(d), out)
-        return sum(int(v) << (32 * i) for i, v in enumerate(out))
-
-    special = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (1 << 29) - 1, 1 << 29, (1 << 232) - 1, p >> 1, (1 << 28) - 1]
-    for _ in range(1500):
-        a, b, c, d = (rng.choice(special) if rng.random() < 0.25 else rng.randrange(p) for _ in range(4))
-        assert op(0, a, b) == a * b * Ri % p
-        assert op(1, a) == a * a * Ri % p
-        assert op(2, a, b) == (a + b) % p
-        assert op(3, a, b) == (a - b) % p and op(4, a, b) == (a - b) % p
-        assert op(5, a, b, c, d) == (a * b + c * d) * Ri % p
-        assert op(6, a) == (-a) % p
-        assert op(7, a) == a                                   # memory -> registers -> memory
-        assert op(8, a) == a * Rp * pow(R, -1, p) % p          # x R -> x R'
-        assert op(9, a, b, c, d) == ((a - b) + (c - d)) ** 2 * Ri % p
-        assert op(11, a, b, c, d) == (4 * a + 2 * b + c + d) % p
-    for k in range(12):
-        if k * p < R:
-            assert op(10, k * p) == 1
-            if k:
-                assert op(10, k * p + 1) == 0 and op(10, k * p - 1) == 0
-
-
-@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
-def test_reduced_radix_mixed_addition_equals_the_32_bit_limb_formulas(field29, curve):
-    """XYZZ29::add_affine (lazy reduction, fused products) gives the SAME four coordinates as ec.cuh's
-    XYZZ::add_affine_signed for generic, doubling, cancelling and infinity operands, with unit and random Z."""
-    cv = po.CURVES[curve]
-    cid, nw = cv.cid, (8 if cv.cid == 0 else 12)
-    R = 1 << (32 * nw)
-    rng = random.Random(29)
-
-    def words(x):
-        return [(x >> (32 * i)) & 0xFFFFFFFF for i in range(nw)]
-
-    def aff(P):
-        return (C.c_uint32 * (2 * nw))(*([0] * (2 * nw) if P is None else words(P[0] * R % cv.p) + words(P[1] * R % cv.p)))
-
-    def xyzz(P, z):
-        if P is None:
-            return (C.c_uint32 * (4 * nw))()
-        zz, zzz = z * z % cv.p, z * z * z % cv.p
-        out = []
-        for v in (P[0] * zz % cv.p, P[1] * zzz % cv.p, zz, zzz):
-            out += words(v * R % cv.p)
-        return (C.c_uint32 * (4 * nw))(*out)
-
-    pts = [po.g1_mul(cv, cv.g1, k) for k in (1, 2, 3, 5, 7, 1000003)] + [None]
-    for A in pts:
-        for B in pts:
-            for neg in (0, 1):
-                for z in (1, 5, rng.randrange(1, cv.p)):
-                    o1, o2 = (C.c_uint32 * (4 * nw))(), (C.c_uint32 * (4 * nw))()
-                    field29.h29_madd(cid, xyzz(A, z), aff(B), neg, o1)
-                    field29.h29_madd_ref(cid, xyzz(A, z), aff(B), neg, o2)
-                    assert list(o1) == list(o2), (A, B, neg, z)

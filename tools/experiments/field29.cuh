@@ -18,7 +18,7 @@
 // a normalized value below 2p.  sub<K>(a, b) = a + K p - b needs b normalized and b <= K p.
 #pragma once
 #include <cstdint>
-#include "field.cuh"
+#include "../../algoplonk_b200/csrc/field.cuh"
 #include "field29_params.cuh"
 
 namespace b2p {

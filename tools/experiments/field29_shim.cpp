@@ -1,7 +1,7 @@
 // Test-only shim: the reduced-radix field of field29.cuh (what the MSM accumulation kernel computes in) behind a C
 // ABI, compiled for the host -- field29.cuh is plain C++ on 32/64-bit integers, so this is the very code the device runs.
 #include <cstring>
-#include "../../algoplonk_b200/csrc/field29.cuh"
+#include "field29.cuh"
 #include "../../algoplonk_b200/csrc/ec.cuh"
 using namespace b2p;
 

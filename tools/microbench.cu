@@ -9,33 +9,22 @@
 #include <cstdint>
 #include <string>
 #include "../algoplonk_b200/csrc/common.cuh"
-#include "../algoplonk_b200/csrc/field29.cuh"
+#include "experiments/field29.cuh"
 using namespace b2p;
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
 
 // MODE 0: mad.lo.u32 (IMAD), 16 independent accumulators.
-// MODE 1: mad.wide.u32 (IMAD.WIDE.U32), 16 independent 64-bit accumulators, multiplicands fixed per lane: every
-//         instruction depends only on its own accumulator, nothing else is in the loop (round 1's version unpacked
-//         the accumulator with mov.b64 inside the loop and fed it back as a multiplicand: it under-read the pipe).
+// (A carry-free IMAD.WIDE.U32 variant was dropped: with constant multiplicands ptxas hoists the products and the loop
+//  measures IADD3, with data-dependent ones it surrounds every IMAD.WIDE with three MOV / IMAD.MOV -- neither number
+//  says anything about the instruction.  The reduced-radix multiplier built on the assumption that it is cheap
+//  measured 34 % SLOWER than the carry-chained one: tools/experiments/field29.cuh, reduced_radix below.)
 // MODE 2: the carry-chained pair the field multiplier is made of -- mad.lo.cc.u32 / madc.hi.cc.u32 on adjacent
 //         registers, which ptxas fuses into IMAD.WIDE.U32.X -- 4 chains of 4 pairs.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_imad(uint32_t* out, int iters, uint32_t seed) {
     const uint32_t a = seed + threadIdx.x * 2654435761u, b = seed * 3 + 1 + blockIdx.x;
-    if (MODE == 1) {
-        uint64_t c[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) c[i] = (uint64_t)(i + threadIdx.x) << 20;
-        for (int it = 0; it < iters; it++) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[i]) : "r"(a + i), "r"(b));
-        }
-        uint64_t s = 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) s += c[i];
-        out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32);
-    } else if (MODE == 2) {
+    if (MODE == 2) {
         uint32_t c[4][9];
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -270,9 +259,8 @@ int main() {
     dim3 grid(sms * 8), block(256);
     double thr = (double)grid.x * block.x;
     float t_lo = time_kernel(k_imad<0>, grid, block, (uint32_t*)buf, iters, 7u);
-    float t_wide = time_kernel(k_imad<1>, grid, block, (uint32_t*)buf, iters, 7u);
     float t_chain = time_kernel(k_imad<2>, grid, block, (uint32_t*)buf, iters, 7u);
-    double imad_lo = thr * iters * 16 / (t_lo * 1e-3), imad_wide = thr * iters * 16 / (t_wide * 1e-3);
+    double imad_lo = thr * iters * 16 / (t_lo * 1e-3);
     double imad_wide_x = thr * iters * 16 / (t_chain * 1e-3);     // fused pairs: 4 chains x 4 IMAD.WIDE.U32.X
     const int fi = 2048;
     float t1 = time_kernel(k_fmul<FrBn254>, grid, block, (FrBn254*)buf, fi);
@@ -327,12 +315,12 @@ int main() {
         cudaFree(A); cudaFree(B); cudaFree(O); cudaFree(S); cudaFree(X); cudaFree(err);
     }
     CK(cudaGetLastError());
-    printf("{\"sms\": %d, \"imad_lo_per_s\": %.4g, \"imad_wide_per_s\": %.4g, \"imad_wide_x_carry_chain_per_s\": %.4g, "
+    printf("{\"sms\": %d, \"imad_lo_per_s\": %.4g, \"imad_wide_x_carry_chain_per_s\": %.4g, "
            "\"fmul_per_s\": {\"fr_bn254\": %.4g, \"fp_bn254\": %.4g, \"fr_bls12381\": %.4g, \"fp_bls12381\": %.4g}, "
            "\"xyzz_madd_per_s\": {\"bn254\": %.4g, \"bls12381\": %.4g}, "
            "\"reduced_radix\": {\"fmul_per_s\": {\"fp_bn254_9x29\": %.4g, \"fr_bls12381_9x29\": %.4g, \"fp_bls12381_14x28\": %.4g}, "
            "\"xyzz_madd_per_s\": {\"bn254\": %.4g, \"bls12381\": %.4g}}, \"batch_affine_bn254\": %s}\n",
-           sms, imad_lo, imad_wide, imad_wide_x, thr * fi * 2 / (t1 * 1e-3), thr * fi * 2 / (t2 * 1e-3), thr * fi * 2 / (t3 * 1e-3),
+           sms, imad_lo, imad_wide_x, thr * fi * 2 / (t1 * 1e-3), thr * fi * 2 / (t2 * 1e-3), thr * fi * 2 / (t3 * 1e-3),
            thr * fi * 2 / (t4 * 1e-3), thr2 * mi / (t5 * 1e-3), thr2 * mi / (t6 * 1e-3),
            thr * fi * 2 / (u1 * 1e-3), thr * fi * 2 / (u2 * 1e-3), thr * fi * 2 / (u3 * 1e-3),
            thr2 * mi / (u5 * 1e-3), thr2 * mi / (u6 * 1e-3), ba.c_str());
