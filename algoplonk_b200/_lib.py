@@ -19,6 +19,7 @@ ERR_ARG, ERR_CUDA, ERR_INTERNAL, ERR_VERIFY = -1, -2, -3, -4
 BASIS_CANONICAL, BASIS_LAGRANGE = 0, 1
 NTT_INVERSE, NTT_COSET = 1, 2
 IPC_HANDLE_BYTES = 64
+SHARD_HANDLES = 8
 STAT_NAMES = ["total_ms", "msm_ms", "msm_accum_ms", "ntt_ms", "quotient_ms", "msm_calls", "msm_accum_adds",
               "h2d_bytes", "d2h_bytes", "launches"]
 STAT_COUNT = 16
@@ -47,10 +48,11 @@ SYMBOLS = [
     ("b2p_srs_stream", _vp, [_vp]),
     ("b2p_srs_set_commit_hook", _int, [_vp, _vp, _vp]),
     ("b2p_device_copy", _int, [_vp, _vp, _u64]),
-    ("b2p_shard_group_create", _int, [_int, _u32, _u32, _u64, _vp, _vp, C.POINTER(_vp)]),
+    ("b2p_shard_group_create", _int, [_int, _u32, _u32, _u64, _vp, _u64, C.POINTER(_vp)]),
+    ("b2p_shard_group_attach", _int, [_vp, _vp, _vp]),
+    ("b2p_shard_group_export", _int, [_vp, _vp]),
     ("b2p_shard_group_connect", _int, [_vp, _vp]),
     ("b2p_shard_group_connect_local", _int, [C.POINTER(_vp), _u32]),
-    ("b2p_shard_group_attach", _int, [_vp, _vp]),
     ("b2p_shard_group_serve_proof", _int, [_vp, _u64]),
     ("b2p_shard_group_free", None, [_vp]),
     ("b2p_ntt", _int, [_int, _vp, _u64, _int]),

@@ -331,15 +331,35 @@ API int b2p_peer_free(void* d_ptr) {
 
 // ---- one proof over the GPUs of a box: commitments sharded over the point set (shard_group.cuh) -------------
 API int b2p_shard_group_create(int curve, uint32_t world, uint32_t rank, uint64_t total_points, b2p_srs* shard,
-                               void* ipc_handles_out, b2p_shard_group** out) {
+                               uint64_t ntt_rows, b2p_shard_group** out) {
     return guarded([&] {
         require(shard && out, "null argument");
         SrsBase* s = reinterpret_cast<SrsBase*>(shard);
         DeviceGuard g(s->device);
-        ShardGroupBase* grp = ops_for(curve)->new_shard_group(world, rank, total_points, s);
+        ShardGroupBase* grp = ops_for(curve)->new_shard_group(world, rank, total_points, s, ntt_rows);
         grp->device = s->device;
-        try { if (ipc_handles_out) grp->ipc_handles(ipc_handles_out); } catch (...) { delete grp; throw; }
         *out = reinterpret_cast<b2p_shard_group*>(grp);
+    });
+}
+API int b2p_shard_group_attach(b2p_shard_group* g, b2p_srs* prover_srs, b2p_circuit* circuit) {
+    return guarded([&] {
+        require(g, "null argument");
+        ShardGroupBase* grp = reinterpret_cast<ShardGroupBase*>(g);
+        DeviceGuard dg(grp->device);
+        if (prover_srs) {
+            SrsBase* s = reinterpret_cast<SrsBase*>(prover_srs);
+            std::lock_guard<std::mutex> lk(s->mu);
+            grp->attach(s, reinterpret_cast<CircuitBase*>(circuit));
+        } else {
+            grp->attach(nullptr, nullptr);
+        }
+    });
+}
+API int b2p_shard_group_export(b2p_shard_group* g, void* ipc_handles_out) {
+    return guarded([&] {
+        require(g && ipc_handles_out, "null argument");
+        DeviceGuard dg(reinterpret_cast<ShardGroupBase*>(g)->device);
+        reinterpret_cast<ShardGroupBase*>(g)->ipc_handles(ipc_handles_out);
     });
 }
 API int b2p_shard_group_connect(b2p_shard_group* g, const void* all_handles) {
@@ -352,32 +372,17 @@ API int b2p_shard_group_connect(b2p_shard_group* g, const void* all_handles) {
 API int b2p_shard_group_connect_local(b2p_shard_group* const* groups, uint32_t world) {
     return guarded([&] {
         require(groups && world >= 1 && world <= 8, "null argument");
-        void* mails[8] = {nullptr};
+        void* all[8 * SHARD_NPTR] = {nullptr};
         for (uint32_t i = 0; i < world; i++) {
             require(groups[i] != nullptr, "null group");
             const ShardGroupBase* gi = reinterpret_cast<const ShardGroupBase*>(groups[i]);
             require(gi->world == world && gi->rank == i, "groups must be listed by rank, all of the same world");
-            mails[i] = gi->mail_ptr();
+            gi->local_ptrs(all + (size_t)i * SHARD_NPTR);
         }
-        void* staging0 = reinterpret_cast<const ShardGroupBase*>(groups[0])->staging_ptr();
         for (uint32_t i = 0; i < world; i++) {
             ShardGroupBase* gi = reinterpret_cast<ShardGroupBase*>(groups[i]);
             DeviceGuard dg(gi->device);
-            gi->connect_local(mails, staging0);
-        }
-    });
-}
-API int b2p_shard_group_attach(b2p_shard_group* g, b2p_srs* prover_srs) {
-    return guarded([&] {
-        require(g, "null argument");
-        ShardGroupBase* grp = reinterpret_cast<ShardGroupBase*>(g);
-        DeviceGuard dg(grp->device);
-        if (prover_srs) {
-            SrsBase* s = reinterpret_cast<SrsBase*>(prover_srs);
-            std::lock_guard<std::mutex> lk(s->mu);
-            grp->attach(s);
-        } else {
-            grp->attach(nullptr);
+            gi->connect_ptrs(all);
         }
     });
 }

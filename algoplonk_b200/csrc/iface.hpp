@@ -48,6 +48,7 @@ struct CircuitBase {
                        const void* blinding, void* out_raw, bool device_inputs) = 0;
     virtual void* stream_handle() = 0;
     virtual void set_profiling(bool on) = 0;
+    virtual void shard_buffers(void** out5, uint64_t* n) = 0;   // el er eo ez h (device), domain size
 };
 
 // One rank's part of an NTT whose domain is sharded over the GPUs of a box (ntt_shard.cuh).
@@ -64,25 +65,27 @@ struct NttShardBase {
 };
 NttShardBase* new_ntt_shard(int curve, uint64_t n, uint32_t world, uint32_t rank);   // inst_ntt.cu
 
-// One rank of a shard group: the commitments of one proof spread over the GPUs of a box (shard_group.cuh).
+// One rank of a shard group: the commitments (and, optionally, the big transforms) of one proof spread over the GPUs
+// of a box (shard_group.cuh).  A rank shares SHARD_NPTR pieces of memory with its peers.
+constexpr int SHARD_NPTR = 8;
 struct ShardGroupBase {
     int curve = -1;
     int device = -1;
     uint32_t world = 1, rank = 0;
     uint64_t total = 0;                         // points of the whole SRS
     virtual ~ShardGroupBase() {}
-    virtual void ipc_handles(void* out) const = 0;              // 2 x B2P_IPC_HANDLE_BYTES: mailbox, staging
-    virtual void connect(const void* all_handles) = 0;          // world x 2 handles, rank-major
-    virtual void connect_local(void* const* mails, void* staging0) = 0;
-    virtual void* mail_ptr() const = 0;
-    virtual void* staging_ptr() const = 0;
-    virtual void attach(SrsBase* prover_srs) = 0;               // rank 0; nullptr detaches
+    virtual void attach(SrsBase* prover_srs, CircuitBase* circuit) = 0;     // rank 0; nullptr detaches
+    virtual void ipc_handles(void* out) const = 0;              // SHARD_NPTR x B2P_IPC_HANDLE_BYTES
+    virtual void local_ptrs(void** out) const = 0;              // SHARD_NPTR pointers (ranks of one process)
+    virtual void connect(const void* all_handles) = 0;          // world x SHARD_NPTR handles, rank-major
+    virtual void connect_ptrs(void* const* all) = 0;            // world x SHARD_NPTR pointers, rank-major
     virtual void serve_proof(uint64_t n) = 0;                   // ranks > 0
 };
 
 struct CurveOps {
     virtual ~CurveOps() {}
-    virtual ShardGroupBase* new_shard_group(uint32_t world, uint32_t rank, uint64_t total, SrsBase* shard) const = 0;
+    virtual ShardGroupBase* new_shard_group(uint32_t world, uint32_t rank, uint64_t total, SrsBase* shard,
+                                            uint64_t ntt_rows) const = 0;
     virtual SrsBase* new_srs() const = 0;
     virtual CircuitBase* new_circuit() const = 0;
     virtual void ntt(void* data, uint64_t n, int flags) const = 0;

@@ -12,13 +12,28 @@ struct MsmPlan {
     uint32_t nbuckets = 0;   // 2^(c-1)
 };
 
+// Cost model, in mixed additions, fitted to profiles/msm_plan_sweep_r2_*.jsonl (one MSM of n = 2^15 ... 2^21 points at
+// every window width, B200):
+//   n W                     digit additions (the accumulation: one thread per bucket slice of <= 128 entries),
+//   x (1 + 0.19 log2(300 k / items))  when there are fewer work items than fill the GPU a few times over
+//                           (148 SMs x 512 resident threads x 4): the accumulation is then latency-bound -- 2^19 points:
+//                           c = 17 (88 k items) 2.31 ms, c = 20 (524 k) 1.81 ms, although c = 17 makes fewer additions,
+//   + 3 * 2^(c-1)           the bucket reduction.
+// Only the smallest c of each window count W is a candidate: a wider window with the same W adds buckets, not speed
+// (2^17 points: c = 17 0.91 ms, c = 18 1.34 ms, both W = 15).
 inline MsmPlan msm_plan(uint64_t npoints, int scalar_bits, int force_c = 0) {
     MsmPlan best;
     double best_cost = 1e300;
     for (int c = 2; c <= 22; c++) {
         if (force_c && c != force_c) continue;
-        int W = (scalar_bits + 1 + c - 1) / c;
-        double cost = (double)npoints * W + 3.0 * (double)(1u << (c - 1));
+        const int W = (scalar_bits + 1 + c - 1) / c;
+        if (!force_c && c > 2 && (scalar_bits + 1 + c - 2) / (c - 1) == W) continue;     // c - 1 reaches the same W
+        const double adds = (double)npoints * W, nb = (double)(1u << (c - 1));
+        double items = adds / 128.0 > nb ? adds / 128.0 : nb;
+        if (items > adds) items = adds;
+        double slow = 1.0;
+        for (double t = items; t < 300000.0 && t >= 1.0; t *= 2.0) slow += 0.19;
+        const double cost = adds * slow + 3.0 * nb;
         if (cost < best_cost) { best_cost = cost; best.c = c; best.W = W; best.nbuckets = 1u << (c - 1); }
     }
     return best;

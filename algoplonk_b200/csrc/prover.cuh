@@ -237,6 +237,11 @@ struct CommitRouter {
     virtual void begin_proof() = 0;
     virtual void commit(const void* d_scalars, uint64_t n, int slot, cudaStream_t st) = 0;
     virtual void fetch(int first, int cnt, void* host_affine_out, cudaStream_t st) = 0;
+    // the proof's size-4n transforms spread over the same ranks (shard_group.cuh); `which`: 0..3 = el er eo ez
+    virtual bool shards_ntt() const = 0;
+    virtual void ntt_forward(const void* d_coeffs, uint64_t len, int which, cudaStream_t st) = 0;
+    virtual void ntt_forward_wait(cudaStream_t st) = 0;
+    virtual void ntt_inverse(uint64_t out_len, cudaStream_t st) = 0;
 };
 
 // ---------------------------------------------------------------------------
@@ -444,6 +449,11 @@ struct Circuit : CircuitBase {
     static constexpr int DOT_BLOCKS = 148 * 2;
 
     void set_profiling(bool on) override { prof.on = on; }
+    // the evaluation buffers a shard group lets the other ranks write into / read from: el er eo ez h
+    void shard_buffers(void** out5, uint64_t* n_out) override {
+        out5[0] = el.p; out5[1] = er.p; out5[2] = eo.p; out5[3] = ez.p; out5[4] = h.p;
+        *n_out = n;
+    }
     void vk_commitments(void* out) override {
         if (!have_vk_points) {
             auto keep = vk_bytes;
@@ -793,10 +803,25 @@ struct Circuit : CircuitBase {
             prof.end(id, st);
             to_coset(eqk.p, tmp, n);
         }
-        to_coset(el.p, cl.p, n + 2);
-        to_coset(er.p, cr.p, n + 2);
-        to_coset(eo.p, co.p, n + 2);
-        to_coset(ez.p, cz.p, n + 3);
+        // the four big forward transforms: here, or spread over the ranks of a shard group (each rank's combine
+        // kernel stores its block of the evaluations straight into el / er / eo / ez)
+        const bool shard_ntt = srs->router && srs->router->shards_ntt();
+        if (shard_ntt) {
+            B2P_REQUIRE(pi_direct && k == 0, "sharded transforms: circuits with BSB22 commitments or more than 8 public "
+                                             "inputs are proved with sharded commitments only (ntt_rows = 0)");
+            int id = prof.begin(B2P_STAT_NTT_MS, st);
+            srs->router->ntt_forward(cl.p, n + 2, 0, st);
+            srs->router->ntt_forward(cr.p, n + 2, 1, st);
+            srs->router->ntt_forward(co.p, n + 2, 2, st);
+            srs->router->ntt_forward(cz.p, n + 3, 3, st);
+            srs->router->ntt_forward_wait(st);
+            prof.end(id, st);
+        } else {
+            to_coset(el.p, cl.p, n + 2);
+            to_coset(er.p, cr.p, n + 2);
+            to_coset(eo.p, co.p, n + 2);
+            to_coset(ez.p, cz.p, n + 3);
+        }
         for (uint32_t c = 0; c < k; c++) {
             int id = prof.begin(B2P_STAT_NTT_MS, st);
             to_canonical(c_pi2[c].p);
@@ -827,7 +852,8 @@ struct Circuit : CircuitBase {
             B2P_LAUNCH((k_quotient<Fr>), div_up(m, 256), 256, 0, st, a);
             prof.end(id, st);
             id = prof.begin(B2P_STAT_NTT_MS, st);
-            d1.coset_inverse_dit(h.p, st);
+            if (shard_ntt) srs->router->ntt_inverse(3 * (n + 2), st);     // deg h = 3n + 5: nothing above is read
+            else d1.coset_inverse_dit(h.p, st);
             prof.end(id, st);
         }
         for (int j = 0; j < 3; j++) srs->commit_async(h.p + (uint64_t)j * (n + 2), n + 2, 4 + j);
@@ -983,7 +1009,8 @@ struct CurveOpsImpl : CurveOps {
     using Aff = Affine<typename C::Fp>;
     SrsBase* new_srs() const override { return new Srs<C>(); }
     CircuitBase* new_circuit() const override { return new Circuit<C>(); }
-    ShardGroupBase* new_shard_group(uint32_t world, uint32_t rank, uint64_t total, SrsBase* shard) const override;  // shard_group.cuh
+    ShardGroupBase* new_shard_group(uint32_t world, uint32_t rank, uint64_t total, SrsBase* shard,
+                                    uint64_t ntt_rows) const override;   // shard_group.cuh
 
     // b2p_ntt: natural order in and out
     void ntt(void* data, uint64_t n, int flags) const override {
@@ -1032,7 +1059,9 @@ struct CurveOpsImpl : CurveOps {
         const Fr* fr = reinterpret_cast<const Fr*>(static_cast<const uint8_t*>(raw) + 9 * sizeof(Aff));
         const Aff* bs = static_cast<const Aff*>(bsb22);
         uint8_t* o = out;
-        auto P = [&](const Aff& a) { point_marshal<C>(a, o, false); o += PB; };
+        // BLS12-381 points go through G1Affine.RawBytes() (helper.go:35): infinity is 0x40 then zeros; BN254 through
+        // MarshalSolidity (helper.go:16-17): raw X || Y, infinity all zero.  point_marshal's flag only acts on BLS12-381.
+        auto P = [&](const Aff& a) { point_marshal<C>(a, o, true); o += PB; };
         auto S = [&](const Fr& f) { field_to_be(f, o); o += 32; };
         for (int i = 0; i < 3; i++) P(pts[i]);          // LRO
         for (int i = 0; i < 3; i++) P(pts[4 + i]);      // H

@@ -19,8 +19,18 @@
 // sent by the host language; algoplonk_b200/shard_group.py), because the ranks queue the proof's fixed sequence of
 // commitments (PROOF_COMMIT_SCHEDULE below -- the order Circuit::prove issues them in) ahead of time.
 // Every wait has a timeout: a missing peer ends in an error code, not in a hung GPU.
+//
+// With ntt_rows != 0 the five size-4n transforms of the proof (coset NTT of l, r, o, z; coset iNTT of the quotient)
+// are spread over the same ranks as well (BASELINE configs[4] "NTT domain alltoall"; ntt_shard.cuh, world a power of
+// two).  Per transform every rank: gathers its cyclic coefficients out of rank 0's staging area (peer loads, stride
+// G), runs the local DIF passes into an exchange buffer that its peers have mapped, raises xready[rank] in every
+// mailbox, waits for the others', and runs the combine kernel -- whose loads ARE the all-to-all (chunk `rank` of every
+// peer's buffer over NVLink) and whose stores land directly in rank 0's evaluation buffer (el / er / eo / ez).  The
+// inverse runs the mirror image on the quotient's evaluations and scatters the coefficients back into rank 0's h.
+// The quotient kernel, the grand product and the openings stay on rank 0.
 #pragma once
 #include "prover.cuh"
+#include "ntt_shard.cuh"
 
 namespace b2p {
 
@@ -32,15 +42,21 @@ struct ShardFlags {
     uint32_t ready[MSM_SLOTS];                        // on rank g > 0, written by rank 0: scalars of slot staged
     uint32_t done[SHARD_MAX_WORLD][MSM_SLOTS];        // on rank 0, written by rank g: partial sum of slot landed
     uint32_t error;                                   // a wait on this rank timed out
+    uint32_t xready[SHARD_MAX_WORLD];                 // on every rank, written by rank g: its exchange buffer of transform # is complete
+    uint32_t ntt_go;                                  // on rank g > 0, written by rank 0: the quotient of transform # is in rank 0's h
+    uint32_t ntt_done[SHARD_MAX_WORLD];               // on rank 0, written by rank g: its part of transform # has landed on rank 0
 };
 static_assert(sizeof(ShardFlags) <= SHARD_MAIL_FLAG_BYTES, "flag block too large");
 
 // The commitments of one proof in the order Circuit::prove issues them: {extra scalars beyond n, result slot},
 // a negative slot entry {first, -cnt} marks the fetch of `cnt` slots starting at `first`.
+// {SHARD_NTT, 0}: the proof's five big transforms happen here (only when the group shards them).
+constexpr int SHARD_NTT = 1000;
 struct ShardStep { int a, b; };
 static const ShardStep PROOF_COMMIT_SCHEDULE[] = {
     {2, 0}, {2, 1}, {2, 2}, {0, -3},          // [L] [R] [O], fetched together
     {3, 3}, {3, -1},                          // [Z]
+    {SHARD_NTT, 0},                           // l r o z -> 4n coset; quotient on rank 0; h back to coefficients
     {2, 4}, {2, 5}, {2, 6}, {4, -3},          // [h0] [h1] [h2]
     {2, 8}, {8, -1},                          // W_{omega zeta}
     {2, 7}, {7, -1},                          // W_zeta
@@ -97,6 +113,18 @@ __global__ void k_shard_sum(XYZZ<Fp>* __restrict__ results, const XYZZ<Fp>* __re
     st_xyzz(results + first + t, acc);
 }
 
+// dst[j] = src[first + j stride] / dst[first + j stride] = src[j]: a rank's cyclic share of a vector that lives on rank 0
+template <class Fr>
+__global__ void k_shard_gather(Fr* __restrict__ dst, const Fr* __restrict__ src, uint64_t first, uint64_t stride, uint64_t cnt) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < cnt) st_field(dst + j, ld_field(src + first + j * stride));
+}
+template <class Fr>
+__global__ void k_shard_scatter(Fr* __restrict__ dst, const Fr* __restrict__ src, uint64_t first, uint64_t stride, uint64_t cnt) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < cnt) st_field(dst + first + j * stride, ld_field(src + j));
+}
+
 // [first, first + count) of rank `rank`: contiguous, balanced (sizes differ by at most one) -- the partition of
 // algoplonk_b200/sharded.py:shard_range
 inline void shard_block(uint64_t total, uint32_t rank, uint32_t world, uint64_t* first, uint64_t* count) {
@@ -104,6 +132,10 @@ inline void shard_block(uint64_t total, uint32_t rank, uint32_t world, uint64_t*
     *first = rank * base + (rank < rem ? rank : rem);
     *count = base + (rank < rem ? 1 : 0);
 }
+
+// the memory a rank shares with its peers, in the order the handles / pointers are exchanged in
+enum { SH_MAIL = 0, SH_STAGING, SH_XBUF, SH_EL, SH_ER, SH_EO, SH_EZ, SH_H, SH_NPTR };
+static_assert(SH_NPTR == SHARD_NPTR, "iface.hpp and shard_group.cuh disagree on the shared pieces");
 
 template <class C>
 struct ShardGroup : ShardGroupBase, CommitRouter {
@@ -115,113 +147,156 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
     Srs<C>* shard = nullptr;              // this rank's block of the SRS (own table, own plan)
     Srs<C>* attached = nullptr;           // rank 0: the proving key whose commitments are routed here
     uint64_t first = 0, count = 0;        // this rank's block of the total points
-    uint32_t proof_no = 0;
+    uint32_t proof_no = 0, ntt_seq = 0;
     bool connected = false, same_process = false;
 
-    uint8_t* mail = nullptr;              // ShardFlags + partial sums, IPC-exported
-    Fr* staging = nullptr;                // rank 0 only: MSM_SLOTS x total scalars, IPC-exported
-    uint8_t* peer_mail[SHARD_MAX_WORLD] = {nullptr};
-    Fr* peer_staging = nullptr;           // ranks > 0: rank 0's staging area, mapped
+    uint8_t* mail = nullptr;              // ShardFlags + partial sums, shared
+    Fr* staging = nullptr;                // rank 0 only: STAGE_SLOTS x total scalars, shared
     uint32_t* h_err = nullptr;            // pinned
+    void* peer[SHARD_MAX_WORLD][SH_NPTR] = {{nullptr}};      // peer[g][what]: rank g's shared memory as seen from here
 
-    ShardFlags* flags(uint8_t* m) const { return reinterpret_cast<ShardFlags*>(m); }
-    Ext* partials(uint8_t* m) const { return reinterpret_cast<Ext*>(m + SHARD_MAIL_FLAG_BYTES); }
+    // sharded transforms (ntt_rows != 0)
+    uint64_t ntt_rows = 0;                // n of the circuits this group proves; the transforms have size 4n
+    NttShard<Fr>* ntt = nullptr;
+    Fr* xbuf = nullptr;                   // 2 exchange buffers of 4n/G elements, shared
+    Fr* loc = nullptr;                    // this rank's cyclic coefficients before the local passes
+    void* circ_buf[5] = {nullptr};        // rank 0: the attached circuit's el er eo ez h
+
+    ShardFlags* flags(void* m) const { return reinterpret_cast<ShardFlags*>(m); }
+    Ext* partials(void* m) const { return reinterpret_cast<Ext*>(static_cast<uint8_t*>(m) + SHARD_MAIL_FLAG_BYTES); }
     static size_t mail_bytes() { return SHARD_MAIL_FLAG_BYTES + (size_t)SHARD_MAX_WORLD * MSM_SLOTS * sizeof(Ext); }
-    // slots a proof uses: 0..8
-    static constexpr int STAGE_SLOTS = 9;
+    static constexpr int STAGE_SLOTS = 9;         // slots a proof uses: 0..8
 
-    ShardGroup(uint32_t world_, uint32_t rank_, uint64_t total_, SrsBase* shard_) {
+    ShardGroup(uint32_t world_, uint32_t rank_, uint64_t total_, SrsBase* shard_, uint64_t ntt_rows_) {
         curve = C::ID;
-        world = world_; rank = rank_; total = total_;
+        world = world_; rank = rank_; total = total_; ntt_rows = ntt_rows_;
         B2P_REQUIRE(world >= 1 && world <= SHARD_MAX_WORLD && rank < world, "shard group: bad rank / world (world <= 8)");
         B2P_REQUIRE(shard_ && shard_->curve == C::ID, "shard group: the SRS block is on another curve");
         shard = static_cast<Srs<C>*>(shard_);
         shard_block(total, rank, world, &first, &count);
         B2P_REQUIRE(shard->msm.npoints == count, "shard group: the SRS block does not hold this rank's share of the points");
-        B2P_CUDA(cudaMalloc(&mail, mail_bytes()));
-        B2P_CUDA(cudaMemset(mail, 0, mail_bytes()));
-        if (rank == 0) B2P_CUDA(cudaMalloc(&staging, (size_t)STAGE_SLOTS * total * sizeof(Fr)));
-        B2P_CUDA(cudaMallocHost(&h_err, sizeof(uint32_t)));
-        *h_err = 0;
-        // Load the four exchange kernels NOW (no-op launches).  CUDA loads a kernel at its first launch, and that
-        // load can wait for kernels that are running -- such as a k_shard_wait spinning on a flag which only a
-        // not-yet-loaded kernel would raise (seen with all ranks of a group in one process: a 20 s stall).
-        {
+        if (ntt_rows) {
+            B2P_REQUIRE((world & (world - 1)) == 0, "shard group: sharded transforms need a power-of-two world");
+            B2P_REQUIRE(ntt_rows >= 64 && (ntt_rows & (ntt_rows - 1)) == 0 && ntt_rows + 3 <= total,
+                        "shard group: ntt_rows must be a power of two >= 64 with ntt_rows + 3 <= total points");
+        }
+        try {
+            B2P_CUDA(cudaMalloc(&mail, mail_bytes()));
+            B2P_CUDA(cudaMemset(mail, 0, mail_bytes()));
+            if (rank == 0) B2P_CUDA(cudaMalloc(&staging, (size_t)STAGE_SLOTS * total * sizeof(Fr)));
+            B2P_CUDA(cudaMallocHost(&h_err, sizeof(uint32_t)));
+            *h_err = 0;
+            if (ntt_rows) {
+                ntt = new NttShard<Fr>();
+                ntt->init(4 * ntt_rows, world, rank);
+                B2P_CUDA(cudaMalloc(&xbuf, 2 * ntt->local_n * sizeof(Fr)));
+                B2P_CUDA(cudaMalloc(&loc, ntt->local_n * sizeof(Fr)));
+            }
+            // Load the exchange kernels NOW (no-op launches).  CUDA loads a kernel at its first launch, and that load
+            // can wait for kernels that are running -- such as a k_shard_wait spinning on a flag which only a
+            // not-yet-loaded kernel would raise (seen with all ranks of a group in one process: a 20 s stall).
             ShardPeerFlags none{};
             ShardFlags* f = flags(mail);
             B2P_LAUNCH(k_shard_signal, 1, 32, 0, 0, none, 0, 0u);
             B2P_LAUNCH(k_shard_wait, 1, 32, 0, 0, &f->ready[0], 0, 1, 0u, &f->error);
             B2P_LAUNCH((k_shard_post<Fp>), 1, 32, 0, 0, partials(mail), partials(mail), &f->done[0][0], 0, 0, 0u);
             B2P_LAUNCH((k_shard_sum<Fp>), 1, 32, 0, 0, partials(mail), partials(mail), 1, 0, 0);
+            B2P_LAUNCH((k_shard_gather<Fr>), 1, 32, 0, 0, (Fr*)nullptr, (const Fr*)nullptr, 0, 1, 0);
+            B2P_LAUNCH((k_shard_scatter<Fr>), 1, 32, 0, 0, (Fr*)nullptr, (const Fr*)nullptr, 0, 1, 0);
+            B2P_CUDA(cudaDeviceSynchronize());
+        } catch (...) {
+            release();
+            throw;
         }
-        B2P_CUDA(cudaDeviceSynchronize());
-        peer_mail[rank] = mail;
+        peer[rank][SH_MAIL] = mail;
+        peer[rank][SH_STAGING] = staging;
+        peer[rank][SH_XBUF] = xbuf;
+    }
+    void release() {
+        if (mail) cudaFree(mail);
+        if (staging) cudaFree(staging);
+        if (xbuf) cudaFree(xbuf);
+        if (loc) cudaFree(loc);
+        if (h_err) cudaFreeHost(h_err);
+        delete ntt;
+        mail = nullptr; staging = nullptr; xbuf = nullptr; loc = nullptr; h_err = nullptr; ntt = nullptr;
     }
     ~ShardGroup() override {
         if (attached) attached->router = nullptr;
-        if (connected && !same_process) {
+        if (connected && !same_process)
             for (uint32_t g = 0; g < world; g++)
-                if (g != rank && peer_mail[g]) cudaIpcCloseMemHandle(peer_mail[g]);
-            if (peer_staging) cudaIpcCloseMemHandle(peer_staging);
-        }
-        if (mail) cudaFree(mail);
-        if (staging) cudaFree(staging);
-        if (h_err) cudaFreeHost(h_err);
+                for (int w = 0; w < SH_NPTR; w++)
+                    if (g != rank && peer[g][w]) cudaIpcCloseMemHandle(peer[g][w]);
+        release();
     }
 
-    void ipc_handles(void* out) const override {
-        uint8_t* o = static_cast<uint8_t*>(out);
-        memset(o, 0, 2 * B2P_IPC_HANDLE_BYTES);
-        cudaIpcMemHandle_t h;
-        B2P_CUDA(cudaIpcGetMemHandle(&h, mail));
-        memcpy(o, &h, sizeof h);
-        if (staging) {
-            B2P_CUDA(cudaIpcGetMemHandle(&h, staging));
-            memcpy(o + B2P_IPC_HANDLE_BYTES, &h, sizeof h);
-        }
-    }
-    // all_handles: world x 2 IPC handles (mail, staging), rank-major.  Rank 0 maps every mailbox, the other ranks map
-    // rank 0's mailbox and staging area.
-    void connect(const void* all_handles) override {
-        B2P_REQUIRE(!connected, "shard group: already connected");
-        const uint8_t* hs = static_cast<const uint8_t*>(all_handles);
-        auto open = [&](uint32_t g, int which) -> void* {
-            cudaIpcMemHandle_t h;
-            memcpy(&h, hs + ((size_t)g * 2 + which) * B2P_IPC_HANDLE_BYTES, sizeof h);
-            void* p = nullptr;
-            B2P_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-            return p;
-        };
-        if (rank == 0) {
-            for (uint32_t g = 1; g < world; g++) peer_mail[g] = static_cast<uint8_t*>(open(g, 0));
-        } else {
-            peer_mail[0] = static_cast<uint8_t*>(open(0, 0));
-            peer_staging = static_cast<Fr*>(open(0, 1));
-        }
-        connected = true;
-    }
-    // the same wiring for ranks that live in ONE process on one device (tests: every rank a host thread)
-    void connect_local(void* const* mails, void* staging0) override {
-        B2P_REQUIRE(!connected, "shard group: already connected");
-        for (uint32_t g = 0; g < world; g++)
-            if (g != rank) peer_mail[g] = static_cast<uint8_t*>(mails[g]);
-        if (rank != 0) peer_staging = static_cast<Fr*>(staging0);
-        connected = same_process = true;
-    }
-    void* mail_ptr() const override { return mail; }
-    void* staging_ptr() const override { return staging; }
-
-    void attach(SrsBase* prover_srs) override {
+    // ---- wiring --------------------------------------------------------------------------------------------------
+    void attach(SrsBase* prover_srs, CircuitBase* circuit) override {
         B2P_REQUIRE(rank == 0, "shard group: only rank 0 runs the prover");
         if (attached) attached->router = nullptr;
         attached = nullptr;
         if (!prover_srs) return;
-        B2P_REQUIRE(connected || world == 1, "shard group: connect the ranks first");
         B2P_REQUIRE(prover_srs->curve == C::ID, "shard group: the proving key is on another curve");
         B2P_REQUIRE(prover_srs->device == shard->device, "shard group: the proving key lives on another device");
-        attached = static_cast<Srs<C>*>(prover_srs);
-        B2P_REQUIRE(attached->msm.npoints >= total, "shard group: the proving key's SRS is smaller than the sharded one");
+        Srs<C>* s = static_cast<Srs<C>*>(prover_srs);
+        B2P_REQUIRE(s->msm.npoints >= total, "shard group: the proving key's SRS is smaller than the sharded one");
+        if (ntt_rows) {
+            B2P_REQUIRE(circuit && circuit->owner == prover_srs, "shard group: sharded transforms need the circuit handle");
+            uint64_t n = 0;
+            void* bufs[5];
+            circuit->shard_buffers(bufs, &n);
+            B2P_REQUIRE(n == ntt_rows, "shard group: the circuit's domain differs from the group's ntt_rows");
+            for (int i = 0; i < 5; i++) {
+                // once the ranks are connected they have mapped the first circuit's buffers: only that one re-attaches
+                B2P_REQUIRE(!connected || peer[0][SH_EL + i] == bufs[i],
+                            "shard group: attach the circuit before the ranks are connected (its buffers are shared)");
+                peer[0][SH_EL + i] = circ_buf[i] = bufs[i];
+            }
+        }
+        attached = s;
         attached->router = this;
+    }
+    // this rank's shared memory: SH_NPTR pointers (same process) or IPC handles (zero where it has none)
+    void local_ptrs(void** out) const override {
+        for (int w = 0; w < SH_NPTR; w++) out[w] = peer[rank][w];
+    }
+    void ipc_handles(void* out) const override {
+        uint8_t* o = static_cast<uint8_t*>(out);
+        memset(o, 0, (size_t)SH_NPTR * B2P_IPC_HANDLE_BYTES);
+        for (int w = 0; w < SH_NPTR; w++) {
+            if (!peer[rank][w]) continue;
+            cudaIpcMemHandle_t h;
+            B2P_CUDA(cudaIpcGetMemHandle(&h, peer[rank][w]));
+            memcpy(o + (size_t)w * B2P_IPC_HANDLE_BYTES, &h, sizeof h);
+        }
+    }
+    // what this rank needs of rank g: rank 0 reads every mailbox; everybody needs rank 0's mailbox, staging area and
+    // (sharded transforms) its evaluation buffers; with sharded transforms every rank needs every mailbox and buffer
+    bool needs(uint32_t g, int w) const {
+        if (g == rank) return false;
+        if (w == SH_MAIL) return rank == 0 || g == 0 || ntt_rows;
+        if (w == SH_XBUF) return ntt_rows != 0;
+        if (w == SH_STAGING) return g == 0;
+        return g == 0 && ntt_rows != 0;
+    }
+    void connect(const void* all_handles) override {
+        B2P_REQUIRE(!connected, "shard group: already connected");
+        const uint8_t* hs = static_cast<const uint8_t*>(all_handles);
+        for (uint32_t g = 0; g < world; g++)
+            for (int w = 0; w < SH_NPTR; w++) {
+                if (!needs(g, w)) continue;
+                cudaIpcMemHandle_t h;
+                memcpy(&h, hs + ((size_t)g * SH_NPTR + w) * B2P_IPC_HANDLE_BYTES, sizeof h);
+                B2P_CUDA(cudaIpcOpenMemHandle(&peer[g][w], h, cudaIpcMemLazyEnablePeerAccess));
+            }
+        connected = true;
+    }
+    void connect_ptrs(void* const* all) override {      // world x SH_NPTR pointers, ranks of one process
+        B2P_REQUIRE(!connected, "shard group: already connected");
+        for (uint32_t g = 0; g < world; g++)
+            for (int w = 0; w < SH_NPTR; w++)
+                if (needs(g, w)) peer[g][w] = all[(size_t)g * SH_NPTR + w];
+        connected = same_process = true;
     }
 
     void slice(uint64_t n, uint64_t* lo, uint64_t* cnt) const {
@@ -237,9 +312,13 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
             throw Error(B2P_ERR_INTERNAL, std::string("shard group: timed out waiting for a peer (") + where + ")");
         }
     }
+    Fr* stage_of(uint32_t g0_view_slot) const { return static_cast<Fr*>(peer[0][SH_STAGING]) + (size_t)g0_view_slot * total; }
 
     // ---- rank 0: CommitRouter -------------------------------------------------------------------------------
-    void begin_proof() override { proof_no++; }
+    void begin_proof() override {
+        B2P_REQUIRE(connected || world == 1, "shard group: connect the ranks first");
+        proof_no++;
+    }
     void commit(const void* d_scalars, uint64_t n, int slot, cudaStream_t st) override {
         B2P_REQUIRE(slot >= 0 && slot < STAGE_SLOTS, "shard group: result slot out of range");
         B2P_REQUIRE(n <= total, "shard group: more scalars than SRS points");
@@ -248,7 +327,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
             Fr* stage = staging + (size_t)slot * total;
             if (n) B2P_CUDA(cudaMemcpyAsync(stage, sc, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
             ShardPeerFlags pf;
-            for (uint32_t g = 1; g < world; g++) pf.p[g - 1] = &flags(peer_mail[g])->ready[slot];
+            for (uint32_t g = 1; g < world; g++) pf.p[g - 1] = &flags(peer[g][SH_MAIL])->ready[slot];
             B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, (int)world - 1, proof_no);
         }
         uint64_t lo, cnt;
@@ -273,40 +352,110 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         for (int i = 0; i < cnt; i++) out[i] = h[i].to_affine();
     }
 
+    // ---- the sharded transforms: the same code on every rank ---------------------------------------------------
+    bool shards_ntt() const override { return ntt_rows != 0 && world > 1; }
+    void xready_barrier(uint32_t seq, cudaStream_t st) {
+        ShardPeerFlags pf;
+        for (uint32_t g = 0; g < world; g++) pf.p[g] = &flags(peer[g][SH_MAIL])->xready[rank];
+        B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, (int)world, seq);
+        B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &flags(mail)->xready[0], (int)world, 1, seq, &flags(mail)->error);
+    }
+    void tell_rank0_done(uint32_t seq, cudaStream_t st) {
+        if (rank == 0) return;
+        ShardPeerFlags pf;
+        pf.p[0] = &flags(peer[0][SH_MAIL])->ntt_done[rank];
+        B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, 1, seq);
+    }
+    // coefficients (len of them, on rank 0: staging slot or `coeffs`) -> 4n coset evaluations in rank 0's buffer `which`
+    void forward_step(const Fr* coeffs_as_seen_here, uint64_t len, int which, cudaStream_t st) {
+        const uint32_t seq = ++ntt_seq, G = world;
+        Fr* x = xbuf + (size_t)(seq & 1) * ntt->local_n;
+        const uint64_t cnt = len > rank ? (len - rank + G - 1) / G : 0;
+        if (cnt) B2P_LAUNCH((k_shard_gather<Fr>), div_up(cnt, 256), 256, 0, st, loc, coeffs_as_seen_here, (uint64_t)rank, (uint64_t)G, cnt);
+        ntt->forward_local(loc, cnt, B2P_NTT_COSET, x, st);
+        xready_barrier(seq, st);
+        const void* chunks[1 << NTT_SHARD_MAX_LOGG] = {nullptr};
+        for (uint32_t g = 0; g < G; g++)
+            chunks[g] = static_cast<Fr*>(peer[g][SH_XBUF]) + (size_t)(seq & 1) * ntt->local_n + (size_t)rank * ntt->chunk_len;
+        ntt->forward_combine(chunks, static_cast<Fr*>(peer[0][which]) + (size_t)rank * ntt->local_n, st);
+        tell_rank0_done(seq, st);
+    }
+    // 4n evaluations in rank 0's h -> the first out_len coefficients, back in rank 0's h
+    void inverse_step(uint64_t out_len, cudaStream_t st) {
+        const uint32_t seq = ++ntt_seq, G = world;
+        Fr* x = xbuf + (size_t)(seq & 1) * ntt->local_n;
+        Fr* h0 = static_cast<Fr*>(peer[0][SH_H]);
+        if (rank == 0) {            // the quotient is complete (stream order): the other ranks may read it
+            ShardPeerFlags pf;
+            for (uint32_t g = 1; g < G; g++) pf.p[g - 1] = &flags(peer[g][SH_MAIL])->ntt_go;
+            B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, (int)G - 1, seq);
+        } else {
+            B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &flags(mail)->ntt_go, 1, 1, seq, &flags(mail)->error);
+        }
+        void* chunks[1 << NTT_SHARD_MAX_LOGG] = {nullptr};
+        for (uint32_t g = 0; g < G; g++)
+            chunks[g] = static_cast<Fr*>(peer[g][SH_XBUF]) + (size_t)(seq & 1) * ntt->local_n + (size_t)rank * ntt->chunk_len;
+        ntt->inverse_split(h0 + (size_t)rank * ntt->local_n, chunks, st);
+        xready_barrier(seq, st);     // every rank has read its block of h and delivered its chunks
+        ntt->inverse_local(x, B2P_NTT_INVERSE | B2P_NTT_COSET, nullptr, st);
+        const uint64_t cnt = out_len > rank ? (out_len - rank + G - 1) / G : 0;
+        if (cnt) B2P_LAUNCH((k_shard_scatter<Fr>), div_up(cnt, 256), 256, 0, st, h0, x, (uint64_t)rank, (uint64_t)G, cnt);
+        tell_rank0_done(seq, st);
+    }
+    void wait_ntt_done(cudaStream_t st) {      // rank 0: every rank's part of transform ntt_seq has landed here
+        ShardFlags* f = flags(mail);
+        if (world > 1) B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &f->ntt_done[1], (int)world - 1, 1, ntt_seq, &f->error);
+    }
+    // CommitRouter (rank 0)
+    void ntt_forward(const void* d_coeffs, uint64_t len, int which, cudaStream_t st) override {
+        forward_step(static_cast<const Fr*>(d_coeffs), len, SH_EL + which, st);
+    }
+    void ntt_forward_wait(cudaStream_t st) override { wait_ntt_done(st); }
+    void ntt_inverse(uint64_t out_len, cudaStream_t st) override {
+        inverse_step(out_len, st);
+        wait_ntt_done(st);
+    }
+
     // ---- ranks > 0 ---------------------------------------------------------------------------------------------
-    // Queues this rank's part of the 9 commitments of ONE proof of an n-row circuit and blocks until it is done.
+    // Queues this rank's part of ONE proof of an n-row circuit and blocks until it is done.
     void serve_proof(uint64_t n) override {
         B2P_REQUIRE(rank != 0, "shard group: rank 0 proves, the other ranks serve");
         B2P_REQUIRE(connected, "shard group: connect the ranks first");
         B2P_REQUIRE(n + 3 <= total, "shard group: circuit too large for the sharded SRS");
+        B2P_REQUIRE(!ntt_rows || n == ntt_rows, "shard group: this group shards the transforms of another circuit size");
         std::lock_guard<std::mutex> lk(shard->mu);
         cudaStream_t st = shard->stream;
         proof_no++;
         ShardFlags* mine = flags(mail);
-        ShardFlags* root = flags(peer_mail[0]);
+        ShardFlags* root = flags(peer[0][SH_MAIL]);
         for (const ShardStep& s : PROOF_COMMIT_SCHEDULE) {
-            if (s.b >= 0) {
+            if (s.a == SHARD_NTT) {
+                if (!shards_ntt()) continue;
+                for (int w = 0; w < 4; w++) forward_step(stage_of(w), n + (w == 3 ? 3 : 2), SH_EL + w, st);
+                inverse_step(3 * (n + 2), st);
+            } else if (s.b >= 0) {
                 const int slot = s.b;
                 uint64_t lo, cnt;
                 slice(n + s.a, &lo, &cnt);
                 B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &mine->ready[slot], 1, 1, proof_no, &mine->error);
-                shard->msm.run_async(peer_staging + (size_t)slot * total + lo, cnt, true, st, slot);
+                shard->msm.run_async(stage_of(slot) + lo, cnt, true, st, slot);
             } else {
                 const int first_slot = s.a, cnt = -s.b;
                 shard->msm.finish_async(first_slot, cnt, st);
-                B2P_LAUNCH((k_shard_post<Fp>), 1, 32, 0, st, partials(peer_mail[0]) + (size_t)rank * MSM_SLOTS,
+                B2P_LAUNCH((k_shard_post<Fp>), 1, 32, 0, st, partials(peer[0][SH_MAIL]) + (size_t)rank * MSM_SLOTS,
                            shard->msm.result.p, &root->done[rank][0], first_slot, cnt, proof_no);
             }
         }
         B2P_CUDA(cudaMemcpyAsync(h_err, &mine->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         B2P_CUDA(cudaStreamSynchronize(st));
-        check_err("the scalars of rank 0", st);
+        check_err("rank 0 or a peer", st);
     }
 };
 
 template <class C>
-ShardGroupBase* CurveOpsImpl<C>::new_shard_group(uint32_t world, uint32_t rank, uint64_t total, SrsBase* shard) const {
-    return new ShardGroup<C>(world, rank, total, shard);
+ShardGroupBase* CurveOpsImpl<C>::new_shard_group(uint32_t world, uint32_t rank, uint64_t total, SrsBase* shard,
+                                                 uint64_t ntt_rows) const {
+    return new ShardGroup<C>(world, rank, total, shard, ntt_rows);
 }
 
 }  // namespace b2p

@@ -56,6 +56,13 @@ static const char* kzg_vk_load_t(const uint8_t* in, uint64_t len, uint8_t* out_g
     for (int i = 0; i < 2; i++)
         if (const char* e = PR::g2_decompress(in + 2 * i * PR::FPB, &q[i])) return e;
     if (const char* e = PR::g1_decompress(in + 4 * PR::FPB, &g)) return e;
+    // gnark's decoders check subgroup membership; G2 has a cofactor on both curves, G1 on BLS12-381: [r] Q == infinity
+    using Fr = typename PC::Fr;
+    uint64_t r[Fr::N];
+    for (int i = 0; i < Fr::N; i++) r[i] = Fr::M(i);
+    for (int i = 0; i < 2; i++)
+        if (!PR::g2_mul(q[i], r, Fr::N).inf) return "vk.bin: a G2 point is not in the r-torsion subgroup";
+    if (!PC::D_TWIST && !hp::HostVerifier<PC>::in_g1_subgroup({g.x, g.y, g.inf})) return "vk.bin: the G1 point is not in the r-torsion subgroup";
     PR::store_g2(q[0], out_g2);
     PR::store_g2(q[1], out_g2 + 4 * PR::FPB);
     if (g.inf) memset(out_g1, 0, 2 * PR::FPB);

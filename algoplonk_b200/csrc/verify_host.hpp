@@ -116,16 +116,30 @@ struct HostVerifier {
         for (int b = 0; b < nbytes; b++) out[nbytes - 1 - b] = (uint8_t)(c.v[b >> 3] >> (8 * (b & 7)));
     }
     static Fr fr_mod(const uint8_t* be32) { Fr r; from_be(be32, 32, &r, true); return r; }
-    // X || Y big-endian, all-zero = infinity (helper.go:35 RawBytes); false: not reduced or not on the curve
+    // X || Y big-endian.  Infinity: all zero (BN254, MarshalSolidity, helper.go:16-17) or, on BLS12-381, 0x40 followed
+    // by zeros -- what G1Affine.RawBytes() writes (helper.go:35; verifier/verifier.go:95-99); all zero is accepted
+    // there too.  false: not reduced, not on the curve, or (BLS12-381) not in the r-torsion subgroup.
     static bool parse_point(const uint8_t* in, Aff* out) {
         bool zero = true;
-        for (int i = 0; i < PB; i++) zero &= in[i] == 0;
-        if (zero) { *out = {Fp::zero(), Fp::zero(), true}; return true; }
+        for (int i = 1; i < PB; i++) zero &= in[i] == 0;
+        if (zero && (in[0] == 0 || (BLS && in[0] == 0x40))) { *out = {Fp::zero(), Fp::zero(), true}; return true; }
         Aff a{Fp::zero(), Fp::zero(), false};
         if (!from_be(in, NB, &a.x, false) || !from_be(in + NB, NB, &a.y, false)) return false;
         if (!(a.y.sqr() == a.x.sqr() * a.x + Fp::from_u64(PC::B))) return false;
+        if (BLS && !in_g1_subgroup(a)) return false;       // BN254's G1 has cofactor 1: the curve equation suffices
         *out = a;
         return true;
+    }
+    // r-torsion test for BLS12-381 G1 (cofactor != 1), as gnark's decoders perform it: [r] P == infinity.
+    // (Plain double-and-add over the 255-bit group order: ~0.1 ms per point, a dozen points per proof.)
+    static bool in_g1_subgroup(const Aff& a) {
+        if (a.inf) return true;
+        Ext acc = Ext::inf();
+        for (int i = Fr::N * 64 - 1; i >= 0; i--) {
+            acc = acc.dbl();
+            if ((Fr::M(i >> 6) >> (i & 63)) & 1) acc = acc.add_affine(a);
+        }
+        return acc.is_inf();
     }
     static void marshal(const Aff& a, uint8_t* out, bool transcript_flag) {
         if (a.inf) {
@@ -382,24 +396,40 @@ struct HostVerifier {
         unsigned T = 1;
         if (count >= 4) {
             const char* e = getenv("B2P_VERIFY_THREADS");
-            unsigned want = e ? (unsigned)atoi(e) : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
-            T = (unsigned)std::min<uint64_t>(std::max(1u, want), count);
+            const int asked = e ? atoi(e) : 0;          // garbage / negative / zero: the default
+            const unsigned want = asked > 0 ? (unsigned)asked : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+            T = (unsigned)std::min<uint64_t>(std::min(64u, want), count);      // never more than 64 threads
         }
         std::vector<uint64_t> first_bad(T, count);
         std::vector<std::string> whys(T);
+        // nothing may escape a worker thread (an exception there is std::terminate, across a C ABI that promises
+        // never to abort): a failure inside reduce() -- bad_alloc -- is recorded like a rejected proof
         auto work = [&](unsigned t) {
-            for (uint64_t i = t; i < count; i += T)
-                if (!reduce(vk, proofs + i * proof_len, proof_len, pubs + i * pub_len, pub_len, &lhs[i], &rhs[i], &whys[t])) {
-                    first_bad[t] = i;
-                    return;
-                }
+            uint64_t i = t;
+            try {
+                for (; i < count; i += T)
+                    if (!reduce(vk, proofs + i * proof_len, proof_len, pubs + i * pub_len, pub_len, &lhs[i], &rhs[i], &whys[t])) {
+                        first_bad[t] = i;
+                        return;
+                    }
+            } catch (...) {
+                first_bad[t] = i < count ? i : count - 1;
+                try { whys[t] = "internal error while reducing the proof (out of memory?)"; } catch (...) {}
+            }
         };
         if (T == 1) {
             work(0);
         } else {
             std::vector<std::thread> pool;
-            for (unsigned t = 1; t < T; t++) pool.emplace_back(work, t);
+            unsigned started = 1;                 // thread 0 is the caller
+            try {
+                pool.reserve(T - 1);
+                for (unsigned t = 1; t < T; t++) { pool.emplace_back(work, t); started = t + 1; }
+            } catch (...) {
+                // thread creation failed (std::system_error): the shares of the threads that never started are done here
+            }
             work(0);
+            for (unsigned t = started; t < T; t++) work(t);
             for (auto& th : pool) th.join();
         }
         unsigned best = 0;                        // every thread stops at its own first failure: the smallest wins

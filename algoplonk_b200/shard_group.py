@@ -27,13 +27,16 @@ OP_PROVE, OP_STOP = 1, 2
 
 
 class ShardGroup:
-    """This rank's end of the group.  Collective constructor (every rank calls it with the same arguments)."""
+    """This rank's end of the group.  Collective: every rank constructs it with the same arguments, then rank 0
+    attaches its proving key (`attach`), then every rank calls `connect()`.
+
+    ntt_rows = n: the proof's five size-4n transforms are spread over the ranks as well (world a power of two)."""
 
     def __init__(self, curve: str, total_points: int, group=None, tau: int = api.TEST_TAU,
-                 srs_points: Optional[bytes] = None, device=None):
+                 srs_points: Optional[bytes] = None, device=None, ntt_rows: int = 0):
         import torch
         import torch.distributed as dist
-        self.curve, self.total, self.group = curve, total_points, group
+        self.curve, self.total, self.group, self.ntt_rows = curve, total_points, group, ntt_rows
         self.dist = dist if dist.is_initialized() else None
         self.rank = dist.get_rank(group) if self.dist else 0
         self.world = dist.get_world_size(group) if self.dist else 1
@@ -45,29 +48,39 @@ class ShardGroup:
                                                      self.rank, self.world)
                       if srs_points is not None else
                       sharded.ShardedSRS.unsafe(curve, total_points, self.rank, self.world, tau))
-        handles = C.create_string_buffer(2 * _lib.IPC_HANDLE_BYTES)
         h = C.c_void_p()
         _lib.check(lib.b2p_shard_group_create(api.CURVE_ID[curve], self.world, self.rank, total_points,
-                                              self.shard.handle, handles, C.byref(h)))
+                                              self.shard.handle, ntt_rows, C.byref(h)))
         self.handle = h.value
         self._attached = None
-        if self.world > 1:
-            mine = torch.frombuffer(bytearray(handles.raw), dtype=torch.uint8).to(self.device)
-            allh = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(allh, mine, group=group)
-            buf = C.create_string_buffer(bytes(allh.cpu().numpy().tobytes()))
-            _lib.check(lib.b2p_shard_group_connect(self.handle, buf))
-            dist.barrier(group=group)           # every rank has mapped its peers before the first flag is written
+
+    def connect(self) -> None:
+        """Collective, after rank 0's attach(): all_gather of the ranks' CUDA IPC handles (torch.distributed:
+        plumbing), every rank maps what it needs of its peers."""
+        import torch
+        lib = _lib.load()
+        if self.world == 1:
+            return
+        nb = _lib.SHARD_HANDLES * _lib.IPC_HANDLE_BYTES
+        handles = C.create_string_buffer(nb)
+        _lib.check(lib.b2p_shard_group_export(self.handle, handles))
+        mine = torch.frombuffer(bytearray(handles.raw), dtype=torch.uint8).to(self.device)
+        allh = torch.empty(self.world * nb, dtype=torch.uint8, device=self.device)
+        self.dist.all_gather_into_tensor(allh, mine, group=self.group)
+        buf = C.create_string_buffer(bytes(allh.cpu().numpy().tobytes()))
+        _lib.check(lib.b2p_shard_group_connect(self.handle, buf))
+        self.dist.barrier(group=self.group)       # every rank has mapped its peers before the first flag is written
 
     # ---- rank 0 ---------------------------------------------------------------------------------------------
-    def attach(self, srs: api.SRS) -> None:
-        """Route the commitments of the proving key loaded on `srs` through the group (after api.Compile)."""
-        _lib.check(_lib.load().b2p_shard_group_attach(self.handle, srs.handle))
-        self._attached = srs
+    def attach(self, cc: "api.CompiledCircuit") -> None:
+        """Rank 0, before connect(): route the commitments (and, with ntt_rows, the transforms) of the proving key
+        `cc` through the group."""
+        _lib.check(_lib.load().b2p_shard_group_attach(self.handle, cc.srs.handle, cc.handle))
+        self._attached = cc
 
     def detach(self) -> None:
         if self._attached is not None and self.handle:
-            _lib.check(_lib.load().b2p_shard_group_attach(self.handle, None))
+            _lib.check(_lib.load().b2p_shard_group_attach(self.handle, None, None))
         self._attached = None
 
     def _header(self, op: int, n: int):
@@ -111,23 +124,25 @@ class ShardGroup:
 
 
 class ShardedProver:
-    """api.CompiledCircuit whose commitments run on every GPU of the process group (rank 0 proves), native path.
+    """api.CompiledCircuit whose commitments (and transforms, shard_ntt=True) run on every GPU of the process group
+    (rank 0 proves), native path.
 
     every rank:  sp = ShardedProver(cs, curve, setup)
     rank 0:      proof = sp.prove_raw(L, R, O, blinding) ...; sp.close()
     ranks > 0:   sp.serve(); sp.close()
     """
 
-    def __init__(self, cs, curve: str, setup_name: int, group=None, tau: int = api.TEST_TAU):
+    def __init__(self, cs, curve: str, setup_name: int, group=None, tau: int = api.TEST_TAU, shard_ntt: bool = False):
         from . import frontend as fe
         n = fe.build_trace(cs).n if hasattr(cs, "constraints") else int(cs)
         self.n = n
-        self.grp = ShardGroup(curve, n + 3, group, tau)
+        self.grp = ShardGroup(curve, n + 3, group, tau, ntt_rows=n if shard_ntt else 0)
         self.rank, self.world = self.grp.rank, self.grp.world
         self.cc = None
         if self.rank == 0:
             self.cc = api.Compile(cs, curve, setup_name)          # full SRS on rank 0: setup commitments are local
-            self.grp.attach(self.cc.srs)
+            self.grp.attach(self.cc)
+        self.grp.connect()
 
     def prove_raw(self, L: bytes, R: bytes, O: bytes, blinding: bytes) -> api.Proof:
         if self.rank != 0:

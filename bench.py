@@ -508,7 +508,8 @@ def measure_sharded_msm(args, rank, world, device, iters: int = 10):
             "scalars": "uniform, resident in HBM"}
 
 
-def measure_sharded_proof(args, rank, world, device, cs, host_cols, blinding, want_raw: bytes, ms_one_gpu: float):
+def measure_sharded_proof(args, rank, world, device, cs, host_cols, blinding, want_raw: bytes, ms_one_gpu: float,
+                          shard_ntt: bool = True):
     """ONE proof at a time with its 9 commitments spread over all the GPUs (algoplonk_b200/shard_group.py,
     csrc/shard_group.cuh: peer loads of the scalars, peer stores of the partial sums, flags; BASELINE configs[2]).
     Rank 0 proves through the reference-facing b2p_prove with pinned host columns, the other ranks serve.  CUDA
@@ -526,7 +527,7 @@ def measure_sharded_proof(args, rank, world, device, cs, host_cols, blinding, wa
     try:
         if args.shard_c:
             os.environ["B2P_MSM_C"] = str(args.shard_c)
-        sp = sg.ShardedProver(cs, curve, setup)
+        sp = sg.ShardedProver(cs, curve, setup, shard_ntt=shard_ntt)
     except Exception as e:  # noqa: BLE001
         res = {"error": f"setup: {type(e).__name__}: {e}"[:300]}
     finally:
@@ -576,6 +577,7 @@ def measure_sharded_proof(args, rank, world, device, cs, host_cols, blinding, wa
                "byte_identical_to_one_gpu_proof": bytes(out.raw) == want_raw,
                "one_gpu_ms_per_proof": ms_one_gpu, "speedup_vs_one_gpu": ms_one_gpu / ms, "n_gpus": world,
                "points_per_gpu": sp.grp.shard.count, "shard_c": c_bits, "shard_windows": windows,
+               "transforms_sharded": bool(shard_ntt),
                "exchange": "scalars: peer loads of 32 n/G bytes per rank and commitment out of rank 0's HBM; partial "
                            "sums: one XYZZ point per rank and commitment stored into rank 0's mailbox; flags in peer "
                            "memory, no collective library on the data path",

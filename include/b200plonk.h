@@ -136,31 +136,39 @@ int b2p_srs_set_commit_hook(b2p_srs* srs, b2p_commit_fn fn, void* ctx);
  * CUDA bindings stage the scalars it was handed into a buffer of its own (e.g. the tensor it broadcasts). */
 int b2p_device_copy(void* d_dst, const void* d_src, uint64_t bytes);
 
-/* ---- one proof over the GPUs of one box: every kzg.Commit sharded over the point set ----------------------
- * The native multi-GPU form of the 9 commitments plonk.Prove makes (BASELINE configs[2]: "2^20 BN254, 1->8 x B200
- * MSM shard over NVLink"; the reference is single-process and has no counterpart).  One process per GPU.  Rank g
- * holds the block [first_g, first_g + count_g) of the SRS (balanced contiguous partition of total_points) as its own
- * b2p_srs `shard` (b2p_srs_generate_unsafe_range, or b2p_srs_load of its slice of pk.Kzg.G1).  Rank 0 runs b2p_prove
- * on an ordinary proving key whose SRS handle is attached to the group: each commitment stages its scalars in an
- * IPC-exported buffer, the other ranks' Pippenger kernels read their slice of it over NVLink (peer loads), store
- * their partial sum into rank 0's mailbox (peer stores) and raise a flag; rank 0 adds the partial sums on the
- * device.  No collective library and no host hop per commitment; the host language only exchanges the IPC handles
- * once and tells the other ranks "a proof of n rows starts" (they call b2p_shard_group_serve_proof(n), which queues
- * their part of the proof's fixed sequence of commitments and returns when it is done).  Proof bytes are identical
- * to the single-GPU proof.  Waits time out (B2P_ERR_INTERNAL) instead of hanging when a rank is missing.
- *   create : ipc_handles_out (may be NULL for world 1) receives 2 x B2P_IPC_HANDLE_BYTES for this rank
- *   connect: all_handles = the world x 2 handles of all ranks, rank-major (gathered by the host language)
- *   attach : rank 0 only; prover_srs = the b2p_srs the circuit was loaded on (NULL detaches).  Attach AFTER
- *            b2p_circuit_load: the verifying-key commitments of the load are not sharded.  While attached, the
- *            handle serves b2p_prove only (b2p_msm_g1 on it fails). */
+/* ---- one proof over the GPUs of one box: commitments and transforms sharded -----------------------------------
+ * The native multi-GPU form of plonk.Prove's two hot primitives (BASELINE configs[2]: "2^20 BN254, 1->8 x B200 MSM
+ * shard over NVLink", configs[4]: "2^21 BLS12-381, 8 x B200, NTT domain alltoall"; the reference is single-process and
+ * has no counterpart).  One process per GPU.  Rank g holds the block [first_g, first_g + count_g) of the SRS (balanced
+ * contiguous partition of total_points) as its own b2p_srs `shard` (b2p_srs_generate_unsafe_range, or b2p_srs_load of
+ * its slice of pk.Kzg.G1).  Rank 0 runs b2p_prove on an ordinary proving key attached to the group:
+ *   commitments (9 kzg.Commit per proof): the scalars are staged in a shared buffer on rank 0, the other ranks'
+ *     Pippenger kernels read their slice of it over NVLink (peer loads), store their partial sum into rank 0's
+ *     mailbox (peer stores) and raise a flag; rank 0 adds the partial sums on the device;
+ *   transforms (ntt_rows = n != 0, world a power of two, circuits without BSB22 commitments and <= 8 public inputs):
+ *     the four coset NTTs and the coset iNTT of size 4n run as ntt-shard transforms over all ranks -- local passes,
+ *     flags, then a combine / split kernel whose loads / stores over NVLink are the all-to-all; evaluations are written
+ *     straight into (read straight from) rank 0's buffers.  Quotient, grand product and openings stay on rank 0.
+ * No collective library and no host hop per commitment or transform: the host language exchanges the shared-memory
+ * handles once and tells the other ranks "a proof of n rows starts" (they call b2p_shard_group_serve_proof(n), which
+ * queues their part of the proof's fixed sequence and returns when it is done).  Proof bytes equal the single-GPU
+ * proof's.  Every wait times out (B2P_ERR_INTERNAL) instead of hanging when a rank is missing.
+ * Order of calls: create (all ranks) -> attach (rank 0, after b2p_circuit_load: the key's own setup commitments are
+ * not sharded; `circuit` is required when ntt_rows != 0) -> export + exchange of the handles by the host language ->
+ * connect (all ranks) -> b2p_prove on rank 0 / serve_proof elsewhere.  While attached the SRS handle serves
+ * b2p_prove only (b2p_msm_g1 on it fails); attach(NULL, NULL) detaches; free the group before the handles it uses. */
 typedef struct b2p_shard_group b2p_shard_group;
+#define B2P_SHARD_HANDLES 8       /* shared pieces per rank: mailbox, staging, exchange buffer, el er eo ez h */
 int b2p_shard_group_create(int curve, uint32_t world, uint32_t rank, uint64_t total_points, b2p_srs* shard,
-                           void* ipc_handles_out, b2p_shard_group** out);
+                           uint64_t ntt_rows, b2p_shard_group** out);
+int b2p_shard_group_attach(b2p_shard_group* g, b2p_srs* prover_srs, b2p_circuit* circuit);
+/* ipc_handles_out: B2P_SHARD_HANDLES x B2P_IPC_HANDLE_BYTES for this rank (zero where it shares nothing) */
+int b2p_shard_group_export(b2p_shard_group* g, void* ipc_handles_out);
+/* all_handles: world x B2P_SHARD_HANDLES x B2P_IPC_HANDLE_BYTES, rank-major (gathered by the host language) */
 int b2p_shard_group_connect(b2p_shard_group* g, const void* all_handles);
 /* The same wiring for `world` groups that live in ONE process on one device (plain pointers instead of IPC
  * handles: CUDA cannot map its own allocations); groups[i] must be rank i.  For tests on a single GPU. */
 int b2p_shard_group_connect_local(b2p_shard_group* const* groups, uint32_t world);
-int b2p_shard_group_attach(b2p_shard_group* g, b2p_srs* prover_srs);
 int b2p_shard_group_serve_proof(b2p_shard_group* g, uint64_t n);
 void b2p_shard_group_free(b2p_shard_group* g);
 

@@ -955,7 +955,7 @@ struct Prover {
 
         // marshal (helper.go:27-88; same field order as gnark's MarshalSolidity, helper.go:16-17)
         uint8_t* o = out;
-        auto P = [&](const A& a) { point_raw_bytes<C>(a, o, false); o += PB; };
+        auto P = [&](const A& a) { point_raw_bytes<C>(a, o, true); o += PB; };   // RawBytes(): BLS infinity = 0x40 ...
         auto S = [&](const Fr& f) { f.to_be(o); o += 32; };
         P(com_l); P(com_r); P(com_o);
         P(com_h[0]); P(com_h[1]); P(com_h[2]);

@@ -731,22 +731,23 @@ def prove(tr: Trace, vk: VerifyingKey, srs: Sequence[Affine],
 # --------------------------------------------------------------------------
 
 def marshal_proof(cv: CurveParams, pf: Proof) -> bytes:
-    """BN254: gnark MarshalSolidity layout (helper.go:16-17); BLS12-381: helper.go:27-88."""
+    """BN254: gnark MarshalSolidity layout (helper.go:16-17: raw X || Y, infinity all zero); BLS12-381:
+    helper.go:27-88, points through RawBytes(), whose infinity is 0x40 followed by zeros."""
     out = b""
     for P in pf.LRO:
-        out += g1_raw_bytes(cv, P)
+        out += g1_raw_bytes(cv, P, True)
     for P in pf.H:
-        out += g1_raw_bytes(cv, P)
+        out += g1_raw_bytes(cv, P, True)
     for i in range(1, 6):
         out += fr_bytes(pf.claimed[i])
-    out += g1_raw_bytes(cv, pf.Z)
+    out += g1_raw_bytes(cv, pf.Z, True)
     out += fr_bytes(pf.zshift_claimed)
-    out += g1_raw_bytes(cv, pf.batched_H)
-    out += g1_raw_bytes(cv, pf.zshift_H)
+    out += g1_raw_bytes(cv, pf.batched_H, True)
+    out += g1_raw_bytes(cv, pf.zshift_H, True)
     for i in range(len(pf.bsb22)):
         out += fr_bytes(pf.claimed[6 + i])
     for P in pf.bsb22:
-        out += g1_raw_bytes(cv, P)
+        out += g1_raw_bytes(cv, P, True)
     return out
 
 
@@ -788,7 +789,19 @@ class _EC:
 
 
 def verify_proof(vk: VerifyingKey, proof: bytes, public_inputs: bytes) -> bool:
-    """Returns True iff the reference's generated verifier would accept.
+    """Returns True iff the reference's generated verifier would accept.  A point the AVM's ec opcodes cannot decode
+    (not on the curve, or the 0x40 infinity flag RawBytes() puts on a BLS12-381 point: the AVM takes raw X || Y only)
+    fails the program, i.e. rejects."""
+    try:
+        return _verify_proof(vk, proof, public_inputs)
+    except ValueError as e:
+        if "point not on curve" in str(e):
+            return False
+        raise
+
+
+def _verify_proof(vk: VerifyingKey, proof: bytes, public_inputs: bytes) -> bool:
+    """The restatement proper.
     Line references are to verifier/templateLogicSigBN254.go; the BLS12-381
     template differs only in offsets, 48-byte coordinates and fs()."""
     cv = vk.curve

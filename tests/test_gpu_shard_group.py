@@ -25,7 +25,7 @@ sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
 import helpers as H
 from algoplonk_b200 import _lib, api, frontend as fe, sharded
 from oracle import plonk_oracle as po
-curve, logn, world = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+curve, logn, world, shard_ntt = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 _lib.init(0)
 lib = _lib.load()
 cv = po.CURVES[curve]
@@ -41,10 +41,11 @@ shards = [sharded.ShardedSRS.unsafe(curve, n + 3, r, world) for r in range(world
 groups = []
 for r in range(world):
     h = C.c_void_p()
-    _lib.check(lib.b2p_shard_group_create(api.CURVE_ID[curve], world, r, n + 3, shards[r].handle, None, C.byref(h)))
+    _lib.check(lib.b2p_shard_group_create(api.CURVE_ID[curve], world, r, n + 3, shards[r].handle,
+                                          n if shard_ntt else 0, C.byref(h)))
     groups.append(h.value)
+_lib.check(lib.b2p_shard_group_attach(groups[0], cc.srs.handle, cc.handle))
 _lib.check(lib.b2p_shard_group_connect_local((C.c_void_p * world)(*groups), world))
-_lib.check(lib.b2p_shard_group_attach(groups[0], cc.srs.handle))
 errs = []
 def serve(r):
     try:
@@ -63,23 +64,34 @@ try:
     cc.srs.msm([1, 2, 3]); raise SystemExit("msm on an attached handle did not fail")
 except _lib.B200PlonkError as e:
     assert "shard group" in str(e)
-_lib.check(lib.b2p_shard_group_attach(groups[0], None))
+_lib.check(lib.b2p_shard_group_attach(groups[0], None, None))
 assert cc.prove_raw(*cols, blindings[0]).raw == want[0]
 assert cc.srs.msm([1]) == cv.g1
+# ... and it re-attaches (the ranks have mapped THIS circuit's buffers)
+_lib.check(lib.b2p_shard_group_attach(groups[0], cc.srs.handle, cc.handle))
+t = threading.Thread(target=lambda: [_lib.check(lib.b2p_shard_group_serve_proof(groups[r], n)) for r in range(1, world)])
+if world == 2:
+    t.start()
+    assert cc.prove_raw(*cols, blindings[1]).raw == want[1]
+    t.join()
 for g in groups: lib.b2p_shard_group_free(g)
 print("SHARD_GROUP_OK")
 """
 
 
-@pytest.mark.parametrize("curve,logn,world", [("BN254", 10, 2), ("BN254", 13, 3), ("BN254", 12, 8), ("BLS12_381", 11, 4)])
-def test_sharded_commitments_on_one_device_equal_single_gpu_proof(gpu, curve, logn, world, tmp_path):
+@pytest.mark.parametrize("curve,logn,world,shard_ntt", [
+    ("BN254", 10, 2, 0), ("BN254", 13, 3, 0), ("BN254", 12, 8, 0), ("BLS12_381", 11, 4, 0),
+    # ... and with the five size-4n transforms spread over the ranks as well (single- and multi-pass local transforms)
+    ("BN254", 10, 2, 1), ("BN254", 13, 4, 1), ("BN254", 14, 8, 1), ("BLS12_381", 12, 8, 1), ("BN254", 6, 2, 1)])
+def test_sharded_commitments_on_one_device_equal_single_gpu_proof(gpu, curve, logn, world, shard_ntt, tmp_path):
     """Own process with CUDA_DEVICE_MAX_CONNECTIONS=32 and eager module loading: with every rank in ONE process, a
     kernel that spins on a flag must never sit in front of the kernel that will raise it -- neither in a shared
     hardware queue nor behind a lazy kernel load (one process per GPU in the real runs: neither arises there)."""
     script = tmp_path / "one_device.py"
     script.write_text(ONE_DEVICE.format(root=ROOT))
     env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER")
-    out = subprocess.run([sys.executable, str(script), curve, str(logn), str(world)], capture_output=True, text=True,
+    out = subprocess.run([sys.executable, str(script), curve, str(logn), str(world), str(shard_ntt)],
+                         capture_output=True, text=True,
                          env=env, timeout=600)
     assert out.returncode == 0 and "SHARD_GROUP_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
 
@@ -89,12 +101,14 @@ def test_shard_group_argument_errors(gpu):
     whole = api.SRS.unsafe("BN254", 67, H.TAU)
     h = C.c_void_p()
     # the block handed in must be exactly this rank's share of the points
-    assert lib.b2p_shard_group_create(0, 2, 0, 67, whole.handle, None, C.byref(h)) == _lib.ERR_ARG
+    assert lib.b2p_shard_group_create(0, 2, 0, 67, whole.handle, 0, C.byref(h)) == _lib.ERR_ARG
     assert b"share" in lib.b2p_last_error()
-    assert lib.b2p_shard_group_create(0, 9, 0, 67, whole.handle, None, C.byref(h)) == _lib.ERR_ARG
-    assert lib.b2p_shard_group_create(1, 1, 0, 67, whole.handle, None, C.byref(h)) == _lib.ERR_ARG
+    assert lib.b2p_shard_group_create(0, 9, 0, 67, whole.handle, 0, C.byref(h)) == _lib.ERR_ARG
+    assert lib.b2p_shard_group_create(1, 1, 0, 67, whole.handle, 0, C.byref(h)) == _lib.ERR_ARG
+    assert lib.b2p_shard_group_create(0, 1, 0, 67, whole.handle, 48, C.byref(h)) == _lib.ERR_ARG     # not a power of two
+    assert lib.b2p_shard_group_create(0, 1, 0, 67, whole.handle, 128, C.byref(h)) == _lib.ERR_ARG    # 128 + 3 > 67 points
     # world 1: the group is the SRS itself
-    _lib.check(lib.b2p_shard_group_create(0, 1, 0, 67, whole.handle, None, C.byref(h)))
+    _lib.check(lib.b2p_shard_group_create(0, 1, 0, 67, whole.handle, 0, C.byref(h)))
     assert lib.b2p_shard_group_serve_proof(h, 64) == _lib.ERR_ARG            # rank 0 does not serve
     lib.b2p_shard_group_free(h)
     whole.free()

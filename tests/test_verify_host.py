@@ -180,6 +180,25 @@ def test_golden_proofs_are_accepted_and_tampered_ones_rejected(case):
     bad[: cv.fp_bytes] = b"\xff" * cv.fp_bytes
     with pytest.raises(ValueError, match="not a point"):
         api.verify(*args, bytes(bad), pub)
+    # infinity encodings: all zero on both curves; on BLS12-381 also RawBytes()' 0x40 flag (helper.go:35) -- a point
+    # at infinity is a well-formed point (the proof then fails at the pairing), any other flag byte is not
+    for enc_ok, first in ((True, 0x00), (curve_is_bls := case["curve"] == "BLS12_381", 0x40), (False, 0x80)):
+        bad = bytearray(proof)
+        bad[:pb] = bytes([first]) + bytes(pb - 1)
+        with pytest.raises(ValueError, match="pairing" if enc_ok else "not a point"):
+            api.verify(*args, bytes(bad), pub)
+    # BLS12-381: a point on the curve outside the r-torsion subgroup is refused (gnark's decoder checks it; BN254's
+    # G1 has cofactor 1)
+    if curve_is_bls:
+        x = 5
+        while po.fp_sqrt(cv, (x ** 3 + cv.b) % cv.p) is None:
+            x += 1
+        P = (x, po.fp_sqrt(cv, (x ** 3 + cv.b) % cv.p))
+        assert po.g1_add(cv, po.g1_mul(cv, P, cv.r - 1), P) is not None     # on the curve, [r] P != infinity
+        bad = bytearray(proof)
+        bad[:pb] = po.g1_raw_bytes(cv, P)
+        with pytest.raises(ValueError, match="not a point"):
+            api.verify(*args, bytes(bad), pub)
     # another key: a different Ql commitment, or the wrong G2 pair
     other = list(vk_pts)
     other[3] = po.g1_add(cv, other[3], cv.g1)
@@ -312,17 +331,16 @@ def test_vk_bin_of_the_reference_setups_decodes_like_the_oracle(name):
                         (lambda b: bytes([b[0] | (0x3F if curve == "BN254" else 0x1F)]) + b[1:], "not reduced")):
         with pytest.raises(_lib.B200PlonkError, match=why):
             api.kzg_vk_load(curve, damage(vk_bin))
-    # an x that is not on the twist (search a few)
-    for delta in range(1, 40):
+    # a perturbed x is either off the twist or -- the twist has a cofactor -- on it but outside the r-torsion subgroup
+    # (gnark's decoder checks both); it is never accepted
+    seen = set()
+    for delta in range(1, 24):
         bad = bytearray(vk_bin)
         bad[2 * nb - 1] = (bad[2 * nb - 1] + delta) & 0xFF
-        try:
+        with pytest.raises(_lib.B200PlonkError, match="not on the twist|r-torsion subgroup") as ei:
             api.kzg_vk_load(curve, bytes(bad))
-        except _lib.B200PlonkError as e:
-            assert "not on the twist" in str(e)
-            break
-    else:
-        raise AssertionError("every perturbed x was on the twist")
+        seen.add("twist" if "not on the twist" in str(ei.value) else "subgroup")
+    assert seen == {"twist", "subgroup"}
     # infinity encodings
     inf = bytes([0x40 if curve == "BN254" else 0xC0]) + bytes(2 * nb - 1)
     g2i, _ = api.kzg_vk_load(curve, inf + inf + vk_bin[4 * nb:])
