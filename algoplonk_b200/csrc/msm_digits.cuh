@@ -13,14 +13,18 @@ struct MsmPlan {
 };
 
 // Cost model, in mixed additions, fitted to profiles/msm_plan_sweep_r2_*.jsonl (one MSM of n = 2^15 ... 2^21 points at
-// every window width, B200):
+// every window width, B200) and the per-kernel times of profiles/msm_once_r2_c*.txt:
 //   n W                     digit additions (the accumulation: one thread per bucket slice of <= 128 entries),
 //   x (1 + 0.19 log2(300 k / items))  when there are fewer work items than fill the GPU a few times over
 //                           (148 SMs x 512 resident threads x 4): the accumulation is then latency-bound -- 2^19 points:
-//                           c = 17 (88 k items) 2.31 ms, c = 20 (524 k) 1.81 ms, although c = 17 makes fewer additions,
+//                           c = 17 (88 k items) 2.31 ms, c = 20 (524 k) 1.81 ms, although c = 17 makes fewer additions;
+//   >= 30 k x longest chain the accumulation cannot finish before its longest item: one dependent mixed addition is
+//                           ~3.3 us (22 k additions' worth of throughput; 30 k with the merging of split buckets).  The partial TOP window matters here: it has
+//                           t = bits + 1 - (W-1) c real bits, so its n digits land in only 2^(t-1) buckets -- 2^17
+//                           points, c = 19: t = 8, 1024 entries per bucket, 128-entry items: 0.67 ms of accumulation
+//                           against 0.21 ms at c = 20 (t = 15);
 //   + 3 * 2^(c-1)           the bucket reduction.
-// Only the smallest c of each window count W is a candidate: a wider window with the same W adds buckets, not speed
-// (2^17 points: c = 17 0.91 ms, c = 18 1.34 ms, both W = 15).
+// Only the smallest c of each window count W is a candidate: a wider window with the same W adds buckets, not speed.
 inline MsmPlan msm_plan(uint64_t npoints, int scalar_bits, int force_c = 0) {
     MsmPlan best;
     double best_cost = 1e300;
@@ -33,7 +37,12 @@ inline MsmPlan msm_plan(uint64_t npoints, int scalar_bits, int force_c = 0) {
         if (items > adds) items = adds;
         double slow = 1.0;
         for (double t = items; t < 300000.0 && t >= 1.0; t *= 2.0) slow += 0.19;
-        const double cost = adds * slow + 3.0 * nb;
+        const int t_top = scalar_bits + 1 - (W - 1) * c;                                  // >= 1
+        double chain = (double)npoints * (W - 1) / nb + (double)npoints / (double)(1ull << (t_top - 1));
+        if (chain > 128.0) chain = 128.0;
+        double acc = adds * slow;
+        if (acc < 30000.0 * chain) acc = 30000.0 * chain;
+        const double cost = acc + 3.0 * nb;
         if (cost < best_cost) { best_cost = cost; best.c = c; best.W = W; best.nbuckets = 1u << (c - 1); }
     }
     return best;
