@@ -31,6 +31,8 @@
 #pragma once
 #include "prover.cuh"
 #include "ntt_shard.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace b2p {
 
@@ -162,6 +164,37 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
     Fr* loc = nullptr;                    // this rank's cyclic coefficients before the local passes
     void* circ_buf[5] = {nullptr};        // rank 0: the attached circuit's el er eo ez h
 
+    // B2P_SHARD_TRACE=1: CUDA events around the steps of every sharded transform, printed per proof to stderr
+    // (where the time of a transform goes on each rank: local passes / waiting for the peers / exchange kernel)
+    struct Trace {
+        bool on = false;
+        std::vector<cudaEvent_t> ev;
+        std::vector<const char*> what;
+        void mark(const char* w, cudaStream_t st) {
+            if (!on) return;
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            ev.push_back(e);
+            what.push_back(w);
+        }
+        void dump(uint32_t rank) {
+            if (!on || ev.empty()) return;
+            cudaEventSynchronize(ev.back());
+            std::string line = "[shard trace rank " + std::to_string(rank) + "]";
+            for (size_t i = 1; i < ev.size(); i++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+                char buf[64];
+                snprintf(buf, sizeof buf, " %s=%.3f", what[i], ms);
+                line += buf;
+            }
+            fprintf(stderr, "%s\n", line.c_str());
+            for (auto e : ev) cudaEventDestroy(e);
+            ev.clear();
+            what.clear();
+        }
+    } trace;
     ShardFlags* flags(void* m) const { return reinterpret_cast<ShardFlags*>(m); }
     Ext* partials(void* m) const { return reinterpret_cast<Ext*>(static_cast<uint8_t*>(m) + SHARD_MAIL_FLAG_BYTES); }
     static size_t mail_bytes() { return SHARD_MAIL_FLAG_BYTES + (size_t)SHARD_MAX_WORLD * MSM_SLOTS * sizeof(Ext); }
@@ -170,6 +203,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
     ShardGroup(uint32_t world_, uint32_t rank_, uint64_t total_, SrsBase* shard_, uint64_t ntt_rows_) {
         curve = C::ID;
         world = world_; rank = rank_; total = total_; ntt_rows = ntt_rows_;
+        { const char* e = getenv("B2P_SHARD_TRACE"); trace.on = e && atoi(e) != 0; }
         B2P_REQUIRE(world >= 1 && world <= SHARD_MAX_WORLD && rank < world, "shard group: bad rank / world (world <= 8)");
         B2P_REQUIRE(shard_ && shard_->curve == C::ID, "shard group: the SRS block is on another curve");
         shard = static_cast<Srs<C>*>(shard_);
@@ -347,6 +381,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         }
         B2P_CUDA(cudaMemcpyAsync(h, shard->msm.result.p + first_slot, cnt * sizeof(Ext), cudaMemcpyDeviceToHost, st));
         B2P_CUDA(cudaStreamSynchronize(st));
+        if (first_slot == 7) trace.dump(rank);           // the last fetch of a proof
         check_err("partial sums of the other ranks", st);
         Aff* out = static_cast<Aff*>(host_affine_out);
         for (int i = 0; i < cnt; i++) out[i] = h[i].to_affine();
@@ -371,13 +406,18 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         const uint32_t seq = ++ntt_seq, G = world;
         Fr* x = xbuf + (size_t)(seq & 1) * ntt->local_n;
         const uint64_t cnt = len > rank ? (len - rank + G - 1) / G : 0;
+        trace.mark("fwd", st);
         if (cnt) B2P_LAUNCH((k_shard_gather<Fr>), div_up(cnt, 256), 256, 0, st, loc, coeffs_as_seen_here, (uint64_t)rank, (uint64_t)G, cnt);
+        trace.mark("gather", st);
         ntt->forward_local(loc, cnt, B2P_NTT_COSET, x, st);
+        trace.mark("local", st);
         xready_barrier(seq, st);
+        trace.mark("barrier", st);
         const void* chunks[1 << NTT_SHARD_MAX_LOGG] = {nullptr};
         for (uint32_t g = 0; g < G; g++)
             chunks[g] = static_cast<Fr*>(peer[g][SH_XBUF]) + (size_t)(seq & 1) * ntt->local_n + (size_t)rank * ntt->chunk_len;
         ntt->forward_combine(chunks, static_cast<Fr*>(peer[0][which]) + (size_t)rank * ntt->local_n, st);
+        trace.mark("combine", st);
         tell_rank0_done(seq, st);
     }
     // 4n evaluations in rank 0's h -> the first out_len coefficients, back in rank 0's h
@@ -395,16 +435,22 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         void* chunks[1 << NTT_SHARD_MAX_LOGG] = {nullptr};
         for (uint32_t g = 0; g < G; g++)
             chunks[g] = static_cast<Fr*>(peer[g][SH_XBUF]) + (size_t)(seq & 1) * ntt->local_n + (size_t)rank * ntt->chunk_len;
+        trace.mark("inv-go", st);
         ntt->inverse_split(h0 + (size_t)rank * ntt->local_n, chunks, st);
+        trace.mark("split", st);
         xready_barrier(seq, st);     // every rank has read its block of h and delivered its chunks
+        trace.mark("barrier", st);
         ntt->inverse_local(x, B2P_NTT_INVERSE | B2P_NTT_COSET, nullptr, st);
+        trace.mark("local", st);
         const uint64_t cnt = out_len > rank ? (out_len - rank + G - 1) / G : 0;
         if (cnt) B2P_LAUNCH((k_shard_scatter<Fr>), div_up(cnt, 256), 256, 0, st, h0, x, (uint64_t)rank, (uint64_t)G, cnt);
+        trace.mark("scatter", st);
         tell_rank0_done(seq, st);
     }
     void wait_ntt_done(cudaStream_t st) {      // rank 0: every rank's part of transform ntt_seq has landed here
         ShardFlags* f = flags(mail);
         if (world > 1) B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &f->ntt_done[1], (int)world - 1, 1, ntt_seq, &f->error);
+        trace.mark("wait-done", st);
     }
     // CommitRouter (rank 0)
     void ntt_forward(const void* d_coeffs, uint64_t len, int which, cudaStream_t st) override {
@@ -448,6 +494,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         }
         B2P_CUDA(cudaMemcpyAsync(h_err, &mine->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         B2P_CUDA(cudaStreamSynchronize(st));
+        trace.dump(rank);
         check_err("rank 0 or a peer", st);
     }
 };

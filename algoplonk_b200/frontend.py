@@ -288,3 +288,147 @@ def random_dense_circuit(curve: str, log2_rows: int, seed: int = 0, nb_public: i
             c = len(values) - 1
         constraints.append((ql, qr, qm, qo, qk, a, b, c))
     return SparseR1CS(curve, nb_public, len(values), constraints), values
+
+
+# ---------------------------------------------------------------------------
+# MiMC + Merkle proof: the circuit of the reference's examples/merkle and of its integration tests
+# (examples/merkle/logicsigVerifier/main.go:35-61, testutils/verifier_integration_test.go)
+# ---------------------------------------------------------------------------
+_KECCAK_RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
+              0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
+              0x0000000080008009, 0x000000008000000A, 0x000000008000808B, 0x800000000000008B, 0x8000000000008089,
+              0x8000000000008003, 0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+              0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+_KECCAK_ROT = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]
+
+
+def keccak256_legacy(data: bytes) -> bytes:
+    """Keccak-256 with the original 0x01 padding (Go's sha3.NewLegacyKeccak256; hashlib only has the NIST 0x06
+    variant).  Used for the MiMC round constants exactly as gnark-crypto derives them."""
+    rate, M = 136, (1 << 64) - 1
+    msg = bytearray(data) + b"\x01" + bytes((-len(data) - 2) % rate) + b"\x80" if (len(data) + 1) % rate else \
+        bytearray(data) + b"\x81"
+    A = [[0] * 5 for _ in range(5)]
+    rol = lambda v, r: ((v << r) | (v >> (64 - r))) & M if r else v
+    for off in range(0, len(msg), rate):
+        for i in range(rate // 8):
+            A[i % 5][i // 5] ^= int.from_bytes(msg[off + 8 * i: off + 8 * i + 8], "little")
+        for rc in _KECCAK_RC:
+            Cc = [A[x][0] ^ A[x][1] ^ A[x][2] ^ A[x][3] ^ A[x][4] for x in range(5)]
+            D = [Cc[(x - 1) % 5] ^ rol(Cc[(x + 1) % 5], 1) for x in range(5)]
+            A = [[A[x][y] ^ D[x] for y in range(5)] for x in range(5)]
+            B = [[0] * 5 for _ in range(5)]
+            for x in range(5):
+                for y in range(5):
+                    B[y][(2 * x + 3 * y) % 5] = rol(A[x][y], _KECCAK_ROT[x][y])
+            A = [[B[x][y] ^ ((~B[(x + 1) % 5][y]) & B[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+            A[0][0] ^= rc
+    return b"".join(A[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
+
+
+_MIMC_ROUNDS = {"BN254": 110, "BLS12_381": 111}
+_MIMC_CONSTANTS: dict = {}
+
+
+def mimc_constants(curve: str) -> List[int]:
+    """gnark-crypto ecc/<curve>/fr/mimc initConstants [UPSTREAM-RECALL: un-vendored dependency, go.mod:9]: seed "seed",
+    rnd = Keccak(seed); then repeatedly rnd = Keccak(rnd), constant_i = rnd mod r."""
+    if curve not in _MIMC_CONSTANTS:
+        rnd = keccak256_legacy(b"seed")
+        out = []
+        for _ in range(_MIMC_ROUNDS[curve]):
+            rnd = keccak256_legacy(rnd)
+            out.append(int.from_bytes(rnd, "big") % R_MOD[curve])
+        _MIMC_CONSTANTS[curve] = out
+    return _MIMC_CONSTANTS[curve]
+
+
+def mimc_hash(curve: str, blocks: Sequence[int]) -> int:
+    """MiMC (x^5 rounds) in Miyaguchi-Preneel mode over field elements: what the Merkle example hashes with
+    (examples/merkle/logicsigVerifier/main.go:19,177-190 `mimcHash`), outside any circuit."""
+    r, cs_ = R_MOD[curve], mimc_constants(curve)
+    h = 0
+    for m in blocks:
+        x = m % r
+        for c in cs_:
+            t = (x + h + c) % r
+            x = pow(t, 5, r)
+        x = (x + h) % r
+        h = (h + x + m) % r
+    return h
+
+
+def _mimc_in_circuit(B: Builder, h: int, blocks: Sequence[int]) -> int:
+    """std/hash/mimc: per block  r = encrypt(block, key = h);  h = h + r + block.  Returns the variable of the digest.
+    A round is  t = m + h + c_i  (one addition gate with a constant) and  m = t^5  (three multiplication gates)."""
+    cs_ = mimc_constants(B.curve)
+    for m0 in blocks:
+        m = m0
+        for c in cs_:
+            t = B.internal(B.values[m] + B.values[h] + c)
+            B.add_constraint(ql=1, qr=1, qo=-1, qk=c, xa=m, xb=h, xc=t)
+            t2 = B.mul(t, t)
+            t4 = B.mul(t2, t2)
+            m = B.mul(t4, t)
+        enc = B.add(m, h)
+        h = B.add(B.add(h, enc), m0)
+    return h
+
+
+def merkle_circuit(curve: str, depth: int = 16, nb_leaves: int = 6, index: int = 3):
+    """MerkleCircuit (examples/merkle/logicsigVerifier/main.go:45-61): public RootHash, secret Path[depth + 1] (the
+    unhashed leaf, then the siblings up to the root) and Index; Define() = merkle.MerkleProof.VerifyProof with MiMC:
+    the leaf is hashed, the index is split into bits, every level selects (left, right) by its bit and hashes them,
+    the result must equal RootHash.  The tree of main.go:63-92: `nb_leaves` leaves "leaf<i>", zero elsewhere, proof for
+    leaf `index`.  The gate-level shape is this front end's (gnark's compiler is not available here); the
+    statement proved and the witness are the example's.  Returns (Builder, root)."""
+    r = R_MOD[curve]
+    leaves = [int.from_bytes(b"leaf%d" % i, "big") % r for i in range(nb_leaves)]
+    H = lambda *xs: mimc_hash(curve, xs)
+    level = [H(x) for x in leaves]
+    zero = [H(0)]                                # zero[i]: node at level i over uninitialised leaves (main.go:197-208)
+    for _ in range(depth):
+        zero.append(H(zero[-1], zero[-1]))
+    path, pos = [leaves[index]], index
+    for lvl in range(depth):
+        sib = pos ^ 1
+        path.append(level[sib] if sib < len(level) else zero[lvl])
+        nxt = []
+        for i in range(0, len(level), 2):
+            nxt.append(H(level[i], level[i + 1] if i + 1 < len(level) else zero[lvl]))
+        level, pos = nxt, pos >> 1
+    root = level[0]
+
+    B = Builder(curve)
+    v_root = B.public(root)
+    v_path = [B.secret(p) for p in path]
+    v_index = B.secret(index)
+    zero_h = B.secret(0)
+    B.add_constraint(ql=1, xa=zero_h)            # the initial chaining value is the constant 0
+    total = _mimc_in_circuit(B, zero_h, [v_path[0]])          # leafSum
+    # api.ToBinary(index, depth): boolean bits that recompose to the index
+    bits, acc = [], None
+    for i in range(depth):
+        b = B.secret((index >> i) & 1)
+        B.add_constraint(qm=1, ql=-1, xa=b, xb=b)             # b * b - b = 0
+        bits.append(b)
+        if acc is None:
+            acc = b
+        else:
+            nxt = B.internal(B.values[acc] + (B.values[b] << i))
+            B.add_constraint(ql=1, qr=1 << i, qo=-1, xa=acc, xb=b, xc=nxt)
+            acc = nxt
+    B.assert_is_equal(acc, v_index)
+    for i in range(depth):
+        b, sib = bits[i], v_path[i + 1]
+        # d1 = Select(b, sibling, sum), d2 = Select(b, sum, sibling):  d1 = sum + b (sib - sum), d2 = sib + sum - d1
+        diff = B.internal(B.values[sib] - B.values[total])
+        B.add_constraint(ql=1, qr=-1, qo=-1, xa=sib, xb=total, xc=diff)
+        bd = B.mul(b, diff)
+        d1 = B.add(total, bd)
+        s = B.add(sib, total)
+        d2 = B.internal(B.values[s] - B.values[d1])
+        B.add_constraint(ql=1, qr=-1, qo=-1, xa=s, xb=d1, xc=d2)
+        total = _mimc_in_circuit(B, zero_h, [d1, d2])         # nodeSum
+    B.assert_is_equal(total, v_root)
+    return B, root

@@ -358,6 +358,30 @@ def run_b200(args):
     clocks = sampler.stop()
     for o in outs:
         assert bytes(o.raw) == proof_resident, "host-buffer and resident-buffer proofs differ"
+    # pass 4 (boundary cost, reported next to e2e): the columns as a Go caller holds them -- PAGEABLE memory.
+    #   pageable: b2p_prove straight on pageable buffers (the driver stages them; no overlap with compute)
+    #   shim:     what go/gpuplonk does per proof: memcpy of the three columns into the proving key's own
+    #             page-locked columns (allocated once per key), then b2p_prove on those
+    pageable = [C.create_string_buffer(bytes(t.numpy().tobytes()), t.numel()) for t in (hL, hR, hO)]
+    lane_pinned = [[torch.empty_like(hL).pin_memory() for _ in range(3)] for _ in range(F)]
+
+    def prove_pageable(i):
+        _lib.check(lib.b2p_prove(ccs[i].handle, pageable[0], pageable[1], pageable[2], None, None, blinding, outs[i]))
+
+    def prove_shim(i):
+        for dst, src in zip(lane_pinned[i], pageable):
+            C.memmove(dst.data_ptr(), src, dst.numel())
+        _lib.check(lib.b2p_prove(ccs[i].handle, lane_pinned[i][0].data_ptr(), lane_pinned[i][1].data_ptr(),
+                                 lane_pinned[i][2].data_ptr(), None, None, blinding, outs[i]))
+    boundary = {}
+    for name, fn in (("pageable", prove_pageable), ("shim", prove_shim)):
+        for i in range(F):
+            fn(i)
+        ms_b = timed(fn, args.steps, F)
+        tot_b, _ = reduce_over_ranks(ms_b, args.steps, world, device)
+        boundary[name] = tot_b
+        for o in outs:
+            assert bytes(o.raw) == proof_resident, f"{name}: proof differs"
 
     sharded_line = measure_sharded_msm(args, rank, world, device) if world > 1 else None
     # one proof over all the GPUs (commitments sharded over the point set, native peer-memory path)
@@ -405,6 +429,11 @@ def run_b200(args):
         "dtype": "u32", "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * 32 * n + 9 * 32,
                 "d2h_bytes_per_step": int(lib.b2p_proof_raw_size(cid, 0)), "ms_per_step": tot_ms_e2e / args.steps},
+        "e2e_pageable": {"value": units / (boundary["pageable"] / 1e3), "ms_per_step": boundary["pageable"] / args.steps,
+                         "unit": UNIT, "what": "b2p_prove on PAGEABLE host columns (a Go slice handed over as it is)"},
+        "e2e_shim": {"value": units / (boundary["shim"] / 1e3), "ms_per_step": boundary["shim"] / args.steps, "unit": UNIT,
+                     "what": "go/gpuplonk's per-proof path: memcpy of the pageable columns into the key's page-locked "
+                             "columns (allocated once per key), then b2p_prove"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks,

@@ -232,6 +232,51 @@ def test_config2_real_ppot_srs_at_2p17(gpu):
     srs.free()
 
 
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+def test_merkle_mimc_circuit_of_the_reference_example(gpu, curve):
+    """The circuit every integration test of the reference proves (examples/merkle/logicsigVerifier/main.go:45-61,
+    testutils/verifier_integration_test.go:175-230): MiMC Merkle proof, depth 16, public root.  BN254 on the REAL
+    PerpetualPowersOfTau points, as main.go:113 compiles it (cc.Verify then checks the pairing against the setup's
+    vk.bin); BLS12-381 on the TestOnly setup.  Proof and verifying key byte for byte the C++ oracle's, accepted by
+    the restated AVM verifier, rejected for another root."""
+    import os
+    cv = po.CURVES[curve]
+    B, root = fe.merkle_circuit(curve)
+    cs = B.build()
+    if curve == "BN254":
+        with open(os.path.join(H.GOLDEN, "ppot_bn254_first_131075.bin"), "rb") as f:
+            pk_bin = f.read()
+        name = "PerpetualPowersOfTauBN254"
+        count = (1 << 14) + 3
+        srs = api.SRS.from_pk_bin(curve, pk_bin, count, vk_bin=bytes.fromhex(H.srs_kat()[name]["vk_bin"]))
+        cc = api.Compile(cs, curve, api.SetupName.PerpetualPowersOfTauBN254, srs=srs)
+        srs_le = co.g1_decompress_bytes(0, pk_bin[4:4 + 32 * count])
+        g1, tau, g2 = H.real_srs_points(name)[0], None, H.real_srs_g2(name)
+    else:
+        cc = api.Compile(cs, curve, SETUP[curve])
+        srs_le = co.srs_from_tau_bytes(cv.cid, api.TEST_TAU, cc.trace.n + 3)
+        g1, tau, g2 = cv.g1, api.TEST_TAU, None
+    tc = cc.trace
+    assert tc.n == 1 << 14 and tc.nb_public == 1
+    L, R, O = fe.solve_lro(cs, B.values, tc.n)
+    blinding = H.scalars_uniform(cv.r, 9, 16)
+    vp = cc.Verify(L, R, O, blinding)                         # plonk.Prove + plonk.Verify (b2p_verify)
+    assert vp.Witness == [root]
+    blob = api.MarshalProof(vp.Proof)
+    circ = co.Circuit(cv.cid, tc.n, 1, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
+    assert cc.vk_commitments() == circ.vk_points()
+    assert blob == circ.prove(L, R, O, blinding)
+    circ.free()
+    vk = H.vk_from_points(tc, cc.vk_commitments(), g1, tau=tau, g2=g2)
+    pub = api.MarshalPublicInputs(curve, [root])
+    assert po.verify_proof(vk, blob, pub)
+    assert not po.verify_proof(vk, blob, api.MarshalPublicInputs(curve, [root + 1]))
+    with pytest.raises(ValueError):
+        cc.VerifyProof(blob, api.MarshalPublicInputs(curve, [root + 1]))
+    cc.free()
+    cc.srs.free()
+
+
 def test_two_proofs_in_flight_on_two_handles(gpu):
     """The library is re-entrant across handles and calls may come from any host thread (fresh threads start
     on CUDA device 0; every entry point switches to its handle's device): two keys, two threads, the same

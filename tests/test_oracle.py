@@ -479,3 +479,49 @@ def test_config2_golden_on_the_real_ppot_bytes():
     with pytest.raises(ValueError):
         api.verify("BN254", tc.n, tc.nb_public, [], api.points_to_mont_bytes("BN254", vk_pts), g1, g2,
                    proof[:100] + bytes([proof[100] ^ 1]) + proof[101:], pub)
+
+
+@pytest.mark.parametrize("curve", ["BN254", "BLS12_381"])
+def test_merkle_mimc_circuit_of_the_reference_example(curve):
+    """examples/merkle/logicsigVerifier/main.go: MiMC (Keccak-derived round constants, x^5, Miyaguchi-Preneel), the
+    depth-16 tree with six leaves "leaf<i>", proof for the fourth.  The circuit's public root equals the root main.go
+    computes by hand (:70-92); a wrong index or sibling violates a gate; the C++ oracle's proof is accepted by the
+    restated AVM verifier and by the library's plonk.Verify, and is rejected for another root."""
+    from algoplonk_b200 import api, frontend as fe
+    cv = po.CURVES[curve]
+    assert fe.keccak256_legacy(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert fe.keccak256_legacy(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    assert fe.keccak256_legacy(bytes(135))[:4] != fe.keccak256_legacy(bytes(136))[:4]      # padding at the rate boundary
+    B, root = fe.merkle_circuit(curve)
+    Hh = lambda *xs: fe.mimc_hash(curve, xs)
+    leaves = [int.from_bytes(b"leaf%d" % i, "big") % cv.r for i in range(6)]
+    z = [Hh(0)]
+    for _ in range(16):
+        z.append(Hh(z[-1], z[-1]))
+    path = [leaves[3], Hh(leaves[2]), Hh(Hh(leaves[0]), Hh(leaves[1])), Hh(Hh(Hh(leaves[4]), Hh(leaves[5])), z[1])] \
+        + [z[i - 1] for i in range(4, 17)]
+    want = Hh(path[2], Hh(path[1], Hh(path[0])))
+    for i in range(3, 17):
+        want = Hh(want, path[i])
+    assert root == want
+    cs = B.build()
+    tc = fe.build_trace(cs)
+    assert tc.nb_public == 1 and tc.n == 1 << 14
+    L, R, O = fe.solve_lro(cs, B.values, tc.n)
+    assert fe.check_gates(tc, L, R, O)
+    B2, _ = fe.merkle_circuit(curve, index=2)            # another leaf: another witness, the same root
+    assert B2.values[0] == root
+    bad = list(B.values)
+    bad[3] = (bad[3] + 1) % cv.r                         # a sibling of the path
+    assert not fe.check_gates(tc, *fe.solve_lro(cs, bad, tc.n))
+    srs_le = co.srs_from_tau_bytes(cv.cid, H.TAU, tc.n + 3)
+    circ = co.Circuit(cv.cid, tc.n, 1, tc.ql, tc.qr, tc.qm, tc.qo, tc.qk, tc.perm, (), (), srs_le)
+    blob = circ.prove(L, R, O, list(range(1, 10)))
+    vk_pts = circ.vk_points()
+    circ.free()
+    vk = H.vk_from_points(tc, vk_pts, cv.g1, tau=H.TAU)
+    pub = po.marshal_public_inputs([root])
+    assert po.verify_proof(vk, blob, pub)
+    assert not po.verify_proof(vk, blob, po.marshal_public_inputs([root + 1]))
+    g1 = api.points_to_mont_bytes(curve, [cv.g1])
+    api.verify(curve, tc.n, 1, [], api.points_to_mont_bytes(curve, vk_pts), g1, api.g2_unsafe(curve, H.TAU), blob, pub)
