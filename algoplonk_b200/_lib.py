@@ -19,7 +19,7 @@ ERR_ARG, ERR_CUDA, ERR_INTERNAL, ERR_VERIFY = -1, -2, -3, -4
 BASIS_CANONICAL, BASIS_LAGRANGE = 0, 1
 NTT_INVERSE, NTT_COSET = 1, 2
 IPC_HANDLE_BYTES = 64
-SHARD_HANDLES = 8
+SHARD_HANDLES = 9
 STAT_NAMES = ["total_ms", "msm_ms", "msm_accum_ms", "ntt_ms", "quotient_ms", "msm_calls", "msm_accum_adds",
               "h2d_bytes", "d2h_bytes", "launches"]
 STAT_COUNT = 16
@@ -38,6 +38,7 @@ SYMBOLS = [
     ("b2p_srs_generate_unsafe", _int, [_int, _vp, _u64, C.POINTER(_vp)]),
     ("b2p_srs_generate_unsafe_range", _int, [_int, _vp, _u64, _u64, C.POINTER(_vp)]),
     ("b2p_srs_generate_unsafe_strided", _int, [_int, _vp, _u64, _u64, _u64, C.POINTER(_vp)]),
+    ("b2p_srs_to_lagrange", _int, [_vp, _u64, _vp]),
     ("b2p_srs_get_points", _int, [_vp, _u64, _u64, _vp]),
     ("b2p_srs_size", _u64, [_vp]),
     ("b2p_srs_msm_params", _int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_u64)]),

@@ -240,6 +240,15 @@ class SRS:
         _lib.check(_lib.load().b2p_srs_get_points(self.handle, first, count, out))
         return points_from_mont_bytes(self.curve, out.raw)
 
+    def to_lagrange_raw(self, n: int) -> bytes:
+        """kzg.ToLagrangeG1(srs.Pk.G1[:n]) (setup/setup.go:124,138): n G1Affine in memory layout."""
+        out = C.create_string_buffer(n * 2 * FP_BYTES[self.curve])
+        _lib.check(_lib.load().b2p_srs_to_lagrange(self.handle, n, out))
+        return out.raw
+
+    def to_lagrange(self, n: int):
+        return points_from_mont_bytes(self.curve, self.to_lagrange_raw(n))
+
     def msm(self, scalars: Sequence[int], basis: int = _lib.BASIS_CANONICAL):
         """G1Affine.MultiExp / kzg.Commit: returns an affine int pair (None = infinity)."""
         data = _buf(fr_to_mont_bytes(self.curve, scalars)) if len(scalars) else None

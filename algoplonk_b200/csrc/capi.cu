@@ -170,6 +170,15 @@ API int b2p_srs_get_points(const b2p_srs* srs, uint64_t first, uint64_t count, v
         reinterpret_cast<const SrsBase*>(srs)->get_points(first, count, out);
     });
 }
+API int b2p_srs_to_lagrange(b2p_srs* srs, uint64_t n, void* out_points) {
+    return guarded([&] {
+        require(srs && out_points, "null argument");
+        SrsBase* s = reinterpret_cast<SrsBase*>(srs);
+        std::lock_guard<std::mutex> lk(s->mu);
+        DeviceGuard g(s->device);
+        s->to_lagrange(n, out_points);
+    });
+}
 API uint64_t b2p_srs_size(const b2p_srs* srs) { return srs ? reinterpret_cast<const SrsBase*>(srs)->size() : 0; }
 API int b2p_srs_msm_params(const b2p_srs* srs, int* c, int* windows, uint64_t* buckets) {
     return guarded([&] {

@@ -28,6 +28,7 @@ struct SrsBase {
     virtual void generate_unsafe(const void* tau, uint64_t first, uint64_t stride, uint64_t n) = 0;
     virtual void get_points(uint64_t first, uint64_t count, void* out) const = 0;
     virtual uint64_t size() const = 0;
+    virtual void to_lagrange(uint64_t n, void* out_points) = 0;
     virtual void msm_params(int* c, int* windows, uint64_t* buckets) const = 0;
     virtual void* stream_handle() = 0;
     virtual void set_commit_hook(int (*fn)(void*, const void*, uint64_t, void*), void* ctx) = 0;
@@ -67,7 +68,7 @@ NttShardBase* new_ntt_shard(int curve, uint64_t n, uint32_t world, uint32_t rank
 
 // One rank of a shard group: the commitments (and, optionally, the big transforms) of one proof spread over the GPUs
 // of a box (shard_group.cuh).  A rank shares SHARD_NPTR pieces of memory with its peers.
-constexpr int SHARD_NPTR = 8;
+constexpr int SHARD_NPTR = 9;
 struct ShardGroupBase {
     int curve = -1;
     int device = -1;

@@ -204,6 +204,72 @@ __global__ void k_g1_decompress(const uint8_t* __restrict__ in, Affine<typename 
     st_field(&out[i].y, y);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// kzg.ToLagrangeG1 (setup/setup.go:124,138): the Lagrange-basis SRS  [L_j(tau)]_1 = (1/n) sum_i w^(-ij) [tau^i]_1,
+// i.e. the inverse DFT of the canonical points over the group -- gnark runs it as an FFT whose butterflies multiply a
+// point by a twiddle (minutes on a CPU at 2^20).  Same dataflow here: decimation in time over XYZZ points in HBM, one
+// launch per stage, one butterfly per thread:  B' = [w^-e] B (double-and-add over the twiddle's bits),  A + B', A - B';
+// the 1/n is folded into the last stage (A and B' are multiplied by 1/n and w^-e / n there).  The prover does not need
+// this table (Lagrange commitments are iNTT + canonical MSM, msm.cuh); it exists for callers that want gnark's own
+// pk.KzgLagrange -- the Go shim's fallback to plonk.Prove -- without paying for it on the CPU.
+// ---------------------------------------------------------------------------------------------------------
+template <class C>
+__device__ XYZZ<typename C::Fp> ec_scalar_mul(const XYZZ<typename C::Fp>& P, const typename C::Fr& k_canonical) {
+    using Fp = typename C::Fp;
+    using Fr = typename C::Fr;
+    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+    int top = Fr::Params::BITS - 1;
+    while (top >= 0 && !((k_canonical.v[top >> 5] >> (top & 31)) & 1)) top--;
+    for (int b = top; b >= 0; b--) {
+        acc = acc.dbl();
+        if ((k_canonical.v[b >> 5] >> (b & 31)) & 1) acc.add(P);
+    }
+    return acc;
+}
+// buf[i] = table[brev(i)] lifted to XYZZ (the bit reversal of the DIT input is the gather)
+template <class C>
+__global__ void k_ecntt_load(XYZZ<typename C::Fp>* __restrict__ buf, const Affine<typename C::Fp>* __restrict__ pts, int logn) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << logn)) return;
+    const uint32_t j = logn ? brev32(i, logn) : 0u;
+    Affine<typename C::Fp> p;
+    p.x = ld_field(&pts[j].x);
+    p.y = ld_field(&pts[j].y);
+    st_xyzz(buf + i, XYZZ<typename C::Fp>::from_affine(p));
+}
+// stage s (half-block 2^s) of the inverse transform; tw_inv[k] = w^-k, k < n/2 (Montgomery form)
+template <class C>
+__global__ void __launch_bounds__(128) k_ecntt_stage(XYZZ<typename C::Fp>* __restrict__ buf, const typename C::Fr* __restrict__ tw_inv,
+                                                     int logn, int s, typename C::Fr n_inv, int last) {
+    using Fr = typename C::Fr;
+    using Ext = XYZZ<typename C::Fp>;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (1u << (logn - 1))) return;
+    const uint32_t half = 1u << s, k = t & (half - 1);
+    const uint32_t i = ((t >> s) << (s + 1)) | k, j = i + half;
+    Ext A = ld_xyzz(buf + i), B = ld_xyzz(buf + j);
+    Fr w = ld_field(tw_inv + ((uint64_t)k << (logn - 1 - s)));
+    if (last) {
+        A = ec_scalar_mul<C>(A, n_inv.from_mont());
+        w = w * n_inv;
+    }
+    if (k != 0 || last) B = ec_scalar_mul<C>(B, w.from_mont());       // w = 1 for k = 0: nothing to multiply
+    Ext S = A, D = A;
+    S.add(B);
+    D.add(B.neg());
+    st_xyzz(buf + i, S);
+    st_xyzz(buf + j, D);
+}
+template <class C>
+__global__ void __launch_bounds__(128) k_ecntt_store(Affine<typename C::Fp>* __restrict__ out, const XYZZ<typename C::Fp>* __restrict__ buf,
+                                                     uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Affine<typename C::Fp> a = ld_xyzz(buf + i).to_affine();
+    st_field(&out[i].x, a.x);
+    st_field(&out[i].y, a.y);
+}
+
 template <class C> struct CurveConsts;
 template <> struct CurveConsts<Bn254> {
     static constexpr uint32_t B = 3;      // y^2 = x^3 + 3
@@ -312,6 +378,24 @@ struct Srs : SrsBase {
     void get_points(uint64_t first, uint64_t count, void* out) const override {
         B2P_REQUIRE(count <= msm.npoints && first <= msm.npoints - count, "range exceeds SRS size");
         B2P_CUDA(cudaMemcpy(out, msm.table.p + first, count * sizeof(Aff), cudaMemcpyDeviceToHost));
+    }
+    // kzg.ToLagrangeG1(srs.Pk.G1[:n]) (setup/setup.go:124,138) -> n G1Affine on the host
+    void to_lagrange(uint64_t n, void* out) override {
+        B2P_REQUIRE(n >= 1 && (n & (n - 1)) == 0 && n <= msm.npoints, "ToLagrangeG1: n must be a power of two <= SRS size");
+        int logn = 0;
+        while ((1ull << logn) < n) logn++;
+        B2P_REQUIRE(logn <= Fr::Params::TWO_ADICITY && logn <= 31, "ToLagrangeG1: n exceeds the field's 2-adicity");
+        NttDomain<Fr> d;
+        d.init(logn, false, stream);
+        DevBuf<Ext> buf(n);
+        DevBuf<Aff> res(n);
+        B2P_LAUNCH((k_ecntt_load<C>), div_up(n, 128), 128, 0, stream, buf.p, msm.table.p, logn);
+        for (int s = 0; s < logn; s++)
+            B2P_LAUNCH((k_ecntt_stage<C>), div_up(n / 2, 128), 128, 0, stream, buf.p, d.tw_inv.p, logn, s, d.n_inv,
+                       (int)(s == logn - 1));
+        B2P_LAUNCH((k_ecntt_store<C>), div_up(n, 128), 128, 0, stream, res.p, buf.p, n);
+        B2P_CUDA(cudaMemcpyAsync(out, res.p, n * sizeof(Aff), cudaMemcpyDeviceToHost, stream));
+        B2P_CUDA(cudaStreamSynchronize(stream));
     }
     uint64_t size() const override { return msm.npoints; }
     void* stream_handle() override { return (void*)stream; }

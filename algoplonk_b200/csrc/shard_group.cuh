@@ -127,6 +127,16 @@ __global__ void k_shard_scatter(Fr* __restrict__ dst, const Fr* __restrict__ src
     if (j < cnt) st_field(dst + first + j * stride, ld_field(src + j));
 }
 
+// rank 0, after the inverse transform: h[j G + g] = stage[(g - 1) cap + j] for g = 1 .. G-1 (the other ranks' cyclic
+// shares of the coefficients arrived as contiguous bulk copies; rank 0's own share is already in place)
+template <class Fr>
+__global__ void k_shard_interleave(Fr* __restrict__ h, const Fr* __restrict__ stage, uint32_t G, uint64_t cap, uint64_t out_len) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= out_len) return;
+    const uint32_t g = (uint32_t)(idx % G);
+    if (g) st_field(h + idx, ld_field(stage + (uint64_t)(g - 1) * cap + idx / G));
+}
+
 // [first, first + count) of rank `rank`: contiguous, balanced (sizes differ by at most one) -- the partition of
 // algoplonk_b200/sharded.py:shard_range
 inline void shard_block(uint64_t total, uint32_t rank, uint32_t world, uint64_t* first, uint64_t* count) {
@@ -136,7 +146,7 @@ inline void shard_block(uint64_t total, uint32_t rank, uint32_t world, uint64_t*
 }
 
 // the memory a rank shares with its peers, in the order the handles / pointers are exchanged in
-enum { SH_MAIL = 0, SH_STAGING, SH_XBUF, SH_EL, SH_ER, SH_EO, SH_EZ, SH_H, SH_NPTR };
+enum { SH_MAIL = 0, SH_STAGING, SH_XBUF, SH_EL, SH_ER, SH_EO, SH_EZ, SH_H, SH_HSTAGE, SH_NPTR };
 static_assert(SH_NPTR == SHARD_NPTR, "iface.hpp and shard_group.cuh disagree on the shared pieces");
 
 template <class C>
@@ -162,6 +172,9 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
     NttShard<Fr>* ntt = nullptr;
     Fr* xbuf = nullptr;                   // 2 exchange buffers of 4n/G elements, shared
     Fr* loc = nullptr;                    // this rank's cyclic coefficients before the local passes
+    Fr* outbuf = nullptr;                 // ranks > 0: a block of evaluations on its way to / from rank 0 (bulk copies)
+    Fr* hstage = nullptr;                 // rank 0: where the other ranks' shares of the quotient's coefficients land, shared
+    uint64_t share_cap() const { return (3 * (ntt_rows + 2) + world - 1) / world; }
     void* circ_buf[5] = {nullptr};        // rank 0: the attached circuit's el er eo ez h
 
     // B2P_SHARD_TRACE=1: CUDA events around the steps of every sharded transform, printed per proof to stderr
@@ -225,6 +238,8 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
                 ntt->init(4 * ntt_rows, world, rank);
                 B2P_CUDA(cudaMalloc(&xbuf, 2 * ntt->local_n * sizeof(Fr)));
                 B2P_CUDA(cudaMalloc(&loc, ntt->local_n * sizeof(Fr)));
+                if (rank) B2P_CUDA(cudaMalloc(&outbuf, ntt->local_n * sizeof(Fr)));
+                else if (world > 1) B2P_CUDA(cudaMalloc(&hstage, (size_t)(world - 1) * share_cap() * sizeof(Fr)));
             }
             // Load the exchange kernels NOW (no-op launches).  CUDA loads a kernel at its first launch, and that load
             // can wait for kernels that are running -- such as a k_shard_wait spinning on a flag which only a
@@ -237,6 +252,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
             B2P_LAUNCH((k_shard_sum<Fp>), 1, 32, 0, 0, partials(mail), partials(mail), 1, 0, 0);
             B2P_LAUNCH((k_shard_gather<Fr>), 1, 32, 0, 0, (Fr*)nullptr, (const Fr*)nullptr, 0, 1, 0);
             B2P_LAUNCH((k_shard_scatter<Fr>), 1, 32, 0, 0, (Fr*)nullptr, (const Fr*)nullptr, 0, 1, 0);
+            B2P_LAUNCH((k_shard_interleave<Fr>), 1, 32, 0, 0, (Fr*)nullptr, (const Fr*)nullptr, 1u, 0, 0);
             B2P_CUDA(cudaDeviceSynchronize());
         } catch (...) {
             release();
@@ -245,15 +261,19 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         peer[rank][SH_MAIL] = mail;
         peer[rank][SH_STAGING] = staging;
         peer[rank][SH_XBUF] = xbuf;
+        peer[rank][SH_HSTAGE] = hstage;
     }
     void release() {
         if (mail) cudaFree(mail);
         if (staging) cudaFree(staging);
         if (xbuf) cudaFree(xbuf);
         if (loc) cudaFree(loc);
+        if (outbuf) cudaFree(outbuf);
+        if (hstage) cudaFree(hstage);
         if (h_err) cudaFreeHost(h_err);
         delete ntt;
-        mail = nullptr; staging = nullptr; xbuf = nullptr; loc = nullptr; h_err = nullptr; ntt = nullptr;
+        mail = nullptr; staging = nullptr; xbuf = nullptr; loc = nullptr; outbuf = nullptr; hstage = nullptr;
+        h_err = nullptr; ntt = nullptr;
     }
     ~ShardGroup() override {
         if (attached) attached->router = nullptr;
@@ -416,8 +436,16 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         const void* chunks[1 << NTT_SHARD_MAX_LOGG] = {nullptr};
         for (uint32_t g = 0; g < G; g++)
             chunks[g] = static_cast<Fr*>(peer[g][SH_XBUF]) + (size_t)(seq & 1) * ntt->local_n + (size_t)rank * ntt->chunk_len;
-        ntt->forward_combine(chunks, static_cast<Fr*>(peer[0][which]) + (size_t)rank * ntt->local_n, st);
+        // the exchange (peer LOADS of the chunks) writes this rank's block of the evaluations locally; from the other
+        // ranks it then travels to rank 0's buffer as ONE bulk copy (copy engine over NVLink: ~3x the bandwidth the
+        // combine kernel reached when its stores went to the peer directly, profiles/shard_trace_r2_*.txt)
+        Fr* dst0 = static_cast<Fr*>(peer[0][which]) + (size_t)rank * ntt->local_n;
+        ntt->forward_combine(chunks, rank ? outbuf : dst0, st);
         trace.mark("combine", st);
+        if (rank) {
+            B2P_CUDA(cudaMemcpyAsync(dst0, outbuf, ntt->local_n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            trace.mark("push", st);
+        }
         tell_rank0_done(seq, st);
     }
     // 4n evaluations in rank 0's h -> the first out_len coefficients, back in rank 0's h
@@ -436,14 +464,26 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         for (uint32_t g = 0; g < G; g++)
             chunks[g] = static_cast<Fr*>(peer[g][SH_XBUF]) + (size_t)(seq & 1) * ntt->local_n + (size_t)rank * ntt->chunk_len;
         trace.mark("inv-go", st);
-        ntt->inverse_split(h0 + (size_t)rank * ntt->local_n, chunks, st);
+        const Fr* block = h0 + (size_t)rank * ntt->local_n;
+        if (rank) {                 // pull this rank's block of the quotient's evaluations with one bulk copy
+            B2P_CUDA(cudaMemcpyAsync(outbuf, block, ntt->local_n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            block = outbuf;
+            trace.mark("pull", st);
+        }
+        ntt->inverse_split(block, chunks, st);
         trace.mark("split", st);
         xready_barrier(seq, st);     // every rank has read its block of h and delivered its chunks
         trace.mark("barrier", st);
         ntt->inverse_local(x, B2P_NTT_INVERSE | B2P_NTT_COSET, nullptr, st);
         trace.mark("local", st);
         const uint64_t cnt = out_len > rank ? (out_len - rank + G - 1) / G : 0;
-        if (cnt) B2P_LAUNCH((k_shard_scatter<Fr>), div_up(cnt, 256), 256, 0, st, h0, x, (uint64_t)rank, (uint64_t)G, cnt);
+        B2P_REQUIRE(cnt <= share_cap(), "shard group: more quotient coefficients than the staging area holds");
+        if (rank == 0) {            // own share: in place (local strided stores)
+            if (cnt) B2P_LAUNCH((k_shard_scatter<Fr>), div_up(cnt, 256), 256, 0, st, h0, x, (uint64_t)0, (uint64_t)G, cnt);
+        } else if (cnt) {           // the others': one contiguous bulk copy into rank 0's staging area
+            Fr* slot = static_cast<Fr*>(peer[0][SH_HSTAGE]) + (size_t)(rank - 1) * share_cap();
+            B2P_CUDA(cudaMemcpyAsync(slot, x, cnt * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        }
         trace.mark("scatter", st);
         tell_rank0_done(seq, st);
     }
@@ -460,6 +500,10 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
     void ntt_inverse(uint64_t out_len, cudaStream_t st) override {
         inverse_step(out_len, st);
         wait_ntt_done(st);
+        if (world > 1)
+            B2P_LAUNCH((k_shard_interleave<Fr>), div_up(out_len, 256), 256, 0, st, static_cast<Fr*>(peer[0][SH_H]), hstage,
+                       world, share_cap(), out_len);
+        trace.mark("interleave", st);
     }
 
     // ---- ranks > 0 ---------------------------------------------------------------------------------------------

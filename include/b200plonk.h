@@ -102,6 +102,13 @@ int b2p_srs_generate_unsafe_range(int curve, const void* tau, uint64_t first, ui
 int b2p_srs_generate_unsafe_strided(int curve, const void* tau, uint64_t first, uint64_t stride, uint64_t count,
                                     b2p_srs** out);
 
+/* kzg.ToLagrangeG1(srs.Pk.G1[:n]) (setup.go:124,138: pk.KzgLagrange of gnark's ProvingKey): the n Lagrange-basis
+ * points [L_j(tau)]_1 = (1/n) sum_i omega^(-ij) [tau^i]_1, computed on the GPU as an inverse transform over the group
+ * (XYZZ points, one launch per stage, point-by-twiddle multiplications in the butterflies) and written to the host as n
+ * G1Affine.  n a power of two <= the SRS size.  b2p_prove does not need it (see b2p_srs_load); it is for callers that
+ * keep gnark's own ProvingKey complete, e.g. the shim's fallback to plonk.Prove. */
+int b2p_srs_to_lagrange(b2p_srs* srs, uint64_t n, void* out_points);
+
 /* Copies canonical points [first, first+count) back to the host (G1Affine layout). */
 int b2p_srs_get_points(const b2p_srs* srs, uint64_t first, uint64_t count, void* out);
 uint64_t b2p_srs_size(const b2p_srs* srs);
@@ -158,7 +165,7 @@ int b2p_device_copy(void* d_dst, const void* d_src, uint64_t bytes);
  * connect (all ranks) -> b2p_prove on rank 0 / serve_proof elsewhere.  While attached the SRS handle serves
  * b2p_prove only (b2p_msm_g1 on it fails); attach(NULL, NULL) detaches; free the group before the handles it uses. */
 typedef struct b2p_shard_group b2p_shard_group;
-#define B2P_SHARD_HANDLES 8       /* shared pieces per rank: mailbox, staging, exchange buffer, el er eo ez h */
+#define B2P_SHARD_HANDLES 9       /* shared pieces per rank: mailbox, staging, exchange buffer, el er eo ez h, h staging */
 int b2p_shard_group_create(int curve, uint32_t world, uint32_t rank, uint64_t total_points, b2p_srs* shard,
                            uint64_t ntt_rows, b2p_shard_group** out);
 int b2p_shard_group_attach(b2p_shard_group* g, b2p_srs* prover_srs, b2p_circuit* circuit);

@@ -68,3 +68,42 @@ def test_decompress_signs_infinity_and_errors(gpu, curve):
     big[0] |= 0x80
     with pytest.raises(_lib.B200PlonkError, match="not reduced"):
         api.SRS.from_pk_bin(curve, (1).to_bytes(4, "big") + bytes(big), 1)
+
+
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+@pytest.mark.parametrize("n", (1, 2, 8, 64, 1024))
+def test_to_lagrange_known_tau(gpu, curve, n):
+    """b2p_srs_to_lagrange = kzg.ToLagrangeG1 (setup/setup.go:124,138) on a TestOnly SRS, where tau is known:
+    [L_j(tau)]_1 with L_j(tau) = (tau^n - 1) w^j / (n (tau - w^j)), computed with integers and one scalar
+    multiplication per point by the oracle."""
+    cv = po.CURVES[curve]
+    srs = api.SRS.unsafe(curve, n + 3, H.TAU)
+    got = srs.to_lagrange(n)
+    w = po.domain_generator(cv, n) if n > 1 else 1
+    tn = (pow(H.TAU, n, cv.r) - 1) % cv.r
+    ninv = pow(n, -1, cv.r)
+    for j in ([0, 1, n // 2, n - 1] if n > 8 else range(n)):
+        wj = pow(w, j, cv.r)
+        lj = tn * wj % cv.r * ninv % cv.r * pow((H.TAU - wj) % cv.r, -1, cv.r) % cv.r
+        assert got[j] == po.g1_mul(cv, cv.g1, lj), (n, j)
+    srs.free()
+
+
+def test_to_lagrange_on_the_real_ppot_points_commits_like_the_prover(gpu):
+    """On ceremony points (tau unknown) the Lagrange SRS is pinned through its purpose: MSM(Lagrange points, v) must be
+    the commitment the prover makes for the column v, i.e. MSM(canonical points, iNTT(v)) -- both sides on the oracle's
+    big integers from the GPU's table, and against b2p_msm_g1(B2P_BASIS_LAGRANGE)."""
+    name, curve, n = "PerpetualPowersOfTauBN254", "BN254", 128
+    cv = po.CURVES[curve]
+    pts = H.real_srs_points(name)[: n + 3]
+    srs = api.SRS.from_points(curve, pts)
+    lag = srs.to_lagrange(n)
+    v = H.scalars_uniform(cv.r, n, 5)
+    coeffs = po.intt(cv, v, po.domain_generator(cv, n))
+    want = po.msm_naive(cv, pts[:n], coeffs)
+    assert po.msm_naive(cv, lag, v) == want == srs.msm(v, basis=_lib.BASIS_LAGRANGE)
+    with pytest.raises(_lib.B200PlonkError, match="power of two"):
+        srs.to_lagrange(96)
+    with pytest.raises(_lib.B200PlonkError, match="power of two"):
+        srs.to_lagrange(256)              # more than the SRS holds
+    srs.free()
