@@ -37,14 +37,18 @@ if ROOT not in sys.path:
 METRIC = "plonk_proofs_per_sec"
 UNIT = "proofs/s"
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_msm_accumulate launch, from the ncu --set full capture
-# under profiles/ (per workload): the gather reads W = 13 table points per scalar, so ~13x the algorithmic bytes
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_msm_accumulate launch, from `ncu --set full` captures
+# (profiles/ncu_r1_full_summary.csv; the kernel is unchanged since), keyed by (curve, log2 rows): the gather reads W = 13
+# table points per scalar, so ~13x the algorithmic bytes.  A configuration nobody captured reports null and says so.
 ACCUM_DRAM_TRAFFIC = {("BN254", 20): 1_872_500_000}
-# mixed additions / s at which the IMAD pipe saturates: measured field multiplications / s (tools/microbench.cu,
-# profiles/microbench_r1.json: 6.68e10 BN254 Fp, 3.01e10 BLS12-381 Fp) / 9.4 multiplication-equivalents per XYZZ
-# mixed addition (6 products, 2 squarings at 0.94, one a*b - c*d with a single reduction at 1.5; SASS-counted)
-MADD_ROOFLINE = {"BN254": 7.11e9, "BLS12_381": 3.21e9}
-
+# The roof that binds the accumulation: the SM's multiplier pipe.  IMAD issues at 1.84e13 lanes/s on 148 SMs
+# (tools/microbench.cu, profiles/microbench_r2.json); a 32x32->64 product takes two such slots in whichever form ptxas
+# emits it (IMAD.WIDE.U32.X, measured at half the IMAD rate, or IMAD + IMAD.HI).  One XYZZ mixed addition executes
+# 6 products + 2 squarings + one a*b - c*d = 2 326 slots on BN254 (8 limbs: 256 / 203 / 384 per operation), 5 214 on
+# BLS12-381 (12 limbs: 576 / 447 / 864) -- SASS-counted, profiles/sass_counts_r2.json.
+IMAD_SLOTS_PER_S = 1.84e13
+MADD_SLOTS = {"BN254": 2326, "BLS12_381": 5214}
+MADD_ROOFLINE = {c: IMAD_SLOTS_PER_S / s for c, s in MADD_SLOTS.items()}
 
 # ---------------------------------------------------------------------------------------
 # pieces shared with tests/test_bench_host.py
@@ -407,22 +411,26 @@ def run_b200(args):
     accum_ms = stats["msm_accum_ms"] / msm_calls
     alg_bytes = msm_algorithmic_bytes(n + 2, curve)
     achieved = alg_bytes / (accum_ms * 1e-3) / 1e9
+    traffic = ACCUM_DRAM_TRAFFIC.get((curve, args.log2))
     roofline = {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": ACCUM_DRAM_TRAFFIC.get((curve, args.log2)),
+                "frac": achieved / hbm_peak, "traffic": traffic,
+                "traffic_source": ("ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                                   "(profiles/ncu_r1_full_summary.csv)" if traffic else
+                                   f"null: no ncu --set full capture exists for ({curve}, 2^{args.log2})"),
                 "peak_source": peak_src, "launch_ms": accum_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "measured_in": "the one-proof-at-a-time pass (CUDA events around every launch of the kernel)",
-                "note": "254-bit modular arithmetic makes this kernel INT32-multiplier-bound, not HBM-bound: ncu shows "
-                        "sm__pipe_fmaheavy_cycles_active at 91 % (DESIGN.md section 4); the honest roofline is "
-                        "msm.msm_g1_adds_per_sec against msm.madd_roofline_per_sec"}
-    # the roof that binds this kernel (SURVEY 8d asks for both fractions): G1 mixed additions / s against the rate at
-    # which the INT32 multiplier pipe saturates (MADD_ROOFLINE above, from the measured field-multiplication peak)
+                "note": "254/381-bit modular arithmetic makes this kernel multiplier-bound, not HBM-bound (ncu: "
+                        "sm__pipe_fmaheavy_cycles_active 85 %, DESIGN.md section 4); binding_roof is the roof that binds"}
+    # G1 mixed additions / s against the rate at which the multiplier pipe saturates (constants above)
     adds_per_sec = stats["msm_accum_adds"] / (stats["msm_accum_ms"] * 1e-3)
     if MADD_ROOFLINE.get(curve):
-        roofline["binding_roof"] = {"bound": "int32-multiplier", "achieved": adds_per_sec,
+        roofline["binding_roof"] = {"bound": "int32 multiplier pipe (fmaheavy)", "achieved": adds_per_sec,
                                     "peak": MADD_ROOFLINE[curve], "unit": "G1 mixed additions/s",
                                     "frac": adds_per_sec / MADD_ROOFLINE[curve],
-                                    "peak_source": "profiles/microbench_r1.json (field multiplications/s on all SMs) "
-                                                   "/ 9.4 multiplication-equivalents per XYZZ mixed addition"}
+                                    "peak_source": f"measured IMAD issue rate {IMAD_SLOTS_PER_S:.3g} slots/s (profiles/"
+                                                   f"microbench_r2.json) / {MADD_SLOTS[curve]} slots per mixed addition "
+                                                   "(SASS-counted, profiles/sass_counts_r2.json); ncu reports the same "
+                                                   "fraction as sm__pipe_fmaheavy_cycles_active"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
