@@ -38,7 +38,12 @@ namespace b2p {
 
 constexpr int SHARD_MAX_WORLD = 8;
 constexpr uint64_t SHARD_MAIL_FLAG_BYTES = 4096;     // flags first, the partial sums behind them
-constexpr unsigned long long SHARD_WAIT_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+// how long a kernel spins on a flag before it gives up and raises the error flag (B2P_SHARD_TIMEOUT_MS overrides: tests)
+inline unsigned long long shard_wait_timeout_ns() {
+    const char* e = getenv("B2P_SHARD_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 0;
+    return (ms > 0 ? (unsigned long long)ms : 20000ull) * 1000000ull;
+}
 
 struct ShardFlags {
     uint32_t ready[MSM_SLOTS];                        // on rank g > 0, written by rank 0: scalars of slot staged
@@ -78,12 +83,13 @@ static __global__ void k_shard_signal(ShardPeerFlags flags, int count, uint32_t 
     if ((int)threadIdx.x < count) *reinterpret_cast<volatile uint32_t*>(flags.p[threadIdx.x]) = value;
 }
 // thread t spins until flags[t * stride] reaches `value` (or the timeout sets *err)
-static __global__ void k_shard_wait(const uint32_t* flags, int count, int stride, uint32_t value, uint32_t* err) {
+static __global__ void k_shard_wait(const uint32_t* flags, int count, int stride, uint32_t value, uint32_t* err,
+                                    unsigned long long timeout_ns) {
     if ((int)threadIdx.x >= count) return;
     const volatile uint32_t* f = flags + (size_t)threadIdx.x * stride;
     const unsigned long long t0 = shard_now_ns();
     while (!shard_reached(*f, value)) {
-        if (shard_now_ns() - t0 > SHARD_WAIT_TIMEOUT_NS) { *err = 1; break; }
+        if (shard_now_ns() - t0 > timeout_ns) { *err = 1; break; }
         __nanosleep(200);
     }
     __threadfence_system();
@@ -127,6 +133,12 @@ __global__ void k_shard_scatter(Fr* __restrict__ dst, const Fr* __restrict__ src
     if (j < cnt) st_field(dst + first + j * stride, ld_field(src + j));
 }
 
+// plain copy kernel: stands in for cudaMemcpyAsync when all ranks share one device (see ShardGroup::bulk_copy)
+static __global__ void k_shard_copy(uint4* __restrict__ dst, const uint4* __restrict__ src, uint64_t n16) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 // rank 0, after the inverse transform: h[j G + g] = stage[(g - 1) cap + j] for g = 1 .. G-1 (the other ranks' cyclic
 // shares of the coefficients arrived as contiguous bulk copies; rank 0's own share is already in place)
 template <class Fr>
@@ -160,6 +172,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
     Srs<C>* attached = nullptr;           // rank 0: the proving key whose commitments are routed here
     uint64_t first = 0, count = 0;        // this rank's block of the total points
     uint32_t proof_no = 0, ntt_seq = 0;
+    unsigned long long timeout_ns = shard_wait_timeout_ns();
     bool connected = false, same_process = false;
 
     uint8_t* mail = nullptr;              // ShardFlags + partial sums, shared
@@ -247,12 +260,13 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
             ShardPeerFlags none{};
             ShardFlags* f = flags(mail);
             B2P_LAUNCH(k_shard_signal, 1, 32, 0, 0, none, 0, 0u);
-            B2P_LAUNCH(k_shard_wait, 1, 32, 0, 0, &f->ready[0], 0, 1, 0u, &f->error);
+            B2P_LAUNCH(k_shard_wait, 1, 32, 0, 0, &f->ready[0], 0, 1, 0u, &f->error, timeout_ns);
             B2P_LAUNCH((k_shard_post<Fp>), 1, 32, 0, 0, partials(mail), partials(mail), &f->done[0][0], 0, 0, 0u);
             B2P_LAUNCH((k_shard_sum<Fp>), 1, 32, 0, 0, partials(mail), partials(mail), 1, 0, 0);
             B2P_LAUNCH((k_shard_gather<Fr>), 1, 32, 0, 0, (Fr*)nullptr, (const Fr*)nullptr, 0, 1, 0);
             B2P_LAUNCH((k_shard_scatter<Fr>), 1, 32, 0, 0, (Fr*)nullptr, (const Fr*)nullptr, 0, 1, 0);
             B2P_LAUNCH((k_shard_interleave<Fr>), 1, 32, 0, 0, (Fr*)nullptr, (const Fr*)nullptr, 1u, 0, 0);
+            B2P_LAUNCH(k_shard_copy, 1, 32, 0, 0, (uint4*)nullptr, (const uint4*)nullptr, (uint64_t)0);
             B2P_CUDA(cudaDeviceSynchronize());
         } catch (...) {
             release();
@@ -353,6 +367,18 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         connected = same_process = true;
     }
 
+    // Device-to-device copy on `st`.  Between GPUs: the copy engine (one bulk transfer over NVLink).  With every rank
+    // in ONE process on one device (tests) the ranks' copies would share the device's copy-engine queues, where a copy
+    // whose stream is still waiting on a flag blocks the copies queued behind it -- among them, possibly, the one that
+    // would let the flag be raised; a copy kernel has no such queue.
+    void bulk_copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+        if (!bytes) return;
+        if (same_process) {
+            B2P_LAUNCH(k_shard_copy, 592, 256, 0, st, static_cast<uint4*>(dst), static_cast<const uint4*>(src), (uint64_t)(bytes / 16));
+        } else {
+            B2P_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+        }
+    }
     void slice(uint64_t n, uint64_t* lo, uint64_t* cnt) const {
         *lo = first < n ? first : n;
         const uint64_t hi = first + count < n ? first + count : n;
@@ -379,7 +405,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         const Fr* sc = static_cast<const Fr*>(d_scalars);
         if (world > 1) {
             Fr* stage = staging + (size_t)slot * total;
-            if (n) B2P_CUDA(cudaMemcpyAsync(stage, sc, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            bulk_copy(stage, sc, n * sizeof(Fr), st);
             ShardPeerFlags pf;
             for (uint32_t g = 1; g < world; g++) pf.p[g - 1] = &flags(peer[g][SH_MAIL])->ready[slot];
             B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, (int)world - 1, proof_no);
@@ -395,7 +421,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         if (world > 1) {
             ShardFlags* f = flags(mail);
             for (uint32_t g = 1; g < world; g++)
-                B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &f->done[g][first_slot], cnt, 1, proof_no, &f->error);
+                B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &f->done[g][first_slot], cnt, 1, proof_no, &f->error, timeout_ns);
             B2P_LAUNCH((k_shard_sum<Fp>), 1, 32, 0, st, shard->msm.result.p, partials(mail), (int)world, first_slot, cnt);
             B2P_CUDA(cudaMemcpyAsync(h_err, &f->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
@@ -413,7 +439,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         ShardPeerFlags pf;
         for (uint32_t g = 0; g < world; g++) pf.p[g] = &flags(peer[g][SH_MAIL])->xready[rank];
         B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, (int)world, seq);
-        B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &flags(mail)->xready[0], (int)world, 1, seq, &flags(mail)->error);
+        B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &flags(mail)->xready[0], (int)world, 1, seq, &flags(mail)->error, timeout_ns);
     }
     void tell_rank0_done(uint32_t seq, cudaStream_t st) {
         if (rank == 0) return;
@@ -443,7 +469,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         ntt->forward_combine(chunks, rank ? outbuf : dst0, st);
         trace.mark("combine", st);
         if (rank) {
-            B2P_CUDA(cudaMemcpyAsync(dst0, outbuf, ntt->local_n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            bulk_copy(dst0, outbuf, ntt->local_n * sizeof(Fr), st);
             trace.mark("push", st);
         }
         tell_rank0_done(seq, st);
@@ -458,7 +484,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
             for (uint32_t g = 1; g < G; g++) pf.p[g - 1] = &flags(peer[g][SH_MAIL])->ntt_go;
             B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, (int)G - 1, seq);
         } else {
-            B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &flags(mail)->ntt_go, 1, 1, seq, &flags(mail)->error);
+            B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &flags(mail)->ntt_go, 1, 1, seq, &flags(mail)->error, timeout_ns);
         }
         void* chunks[1 << NTT_SHARD_MAX_LOGG] = {nullptr};
         for (uint32_t g = 0; g < G; g++)
@@ -466,7 +492,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         trace.mark("inv-go", st);
         const Fr* block = h0 + (size_t)rank * ntt->local_n;
         if (rank) {                 // pull this rank's block of the quotient's evaluations with one bulk copy
-            B2P_CUDA(cudaMemcpyAsync(outbuf, block, ntt->local_n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            bulk_copy(outbuf, block, ntt->local_n * sizeof(Fr), st);
             block = outbuf;
             trace.mark("pull", st);
         }
@@ -482,14 +508,14 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
             if (cnt) B2P_LAUNCH((k_shard_scatter<Fr>), div_up(cnt, 256), 256, 0, st, h0, x, (uint64_t)0, (uint64_t)G, cnt);
         } else if (cnt) {           // the others': one contiguous bulk copy into rank 0's staging area
             Fr* slot = static_cast<Fr*>(peer[0][SH_HSTAGE]) + (size_t)(rank - 1) * share_cap();
-            B2P_CUDA(cudaMemcpyAsync(slot, x, cnt * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            bulk_copy(slot, x, cnt * sizeof(Fr), st);
         }
         trace.mark("scatter", st);
         tell_rank0_done(seq, st);
     }
     void wait_ntt_done(cudaStream_t st) {      // rank 0: every rank's part of transform ntt_seq has landed here
         ShardFlags* f = flags(mail);
-        if (world > 1) B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &f->ntt_done[1], (int)world - 1, 1, ntt_seq, &f->error);
+        if (world > 1) B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &f->ntt_done[1], (int)world - 1, 1, ntt_seq, &f->error, timeout_ns);
         trace.mark("wait-done", st);
     }
     // CommitRouter (rank 0)
@@ -527,7 +553,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
                 const int slot = s.b;
                 uint64_t lo, cnt;
                 slice(n + s.a, &lo, &cnt);
-                B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &mine->ready[slot], 1, 1, proof_no, &mine->error);
+                B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &mine->ready[slot], 1, 1, proof_no, &mine->error, timeout_ns);
                 shard->msm.run_async(stage_of(slot) + lo, cnt, true, st, slot);
             } else {
                 const int first_slot = s.a, cnt = -s.b;

@@ -96,6 +96,58 @@ def test_sharded_commitments_on_one_device_equal_single_gpu_proof(gpu, curve, lo
     assert out.returncode == 0 and "SHARD_GROUP_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
 
 
+NO_SERVER = r"""
+import ctypes as C, sys, time
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from algoplonk_b200 import _lib, api, frontend as fe, sharded
+_lib.init(0)
+lib = _lib.load()
+cs, values = fe.squaring_chain("BN254", 9, x0=5)
+cc = api.Compile(cs, "BN254", api.SetupName.TestOnlyBN254)
+n = cc.trace.n
+L, R, O = fe.solve_lro(cs, values, n)
+cols = [api.fr_to_mont_bytes("BN254", c) for c in (L, R, O)]
+bl = api.fr_to_mont_bytes("BN254", list(range(1, 10)))
+want = cc.prove_raw(*cols, bl).raw
+shards = [sharded.ShardedSRS.unsafe("BN254", n + 3, r, 2) for r in range(2)]
+groups = []
+for r in range(2):
+    h = C.c_void_p()
+    _lib.check(lib.b2p_shard_group_create(0, 2, r, n + 3, shards[r].handle, 0, C.byref(h)))
+    groups.append(h.value)
+_lib.check(lib.b2p_shard_group_attach(groups[0], cc.srs.handle, cc.handle))
+_lib.check(lib.b2p_shard_group_connect_local((C.c_void_p * 2)(*groups), 2))
+t0 = time.time()
+try:
+    cc.prove_raw(*cols, bl)                    # rank 1 never serves
+    raise SystemExit("a proof without its peer did not fail")
+except _lib.B200PlonkError as e:
+    assert "timed out waiting for a peer" in str(e), str(e)
+assert time.time() - t0 < 15, "the wait did not time out promptly"
+# the group is usable again: serve this time (the abandoned proof's number is skipped on the serving side too)
+import threading
+def serve():
+    _lib.check(lib.b2p_shard_group_serve_proof(groups[1], n))     # proof number 1: its flags are stale, returns at once or times out
+try:
+    serve()
+except _lib.B200PlonkError:
+    pass
+_lib.check(lib.b2p_shard_group_attach(groups[0], None, None))
+assert cc.prove_raw(*cols, bl).raw == want
+print("NO_SERVER_OK")
+"""
+
+
+def test_a_missing_rank_times_out_instead_of_hanging(gpu, tmp_path):
+    """Rank 0 proves, nobody serves: the kernels spinning on the peers' flags give up after the timeout
+    (B2P_SHARD_TIMEOUT_MS, 20 s by default) and b2p_prove returns B2P_ERR_INTERNAL -- no hung GPU."""
+    script = tmp_path / "no_server.py"
+    script.write_text(NO_SERVER.format(root=ROOT))
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER", B2P_SHARD_TIMEOUT_MS="1500")
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and "NO_SERVER_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
+
+
 def test_shard_group_argument_errors(gpu):
     lib = _lib.load()
     whole = api.SRS.unsafe("BN254", 67, H.TAU)
