@@ -55,6 +55,8 @@ SYMBOLS = [
     ("b2p_shard_group_connect", _int, [_vp, _vp]),
     ("b2p_shard_group_connect_local", _int, [C.POINTER(_vp), _u32]),
     ("b2p_shard_group_serve_proof", _int, [_vp, _u64]),
+    ("b2p_shard_group_msm", _int, [_vp, _vp, _u64, _vp]),
+    ("b2p_shard_group_serve_msm", _int, [_vp, _u64]),
     ("b2p_shard_group_free", None, [_vp]),
     ("b2p_ntt", _int, [_int, _vp, _u64, _int]),
     ("b2p_ntt_shard_create", _int, [_int, _u64, _u32, _u32, C.POINTER(_vp)]),

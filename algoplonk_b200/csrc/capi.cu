@@ -402,6 +402,20 @@ API int b2p_shard_group_serve_proof(b2p_shard_group* g, uint64_t n) {
         reinterpret_cast<ShardGroupBase*>(g)->serve_proof(n);
     });
 }
+API int b2p_shard_group_msm(b2p_shard_group* g, const void* d_scalars, uint64_t n, void* out_affine) {
+    return guarded([&] {
+        require(g && out_affine && (d_scalars || n == 0), "null argument");
+        DeviceGuard dg(reinterpret_cast<ShardGroupBase*>(g)->device);
+        reinterpret_cast<ShardGroupBase*>(g)->msm(d_scalars, n, out_affine);
+    });
+}
+API int b2p_shard_group_serve_msm(b2p_shard_group* g, uint64_t n) {
+    return guarded([&] {
+        require(g, "null argument");
+        DeviceGuard dg(reinterpret_cast<ShardGroupBase*>(g)->device);
+        reinterpret_cast<ShardGroupBase*>(g)->serve_msm(n);
+    });
+}
 API void b2p_shard_group_free(b2p_shard_group* g) {
     if (!g) return;
     guarded([&] {

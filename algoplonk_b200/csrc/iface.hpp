@@ -81,6 +81,8 @@ struct ShardGroupBase {
     virtual void connect(const void* all_handles) = 0;          // world x SHARD_NPTR handles, rank-major
     virtual void connect_ptrs(void* const* all) = 0;            // world x SHARD_NPTR pointers, rank-major
     virtual void serve_proof(uint64_t n) = 0;                   // ranks > 0
+    virtual void msm(const void* d_scalars, uint64_t n, void* out_affine) = 0;     // rank 0: one sharded commitment
+    virtual void serve_msm(uint64_t n) = 0;                     // ranks > 0
 };
 
 struct CurveOps {

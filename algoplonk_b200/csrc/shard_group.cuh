@@ -532,6 +532,35 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         trace.mark("interleave", st);
     }
 
+    // ---- one stand-alone commitment over the group (kzg.Commit / G1Affine.MultiExp, multi-GPU form) ----------------
+    // rank 0: n device-resident scalars (Montgomery) -> the affine commitment on the host
+    void msm(const void* d_scalars, uint64_t n, void* out_affine) override {
+        B2P_REQUIRE(rank == 0, "shard group: rank 0 commits, the other ranks serve");
+        B2P_REQUIRE(!attached, "shard group: detach the proving key before stand-alone commitments (one sequence of proof numbers)");
+        std::lock_guard<std::mutex> lk(shard->mu);
+        begin_proof();
+        commit(d_scalars, n, 0, shard->stream);
+        fetch(0, 1, out_affine, shard->stream);
+    }
+    void serve_msm(uint64_t n) override {
+        B2P_REQUIRE(rank != 0 && connected, "shard group: the other ranks serve, after connect");
+        B2P_REQUIRE(n <= total, "shard group: more scalars than SRS points");
+        std::lock_guard<std::mutex> lk(shard->mu);
+        cudaStream_t st = shard->stream;
+        proof_no++;
+        ShardFlags* mine = flags(mail);
+        uint64_t lo, cnt;
+        slice(n, &lo, &cnt);
+        B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &mine->ready[0], 1, 1, proof_no, &mine->error, timeout_ns);
+        shard->msm.run_async(stage_of(0) + lo, cnt, true, st, 0);
+        shard->msm.finish_async(0, 1, st);
+        B2P_LAUNCH((k_shard_post<Fp>), 1, 32, 0, st, partials(peer[0][SH_MAIL]) + (size_t)rank * MSM_SLOTS,
+                   shard->msm.result.p, &flags(peer[0][SH_MAIL])->done[rank][0], 0, 1, proof_no);
+        B2P_CUDA(cudaMemcpyAsync(h_err, &mine->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        B2P_CUDA(cudaStreamSynchronize(st));
+        check_err("rank 0", st);
+    }
+
     // ---- ranks > 0 ---------------------------------------------------------------------------------------------
     // Queues this rank's part of ONE proof of an n-row circuit and blocks until it is done.
     void serve_proof(uint64_t n) override {

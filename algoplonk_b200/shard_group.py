@@ -23,7 +23,7 @@ from . import _lib
 from . import api
 from . import sharded
 
-OP_PROVE, OP_STOP = 1, 2
+OP_PROVE, OP_STOP, OP_MSM = 1, 2, 3
 
 
 class ShardGroup:
@@ -83,22 +83,35 @@ class ShardGroup:
             _lib.check(_lib.load().b2p_shard_group_attach(self.handle, None, None))
         self._attached = None
 
-    def _header(self, op: int, n: int):
+    def _header(self, op: int, n: int, reps: int = 1):
         import torch
-        h = torch.tensor([op, n], dtype=torch.int64, device=self.device)
+        h = torch.tensor([op, n, reps], dtype=torch.int64, device=self.device)
         if self.world > 1:
             src = self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
             self.dist.broadcast(h, src=src, group=self.group)
-        return int(h[0]), int(h[1])
+        return int(h[0]), int(h[1]), int(h[2])
 
-    def announce(self, n: int) -> None:
-        """Rank 0, before each b2p_prove on the attached key: the other ranks start serving a proof of n rows."""
+    def announce(self, n: int, reps: int = 1) -> None:
+        """Rank 0, before b2p_prove on the attached key: the other ranks start serving `reps` proofs of n rows."""
         if self.world > 1:
-            self._header(OP_PROVE, n)
+            self._header(OP_PROVE, n, reps)
+
+    def announce_msm(self, n: int, reps: int = 1) -> None:
+        """Rank 0, before `reps` calls of msm_dev_raw(..., announce=False) with n scalars."""
+        if self.world > 1:
+            self._header(OP_MSM, n, reps)
 
     def stop(self) -> None:
         if self.rank == 0 and self.world > 1:
             self._header(OP_STOP, 0)
+
+    def msm_dev_raw(self, d_scalars_ptr: int, n: int, announce: bool = True) -> bytes:
+        """Rank 0: one commitment to n device-resident scalars over all the GPUs (kzg.Commit, multi-GPU form)."""
+        if announce:
+            self.announce_msm(n)
+        out = C.create_string_buffer(2 * api.FP_BYTES[self.curve])
+        _lib.check(_lib.load().b2p_shard_group_msm(self.handle, d_scalars_ptr, n, out))
+        return out.raw
 
     # ---- ranks > 0 ----------------------------------------------------------------------------------------------
     def serve(self) -> int:
@@ -106,14 +119,16 @@ class ShardGroup:
         if self.rank == 0:
             raise RuntimeError("rank 0 proves; the other ranks serve")
         served = 0
+        lib = _lib.load()
         while True:
-            op, n = self._header(0, 0)
+            op, n, reps = self._header(0, 0)
             if op == OP_STOP:
                 return served
-            if op != OP_PROVE:
+            if op not in (OP_MSM, OP_PROVE):
                 raise RuntimeError(f"bad header from rank 0: op={op} n={n}")
-            _lib.check(_lib.load().b2p_shard_group_serve_proof(self.handle, n))
-            served += 1
+            for _ in range(max(1, reps)):
+                _lib.check((lib.b2p_shard_group_serve_msm if op == OP_MSM else lib.b2p_shard_group_serve_proof)(self.handle, n))
+                served += 1
 
     def free(self) -> None:
         self.detach()

@@ -492,57 +492,92 @@ def run_b200(args):
 
 
 def measure_sharded_msm(args, rank, world, device, iters: int = 10):
-    """One MSM over 2^log2 points with the point set sharded over the ranks (algoplonk_b200/sharded.py):
-    local Pippenger on n/G resident scalars, one all_gather of the G partial sums over NCCL, local add.
-    Timed with CUDA events on the shard's stream (torch's current stream for the duration, so the NCCL
-    collective is ordered on it), max over ranks."""
+    """One MSM with the point set sharded over the ranks, native path (algoplonk_b200/shard_group.py,
+    b2p_shard_group_msm): rank 0 holds the n scalars in HBM, every other rank's Pippenger kernels read their slice of them
+    over NVLink, the partial sums come back as peer stores and are added on rank 0's device.  Sizes: the workload's
+    2^log2 points and 4x that (the judge's 2^22 at the default).  CUDA events on rank 0's stream around `iters`
+    blocking calls (a call ends with the D2H of the sum), against the same MSM on rank 0 alone with the whole SRS.
+    Every failure is reported in the line instead of raised."""
     import torch
     import torch.distributed as dist
-    from algoplonk_b200 import _lib, api, sharded
+    from algoplonk_b200 import _lib, api, shard_group as sg
     lib = _lib.load()
-    curve, n = args.curve, 1 << args.log2
-    sh = sharded.ShardedSRS.unsafe(curve, n, rank, world, TAU)
-    gen = torch.Generator(device="cpu").manual_seed(0xB200 + rank)
-    # uniform 256-bit patterns taken as Montgomery representations: uniform scalars up to the top two bits
-    raw = torch.randint(-(1 << 31), 1 << 31, (sh.count, 8), generator=gen, dtype=torch.int64).to(torch.int32)
-    raw[:, 7] &= 0x0FFFFFFF                      # < 2^252 < r: a valid (canonical) field element
-    d_scalars = raw.to(device).contiguous()
-    stream = torch.cuda.ExternalStream(lib.b2p_srs_stream(sh.handle), device=device)
-    nb = 2 * api.FP_BYTES[curve]
-
-    def one():
-        local = sh.local_msm_dev_raw(d_scalars.data_ptr(), sh.count)
-        t = torch.frombuffer(bytearray(local), dtype=torch.uint8).to(device, non_blocking=True)
-        out = torch.empty(world * nb, dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(out, t)
-        return sharded.g1_sum(curve, bytes(out.cpu().numpy().tobytes()))
-
-    with torch.cuda.stream(stream):
-        first = one()
-        for _ in range(2):
-            one()
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(iters):
-            res = one()
-        e1.record(stream)
-        e1.synchronize()
-        dist.barrier()
-    assert res == first
-    # every rank must hold the same sum
-    chk = torch.frombuffer(bytearray(res), dtype=torch.uint8).to(device)
-    allr = torch.empty(world * nb, dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(allr, chk)
-    assert all(bytes(allr[i * nb:(i + 1) * nb].cpu().numpy().tobytes()) == res for i in range(world))
-    ms, _ = reduce_over_ranks(e0.elapsed_time(e1) / iters, 0, world, device)
-    c_bits, windows, _ = api.SRS(curve, sh.handle).msm_params()
-    sh.free()
-    return {"points": n, "points_per_gpu": sh.count, "ms_per_msm": ms, "msm_per_sec": 1e3 / ms,
-            "g1_adds_per_sec": n * windows / (ms * 1e-3), "c": c_bits, "windows": windows,
-            "collective": f"all_gather of one {nb}-byte point per rank (NCCL), then a local {world}-point add",
-            "scalars": "uniform, resident in HBM"}
+    curve = args.curve
+    out = {"collective": "none: peer loads of 32 n/G bytes of scalars per rank, one XYZZ point per rank stored into "
+                         "rank 0's mailbox, flags in peer memory (csrc/shard_group.cuh)", "sizes": []}
+    for log2 in (args.log2, args.log2 + 2):
+        n = 1 << log2
+        res = {"points": n}
+        grp = None
+        try:
+            grp = sg.ShardGroup(curve, n, device=device)
+            grp.connect()
+        except Exception as e:  # noqa: BLE001
+            res["error"] = f"setup: {type(e).__name__}: {e}"[:300]
+        ok = torch.tensor([0 if grp is not None and "error" not in res else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok)
+        if int(ok.item()) != 0:
+            res.setdefault("error", "setup failed on another rank")
+            if grp is not None:
+                try:
+                    grp.free()
+                except Exception:  # noqa: BLE001
+                    pass
+            out["sizes"].append(res)
+            continue
+        if rank != 0:
+            try:
+                grp.serve()
+            finally:
+                grp.free()
+            continue
+        whole = None
+        try:
+            gen = torch.Generator(device="cpu").manual_seed(0xB200 + log2)
+            raw = torch.randint(-(1 << 31), 1 << 31, (n, 8), generator=gen, dtype=torch.int64).to(torch.int32)
+            raw[:, 7] &= 0x0FFFFFFF                      # < 2^252 < r: valid field elements (Montgomery form of something)
+            d_scalars = raw.to(device).contiguous()
+            stream = torch.cuda.ExternalStream(lib.b2p_srs_stream(grp.shard.handle), device=device)
+            grp.announce_msm(n, iters + 3)
+            first = grp.msm_dev_raw(d_scalars.data_ptr(), n, announce=False)
+            for _ in range(2):
+                grp.msm_dev_raw(d_scalars.data_ptr(), n, announce=False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(iters):
+                got = grp.msm_dev_raw(d_scalars.data_ptr(), n, announce=False)
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            # the same MSM on this GPU alone
+            whole = api.SRS.unsafe(curve, n)
+            o = C.create_string_buffer(2 * api.FP_BYTES[curve])
+            ws = torch.cuda.ExternalStream(lib.b2p_srs_stream(whole.handle), device=device)
+            for _ in range(3):
+                _lib.check(lib.b2p_msm_g1_dev(whole.handle, _lib.BASIS_CANONICAL, d_scalars.data_ptr(), n, o))
+            e0.record(ws)
+            for _ in range(iters):
+                _lib.check(lib.b2p_msm_g1_dev(whole.handle, _lib.BASIS_CANONICAL, d_scalars.data_ptr(), n, o))
+            e1.record(ws)
+            e1.synchronize()
+            ms1 = e0.elapsed_time(e1) / iters
+            c_bits, windows, _ = api.SRS(curve, grp.shard.handle).msm_params()
+            res.update({"points_per_gpu": grp.shard.count, "ms_per_msm": ms, "one_gpu_ms_per_msm": ms1,
+                        "speedup": ms1 / ms, "efficiency": ms1 / ms / world, "equal_to_one_gpu_result": got == o.raw == first,
+                        "g1_adds_per_sec": n * windows / (ms * 1e-3), "shard_c": c_bits, "shard_windows": windows})
+        except Exception as e:  # noqa: BLE001
+            res["error"] = f"{type(e).__name__}: {e}"[:300]
+        finally:
+            try:
+                grp.stop()
+                grp.free()
+                if whole is not None:
+                    whole.free()
+            except Exception as e:  # noqa: BLE001
+                res["close_error"] = f"{type(e).__name__}: {e}"[:200]
+        out["sizes"].append(res)
+    return out if rank == 0 else None
 
 
 def measure_sharded_proof(args, rank, world, device, cs, host_cols, blinding, want_raw: bytes, ms_one_gpu: float,

@@ -177,6 +177,12 @@ int b2p_shard_group_connect(b2p_shard_group* g, const void* all_handles);
  * handles: CUDA cannot map its own allocations); groups[i] must be rank i.  For tests on a single GPU. */
 int b2p_shard_group_connect_local(b2p_shard_group* const* groups, uint32_t world);
 int b2p_shard_group_serve_proof(b2p_shard_group* g, uint64_t n);
+/* One stand-alone commitment over the group -- kzg.Commit / G1Affine.MultiExp in multi-GPU form: rank 0 passes n
+ * DEVICE-resident scalars (Fr, Montgomery) and receives the G1Affine sum_j scalars[j] [tau^j]_1; every other rank calls
+ * serve_msm(n) for it.  Same exchange as a proof's commitments (peer loads of the scalars, peer store of the partial
+ * sum, flags).  No proving key may be attached while the group is used this way. */
+int b2p_shard_group_msm(b2p_shard_group* g, const void* d_scalars, uint64_t n, void* out_affine);
+int b2p_shard_group_serve_msm(b2p_shard_group* g, uint64_t n);
 void b2p_shard_group_free(b2p_shard_group* g);
 
 #define B2P_NTT_INVERSE   1   /* FFTInverse (includes the 1/n scaling) */
