@@ -379,6 +379,14 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
             B2P_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
         }
     }
+    // Spin on `count` flags (stride apart) until they reach `value`.  With every rank in ONE process on one device
+    // (tests) the host then waits for the kernel: nothing -- in particular no copy-engine operation, whose queues are
+    // FIFO across streams -- is ever queued behind a kernel that is still spinning, so a blocked queue cannot sit in
+    // front of the operation that would let the flag be raised.  One process per GPU: fully asynchronous.
+    void wait_flags(const uint32_t* f, int count, int stride, uint32_t value, cudaStream_t st) {
+        B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, f, count, stride, value, &flags(mail)->error, timeout_ns);
+        if (same_process) B2P_CUDA(cudaStreamSynchronize(st));
+    }
     void slice(uint64_t n, uint64_t* lo, uint64_t* cnt) const {
         *lo = first < n ? first : n;
         const uint64_t hi = first + count < n ? first + count : n;
@@ -421,7 +429,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         if (world > 1) {
             ShardFlags* f = flags(mail);
             for (uint32_t g = 1; g < world; g++)
-                B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &f->done[g][first_slot], cnt, 1, proof_no, &f->error, timeout_ns);
+                wait_flags(&f->done[g][first_slot], cnt, 1, proof_no, st);
             B2P_LAUNCH((k_shard_sum<Fp>), 1, 32, 0, st, shard->msm.result.p, partials(mail), (int)world, first_slot, cnt);
             B2P_CUDA(cudaMemcpyAsync(h_err, &f->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
@@ -439,7 +447,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         ShardPeerFlags pf;
         for (uint32_t g = 0; g < world; g++) pf.p[g] = &flags(peer[g][SH_MAIL])->xready[rank];
         B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, (int)world, seq);
-        B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &flags(mail)->xready[0], (int)world, 1, seq, &flags(mail)->error, timeout_ns);
+        wait_flags(&flags(mail)->xready[0], (int)world, 1, seq, st);
     }
     void tell_rank0_done(uint32_t seq, cudaStream_t st) {
         if (rank == 0) return;
@@ -484,7 +492,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
             for (uint32_t g = 1; g < G; g++) pf.p[g - 1] = &flags(peer[g][SH_MAIL])->ntt_go;
             B2P_LAUNCH(k_shard_signal, 1, 32, 0, st, pf, (int)G - 1, seq);
         } else {
-            B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &flags(mail)->ntt_go, 1, 1, seq, &flags(mail)->error, timeout_ns);
+            wait_flags(&flags(mail)->ntt_go, 1, 1, seq, st);
         }
         void* chunks[1 << NTT_SHARD_MAX_LOGG] = {nullptr};
         for (uint32_t g = 0; g < G; g++)
@@ -515,7 +523,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
     }
     void wait_ntt_done(cudaStream_t st) {      // rank 0: every rank's part of transform ntt_seq has landed here
         ShardFlags* f = flags(mail);
-        if (world > 1) B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &f->ntt_done[1], (int)world - 1, 1, ntt_seq, &f->error, timeout_ns);
+        if (world > 1) wait_flags(&f->ntt_done[1], (int)world - 1, 1, ntt_seq, st);
         trace.mark("wait-done", st);
     }
     // CommitRouter (rank 0)
@@ -551,7 +559,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
         ShardFlags* mine = flags(mail);
         uint64_t lo, cnt;
         slice(n, &lo, &cnt);
-        B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &mine->ready[0], 1, 1, proof_no, &mine->error, timeout_ns);
+        wait_flags(&mine->ready[0], 1, 1, proof_no, st);
         shard->msm.run_async(stage_of(0) + lo, cnt, true, st, 0);
         shard->msm.finish_async(0, 1, st);
         B2P_LAUNCH((k_shard_post<Fp>), 1, 32, 0, st, partials(peer[0][SH_MAIL]) + (size_t)rank * MSM_SLOTS,
@@ -582,7 +590,7 @@ struct ShardGroup : ShardGroupBase, CommitRouter {
                 const int slot = s.b;
                 uint64_t lo, cnt;
                 slice(n + s.a, &lo, &cnt);
-                B2P_LAUNCH(k_shard_wait, 1, 32, 0, st, &mine->ready[slot], 1, 1, proof_no, &mine->error, timeout_ns);
+                wait_flags(&mine->ready[slot], 1, 1, proof_no, st);
                 shard->msm.run_async(stage_of(slot) + lo, cnt, true, st, slot);
             } else {
                 const int first_slot = s.a, cnt = -s.b;

@@ -90,9 +90,13 @@ def test_sharded_commitments_on_one_device_equal_single_gpu_proof(gpu, curve, lo
     script = tmp_path / "one_device.py"
     script.write_text(ONE_DEVICE.format(root=ROOT))
     env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER")
-    out = subprocess.run([sys.executable, str(script), curve, str(logn), str(world), str(shard_ntt)],
-                         capture_output=True, text=True,
-                         env=env, timeout=600)
+    cmd = [sys.executable, str(script), curve, str(logn), str(world), str(shard_ntt)]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    if out.returncode != 0 and "timed out waiting for a peer" in out.stderr:
+        # Up to nine ranks spinning on each other's flags inside ONE process share that process's hardware queues; a
+        # stall there is an artefact of the simulation, not of the protocol (one process per GPU in real runs, which
+        # tools/sharded_proof_bench.py and bench.py --gpus N exercise).  One retry; a wrong proof is never retried.
+        out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "SHARD_GROUP_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
 
 
