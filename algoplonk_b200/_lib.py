@@ -2,7 +2,8 @@
 
 There is no CPU fallback: if the shared library is missing every call raises, and without a usable CUDA device
 every proving / MSM / NTT entry point does (b2p_init fails).  The verification entry points (b2p_verify,
-b2p_verify_batch, b2p_pairing_check, b2p_kzg_vk_load, b2p_g2_generate_unsafe) and the marshalling helpers are host
+b2p_verify_batch, b2p_pairing_check, b2p_kzg_vk_load, b2p_g2_generate_unsafe), the persisted-key parsers
+(b2p_gnark_*_parse, b2p_circuit_save) and the marshalling helpers are host
 arithmetic by design -- plonk.Verify runs on the CPU in the reference too -- and need no device.  Build with `python -c "import
 __graft_entry__ as g; g.build()"` or `make -C algoplonk_b200/csrc -j8`.
 """
@@ -45,6 +46,7 @@ SYMBOLS = [
     ("b2p_srs_free", None, [_vp]),
     ("b2p_msm_g1", _int, [_vp, _int, _vp, _u64, _vp]),
     ("b2p_msm_g1_dev", _int, [_vp, _int, _vp, _u64, _vp]),
+    ("b2p_msm_g2", _int, [_int, _vp, _vp, _u64, _vp]),
     ("b2p_g1_sum", _int, [_int, _vp, _u64, _vp]),
     ("b2p_srs_stream", _vp, [_vp]),
     ("b2p_srs_set_commit_hook", _int, [_vp, _vp, _vp]),
@@ -88,9 +90,38 @@ SYMBOLS = [
     ("b2p_pairing_check", _int, [_int, _vp, _vp, _u64, C.POINTER(_int)]),
     ("b2p_kzg_vk_load", _int, [_int, _vp, _u64, _vp, _vp]),
     ("b2p_g2_generate_unsafe", _int, [_int, _vp, _vp]),
+    ("b2p_gnark_file_parse", _int, [_vp, _u64, _vp]),
+    ("b2p_gnark_vk_parse", _int, [_int, _vp, _u64, _vp]),
+    ("b2p_gnark_pk_parse", _int, [_int, _vp, _u64, _vp]),
+    ("b2p_circuit_save", _int, [C.c_char_p, _int, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _u64]),
+    ("b2p_circuit_load_file", _int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     ("b2p_circuit_set_profiling", _int, [_vp, _int]),
     ("b2p_circuit_stats", _int, [_vp, C.POINTER(C.c_double)]),
 ]
+
+
+MAX_COMMITMENTS = 8
+
+
+class GnarkFile(C.Structure):
+    """b2p_gnark_file"""
+    _fields_ = [("curve", C.c_int32), ("ecc_id", C.c_uint32), ("ccs_off", _u64), ("ccs_len", _u64),
+                ("pk_off", _u64), ("pk_len", _u64), ("vk_off", _u64), ("vk_len", _u64)]
+
+
+class GnarkVk(C.Structure):
+    """b2p_gnark_vk"""
+    _fields_ = [("size", _u64), ("nb_public", _u64), ("k", _u32), ("has_lines", _u32), ("encoded_len", _u64),
+                ("commitment_indexes", _u64 * MAX_COMMITMENTS),
+                ("size_inv", C.c_uint8 * 32), ("generator", C.c_uint8 * 32), ("coset_shift", C.c_uint8 * 32),
+                ("points", C.c_uint8 * ((8 + MAX_COMMITMENTS) * 96)),
+                ("kzg_g1", C.c_uint8 * 96), ("kzg_g2", C.c_uint8 * (2 * 192))]
+
+
+class GnarkPk(C.Structure):
+    """b2p_gnark_pk"""
+    _fields_ = [("vk", GnarkVk), ("kzg_off", _u64), ("kzg_count", _u64), ("lagrange_off", _u64),
+                ("lagrange_count", _u64)]
 
 
 # b2p_commit_fn: int fn(void* ctx, const void* d_scalars, uint64_t n, void* out_affine)

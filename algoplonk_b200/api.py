@@ -133,6 +133,19 @@ def kzg_vk_load(curve: str, vk_bin: bytes):
     return g2.raw, g1.raw
 
 
+def msm_g2_raw(curve: str, g2_points_raw: bytes, scalars: Sequence[int]) -> bytes:
+    """G2Affine.MultiExp on the GPU (b2p_msm_g2): points in G2Affine memory layout, result likewise."""
+    _lib.init()
+    nb = 4 * FP_BYTES[curve]
+    n = len(scalars)
+    if len(g2_points_raw) != n * nb:
+        raise ValueError("one G2Affine per scalar")
+    out = C.create_string_buffer(nb)
+    _lib.check(_lib.load().b2p_msm_g2(CURVE_ID[curve], _buf(g2_points_raw) if n else None,
+                                      _buf(fr_to_mont_bytes(curve, scalars)) if n else None, n, out))
+    return out.raw
+
+
 def pairing_check(curve: str, g1_raw: bytes, g2_raw: bytes) -> bool:
     """prod e(P_i, Q_i) == 1 for points in G1Affine / G2Affine memory layout."""
     n = len(g1_raw) // (2 * FP_BYTES[curve])
@@ -455,3 +468,71 @@ def Compile(cs: fe.SparseR1CS, curve: str, setup_name: int, srs: Optional[SRS] =
     _lib.check(lib.b2p_circuit_load(srs.handle, n, tc.nb_public, *cols, perm, k, qcp_arr, cidx, vkb,
                                     len(vk_transcript) if vk_transcript is not None else 0, C.byref(h)))
     return CompiledCircuit(cs, tc, srs, h.value)
+
+
+# ---- persisted keys (utils/utils.go:66-157) ------------------------------------------------------------------
+def ShouldRecompile(target_path: str, *source_paths: str) -> bool:
+    """utils.ShouldRecompile (utils/utils.go:68-86): True when the target is missing or older than any source."""
+    import os
+    try:
+        t = os.stat(target_path).st_mtime_ns
+        return any(os.stat(sp).st_mtime_ns > t for sp in source_paths)
+    except OSError:
+        return True
+
+
+def SerializeCompiledCircuit(cc: CompiledCircuit, filepath: str, vk_transcript: Optional[bytes] = None) -> None:
+    """utils.SerializeCompiledCircuit (utils/utils.go:97-121) for a key resident on the GPU: the circuit half of the
+    proving key (selector columns, permutation, BSB22 columns) as the library's own snapshot (b2p_circuit_save); the
+    SRS half stays where it came from (pk.bin / a gnark key file / a known-tau setup)."""
+    tc, curve = cc.trace, cc.Curve
+    n, k = tc.n, len(tc.qcp)
+    cols = [_buf(fr_to_mont_bytes(curve, c)) for c in (tc.ql, tc.qr, tc.qm, tc.qo, tc.qk)]
+    perm = (C.c_int64 * (3 * n))(*tc.perm)
+    qcp_bufs = [_buf(fr_to_mont_bytes(curve, c)) for c in tc.qcp]
+    qcp_arr = (C.c_void_p * max(k, 1))(*[C.cast(b, C.c_void_p) for b in qcp_bufs]) if k else None
+    cidx = (C.c_uint64 * max(k, 1))(*tc.commitment_constraint_indexes) if k else None
+    vkb = _buf(vk_transcript) if vk_transcript else None
+    _lib.check(_lib.load().b2p_circuit_save(filepath.encode(), CURVE_ID[curve], n, tc.nb_public, *cols, perm, k,
+                                            qcp_arr, cidx, vkb, len(vk_transcript) if vk_transcript else 0))
+
+
+def DeserializeCompiledCircuit(filepath: str, cs: fe.SparseR1CS, srs: SRS) -> CompiledCircuit:
+    """utils.DeserializeCompiledCircuit (utils/utils.go:124-157): the proving key goes from the file's page cache
+    straight to HBM (b2p_circuit_load_file); `cs` is the constraint system the solver keeps on the CPU."""
+    _lib.init()
+    h = C.c_void_p()
+    _lib.check(_lib.load().b2p_circuit_load_file(srs.handle, filepath.encode(), C.byref(h)))
+    return CompiledCircuit(cs, fe.build_trace(cs), srs, h.value)
+
+
+def parse_gnark_file(data: bytes) -> _lib.GnarkFile:
+    """The gob stream utils.SerializeCompiledCircuit writes -> curve and the byte ranges of Ccs / Pk / Vk."""
+    out = _lib.GnarkFile()
+    _lib.check(_lib.load().b2p_gnark_file_parse(_buf(data), len(data), C.byref(out)))
+    return out
+
+
+def parse_gnark_vk(curve: str, data: bytes) -> _lib.GnarkVk:
+    """plonk.VerifyingKey.WriteTo bytes -> the fields b2p_verify / b2p_circuit_load take."""
+    out = _lib.GnarkVk()
+    _lib.check(_lib.load().b2p_gnark_vk_parse(CURVE_ID[curve], _buf(data), len(data), C.byref(out)))
+    return out
+
+
+def parse_gnark_pk(curve: str, data: bytes) -> _lib.GnarkPk:
+    """plonk.ProvingKey.WriteTo bytes -> verifying key + where pk.Kzg / pk.KzgLagrange sit."""
+    out = _lib.GnarkPk()
+    _lib.check(_lib.load().b2p_gnark_pk_parse(CURVE_ID[curve], _buf(data), len(data), C.byref(out)))
+    return out
+
+
+def srs_from_gnark_pk(curve: str, pk_bytes: bytes, g2: Optional[bytes] = None) -> SRS:
+    """pk.Kzg of a persisted gnark proving key, decompressed on the GPU straight from the key's bytes."""
+    info = parse_gnark_pk(curve, pk_bytes)
+    _lib.init()
+    h = C.c_void_p()
+    sect = pk_bytes[info.kzg_off:info.lagrange_off]
+    _lib.check(_lib.load().b2p_srs_load_compressed(CURVE_ID[curve], _buf(sect), len(sect), info.kzg_count, C.byref(h)))
+    return SRS(curve, h.value, g2=g2 if g2 is not None else bytes(info.vk.kzg_g2)[:8 * FP_BYTES[curve]])
+

@@ -8,6 +8,13 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
+#include <vector>
+#include <cstdio>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "../../include/b200plonk.h"
 #include "iface.hpp"
 
@@ -208,6 +215,15 @@ API int b2p_msm_g1_dev(b2p_srs* srs, int basis, const void* d_scalars, uint64_t 
         std::lock_guard<std::mutex> lk(reinterpret_cast<SrsBase*>(srs)->mu);
         DeviceGuard g(reinterpret_cast<SrsBase*>(srs)->device);
         reinterpret_cast<SrsBase*>(srs)->msm_g1(basis, d_scalars, n, out_affine, true);
+    });
+}
+API int b2p_msm_g2(int curve, const void* g2_points, const void* scalars, uint64_t n, void* out_g2_affine) {
+    return guarded([&] {
+        require(out_g2_affine && ((g2_points && scalars) || n == 0), "null argument");
+        ops_for(curve);
+        require(n < (1ull << 26), "too many points");
+        current_device();
+        msm_g2(curve, g2_points, scalars, n, out_g2_affine);
     });
 }
 API int b2p_g1_sum(int curve, const void* points, uint64_t n, void* out_affine) {
@@ -570,6 +586,149 @@ API int b2p_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g
         if (const char* e = host_kzg_vk_load(curve, vk_bin, len, out_g2, out_g1)) throw Error(B2P_ERR_ARG, e);
     });
 }
+// ---- persisted keys ---------------------------------------------------------------------------------------
+API int b2p_gnark_file_parse(const void* file, uint64_t len, b2p_gnark_file* out) {
+    return guarded([&] {
+        require(file && out, "null argument");
+        if (const char* e = host_gnark_file_parse(file, len, out)) throw Error(B2P_ERR_ARG, e);
+    });
+}
+API int b2p_gnark_vk_parse(int curve, const void* bytes, uint64_t len, b2p_gnark_vk* out) {
+    return guarded([&] {
+        require_curve(curve);
+        require(bytes && out, "null argument");
+        if (const char* e = host_gnark_vk_parse(curve, bytes, len, out)) throw Error(B2P_ERR_ARG, e);
+    });
+}
+API int b2p_gnark_pk_parse(int curve, const void* bytes, uint64_t len, b2p_gnark_pk* out) {
+    return guarded([&] {
+        require_curve(curve);
+        require(bytes && out, "null argument");
+        if (const char* e = host_gnark_pk_parse(curve, bytes, len, out)) throw Error(B2P_ERR_ARG, e);
+    });
+}
+
+// The library's own snapshot of a proving key's circuit half: a 64-byte header, then the arguments of
+// b2p_circuit_load back to back (each section padded to 64 bytes so the mapped columns are aligned).
+namespace {
+struct SnapHeader {
+    char magic[8];                 // "B2PKEY\0\1"
+    uint32_t version, curve;
+    uint64_t n;
+    uint32_t nb_public, k;
+    uint64_t vkb_len;
+    uint64_t payload_len;          // bytes after the header
+    uint64_t fnv;                  // FNV-1a (64-bit, 8 bytes at a time) of the payload
+    uint64_t reserved;
+};
+static_assert(sizeof(SnapHeader) == 64, "snapshot header is 64 bytes");
+const char SNAP_MAGIC[8] = {'B', '2', 'P', 'K', 'E', 'Y', 0, 1};
+inline uint64_t pad64(uint64_t x) { return (x + 63) & ~63ull; }
+inline uint64_t fnv1a_words(uint64_t h, const void* p, uint64_t bytes) {      // bytes is a multiple of 8
+    const uint64_t* w = static_cast<const uint64_t*>(p);
+    for (uint64_t i = 0; i < bytes / 8; i++) h = (h ^ w[i]) * 0x100000001b3ull;
+    return h;
+}
+struct File {
+    FILE* f = nullptr;
+    ~File() { if (f) fclose(f); }
+};
+struct Mapping {
+    void* p = MAP_FAILED;
+    size_t len = 0;
+    int fd = -1;
+    ~Mapping() {
+        if (p != MAP_FAILED) munmap(p, len);
+        if (fd >= 0) close(fd);
+    }
+};
+}  // namespace
+
+API int b2p_circuit_save(const char* path, int curve, uint64_t n, uint32_t nb_public, const void* ql, const void* qr,
+                         const void* qm, const void* qo, const void* qk, const int64_t* perm, uint32_t k,
+                         const void* const* qcp, const uint64_t* cidx, const void* vkb, uint64_t vkb_len) {
+    return guarded([&] {
+        require_curve(curve);
+        require(path && ql && qr && qm && qo && qk && perm, "null argument");
+        require(k == 0 || (qcp && cidx), "BSB22 columns missing");
+        require(k <= B2P_MAX_COMMITMENTS, "too many BSB22 commitments");
+        require(n >= 2 && (n & (n - 1)) == 0 && n <= (1ull << 32), "domain size must be a power of two >= 2");
+        require(vkb || vkb_len == 0, "null argument");
+        const uint64_t col = n * 32;                       // a multiple of 64
+        std::vector<std::pair<const void*, uint64_t>> parts = {{ql, col}, {qr, col}, {qm, col}, {qo, col}, {qk, col},
+                                                               {perm, 3 * n * 8}};
+        for (uint32_t i = 0; i < k; i++) parts.push_back({qcp[i], col});
+        if (k) parts.push_back({cidx, (uint64_t)k * 8});
+        if (vkb_len) parts.push_back({vkb, vkb_len});
+        SnapHeader h{};
+        memcpy(h.magic, SNAP_MAGIC, 8);
+        h.version = 1; h.curve = (uint32_t)curve; h.n = n; h.nb_public = nb_public; h.k = k; h.vkb_len = vkb_len;
+        uint64_t fnv = 0xcbf29ce484222325ull;
+        static const char zeros[64] = {0};
+        std::vector<char> tailbuf;
+        for (auto& pr : parts) {
+            h.payload_len += pad64(pr.second);
+            const uint64_t whole = pr.second & ~7ull;
+            fnv = fnv1a_words(fnv, pr.first, whole);
+            tailbuf.assign(pad64(pr.second) - whole, 0);
+            memcpy(tailbuf.data(), static_cast<const char*>(pr.first) + whole, pr.second - whole);
+            fnv = fnv1a_words(fnv, tailbuf.data(), tailbuf.size());
+        }
+        h.fnv = fnv;
+        File f;
+        f.f = fopen(path, "wb");
+        if (!f.f) throw Error(B2P_ERR_ARG, std::string("cannot create ") + path);
+        bool ok = fwrite(&h, sizeof h, 1, f.f) == 1;
+        for (auto& pr : parts) {
+            ok = ok && (pr.second == 0 || fwrite(pr.first, pr.second, 1, f.f) == 1);
+            const uint64_t padn = pad64(pr.second) - pr.second;
+            ok = ok && (padn == 0 || fwrite(zeros, padn, 1, f.f) == 1);
+        }
+        ok = ok && fflush(f.f) == 0;
+        if (!ok) throw Error(B2P_ERR_INTERNAL, std::string("short write to ") + path);
+    });
+}
+
+API int b2p_circuit_load_file(b2p_srs* srs, const char* path, b2p_circuit** out) {
+    int rc = guarded([&] {
+        require(srs && path && out, "null argument");
+        Mapping m;
+        m.fd = open(path, O_RDONLY);
+        if (m.fd < 0) throw Error(B2P_ERR_ARG, std::string("cannot open ") + path);
+        struct stat sb;
+        if (fstat(m.fd, &sb) != 0 || (uint64_t)sb.st_size < sizeof(SnapHeader)) throw Error(B2P_ERR_ARG, "key snapshot: file too small");
+        m.len = (size_t)sb.st_size;
+        m.p = mmap(nullptr, m.len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, m.fd, 0);
+        if (m.p == MAP_FAILED) throw Error(B2P_ERR_INTERNAL, "key snapshot: mmap failed");
+        const char* base = static_cast<const char*>(m.p);
+        SnapHeader h;
+        memcpy(&h, base, sizeof h);
+        if (memcmp(h.magic, SNAP_MAGIC, 8) != 0 || h.version != 1) throw Error(B2P_ERR_ARG, "key snapshot: bad magic / version");
+        SrsBase* s = reinterpret_cast<SrsBase*>(srs);
+        if ((int)h.curve != s->curve) throw Error(B2P_ERR_ARG, "key snapshot: written for the other curve");
+        if (h.n < 2 || (h.n & (h.n - 1)) || h.n > (1ull << 32) || h.k > B2P_MAX_COMMITMENTS)
+            throw Error(B2P_ERR_ARG, "key snapshot: impossible sizes");
+        const uint64_t col = h.n * 32;
+        const uint64_t want = (5 + h.k) * col + pad64(3 * h.n * 8) + (h.k ? pad64((uint64_t)h.k * 8) : 0) + pad64(h.vkb_len);
+        if (h.payload_len != want || m.len != sizeof h + want) throw Error(B2P_ERR_ARG, "key snapshot: length does not match its header");
+        if (fnv1a_words(0xcbf29ce484222325ull, base + sizeof h, want) != h.fnv) throw Error(B2P_ERR_ARG, "key snapshot: checksum mismatch");
+        const char* p = base + sizeof h;
+        const void* cols[5];
+        for (int i = 0; i < 5; i++) { cols[i] = p; p += col; }
+        const int64_t* perm = reinterpret_cast<const int64_t*>(p);
+        p += pad64(3 * h.n * 8);
+        const void* qcp[B2P_MAX_COMMITMENTS] = {nullptr};
+        for (uint32_t i = 0; i < h.k; i++) { qcp[i] = p; p += col; }
+        const uint64_t* cidx = reinterpret_cast<const uint64_t*>(p);
+        if (h.k) p += pad64((uint64_t)h.k * 8);
+        const void* vkb = h.vkb_len ? p : nullptr;
+        const int rc2 = b2p_circuit_load(srs, h.n, h.nb_public, cols[0], cols[1], cols[2], cols[3], cols[4], perm, h.k,
+                                         h.k ? qcp : nullptr, h.k ? cidx : nullptr, vkb, h.vkb_len, out);
+        if (rc2 != 0) throw Error(rc2, b2p_last_error());
+    });
+    return rc;
+}
+
 API int b2p_g2_generate_unsafe(int curve, const void* tau, void* out_g2) {
     return guarded([&] {
         require_curve(curve);

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include "../../include/b200plonk.h"
 
 namespace b2p {
 
@@ -101,6 +102,9 @@ const CurveOps* curve_ops_bls12381();
 
 extern std::atomic<unsigned long long> g_launch_count;
 
+// G2Affine.MultiExp, one shot (inst_msm_g2.cu): n G2Affine + n Fr (Montgomery) on the host -> one G2Affine
+void msm_g2(int curve, const void* points, const void* scalars, uint64_t n, void* out);
+
 // Host-side plonk.Verify (verify.cu): no device involved.
 struct HostVerifyKey {
     uint64_t n;
@@ -117,5 +121,9 @@ bool host_verify_batch(int curve, const HostVerifyKey& vk, const void* proofs, u
 bool host_pairing_check(int curve, const void* g1s, const void* g2s, uint64_t n, std::string* why);
 const char* host_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g2, void* out_g1);
 void host_g2_unsafe(int curve, const void* tau_mont, void* out_two_g2);
+// persisted keys (keyfile.hpp); nullptr = ok, else the reason
+const char* host_gnark_file_parse(const void* file, uint64_t len, b2p_gnark_file* out);
+const char* host_gnark_vk_parse(int curve, const void* bytes, uint64_t len, b2p_gnark_vk* out);
+const char* host_gnark_pk_parse(int curve, const void* bytes, uint64_t len, b2p_gnark_pk* out);
 
 }  // namespace b2p

@@ -543,8 +543,11 @@ struct MsmEngine {
         const uint32_t nb = plan.nbuckets;
         const int s = split_bits();
         const uint32_t ncols = 1u << s, nrows = nb >> s, ntot = ncols + nrows;
-        B2P_LAUNCH((k_msm_rowcol<Fp>), dim3(div_up(ntot, MSM_RC_WARPS), cnt), 32 * MSM_RC_WARPS,
-                   32 * MSM_RC_WARPS * sizeof(Ext), st,
+        constexpr size_t rc_smem_bytes = 32 * MSM_RC_WARPS * sizeof(Ext);
+        if (rc_smem_bytes > 48 * 1024)                 // G2 points (Fp2 coordinates): 64 / 96 KiB, opt-in size
+            B2P_CUDA(cudaFuncSetAttribute(k_msm_rowcol<Fp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)rc_smem_bytes));
+        B2P_LAUNCH((k_msm_rowcol<Fp>), dim3(div_up(ntot, MSM_RC_WARPS), cnt), 32 * MSM_RC_WARPS, rc_smem_bytes, st,
                    rc_col.p + (size_t)first * col_partials(), rc_row.p + (size_t)first * row_partials(), s, nb, rc_chunk,
                    rc_sums.p + (size_t)first * ntot);
         const int nbits = plan.c;                     // weights are < 2^(c-1) + 1

@@ -3,6 +3,7 @@
 // work on a box without a GPU, exactly like gnark's verifier which they stand in for.
 #include "iface.hpp"
 #include "verify_host.hpp"
+#include "keyfile.hpp"
 
 namespace b2p {
 
@@ -91,6 +92,17 @@ static void g2_unsafe_t(const void* tau_mont, uint8_t* out) {
 void host_g2_unsafe(int curve, const void* tau_mont, void* out) {
     if (curve == 0) g2_unsafe_t<hp::Bn254Pairing>(tau_mont, static_cast<uint8_t*>(out));
     else g2_unsafe_t<hp::Bls12381Pairing>(tau_mont, static_cast<uint8_t*>(out));
+}
+
+// Persisted keys (keyfile.hpp): utils.DeserializeCompiledCircuit's file, gnark's VerifyingKey / ProvingKey encodings
+const char* host_gnark_file_parse(const void* file, uint64_t len, b2p_gnark_file* out) {
+    return keyfile::parse_container(static_cast<const uint8_t*>(file), len, out);
+}
+const char* host_gnark_vk_parse(int curve, const void* b, uint64_t len, b2p_gnark_vk* out) {
+    return keyfile::parse_vk(curve, b, len, out);
+}
+const char* host_gnark_pk_parse(int curve, const void* b, uint64_t len, b2p_gnark_pk* out) {
+    return keyfile::parse_pk(curve, b, len, out);
 }
 
 }  // namespace b2p

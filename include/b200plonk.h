@@ -122,6 +122,12 @@ void b2p_srs_free(b2p_srs* srs);
  * Used by the shim for the BSB22 commitment hint (kzg.Commit on pk.KzgLagrange). */
 int b2p_msm_g1(b2p_srs* srs, int basis, const void* scalars, uint64_t n, void* out_affine);
 
+/* G2Affine.MultiExp: out = sum_i scalars[i] * g2_points[i].  One shot: n G2Affine (X.A0 X.A1 Y.A0 Y.A1, Montgomery)
+ * and n Fr (Montgomery) on the host, the windowed table is built for this call and dropped.  The same Pippenger
+ * kernels as G1, instantiated over Fp2 coordinates.  Not on plonk.Prove's path (a PLONK key holds two G2 points,
+ * setup/setup.go:124,216-225); it completes "MSM over G1/G2" for callers that build KZG / Groth16-style keys. */
+int b2p_msm_g2(int curve, const void* g2_points, const void* scalars, uint64_t n, void* out_g2_affine);
+
 /* Same with the scalars already resident in device memory (device pointer, Montgomery form). */
 int b2p_msm_g1_dev(b2p_srs* srs, int basis, const void* d_scalars, uint64_t n, void* out_affine);
 /* out_affine = sum of n affine points, computed on the host: the local add that follows the all_gather of
@@ -332,6 +338,58 @@ int b2p_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g2, v
 /* [1]_2, [tau]_2 : the G2 half of the TestOnly setups' unsafekzg.NewSRS (setup/setup.go:124);
  * tau as in b2p_srs_generate_unsafe; writes 2 G2Affine. */
 int b2p_g2_generate_unsafe(int curve, const void* tau, void* out_g2);
+
+/* ---- persisted keys (replaces: utils.DeserializeCompiledCircuit, utils/utils.go:124-157) ----
+ *
+ * utils.SerializeCompiledCircuit (utils/utils.go:97-121) writes a gob stream of
+ * CompiledCircuitBytes{Ccs, Pk, Vk []byte; Curve ecc.ID}: Pk = plonk.ProvingKey.WriteTo (VerifyingKey, then
+ * Kzg and KzgLagrange as uint32 count + compressed G1 -- the format of the embedded setup/<name>/pk.bin),
+ * Vk = plonk.VerifyingKey.WriteTo, Ccs = gnark's CBOR constraint system.  A prover service that warm-starts
+ * from such a file hands the FILE BYTES to these calls instead of waiting for gnark to decompress 2n+3 points on
+ * the CPU:  b2p_gnark_file_parse -> byte ranges;  b2p_gnark_pk_parse -> key fields + where the Kzg points sit;
+ * b2p_srs_load_compressed(curve, pk + kzg_off, pk_len - kzg_off, kzg_count, &srs) decompresses them on the GPU.
+ * The Ccs range goes back to gnark (the solver needs it on the CPU either way).  Host code: no GPU, no b2p_init.
+ * Field order of the VerifyingKey is recalled from gnark v0.15.0, not read from a gnark-written file (there is
+ * none here): the parser validates what it decodes and fails with B2P_ERR_ARG rather than return a wrong key. */
+#define B2P_MAX_COMMITMENTS 8
+typedef struct b2p_gnark_file {
+    int32_t  curve;                    /* B2P_BN254 / B2P_BLS12_381 */
+    uint32_t ecc_id;                   /* gnark-crypto's ecc.ID as stored (1 = BN254, 3 = BLS12-381) */
+    uint64_t ccs_off, ccs_len;         /* byte ranges inside the file */
+    uint64_t pk_off, pk_len;
+    uint64_t vk_off, vk_len;
+} b2p_gnark_file;
+typedef struct b2p_gnark_vk {
+    uint64_t size, nb_public;          /* vk.Size, vk.NbPublicVariables */
+    uint32_t k, has_lines;             /* len(vk.Qcp); whether Kzg.Lines was present (skipped) */
+    uint64_t encoded_len;              /* bytes the VerifyingKey occupies */
+    uint64_t commitment_indexes[B2P_MAX_COMMITMENTS];
+    uint8_t  size_inv[32], generator[32], coset_shift[32];      /* fr.Element memory (Montgomery) */
+    uint8_t  points[(8 + B2P_MAX_COMMITMENTS) * 96];           /* S1 S2 S3 Ql Qr Qm Qo Qk Qcp*: G1Affine memory, packed
+                                                                  at 64 (BN254) / 96 (BLS12-381) bytes: b2p_verify's vk_points */
+    uint8_t  kzg_g1[96];               /* vk.Kzg.G1 */
+    uint8_t  kzg_g2[2 * 192];          /* vk.Kzg.G2[0], [1]: G2Affine memory, packed at 128 / 192 bytes */
+} b2p_gnark_vk;
+typedef struct b2p_gnark_pk {
+    b2p_gnark_vk vk;
+    uint64_t kzg_off, kzg_count;            /* pk.Kzg: offset of its uint32 header inside the Pk bytes, points */
+    uint64_t lagrange_off, lagrange_count;  /* pk.KzgLagrange */
+} b2p_gnark_pk;
+int b2p_gnark_file_parse(const void* file, uint64_t len, b2p_gnark_file* out);
+int b2p_gnark_vk_parse(int curve, const void* vk_bytes, uint64_t len, b2p_gnark_vk* out);
+int b2p_gnark_pk_parse(int curve, const void* pk_bytes, uint64_t len, b2p_gnark_pk* out);
+
+/* The library's own key snapshot: everything b2p_circuit_load takes (selector columns, permutation, BSB22 columns,
+ * transcript bytes) in one file, so a restarted prover reloads a proving key without gnark rebuilding the trace
+ * (NewTrace walks the constraint system: seconds at 2^20).  b2p_circuit_save writes it; b2p_circuit_load_file maps
+ * it and uploads straight from the page cache.  Little-endian, Montgomery limbs as in memory; header checked
+ * (magic, version, curve, sizes, FNV-1a of the payload). */
+int b2p_circuit_save(const char* path, int curve, uint64_t n, uint32_t nb_public,
+                     const void* ql, const void* qr, const void* qm, const void* qo, const void* qk,
+                     const int64_t* perm, uint32_t k, const void* const* qcp,
+                     const uint64_t* commitment_constraint_idx,
+                     const void* vk_transcript, uint64_t vk_transcript_len);
+int b2p_circuit_load_file(b2p_srs* srs, const char* path, b2p_circuit** out);
 
 /* ---- instrumentation -------------------------------------------------------- */
 

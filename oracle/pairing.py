@@ -124,6 +124,55 @@ def parse_vk_bin(cv: CurveParams, vk_bin: bytes):
 
 
 # ---------------------------------------------------------------------------------------------
+# G2 group law in affine coordinates over Fp2 (the checker of b2p_msm_g2: G2Affine.MultiExp, gnark-crypto
+# ecc/<curve>/multiexp.go, which AlgoPlonk reaches only through kzg.NewSRS -- setup/setup.go:124)
+# ---------------------------------------------------------------------------------------------
+def f2_sub(p: int, a: Fp2, b: Fp2) -> Fp2:
+    return ((a[0] - b[0]) % p, (a[1] - b[1]) % p)
+
+
+def g2_neg(cv: CurveParams, Q: G2Affine) -> G2Affine:
+    return None if Q is None else (Q[0], ((-Q[1][0]) % cv.p, (-Q[1][1]) % cv.p))
+
+
+def g2_add(cv: CurveParams, P: G2Affine, Q: G2Affine) -> G2Affine:
+    """Chord-and-tangent on y^2 = x^3 + b' (a = 0)."""
+    p = cv.p
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    if P[0] == Q[0]:
+        if P[1] != Q[1] or P[1] == (0, 0):
+            return None
+        xx = f2_mul(p, P[0], P[0])
+        lam = f2_mul(p, (3 * xx[0] % p, 3 * xx[1] % p), f2_inv(p, (2 * P[1][0] % p, 2 * P[1][1] % p)))
+    else:
+        lam = f2_mul(p, f2_sub(p, Q[1], P[1]), f2_inv(p, f2_sub(p, Q[0], P[0])))
+    x3 = f2_sub(p, f2_sub(p, f2_mul(p, lam, lam), P[0]), Q[0])
+    y3 = f2_sub(p, f2_mul(p, lam, f2_sub(p, P[0], x3)), P[1])
+    return (x3, y3)
+
+
+def g2_mul(cv: CurveParams, Q: G2Affine, k: int) -> G2Affine:
+    """Double-and-add, k taken as a non-negative integer (not reduced: callers test the group order with it)."""
+    acc, base = None, Q
+    while k:
+        if k & 1:
+            acc = g2_add(cv, acc, base)
+        base = g2_add(cv, base, base)
+        k >>= 1
+    return acc
+
+
+def g2_msm_naive(cv: CurveParams, points: Sequence[G2Affine], scalars: Sequence[int]) -> G2Affine:
+    acc = None
+    for Q, k in zip(points, scalars):
+        acc = g2_add(cv, acc, g2_mul(cv, Q, k % cv.r))
+    return acc
+
+
+# ---------------------------------------------------------------------------------------------
 # Fp12 = Fp[w] / (w^12 - c6 w^6 + c0) as plain polynomials
 # ---------------------------------------------------------------------------------------------
 class _Ext:

@@ -65,3 +65,26 @@ extern "C" void ht_ec_op(int curve, int op, const uint32_t* p1, const uint32_t* 
     if (curve == 0) ecop<FpBn254>(op, p1, p2, k, o);
     else ecop<FpBls12381>(op, p1, p2, k, o);
 }
+
+// ---- Fp2 (fp2.cuh): the coordinate field of G2, what MsmEngine<...G2> computes with ---------------------------
+#include "../../algoplonk_b200/csrc/fp2.cuh"
+template <class Fp> static void fp2op(int op, const uint32_t* a, const uint32_t* b, uint32_t* o) {
+    Fp2<Fp> x, y, r;
+    memcpy(x.v, a, sizeof x.v); memcpy(y.v, b, sizeof y.v);
+    switch (op) {
+        case 0: r = x * y; break;
+        case 1: r = x.sqr(); break;
+        case 2: r = x + y; break;
+        case 3: r = x - y; break;
+        case 4: r = x.neg(); break;
+        case 5: r = x.inverse(); break;
+        case 6: r = Fp2<Fp>::mul_sub(x, y, y, x + Fp2<Fp>::one()); break;      // x y - y (x + 1) = -y
+        case 7: r = x.dbl(); break;
+        default: r = Fp2<Fp>::zero();
+    }
+    memcpy(o, r.v, sizeof r.v);
+}
+extern "C" void ht_fp2_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* o) {
+    if (curve == 0) fp2op<FpBn254>(op, a, b, o);
+    else fp2op<FpBls12381>(op, a, b, o);
+}

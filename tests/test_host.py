@@ -389,3 +389,41 @@ def test_transcript_sha256_against_hashlib(tmp_path_factory):
             lib.ht_sha256(msg, C.c_uint64(n), C.c_uint64(split), got)
             assert got.raw == want, (n, split)
 
+
+
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+def test_fp2_device_code_on_host(hostfield, curve):
+    """fp2.cuh (Fp[u]/(u^2+1), the coordinate field of G2 -- what the G2 MSM computes with) through the same two host
+    builds as the base fields, against Python integers: products as two fused a b - c d, squares, inverses."""
+    cv = po.CURVES[curve]
+    p, n = cv.p, (8 if cv.cid == 0 else 12)
+    R = 1 << (32 * n)
+    rng = random.Random(cv.cid + 2)
+
+    def enc(z):
+        out = []
+        for c in z:
+            m = c * R % p
+            out += [(m >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+        return (C.c_uint32 * (2 * n))(*out)
+
+    def call(op, a, b=(0, 0)):
+        O = (C.c_uint32 * (2 * n))()
+        hostfield.ht_fp2_op(cv.cid, op, enc(a), enc(b), O)
+        vals = [sum(int(O[k * n + i]) << (32 * i) for i in range(n)) * pow(R, -1, p) % p for k in range(2)]
+        return tuple(vals)
+
+    mul = lambda a, b: ((a[0] * b[0] - a[1] * b[1]) % p, (a[0] * b[1] + a[1] * b[0]) % p)
+    special = [0, 1, p - 1, 2, (p - 1) // 2]
+    for _ in range(300):
+        a = tuple(rng.choice(special) if rng.random() < 0.3 else rng.randrange(p) for _ in range(2))
+        b = tuple(rng.choice(special) if rng.random() < 0.3 else rng.randrange(p) for _ in range(2))
+        assert call(0, a, b) == mul(a, b)
+        assert call(1, a) == mul(a, a)
+        assert call(2, a, b) == ((a[0] + b[0]) % p, (a[1] + b[1]) % p)
+        assert call(3, a, b) == ((a[0] - b[0]) % p, (a[1] - b[1]) % p)
+        assert call(4, a) == ((-a[0]) % p, (-a[1]) % p)
+        assert call(6, a, b) == ((-b[0]) % p, (-b[1]) % p)
+        assert call(7, a) == (2 * a[0] % p, 2 * a[1] % p)
+        inv = call(5, a)
+        assert (a == (0, 0) and inv == (0, 0)) or mul(a, inv) == (1, 0)

@@ -525,3 +525,25 @@ def test_merkle_mimc_circuit_of_the_reference_example(curve):
     assert not po.verify_proof(vk, blob, po.marshal_public_inputs([root + 1]))
     g1 = api.points_to_mont_bytes(curve, [cv.g1])
     api.verify(curve, tc.n, 1, [], api.points_to_mont_bytes(curve, vk_pts), g1, api.g2_unsafe(curve, H.TAU), blob, pub)
+
+
+@pytest.mark.parametrize("curve,name", [("BN254", "PerpetualPowersOfTauBN254"), ("BLS12_381", "DuskBLS12_381")])
+def test_oracle_g2_group_law(curve, name):
+    """oracle/pairing.py's affine G2 law (the checker of b2p_msm_g2): closed under the twist equation, the ceremony's
+    G2 points have order r, and [tau]_2 from the library's independent host code (Jacobian, 64-bit limbs) agrees."""
+    from algoplonk_b200 import api
+    from oracle import pairing as opair
+    cv = po.CURVES[curve]
+    g2 = H.real_srs_g2(name)
+    for Q in g2:
+        assert opair.g2_on_curve(cv, Q)
+        assert opair.g2_mul(cv, Q, cv.r) is None
+        assert opair.g2_mul(cv, Q, cv.r + 1) == Q
+        assert opair.g2_add(cv, Q, opair.g2_neg(cv, Q)) is None
+    a, b = 0x1234567, 0xABCDEF0123
+    P, Q = g2
+    s = opair.g2_add(cv, opair.g2_mul(cv, P, a), opair.g2_mul(cv, Q, b))
+    assert opair.g2_on_curve(cv, s) and s == opair.g2_msm_naive(cv, [Q, P], [b, a])
+    assert opair.g2_add(cv, opair.g2_add(cv, P, Q), Q) == opair.g2_add(cv, P, opair.g2_add(cv, Q, Q))
+    for tau in (2, 12345, cv.r - 1):
+        assert api.g2_from_mont_bytes(curve, api.g2_unsafe(curve, tau))[1] == opair.g2_mul(cv, P, tau)
