@@ -19,6 +19,7 @@ B2P_BN254, B2P_BLS12_381 = 0, 1
 ERR_ARG, ERR_CUDA, ERR_INTERNAL, ERR_VERIFY = -1, -2, -3, -4
 BASIS_CANONICAL, BASIS_LAGRANGE = 0, 1
 NTT_INVERSE, NTT_COSET = 1, 2
+SOLVE_AUTO, SOLVE_HOST, SOLVE_DEVICE = 0, 1, 2
 IPC_HANDLE_BYTES = 64
 SHARD_HANDLES = 9
 STAT_NAMES = ["total_ms", "msm_ms", "msm_accum_ms", "ntt_ms", "quotient_ms", "msm_calls", "msm_accum_adds",
@@ -90,6 +91,11 @@ SYMBOLS = [
     ("b2p_pairing_check", _int, [_int, _vp, _vp, _u64, C.POINTER(_int)]),
     ("b2p_kzg_vk_load", _int, [_int, _vp, _u64, _vp, _vp]),
     ("b2p_g2_generate_unsafe", _int, [_int, _vp, _vp]),
+    ("b2p_solver_create", _int, [_int, _u64, _u32, _u64, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    ("b2p_solver_solve", _int, [_vp, _vp, _int, _vp, _vp, _vp]),
+    ("b2p_solver_solve_dev", _int, [_vp, _vp, _int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    ("b2p_solver_info", _int, [_vp, C.POINTER(_u64)]),
+    ("b2p_solver_free", None, [_vp]),
     ("b2p_gnark_file_parse", _int, [_vp, _u64, _vp]),
     ("b2p_gnark_vk_parse", _int, [_int, _vp, _u64, _vp]),
     ("b2p_gnark_pk_parse", _int, [_int, _vp, _u64, _vp]),

@@ -470,6 +470,74 @@ def Compile(cs: fe.SparseR1CS, curve: str, setup_name: int, srs: Optional[SRS] =
     return CompiledCircuit(cs, tc, srs, h.value)
 
 
+# ---- witness solver (spr.Solve inside plonk.Prove, algoplonk.go:81-89) ---------------------------------------
+class Solver:
+    """b2p_solver_*: assigns every internal variable from the public + secret inputs, level by level on the GPU
+    (or on one host thread when the circuit is a dependency chain), and hands L, R, O to the prover."""
+    INFO = ["levels", "widest_level", "solved_rows", "launches", "est_host_us", "est_device_us", "last_us", "last_where"]
+
+    def __init__(self, cs: fe.SparseR1CS, trace: Optional[fe.TraceColumns] = None):
+        if cs.commitments:
+            raise ValueError("circuits with BSB22 commitments need gnark's hint: not solved by the library")
+        if cs.input_vars is None:
+            raise ValueError("the constraint system does not say which variables are inputs")
+        _lib.init()
+        tc = trace if trace is not None else fe.build_trace(cs)
+        self.curve, self.n, self.nb_public, self.nb_inputs = cs.curve, tc.n, cs.nb_public, len(cs.input_vars)
+        n = tc.n
+        cols = [_buf(fr_to_mont_bytes(cs.curve, c)) for c in (tc.ql, tc.qr, tc.qm, tc.qo, tc.qk)]
+        xa, xb, xc = ((C.c_uint32 * n)(*w) for w in fe.solver_wires(cs, n))
+        ids = (C.c_uint32 * max(self.nb_inputs, 1))(*cs.input_vars)
+        h = C.c_void_p()
+        _lib.check(_lib.load().b2p_solver_create(CURVE_ID[cs.curve], n, cs.nb_public, cs.nb_variables, ids, self.nb_inputs,
+                                                 *cols, xa, xb, xc, C.byref(h)))
+        self.handle = h.value
+
+    def info(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        _lib.check(_lib.load().b2p_solver_info(self.handle, out))
+        return dict(zip(self.INFO, out))
+
+    def solve_raw(self, inputs: Sequence[int], where: int = _lib.SOLVE_AUTO):
+        """-> (L, R, O) as n*32 bytes each, Montgomery form: what b2p_prove takes."""
+        if len(inputs) != self.nb_inputs:
+            raise ValueError("one value per input variable")
+        bufs = [C.create_string_buffer(32 * self.n) for _ in range(3)]
+        _lib.check(_lib.load().b2p_solver_solve(self.handle, _buf(fr_to_mont_bytes(self.curve, inputs)), where, *bufs))
+        return tuple(b.raw for b in bufs)
+
+    def solve(self, inputs: Sequence[int], where: int = _lib.SOLVE_AUTO):
+        return tuple(fr_from_mont_bytes(self.curve, b) for b in self.solve_raw(inputs, where))
+
+    def solve_dev(self, inputs: Sequence[int], where: int = _lib.SOLVE_AUTO):
+        """-> device pointers of L, R, O (owned by the solver, valid until its next solve) for b2p_prove_dev."""
+        ptrs = [C.c_void_p() for _ in range(3)]
+        _lib.check(_lib.load().b2p_solver_solve_dev(self.handle, _buf(fr_to_mont_bytes(self.curve, inputs)), where,
+                                                    *[C.byref(p) for p in ptrs]))
+        return tuple(p.value for p in ptrs)
+
+    def free(self):
+        if self.handle:
+            _lib.load().b2p_solver_free(self.handle)
+            self.handle = None
+
+
+def VerifyFromInputs(cc: CompiledCircuit, solver: Solver, inputs: Sequence[int], blinding: Sequence[int],
+                     where: int = _lib.SOLVE_AUTO, verify: bool = True) -> VerifiedProof:
+    """(*CompiledCircuit).Verify as the reference runs it (algoplonk.go:79-98): the caller assigns the circuit's
+    inputs only; solving, proving and plonk.Verify happen in the library, and L, R, O never leave the GPU."""
+    lib = _lib.load()
+    dL, dR, dO = solver.solve_dev(inputs, where)
+    cid = CURVE_ID[cc.Curve]
+    out = C.create_string_buffer(lib.b2p_proof_raw_size(cid, 0))
+    _lib.check(lib.b2p_prove_dev(cc.handle, dL, dR, dO, None, None, _buf(fr_to_mont_bytes(cc.Curve, blinding)), out))
+    proof = Proof(cc.Curve, 0, out.raw, b"")
+    public = [v % R_MOD[cc.Curve] for v in inputs[: cc.trace.nb_public]]
+    if verify:
+        cc.VerifyProof(MarshalProof(proof), MarshalPublicInputs(cc.Curve, public))
+    return VerifiedProof(proof, public)
+
+
 # ---- persisted keys (utils/utils.go:66-157) ------------------------------------------------------------------
 def ShouldRecompile(target_path: str, *source_paths: str) -> bool:
     """utils.ShouldRecompile (utils/utils.go:68-86): True when the target is missing or older than any source."""

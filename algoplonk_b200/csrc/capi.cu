@@ -586,6 +586,54 @@ API int b2p_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g
         if (const char* e = host_kzg_vk_load(curve, vk_bin, len, out_g2, out_g1)) throw Error(B2P_ERR_ARG, e);
     });
 }
+// ---- witness solver ---------------------------------------------------------------------------------------
+API int b2p_solver_create(int curve, uint64_t n, uint32_t nb_public, uint64_t nb_variables, const uint32_t* input_ids,
+                          uint32_t nb_inputs, const void* ql, const void* qr, const void* qm, const void* qo,
+                          const void* qk, const uint32_t* xa, const uint32_t* xb, const uint32_t* xc, b2p_solver** out) {
+    return guarded([&] {
+        require_curve(curve);
+        require(ql && qr && qm && qo && qk && xa && xb && xc && out && (input_ids || nb_inputs == 0), "null argument");
+        const void* cols[5] = {ql, qr, qm, qo, qk};
+        const int dev = current_device();
+        SolverBase* s = new_solver(curve, n, nb_public, nb_variables, input_ids, nb_inputs, cols, xa, xb, xc);
+        s->device = dev;
+        *out = reinterpret_cast<b2p_solver*>(s);
+    });
+}
+API int b2p_solver_solve(b2p_solver* s, const void* inputs, int where, void* L, void* R, void* O) {
+    return guarded([&] {
+        require(s && L && R && O, "null argument");
+        SolverBase* b = reinterpret_cast<SolverBase*>(s);
+        std::lock_guard<std::mutex> lk(b->mu);
+        DeviceGuard g(b->device);
+        b->solve(inputs, where, L, R, O, false, nullptr);
+    });
+}
+API int b2p_solver_solve_dev(b2p_solver* s, const void* inputs, int where, void** dL, void** dR, void** dO) {
+    return guarded([&] {
+        require(s && dL && dR && dO, "null argument");
+        SolverBase* b = reinterpret_cast<SolverBase*>(s);
+        std::lock_guard<std::mutex> lk(b->mu);
+        DeviceGuard g(b->device);
+        void* p[3] = {nullptr, nullptr, nullptr};
+        b->solve(inputs, where, nullptr, nullptr, nullptr, true, p);
+        *dL = p[0]; *dR = p[1]; *dO = p[2];
+    });
+}
+API int b2p_solver_info(const b2p_solver* s, uint64_t* out) {
+    return guarded([&] {
+        require(s && out, "null argument");
+        reinterpret_cast<const SolverBase*>(s)->info(out);
+    });
+}
+API void b2p_solver_free(b2p_solver* s) {
+    if (!s) return;
+    guarded([&] {
+        DeviceGuard g(reinterpret_cast<SolverBase*>(s)->device);
+        delete reinterpret_cast<SolverBase*>(s);
+    });
+}
+
 // ---- persisted keys ---------------------------------------------------------------------------------------
 API int b2p_gnark_file_parse(const void* file, uint64_t len, b2p_gnark_file* out) {
     return guarded([&] {

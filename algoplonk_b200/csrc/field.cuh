@@ -128,6 +128,11 @@ struct Field {
     // adjacent registers of one carry chain: ptxas fuses each
     // mad.lo.cc/madc.hi.cc pair into one IMAD.WIDE.U32(.X).
     //   acc[j] of `even` is column j, acc[j] of `odd` is column j+1.
+    // Provenance: the even/odd two-accumulator scheme and the helper names below (mul_n, cmad_n, madc_n_rshift,
+    // mad_n_redc) follow the widely used `mont_t` GPU multiplier of Supranational's sppark (Apache-2.0), as
+    // published with the ZPrize MSM entries; re-typed here for this template (any N, host emulation of the carry
+    // flag, the separated product/reduction variants further down are this repo's).  Nothing of it comes from the
+    // reference repository, which holds no field arithmetic of its own (gnark-crypto is un-vendored).
 
     // acc[0..N) = a[0], a[2], ... times bi (disjoint 64-bit products)
     HD static void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {

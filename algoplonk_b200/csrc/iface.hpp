@@ -86,6 +86,19 @@ struct ShardGroupBase {
     virtual void serve_msm(uint64_t n) = 0;                     // ranks > 0
 };
 
+// Level-parallel witness solver (solver.cuh, inst_solver.cu)
+struct SolverBase {
+    int curve = -1;
+    int device = -1;
+    std::mutex mu;
+    virtual ~SolverBase() {}
+    virtual void solve(const void* inputs, int where, void* L, void* R, void* O, bool device_out, void** dptrs) = 0;
+    virtual void info(uint64_t* out8) const = 0;
+};
+SolverBase* new_solver(int curve, uint64_t n, uint32_t nb_public, uint64_t nb_variables, const uint32_t* input_ids,
+                       uint32_t nb_inputs, const void* const cols[5], const uint32_t* xa, const uint32_t* xb,
+                       const uint32_t* xc);
+
 struct CurveOps {
     virtual ~CurveOps() {}
     virtual ShardGroupBase* new_shard_group(uint32_t world, uint32_t rank, uint64_t total, SrsBase* shard,

@@ -1,0 +1,390 @@
+// Witness solver: what gnark's spr.Solve does between frontend.NewWitness and the prover's
+// first round (/root/reference/algoplonk.go:81-89) -- every PLONK row  ql*a + qr*b + qm*a*b + qo*c + qk = 0  with
+// exactly one unassigned wire determines that wire -- as a LEVEL-PARALLEL pass on the GPU.
+//
+//  * create(): one host pass over the rows in order finds, for every row, the wire it solves (if any) and the row's
+//    level = 1 + the deepest level among the wires it reads; rows are counting-sorted by level.  gnark computes the
+//    same levels at compile time and runs the rows of a level on goroutines; here a level is one kernel launch
+//    (one thread per row), and runs of consecutive NARROW levels share one single-block launch that steps through
+//    them with __syncthreads() -- a dependency chain costs one barrier per link instead of one launch.
+//  * solve(): inputs up, levels, then one gather kernel writes L, R, O (n rows, padding rows = variable 0 as
+//    gnark's NewTrace pads) and checks EVERY row's gate equation; L, R, O stay in HBM for b2p_prove_dev.
+//  * A chain is still a chain: a depth-2^20 squaring chain takes ~2 us per link on one SM against 46 ns on a host
+//    core (profiles/solver_floor_r2.json), so solve() also has a host path (same rows, 64-bit limbs, one thread) and
+//    B2P_SOLVE_AUTO picks by a cost model of the level structure.  The device pays for wide, shallow circuits.
+//  * Not handled: hints (BSB22 commitments, gnark's hint functions): a row whose unassigned wire occurs twice, or
+//    that has two unassigned wires, is refused at create().
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "pairing_host.hpp"
+
+namespace b2p {
+
+constexpr uint32_t SOLVE_NONE = 0, SOLVE_O = 1, SOLVE_A = 2, SOLVE_B = 3;
+constexpr uint32_t SOLVER_NARROW_MAX = 256;      // levels up to this width (one row per thread) run inside the single-block kernel
+constexpr int SOLVER_NARROW_THREADS = 256;
+
+template <class F>
+struct SolverCols {
+    const F *ql, *qr, *qm, *qo, *qk, *ninv_qo;   // n rows each; ninv_qo = -1/qo where the row solves its O wire
+    const uint32_t *xa, *xb, *xc;
+};
+
+// one row: the unassigned wire from the assigned ones.  false: division by zero (the row cannot determine its wire)
+template <class F>
+__device__ __forceinline__ bool solve_row(const SolverCols<F>& c, F* values, uint32_t row, uint32_t kind) {
+    const uint32_t ia = c.xa[row], ib = c.xb[row], ic = c.xc[row];
+    const F ql = ld_field(c.ql + row), qr = ld_field(c.qr + row), qm = ld_field(c.qm + row), qk = ld_field(c.qk + row);
+    if (kind == SOLVE_O) {
+        const F a = ld_field(values + ia), b = ld_field(values + ib);
+        F t = qk;
+        if (!ql.is_zero()) t = t + ql * a;
+        if (!qr.is_zero()) t = t + qr * b;
+        if (!qm.is_zero()) t = t + qm * (a * b);
+        st_field(values + ic, t * ld_field(c.ninv_qo + row));
+        return true;
+    }
+    const F qo = ld_field(c.qo + row);
+    const F other = ld_field(values + (kind == SOLVE_A ? ib : ia));
+    F num = qk + (kind == SOLVE_A ? qr : ql) * other;
+    if (!qo.is_zero()) num = num + qo * ld_field(values + ic);
+    const F den = (kind == SOLVE_A ? ql : qr) + qm * other;
+    if (den.is_zero()) return false;
+    st_field(values + (kind == SOLVE_A ? ia : ib), (num * den.inverse()).neg());
+    return true;
+}
+
+// ops[i] = row | kind << 30 (n <= 2^30), sorted by level
+template <class F>
+__global__ void __launch_bounds__(128) k_solve_level(SolverCols<F> c, F* values, const uint32_t* __restrict__ ops,
+                                                     uint32_t first, uint32_t count, uint32_t* first_bad) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint32_t op = ops[first + t];
+    if (!solve_row(c, values, op & 0x3FFFFFFFu, op >> 30)) atomicMin(first_bad, op & 0x3FFFFFFFu);
+}
+// levels [l0, l0 + nl): one block steps through them; level_off[l] = first op of level l
+template <class F>
+__global__ void __launch_bounds__(SOLVER_NARROW_THREADS) k_solve_narrow(SolverCols<F> c, F* values,
+                                                                          const uint32_t* __restrict__ ops,
+                                                                          const uint32_t* __restrict__ level_off,
+                                                                          uint32_t l0, uint32_t nl, uint32_t* first_bad) {
+#pragma unroll 1
+    for (uint32_t l = l0; l < l0 + nl; l++) {
+        const uint32_t a = level_off[l], b = level_off[l + 1];
+#pragma unroll 1
+        for (uint32_t i = a + threadIdx.x; i < b; i += SOLVER_NARROW_THREADS) {
+            const uint32_t op = ops[i];
+            if (!solve_row(c, values, op & 0x3FFFFFFFu, op >> 30)) atomicMin(first_bad, op & 0x3FFFFFFFu);
+        }
+        __syncthreads();
+    }
+}
+// -1 / qo for the rows that solve their O wire (once, at create)
+template <class F>
+__global__ void k_solver_ninv(F* ninv, const F* __restrict__ qo, const uint8_t* __restrict__ kind, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F r = F::zero();
+    if (kind[i] == SOLVE_O) {
+        const F q = ld_field(qo + i);
+        r = (q.neg() == F::one()) ? F::one() : q.inverse().neg();
+    }
+    st_field(ninv + i, r);
+}
+// L, R, O of every row and the gate check; public rows: the public value enters through qk (gnark's completeQk)
+template <class F>
+__global__ void k_solver_gather(SolverCols<F> c, const F* __restrict__ values, F* L, F* R, F* O, uint64_t n,
+                                uint32_t nb_public, uint32_t* first_unsat) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const F a = ld_field(values + c.xa[i]), b = ld_field(values + c.xb[i]), o = ld_field(values + c.xc[i]);
+    st_field(L + i, a);
+    st_field(R + i, b);
+    st_field(O + i, o);
+    F t = ld_field(c.ql + i) * a + ld_field(c.qr + i) * b + ld_field(c.qm + i) * (a * b) + ld_field(c.qo + i) * o;
+    t = t + (i < nb_public ? a : ld_field(c.qk + i));
+    if (!t.is_zero()) atomicMin(first_unsat, (uint32_t)i);
+}
+
+struct SolverLaunch {
+    uint32_t first_level, levels, first_op, ops;
+    bool narrow;
+};
+
+template <class Fr>
+struct Solver : SolverBase {
+    using HF = hp::Fe<typename Fr::Params>;
+    static_assert(sizeof(HF) == sizeof(Fr), "host and device scalars share one memory layout");
+
+    uint64_t n = 0, nb_variables = 0;
+    uint32_t nb_public = 0, nb_inputs = 0;
+    cudaStream_t st = nullptr;
+    // host copies (the host path and the analysis)
+    std::vector<HF> h_cols[5], h_ninv;
+    std::vector<uint32_t> h_x[3], h_inputs;
+    std::vector<uint8_t> h_kind;
+    std::vector<uint32_t> h_ops, h_level_off;
+    std::vector<SolverLaunch> plan;
+    uint32_t depth = 0, widest = 0;
+    double est_host_us = 0, est_dev_us = 0, last_ms = 0;
+    int last_where = 0;
+    // device
+    DevBuf<Fr> d_cols[5], d_ninv, d_values, dL, dR, dO, d_in;
+    DevBuf<uint32_t> d_x[3], d_ops, d_level_off, d_flags, d_inputs;
+    DevBuf<uint8_t> d_kind;
+    std::vector<HF> h_values;
+
+    ~Solver() override {
+        if (st) cudaStreamDestroy(st);
+    }
+
+    void create(uint64_t n_, uint32_t nb_public_, uint64_t nb_variables_, const uint32_t* input_ids, uint32_t nb_inputs_,
+                const void* const cols[5], const uint32_t* xa, const uint32_t* xb, const uint32_t* xc) {
+        n = n_; nb_public = nb_public_; nb_variables = nb_variables_; nb_inputs = nb_inputs_;
+        B2P_REQUIRE(n >= 1 && n <= (1ull << 30), "solver: at most 2^30 rows");
+        B2P_REQUIRE(nb_variables >= 1 && nb_variables < (1ull << 32), "solver: variable count out of range");
+        B2P_REQUIRE(nb_public <= n && nb_public <= nb_inputs && nb_inputs <= nb_variables, "solver: input counts out of range");
+        for (int k = 0; k < 5; k++) {
+            h_cols[k].resize(n);
+            memcpy(h_cols[k].data(), cols[k], n * sizeof(HF));
+        }
+        const uint32_t* xs[3] = {xa, xb, xc};
+        for (int k = 0; k < 3; k++) {
+            h_x[k].assign(xs[k], xs[k] + n);
+            for (uint32_t v : h_x[k]) B2P_REQUIRE(v < nb_variables, "solver: wire refers to a variable that does not exist");
+        }
+        h_inputs.assign(input_ids, input_ids + nb_inputs);
+        // ---- analysis: which wire a row solves, and at which level
+        constexpr uint32_t UNKNOWN = 0xFFFFFFFFu;
+        std::vector<uint32_t> var_level(nb_variables, UNKNOWN);
+        for (uint32_t v : h_inputs) {
+            B2P_REQUIRE(v < nb_variables, "solver: input id out of range");
+            B2P_REQUIRE(var_level[v] == UNKNOWN, "solver: an input variable is listed twice");
+            var_level[v] = 0;
+        }
+        for (uint32_t i = 0; i < nb_public; i++)
+            B2P_REQUIRE(var_level[h_x[0][i]] == 0, "solver: a public row's L wire is not an input");
+        h_kind.assign(n, SOLVE_NONE);
+        std::vector<uint32_t> row_level(n, 0);
+        for (uint64_t i = nb_public; i < n; i++) {
+            const bool use[3] = {!h_cols[0][i].is_zero() || !h_cols[2][i].is_zero(),
+                                 !h_cols[1][i].is_zero() || !h_cols[2][i].is_zero(), !h_cols[3][i].is_zero()};
+            const uint32_t w[3] = {h_x[0][i], h_x[1][i], h_x[2][i]};
+            uint32_t unknown_var = UNKNOWN, lvl = 0;
+            int unknown_pos = -1, occurrences = 0;
+            bool two = false;
+            for (int k = 0; k < 3; k++) {
+                if (!use[k]) continue;
+                if (var_level[w[k]] == UNKNOWN) {
+                    if (unknown_var != UNKNOWN && unknown_var != w[k]) two = true;
+                    unknown_var = w[k];
+                    unknown_pos = k;
+                    occurrences++;
+                } else {
+                    lvl = std::max(lvl, var_level[w[k]]);
+                }
+            }
+            if (unknown_var == UNKNOWN) continue;            // an assertion: checked with every other row at the end
+            if (two)
+                throw Error(B2P_ERR_ARG, "solver: row " + std::to_string(i) + " has two unassigned wires (a hint would be needed)");
+            if (occurrences > 1)
+                throw Error(B2P_ERR_ARG, "solver: row " + std::to_string(i) + " uses its unassigned wire twice (not linear in it)");
+            h_kind[i] = unknown_pos == 2 ? SOLVE_O : unknown_pos == 0 ? SOLVE_A : SOLVE_B;
+            row_level[i] = lvl + 1;
+            var_level[unknown_var] = lvl + 1;
+            depth = std::max(depth, lvl + 1);
+        }
+        for (uint64_t i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++)
+                if (var_level[h_x[k][i]] == UNKNOWN)
+                    throw Error(B2P_ERR_ARG, "solver: variable " + std::to_string(h_x[k][i]) + " (row " + std::to_string(i) +
+                                                 ") is neither an input nor determined by a row");
+        // ---- rows by level (counting sort keeps the row order inside a level)
+        h_level_off.assign(depth + 2, 0);
+        for (uint64_t i = 0; i < n; i++)
+            if (h_kind[i]) h_level_off[row_level[i] + 1]++;
+        for (uint32_t l = 1; l < depth + 2; l++) h_level_off[l] += h_level_off[l - 1];
+        h_ops.resize(h_level_off[depth + 1]);
+        {
+            std::vector<uint32_t> cur(h_level_off.begin(), h_level_off.end() - 1);
+            for (uint64_t i = 0; i < n; i++)
+                if (h_kind[i]) h_ops[cur[row_level[i]]++] = (uint32_t)i | ((uint32_t)h_kind[i] << 30);
+        }
+        // ---- launch plan + cost model (us): a wide level = one launch, a run of narrow levels = one block
+        est_dev_us = 0;
+        for (uint32_t l = 1; l <= depth;) {
+            const uint32_t w = h_level_off[l + 1] - h_level_off[l];
+            widest = std::max(widest, w);
+            if (w > SOLVER_NARROW_MAX) {
+                plan.push_back({l, 1, h_level_off[l], w, false});
+                est_dev_us += 4.0 + w * 2.5e-4;
+                l++;
+                continue;
+            }
+            uint32_t e = l;
+            while (e <= depth && h_level_off[e + 1] - h_level_off[e] <= SOLVER_NARROW_MAX) {
+                widest = std::max(widest, h_level_off[e + 1] - h_level_off[e]);
+                e++;
+            }
+            plan.push_back({l, e - l, h_level_off[l], h_level_off[e] - h_level_off[l], true});
+            est_dev_us += 4.0 + (e - l) * 2.2;
+            l = e;
+        }
+        est_dev_us += 10 + n * 1e-4;
+        est_host_us = h_ops.size() * 0.15 + n * 0.05;        // measured: solve + gather + upload of L, R, O
+        // ---- device copies
+        B2P_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (int k = 0; k < 5; k++) {
+            d_cols[k].alloc(n);
+            B2P_CUDA(cudaMemcpyAsync(d_cols[k].p, h_cols[k].data(), n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        }
+        for (int k = 0; k < 3; k++) {
+            d_x[k].alloc(n);
+            B2P_CUDA(cudaMemcpyAsync(d_x[k].p, h_x[k].data(), n * 4, cudaMemcpyHostToDevice, st));
+        }
+        d_kind.alloc(n);
+        B2P_CUDA(cudaMemcpyAsync(d_kind.p, h_kind.data(), n, cudaMemcpyHostToDevice, st));
+        d_ops.alloc(std::max<size_t>(h_ops.size(), 1));
+        if (!h_ops.empty()) B2P_CUDA(cudaMemcpyAsync(d_ops.p, h_ops.data(), h_ops.size() * 4, cudaMemcpyHostToDevice, st));
+        d_level_off.alloc(h_level_off.size());
+        B2P_CUDA(cudaMemcpyAsync(d_level_off.p, h_level_off.data(), h_level_off.size() * 4, cudaMemcpyHostToDevice, st));
+        d_inputs.alloc(std::max<uint32_t>(nb_inputs, 1));
+        if (nb_inputs) B2P_CUDA(cudaMemcpyAsync(d_inputs.p, h_inputs.data(), nb_inputs * 4, cudaMemcpyHostToDevice, st));
+        d_ninv.alloc(n);
+        B2P_LAUNCH((k_solver_ninv<Fr>), div_up(n, 128), 128, 0, st, d_ninv.p, d_cols[3].p, d_kind.p, n);
+        h_ninv.resize(n);
+        B2P_CUDA(cudaMemcpyAsync(h_ninv.data(), d_ninv.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        d_values.alloc(nb_variables);
+        d_in.alloc(std::max<uint32_t>(nb_inputs, 1));
+        dL.alloc(n); dR.alloc(n); dO.alloc(n);
+        d_flags.alloc(2);
+        B2P_CUDA(cudaStreamSynchronize(st));
+    }
+
+    SolverCols<Fr> dcols() const {
+        return {d_cols[0].p, d_cols[1].p, d_cols[2].p, d_cols[3].p, d_cols[4].p, d_ninv.p, d_x[0].p, d_x[1].p, d_x[2].p};
+    }
+
+    void info(uint64_t* out) const override {
+        out[0] = depth; out[1] = widest; out[2] = h_ops.size(); out[3] = plan.size();
+        out[4] = (uint64_t)est_host_us; out[5] = (uint64_t)est_dev_us; out[6] = (uint64_t)(last_ms * 1000.0); out[7] = last_where;
+    }
+
+    int choose(int where) const {
+        if (where == B2P_SOLVE_HOST || where == B2P_SOLVE_DEVICE) return where;
+        B2P_REQUIRE(where == B2P_SOLVE_AUTO, "solver: unknown placement");
+        return est_dev_us < est_host_us ? B2P_SOLVE_DEVICE : B2P_SOLVE_HOST;
+    }
+
+    // inputs: nb_inputs Fr (Montgomery) in the order of the input ids given at create
+    void solve(const void* inputs, int where, void* L, void* R, void* O, bool device_out, void** dptrs) override {
+        B2P_REQUIRE(inputs || nb_inputs == 0, "null argument");
+        where = choose(where);
+        last_where = where;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (where == B2P_SOLVE_DEVICE) solve_device(inputs);
+        else solve_host(inputs);
+        if (device_out) {
+            dptrs[0] = dL.p; dptrs[1] = dR.p; dptrs[2] = dO.p;
+        } else if (where == B2P_SOLVE_DEVICE) {
+            B2P_CUDA(cudaMemcpyAsync(L, dL.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            B2P_CUDA(cudaMemcpyAsync(R, dR.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            B2P_CUDA(cudaMemcpyAsync(O, dO.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            B2P_CUDA(cudaStreamSynchronize(st));
+        } else {
+            gather_host(static_cast<HF*>(L), static_cast<HF*>(R), static_cast<HF*>(O));
+        }
+        if (device_out && where == B2P_SOLVE_HOST) {        // host-solved columns up to the device for b2p_prove_dev
+            std::vector<HF> l(n), r(n), o(n);
+            gather_host(l.data(), r.data(), o.data());
+            B2P_CUDA(cudaMemcpyAsync(dL.p, l.data(), n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            B2P_CUDA(cudaMemcpyAsync(dR.p, r.data(), n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            B2P_CUDA(cudaMemcpyAsync(dO.p, o.data(), n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            B2P_CUDA(cudaStreamSynchronize(st));
+        }
+        last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+
+    void solve_device(const void* inputs) {
+        const SolverCols<Fr> c = dcols();
+        const uint32_t init[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        B2P_CUDA(cudaMemcpyAsync(d_flags.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+        // inputs are scattered to their variables on the host side of the copy: ids are arbitrary
+        h_values.assign(nb_variables, HF::zero());
+        const HF* in = static_cast<const HF*>(inputs);
+        for (uint32_t i = 0; i < nb_inputs; i++) h_values[h_inputs[i]] = in[i];
+        B2P_CUDA(cudaMemcpyAsync(d_values.p, h_values.data(), nb_variables * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        for (const SolverLaunch& s : plan) {
+            if (s.narrow)
+                B2P_LAUNCH((k_solve_narrow<Fr>), 1, SOLVER_NARROW_THREADS, 0, st, c, d_values.p, d_ops.p, d_level_off.p,
+                           s.first_level, s.levels, d_flags.p);
+            else
+                B2P_LAUNCH((k_solve_level<Fr>), div_up(s.ops, 128), 128, 0, st, c, d_values.p, d_ops.p, s.first_op, s.ops,
+                           d_flags.p);
+        }
+        B2P_LAUNCH((k_solver_gather<Fr>), div_up(n, 128), 128, 0, st, c, d_values.p, dL.p, dR.p, dO.p, n, nb_public,
+                   d_flags.p + 1);
+        uint32_t flags[2];
+        B2P_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+        B2P_CUDA(cudaStreamSynchronize(st));
+        report(flags[0], flags[1]);
+    }
+
+    static void report(uint32_t div0_row, uint32_t unsat_row) {
+        if (div0_row != 0xFFFFFFFFu)
+            throw Error(B2P_ERR_VERIFY, "solver: row " + std::to_string(div0_row) + " cannot determine its wire (division by zero)");
+        if (unsat_row != 0xFFFFFFFFu)
+            throw Error(B2P_ERR_VERIFY, "constraint #" + std::to_string(unsat_row) + " is not satisfied");
+    }
+
+    void solve_host(const void* inputs) {
+        h_values.assign(nb_variables, HF::zero());
+        const HF* in = static_cast<const HF*>(inputs);
+        for (uint32_t i = 0; i < nb_inputs; i++) h_values[h_inputs[i]] = in[i];
+        HF* v = h_values.data();
+        uint32_t div0 = 0xFFFFFFFFu;
+        for (uint64_t i = nb_public; i < n; i++) {
+            const uint32_t kind = h_kind[i];
+            if (!kind) continue;
+            const HF &ql = h_cols[0][i], &qr = h_cols[1][i], &qm = h_cols[2][i], &qo = h_cols[3][i], &qk = h_cols[4][i];
+            const uint32_t ia = h_x[0][i], ib = h_x[1][i], ic = h_x[2][i];
+            if (kind == SOLVE_O) {
+                HF t = qk;
+                if (!ql.is_zero()) t = t + ql * v[ia];
+                if (!qr.is_zero()) t = t + qr * v[ib];
+                if (!qm.is_zero()) t = t + qm * (v[ia] * v[ib]);
+                v[ic] = t * h_ninv[i];
+                continue;
+            }
+            const HF other = v[kind == SOLVE_A ? ib : ia];
+            HF num = qk + (kind == SOLVE_A ? qr : ql) * other;
+            if (!qo.is_zero()) num = num + qo * v[ic];
+            const HF den = (kind == SOLVE_A ? ql : qr) + qm * other;
+            if (den.is_zero()) { div0 = std::min<uint32_t>(div0, (uint32_t)i); continue; }
+            v[kind == SOLVE_A ? ia : ib] = (num * den.inverse()).neg();
+        }
+        uint32_t unsat = 0xFFFFFFFFu;
+        for (uint64_t i = 0; i < n && unsat == 0xFFFFFFFFu; i++) {
+            const HF a = v[h_x[0][i]], b = v[h_x[1][i]], o = v[h_x[2][i]];
+            HF t = h_cols[0][i] * a + h_cols[1][i] * b + h_cols[2][i] * (a * b) + h_cols[3][i] * o;
+            t = t + (i < nb_public ? a : h_cols[4][i]);
+            if (!t.is_zero()) unsat = (uint32_t)i;
+        }
+        report(div0, unsat);
+    }
+    void gather_host(HF* L, HF* R, HF* O) const {
+        for (uint64_t i = 0; i < n; i++) {
+            L[i] = h_values[h_x[0][i]];
+            R[i] = h_values[h_x[1][i]];
+            O[i] = h_values[h_x[2][i]];
+        }
+    }
+};
+
+}  // namespace b2p

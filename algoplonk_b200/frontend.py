@@ -15,7 +15,7 @@ L[i] = public input i; constraint j sits on row nb_public + j and states
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Callable, List, Sequence
+from typing import Callable, List, Optional, Sequence
 
 R_MOD = {
     "BN254": 21888242871839275222246405745257275088548364400416034343698204186575808495617,
@@ -46,6 +46,9 @@ class SparseR1CS:
     # one tuple per constraint: (ql, qr, qm, qo, qk, xa, xb, xc)
     constraints: List[tuple]
     commitments: List[Commitment] = field(default_factory=list)
+    # variables the caller assigns (frontend.NewWitness: public, then secret); None: the first nb_public + 1 ...
+    # are not known -- circuits built by Builder / the generators below always record them
+    input_vars: Optional[List[int]] = None
 
     @property
     def nb_constraints(self) -> int:
@@ -70,20 +73,27 @@ class Builder:
         self._secret_started = False
         # filled by commit(): callbacks the solver runs to obtain hash(commitment)
         self._commit_hooks: List[Callable] = []
+        self.input_vars: List[int] = []          # variables assigned by the caller, in declaration order
 
     # -- variables ---------------------------------------------------------
     def public(self, value: int) -> int:
         assert not self._secret_started, "public variables first (gnark witness order)"
         self.values.append(value % self.r)
         self.nb_public += 1
+        self.input_vars.append(len(self.values) - 1)
         return len(self.values) - 1
 
     def secret(self, value: int) -> int:
         self._secret_started = True
         self.values.append(value % self.r)
+        self.input_vars.append(len(self.values) - 1)
         return len(self.values) - 1
 
-    internal = secret
+    def internal(self, value: int) -> int:
+        """A variable the solver determines from a constraint (not part of the witness assignment)."""
+        self._secret_started = True
+        self.values.append(value % self.r)
+        return len(self.values) - 1
 
     # -- constraints -------------------------------------------------------
     def add_constraint(self, ql=0, qr=0, qm=0, qo=0, qk=0, xa=0, xb=0, xc=0) -> int:
@@ -125,7 +135,7 @@ class Builder:
 
     def build(self) -> SparseR1CS:
         return SparseR1CS(self.curve, self.nb_public, len(self.values), list(self.constraints),
-                          list(self.commitments))
+                          list(self.commitments), list(self.input_vars))
 
 
 @dataclass
@@ -200,6 +210,18 @@ def solve_lro(cs: SparseR1CS, values: Sequence[int], n: int):
     return L, R, O
 
 
+def solver_wires(cs: SparseR1CS, n: int):
+    """The variable of every row's L, R, O wire (xa, xb, xc of b2p_solver_create): public rows carry their variable
+    on L, padding rows and unused wires variable 0 -- the same rule solve_lro applies to values."""
+    xa, xb, xc = [0] * n, [0] * n, [0] * n
+    for i in range(cs.nb_public):
+        xa[i] = i
+    off = cs.nb_public
+    for j, (_, _, _, _, _, a, b, c) in enumerate(cs.constraints):
+        xa[off + j], xb[off + j], xc[off + j] = a, b, c
+    return xa, xb, xc
+
+
 def check_gates(tc: TraceColumns, L, R, O, pi2=()) -> bool:
     """Plain constraint check with public inputs written into qk (gnark completeQk)."""
     r = R_MOD[tc.curve]
@@ -256,7 +278,48 @@ def squaring_chain(curve: str, log2_rows: int, x0: int = 2):
     one, neg1 = 1, r - 1
     constraints = [(0, 0, one, neg1, 0, 1 + i, 1 + i, 2 + i) for i in range(m)]
     constraints.append((one, neg1, 0, 0, 0, 0, 1 + m, 0))          # y == x_m
-    cs = SparseR1CS(curve, 1, m + 2, constraints)
+    cs = SparseR1CS(curve, 1, m + 2, constraints, input_vars=[0, 1])
+    return cs, values
+
+
+def wide_mimc_circuit(curve: str, lanes: int, rounds: int, seed: int = 1):
+    """A wide, shallow circuit (SURVEY 8f rank 4's case for solving on the GPU): `lanes` independent MiMC-style
+    permutations of `rounds` rounds  x <- (x + c_i)^5  (one addition gate with a constant, three multiplication
+    gates), e.g. the leaves of a Merkle tree hashed side by side.  Public: the output of lane 0.  Depth 4*rounds
+    levels, every level `lanes` rows wide.  Returns (SparseR1CS, values); built directly, like squaring_chain."""
+    import random
+    r = R_MOD[curve]
+    rng = random.Random(seed)
+    consts = mimc_constants(curve)
+    neg1 = r - 1
+    values = [0] + [rng.randrange(r) for _ in range(lanes)]      # var 0 = public output of lane 0, then the lane inputs
+    cur = list(range(1, lanes + 1))
+    constraints = []
+
+    def gate_level(make):                                        # one row per lane: row order = level order
+        for j in range(lanes):
+            row, val = make(j)
+            values.append(val % r)
+            constraints.append(row + (len(values) - 1,))
+            cur_next[j] = len(values) - 1
+
+    for i in range(rounds):
+        c = consts[i % len(consts)]
+        cur_next = [0] * lanes
+        gate_level(lambda j: ((1, 0, 0, neg1, c, cur[j], 0), values[cur[j]] + c))                 # t = x + c
+        t = cur_next
+        cur_next = [0] * lanes
+        gate_level(lambda j: ((0, 0, 1, neg1, 0, t[j], t[j]), values[t[j]] * values[t[j]]))       # t^2
+        t2 = cur_next
+        cur_next = [0] * lanes
+        gate_level(lambda j: ((0, 0, 1, neg1, 0, t2[j], t2[j]), values[t2[j]] * values[t2[j]]))   # t^4
+        t4 = cur_next
+        cur_next = [0] * lanes
+        gate_level(lambda j: ((0, 0, 1, neg1, 0, t4[j], t[j]), values[t4[j]] * values[t[j]]))     # t^5
+        cur = cur_next
+    values[0] = values[cur[0]]
+    constraints.append((1, neg1, 0, 0, 0, 0, cur[0], 0))         # y == lane 0's output
+    cs = SparseR1CS(curve, 1, len(values), constraints, input_vars=list(range(0, lanes + 1)))
     return cs, values
 
 
@@ -287,7 +350,7 @@ def random_dense_circuit(curve: str, log2_rows: int, seed: int = 0, nb_public: i
             values.append((-(lin + qk)) * pow(qo, -1, r) % r)
             c = len(values) - 1
         constraints.append((ql, qr, qm, qo, qk, a, b, c))
-    return SparseR1CS(curve, nb_public, len(values), constraints), values
+    return SparseR1CS(curve, nb_public, len(values), constraints, input_vars=list(range(nb_public + 1))), values
 
 
 # ---------------------------------------------------------------------------

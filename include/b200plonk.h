@@ -391,6 +391,35 @@ int b2p_circuit_save(const char* path, int curve, uint64_t n, uint32_t nb_public
                      const void* vk_transcript, uint64_t vk_transcript_len);
 int b2p_circuit_load_file(b2p_srs* srs, const char* path, b2p_circuit** out);
 
+/* ---- witness solver (replaces: spr.Solve inside plonk.Prove, algoplonk.go:81-89) ----
+ *
+ * Every row  ql*a + qr*b + qm*a*b + qo*c + qk = 0  with exactly one unassigned wire determines that wire (gnark's
+ * solver rule).  b2p_solver_create analyses the rows once (which wire each row solves, dependency levels -- the
+ * levels gnark computes at compile time for its goroutines); b2p_solver_solve runs level after level on the GPU
+ * (one thread per row, runs of narrow levels inside one block) or, for deep narrow circuits where a dependency
+ * chain is the whole job, on one host thread; B2P_SOLVE_AUTO picks by a cost model of the level structure.
+ * Columns are the padded trace of b2p_circuit_load (n rows, public rows first, qk WITHOUT public inputs); xa xb xc
+ * give the variable of each row's L R O wire (padding rows and unused wires: variable 0, as gnark pads).
+ * input_ids: the variables assigned by the caller (public, then secret), values in the same order in `inputs`.
+ * Hints (BSB22 commitments, gnark hint functions) are not solved: such rows make create fail with B2P_ERR_ARG.
+ * solve: B2P_ERR_VERIFY "constraint #i is not satisfied" when the assignment breaks a row (every row is checked).
+ * L R O: n Fr each (Montgomery), what b2p_prove takes; the _dev form leaves them in HBM (valid until the next
+ * solve on this handle) for b2p_prove_dev.  One call at a time per handle. */
+#define B2P_SOLVE_AUTO   0
+#define B2P_SOLVE_HOST   1
+#define B2P_SOLVE_DEVICE 2
+typedef struct b2p_solver b2p_solver;
+int b2p_solver_create(int curve, uint64_t n, uint32_t nb_public, uint64_t nb_variables,
+                      const uint32_t* input_ids, uint32_t nb_inputs,
+                      const void* ql, const void* qr, const void* qm, const void* qo, const void* qk,
+                      const uint32_t* xa, const uint32_t* xb, const uint32_t* xc, b2p_solver** out);
+int b2p_solver_solve(b2p_solver* s, const void* inputs, int where, void* L, void* R, void* O);
+int b2p_solver_solve_dev(b2p_solver* s, const void* inputs, int where, void** dL, void** dR, void** dO);
+/* out[8]: levels, widest level, solved rows, launches per solve, estimated host us, estimated device us,
+ * last solve in us (wall), where the last solve ran (B2P_SOLVE_HOST / B2P_SOLVE_DEVICE) */
+int b2p_solver_info(const b2p_solver* s, uint64_t* out);
+void b2p_solver_free(b2p_solver* s);
+
 /* ---- instrumentation -------------------------------------------------------- */
 
 #define B2P_STAT_TOTAL_MS        0   /* b2p_prove wall time incl. H2D/D2H               */

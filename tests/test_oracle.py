@@ -547,3 +547,26 @@ def test_oracle_g2_group_law(curve, name):
     assert opair.g2_add(cv, opair.g2_add(cv, P, Q), Q) == opair.g2_add(cv, P, opair.g2_add(cv, Q, Q))
     for tau in (2, 12345, cv.r - 1):
         assert api.g2_from_mont_bytes(curve, api.g2_unsafe(curve, tau))[1] == opair.g2_mul(cv, P, tau)
+
+
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+def test_oracle_solver_against_the_eager_front_end(curve):
+    """oracle/solver.py (gnark's solving rule, the checker of b2p_solver_solve) reproduces the witness the front end
+    computed while it built the circuit -- two independent routes to the same assignment -- and reports broken inputs."""
+    from algoplonk_b200 import frontend as fe
+    from oracle import solver as osolver
+    cv = po.CURVES[curve]
+    B = fe.basic_circuit(curve)
+    M, _ = fe.merkle_circuit(curve, depth=2)
+    for cs, values in ((B.build(), B.values), (M.build(), M.values), fe.squaring_chain(curve, 8, x0=3),
+                       fe.random_dense_circuit(curve, 8, seed=1), fe.wide_mimc_circuit(curve, 9, 3)):
+        inputs = [values[v] for v in cs.input_vars]
+        val, levels = osolver.solve(cv.r, cs.nb_public, cs.nb_variables, cs.constraints, cs.input_vars, inputs)
+        assert val == [v % cv.r for v in values]
+        tc = fe.build_trace(cs)
+        assert fe.check_gates(tc, *fe.solve_lro(cs, val, tc.n))
+        assert [fe.solver_wires(cs, tc.n)[k][cs.nb_public + j] for k in range(3) for j in (0,)] == list(cs.constraints[0][5:8])
+    cs = B.build()
+    with pytest.raises(osolver.Unsatisfied):
+        osolver.solve(cv.r, cs.nb_public, cs.nb_variables, cs.constraints, cs.input_vars, [3, 4, 6])
+    assert max(osolver.solve(cv.r, 1, *(lambda c, v: (c.nb_variables, c.constraints, c.input_vars, [v[0], v[1]]))(*fe.squaring_chain(curve, 6)))[1]) == 62
