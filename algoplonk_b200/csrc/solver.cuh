@@ -85,6 +85,12 @@ __global__ void __launch_bounds__(SOLVER_NARROW_THREADS) k_solve_narrow(SolverCo
         __syncthreads();
     }
 }
+// the caller's assignment: values[ids[i]] = in[i]
+template <class F>
+__global__ void k_solver_inputs(F* values, const F* __restrict__ in, const uint32_t* __restrict__ ids, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) st_field(values + ids[i], ld_field(in + i));
+}
 // -1 / qo for the rows that solve their O wire (once, at create)
 template <class F>
 __global__ void k_solver_ninv(F* ninv, const F* __restrict__ qo, const uint8_t* __restrict__ kind, uint64_t n) {
@@ -315,11 +321,11 @@ struct Solver : SolverBase {
         const SolverCols<Fr> c = dcols();
         const uint32_t init[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
         B2P_CUDA(cudaMemcpyAsync(d_flags.p, init, sizeof init, cudaMemcpyHostToDevice, st));
-        // inputs are scattered to their variables on the host side of the copy: ids are arbitrary
-        h_values.assign(nb_variables, HF::zero());
-        const HF* in = static_cast<const HF*>(inputs);
-        for (uint32_t i = 0; i < nb_inputs; i++) h_values[h_inputs[i]] = in[i];
-        B2P_CUDA(cudaMemcpyAsync(d_values.p, h_values.data(), nb_variables * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        // only the inputs travel; every other variable is written by the row that determines it (create() checked that)
+        if (nb_inputs) {
+            B2P_CUDA(cudaMemcpyAsync(d_in.p, inputs, nb_inputs * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            B2P_LAUNCH((k_solver_inputs<Fr>), div_up(nb_inputs, 128), 128, 0, st, d_values.p, d_in.p, d_inputs.p, nb_inputs);
+        }
         for (const SolverLaunch& s : plan) {
             if (s.narrow)
                 B2P_LAUNCH((k_solve_narrow<Fr>), 1, SOLVER_NARROW_THREADS, 0, st, c, d_values.p, d_ops.p, d_level_off.p,

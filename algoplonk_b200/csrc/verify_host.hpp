@@ -119,14 +119,14 @@ struct HostVerifier {
     // X || Y big-endian.  Infinity: all zero (BN254, MarshalSolidity, helper.go:16-17) or, on BLS12-381, 0x40 followed
     // by zeros -- what G1Affine.RawBytes() writes (helper.go:35; verifier/verifier.go:95-99); all zero is accepted
     // there too.  false: not reduced, not on the curve, or (BLS12-381) not in the r-torsion subgroup.
-    static bool parse_point(const uint8_t* in, Aff* out) {
+    static bool parse_point(const uint8_t* in, Aff* out, bool check_subgroup = true) {
         bool zero = true;
         for (int i = 1; i < PB; i++) zero &= in[i] == 0;
         if (zero && (in[0] == 0 || (BLS && in[0] == 0x40))) { *out = {Fp::zero(), Fp::zero(), true}; return true; }
         Aff a{Fp::zero(), Fp::zero(), false};
         if (!from_be(in, NB, &a.x, false) || !from_be(in + NB, NB, &a.y, false)) return false;
         if (!(a.y.sqr() == a.x.sqr() * a.x + Fp::from_u64(PC::B))) return false;
-        if (BLS && !in_g1_subgroup(a)) return false;       // BN254's G1 has cofactor 1: the curve equation suffices
+        if (BLS && check_subgroup && !in_g1_subgroup(a)) return false;   // BN254's G1 has cofactor 1: the curve equation suffices
         *out = a;
         return true;
     }
@@ -199,10 +199,26 @@ struct HostVerifier {
     };
     static uint64_t proof_size(uint32_t k) { return 9ull * PB + 6 * 32 + (uint64_t)k * (32 + PB); }
 
-    // Steps 1-5: everything but the pairing.  On success the proof is valid iff e(lhs, G2[0]) e(rhs, G2[1]) == 1.
-    // false = rejected before the pairing, *why says at which check
-    static bool reduce(const Key& vk, const uint8_t* proof, uint64_t proof_len, const uint8_t* pub, uint64_t pub_len,
-                       Aff* lhs_out, Aff* rhs_out, std::string* why) {
+    // One proof on its way through the checks.  The three point combinations of the verifier ([Lin], the folded digest,
+    // the pair for the pairing check) are REQUESTS (pts / sc / plus): reduce() answers them with lincomb on the host,
+    // the device batch verifier (verify_batch.cuh) answers the requests of a whole batch with one kernel per stage.
+    struct Staged {
+        Aff LRO[3], H[3], Z, Wz, Wzw;
+        Fr l_z, r_z, o_z, s1_z, s2_z, z_zw, zeta, omega, lin_z, claims, v;
+        std::vector<Fr> qcp_z;
+        std::vector<Aff> bsb, vkp;
+        std::vector<uint8_t> vk_fs, lro_fs;
+        Aff G1, lin, digest;
+        // the current request:  result = sum sc[i] pts[i] + sum plus[j]   (stage 3 has a second one for rhs, negated)
+        std::vector<Aff> pts, plus, pts2, plus2;
+        std::vector<Fr> sc, sc2;
+        std::vector<Aff> to_check;      // points whose r-torsion test was deferred (stage1's defer_subgroup)
+    };
+    // Steps 1-3: parse, challenges, PI(zeta), the scalars of [Lin].  false = rejected, *why says at which check
+    // defer_subgroup: the r-torsion tests of the proof's points (BLS12-381) are left to the caller, which finds the
+    // points in st.to_check -- the device batch verifier runs them as [r] P on the GPU with the stage-1 combinations
+    static bool stage1(const Key& vk, const uint8_t* proof, uint64_t proof_len, const uint8_t* pub, uint64_t pub_len,
+                       Staged& st, std::string* why, bool defer_subgroup = false) {
         auto fail = [&](const char* m) { if (why) *why = m; return false; };
         const uint32_t k = vk.k;
         if (vk.n < 2 || (vk.n & (vk.n - 1))) return fail("domain size is not a power of two");
@@ -212,11 +228,20 @@ struct HostVerifier {
 
         // -- proof fields (helper.go:27-88) -------------------------------------------------------------
         const uint8_t* p = proof;
-        Aff LRO[3], H[3], Z, Wz, Wzw;
-        Fr l_z, r_z, o_z, s1_z, s2_z, z_zw;
-        std::vector<Fr> qcp_z(k);
-        std::vector<Aff> bsb(k);
-        auto point = [&](Aff* a) { bool ok = parse_point(p, a); p += PB; return ok; };
+        Aff (&LRO)[3] = st.LRO, (&H)[3] = st.H;
+        Aff &Z = st.Z, &Wz = st.Wz, &Wzw = st.Wzw;
+        Fr &l_z = st.l_z, &r_z = st.r_z, &o_z = st.o_z, &s1_z = st.s1_z, &s2_z = st.s2_z, &z_zw = st.z_zw;
+        std::vector<Fr>& qcp_z = st.qcp_z;
+        std::vector<Aff>& bsb = st.bsb;
+        qcp_z.assign(k, Fr::zero());
+        bsb.assign(k, Aff{Fp::zero(), Fp::zero(), true});
+        st.to_check.clear();
+        auto point = [&](Aff* a) {
+            bool ok = parse_point(p, a, !defer_subgroup);
+            p += PB;
+            if (ok && BLS && defer_subgroup && !a->inf) st.to_check.push_back(*a);
+            return ok;
+        };
         auto scalar = [&](Fr* f) { bool ok = from_be(p, 32, f, false); p += 32; return ok; };
         bool ok = true;
         for (int i = 0; i < 3; i++) ok &= point(&LRO[i]);
@@ -234,19 +259,22 @@ struct HostVerifier {
             if (!from_be(pub + 32 * i, 32, &pubv[i], false)) return fail("a public input is not reduced mod r");
 
         // -- verifying key ----------------------------------------------------------------------------------
-        std::vector<Aff> vkp(8 + k);
-        std::vector<uint8_t> vk_fs((size_t)(8 + k) * PB);
+        std::vector<Aff>& vkp = st.vkp;
+        std::vector<uint8_t>& vk_fs = st.vk_fs;
+        vkp.resize(8 + k);
+        vk_fs.resize((size_t)(8 + k) * PB);
         for (uint32_t i = 0; i < 8 + k; i++) {
             vkp[i] = load_aff(vk.vk_points + (size_t)i * PB);
             marshal(vkp[i], &vk_fs[(size_t)i * PB], true);
         }
-        const Aff &S1 = vkp[0], &S2 = vkp[1], &S3 = vkp[2], &Ql = vkp[3], &Qr = vkp[4], &Qm = vkp[5], &Qo = vkp[6],
-                  &Qk = vkp[7];
-        const Aff G1 = load_aff(vk.g1);
+        const Aff &S3 = vkp[2], &Ql = vkp[3], &Qr = vkp[4], &Qm = vkp[5], &Qo = vkp[6], &Qk = vkp[7];
+        st.G1 = load_aff(vk.g1);
 
         // -- challenges (templateLogicSigBN254.go:131-140) ---------------------------------------------------
-        uint8_t gamma_pre[32], beta_pre[32], alpha_pre[32], zeta_pre[32], pb[PB], b32[32];
-        std::vector<uint8_t> lro_fs(3 * PB), bsb_fs((size_t)k * PB);
+        uint8_t gamma_pre[32], beta_pre[32], alpha_pre[32], zeta_pre[32], pb[PB];
+        std::vector<uint8_t>& lro_fs = st.lro_fs;
+        std::vector<uint8_t> bsb_fs((size_t)k * PB);
+        lro_fs.resize(3 * PB);
         for (int j = 0; j < 3; j++) marshal(LRO[j], &lro_fs[j * PB], true);
         for (uint32_t c = 0; c < k; c++) marshal(bsb[c], &bsb_fs[(size_t)c * PB], true);
         Sha256 hs;
@@ -258,10 +286,12 @@ struct HostVerifier {
         for (int j = 0; j < 3; j++) { marshal(H[j], pb, true); hs.update(pb, PB); }
         hs.final(zeta_pre);
         const Fr gamma = fr_mod(gamma_pre), beta = fr_mod(beta_pre), alpha = fr_mod(alpha_pre), zeta = fr_mod(zeta_pre);
+        st.zeta = zeta;
 
         // -- PI(zeta), alpha^2 L_1(zeta) (:142-201) ----------------------------------------------------------
         const Fr one = Fr::one();
         const Fr omega = root_of_unity(vk.n);
+        st.omega = omega;
         const Fr zn = pow_u64(zeta, vk.n);
         const Fr zh = zn - one;
         const Fr zh_n = zh * Fr::from_u64(vk.n).inverse();
@@ -297,7 +327,7 @@ struct HostVerifier {
 
         // -- constant term of the linearised polynomial (:203-218) --------------------------------------------
         const Fr t1 = l_z + beta * s1_z + gamma, t2 = r_z + beta * s2_z + gamma;
-        const Fr lin_z = (t1 * t2 * (o_z + gamma) * alpha * z_zw + PI - a2l).neg();
+        st.lin_z = (t1 * t2 * (o_z + gamma) * alpha * z_zw + PI - a2l).neg();
 
         // -- [Lin] (:220-278) ---------------------------------------------------------------------------------
         const Fr u = Fr::from_u64(PC::FrP::SHIFT_SMALL), u2 = u * u;
@@ -306,60 +336,109 @@ struct HostVerifier {
         const Fr s2p = a2l - alpha * (l_z + bz + gamma) * (r_z + bz * u + gamma) * (o_z + bz * u2 + gamma);
         const Fr zn2 = pow_u64(zeta, vk.n + 2);
         const Fr mzh = zh.neg();
-        std::vector<Aff> pts = {Ql, Qr, Qm, Qo};               // Qk enters with coefficient one
-        std::vector<Fr> sc = {l_z, r_z, l_z * r_z, o_z};
+        std::vector<Aff>& pts = st.pts;
+        std::vector<Fr>& sc = st.sc;
+        pts = {Ql, Qr, Qm, Qo};                                // Qk enters with coefficient one
+        sc = {l_z, r_z, l_z * r_z, o_z};
         for (uint32_t c = 0; c < k; c++) { pts.push_back(bsb[c]); sc.push_back(qcp_z[c]); }
         pts.push_back(S3); sc.push_back(s1p);
         pts.push_back(Z); sc.push_back(s2p);
         pts.push_back(H[0]); sc.push_back(mzh);
         pts.push_back(H[1]); sc.push_back(mzh * zn2);
         pts.push_back(H[2]); sc.push_back(mzh * zn2 * zn2);
-        const Aff lin = lincomb(pts, sc, {Qk});
-
-        // -- fold challenge and folded opening at zeta (:280-321) ----------------------------------------------
-        uint8_t v_pre[32];
-        hs.reset();
+        st.plus = {Qk};
+        return true;
+    }
+    // Step 4: the fold challenge and the request for the folded digest at zeta (:280-321); consumes [Lin]
+    static void stage2(const Key& vk, Staged& st, const Aff& lin) {
+        const uint32_t k = vk.k;
+        st.lin = lin;
+        uint8_t v_pre[32], pb[PB], b32[32];
+        Sha256 hs;
         hs.update("gamma");
-        to_be(zeta, b32); hs.update(b32, 32);
+        to_be(st.zeta, b32); hs.update(b32, 32);
         marshal(lin, pb, false); hs.update(pb, PB);
-        hs.update(lro_fs);
-        hs.update(vk_fs.data(), 2 * PB);
-        hs.update(vk_fs.data() + 8 * PB, (size_t)k * PB);
-        to_be(lin_z, b32); hs.update(b32, 32);
-        const Fr evs[5] = {l_z, r_z, o_z, s1_z, s2_z};
+        hs.update(st.lro_fs);
+        hs.update(st.vk_fs.data(), 2 * PB);
+        hs.update(st.vk_fs.data() + 8 * PB, (size_t)k * PB);
+        to_be(st.lin_z, b32); hs.update(b32, 32);
+        const Fr evs[5] = {st.l_z, st.r_z, st.o_z, st.s1_z, st.s2_z};
         for (int i = 0; i < 5; i++) { to_be(evs[i], b32); hs.update(b32, 32); }
-        for (uint32_t c = 0; c < k; c++) { to_be(qcp_z[c], b32); hs.update(b32, 32); }
-        to_be(z_zw, b32); hs.update(b32, 32);
+        for (uint32_t c = 0; c < k; c++) { to_be(st.qcp_z[c], b32); hs.update(b32, 32); }
+        to_be(st.z_zw, b32); hs.update(b32, 32);
         hs.final(v_pre);
         const Fr v = fr_mod(v_pre);
-        pts = {lin, LRO[0], LRO[1], LRO[2], S1, S2};
-        std::vector<Fr> vals = {lin_z, l_z, r_z, o_z, s1_z, s2_z};
-        for (uint32_t c = 0; c < k; c++) { pts.push_back(vkp[8 + c]); vals.push_back(qcp_z[c]); }
-        sc.clear();
-        Fr claims = Fr::zero(), acc = one;
+        st.v = v;
+        std::vector<Aff> pts = {lin, st.LRO[0], st.LRO[1], st.LRO[2], st.vkp[0], st.vkp[1]};
+        std::vector<Fr> vals = {st.lin_z, st.l_z, st.r_z, st.o_z, st.s1_z, st.s2_z};
+        for (uint32_t c = 0; c < k; c++) { pts.push_back(st.vkp[8 + c]); vals.push_back(st.qcp_z[c]); }
+        std::vector<Fr> sc;
+        Fr claims = Fr::zero(), acc = Fr::one();
         for (size_t i = 0; i < pts.size(); i++) {
             sc.push_back(acc);
             claims = claims + vals[i] * acc;
             acc = acc * v;
         }
-        const Aff digest = lincomb(std::vector<Aff>(pts.begin() + 1, pts.end()), std::vector<Fr>(sc.begin() + 1, sc.end()),
-                                   {lin});                     // [Lin] enters with coefficient v^0 = 1
-
-        // -- both openings in one pairing check (:323-356) ------------------------------------------------------
-        uint8_t u_pre[32];
-        hs.reset();
+        st.claims = claims;
+        st.pts.assign(pts.begin() + 1, pts.end());
+        st.sc.assign(sc.begin() + 1, sc.end());
+        st.plus = {lin};                                       // [Lin] enters with coefficient v^0 = 1
+    }
+    // Step 5: both openings in one pairing check (:323-356); consumes the digest.  Requests: lhs = sum sc pts + plus,
+    // rhs = -(sum sc2 pts2 + plus2)
+    static void stage3(Staged& st, const Aff& digest) {
+        st.digest = digest;
+        uint8_t u_pre[32], pb[PB], b32[32];
+        Sha256 hs;
         marshal(digest, pb, false); hs.update(pb, PB);
-        marshal(Wz, pb, false); hs.update(pb, PB);
-        marshal(Z, pb, true); hs.update(pb, PB);
-        marshal(Wzw, pb, false); hs.update(pb, PB);
-        to_be(zeta, b32); hs.update(b32, 32);
-        to_be(v, b32); hs.update(b32, 32);
+        marshal(st.Wz, pb, false); hs.update(pb, PB);
+        marshal(st.Z, pb, true); hs.update(pb, PB);
+        marshal(st.Wzw, pb, false); hs.update(pb, PB);
+        to_be(st.zeta, b32); hs.update(b32, 32);
+        to_be(st.v, b32); hs.update(b32, 32);
         hs.final(u_pre);
         const Fr ub = fr_mod(u_pre);
-        claims = claims + z_zw * ub;
-        *lhs_out = lincomb({Z, G1, Wz, Wzw}, {ub, claims.neg(), zeta, ub * zeta * omega}, {digest});
-        *rhs_out = neg(lincomb({Wzw}, {ub}, {Wz}));
+        const Fr claims = st.claims + st.z_zw * ub;
+        st.pts = {st.Z, st.G1, st.Wz, st.Wzw};
+        st.sc = {ub, claims.neg(), st.zeta, ub * st.zeta * st.omega};
+        st.plus = {digest};
+        st.pts2 = {st.Wzw};
+        st.sc2 = {ub};
+        st.plus2 = {st.Wz};
+    }
+
+    // Steps 1-5: everything but the pairing.  On success the proof is valid iff e(lhs, G2[0]) e(rhs, G2[1]) == 1.
+    // false = rejected before the pairing, *why says at which check
+    static bool reduce(const Key& vk, const uint8_t* proof, uint64_t proof_len, const uint8_t* pub, uint64_t pub_len,
+                       Aff* lhs_out, Aff* rhs_out, std::string* why) {
+        Staged st;
+        if (!stage1(vk, proof, proof_len, pub, pub_len, st, why)) return false;
+        stage2(vk, st, lincomb(st.pts, st.sc, st.plus));
+        stage3(st, lincomb(st.pts, st.sc, st.plus));
+        *lhs_out = lincomb(st.pts, st.sc, st.plus);
+        *rhs_out = neg(lincomb(st.pts2, st.sc2, st.plus2));
         return true;
+    }
+
+    // The folding weights of a batch: rho_0 = 1, rho_i = 128 bits hashed from the whole batch
+    static std::vector<Fr> batch_weights(const uint8_t* proofs, uint64_t proof_len, const uint8_t* pubs, uint64_t pub_len,
+                                         uint64_t count) {
+        uint8_t seed[32];
+        Sha256 hs;
+        hs.update("b2p-batch-verify");
+        hs.update(proofs, count * proof_len);
+        hs.update(pubs, count * pub_len);
+        hs.final(seed);
+        std::vector<Fr> rho(count);
+        if (count) rho[0] = Fr::one();
+        for (uint64_t i = 1; i < count; i++) {
+            uint8_t d[32], ctr[8], lo[32] = {0};
+            for (int b = 0; b < 8; b++) ctr[b] = (uint8_t)(i >> (8 * b));
+            hs.reset(); hs.update(seed, 32); hs.update(ctr, 8); hs.final(d);
+            memcpy(lo + 16, d, 16);
+            rho[i] = fr_mod(lo);
+        }
+        return rho;
     }
 
     static bool pair_is_one(const Key& vk, const Aff& lhs, const Aff& rhs, std::string* why) {
@@ -440,21 +519,7 @@ struct HostVerifier {
             if (why) *why = whys[best];
             return false;
         }
-        uint8_t seed[32];
-        Sha256 hs;
-        hs.update("b2p-batch-verify");
-        hs.update(proofs, count * proof_len);
-        hs.update(pubs, count * pub_len);
-        hs.final(seed);
-        std::vector<Fr> rho(count);
-        rho[0] = Fr::one();
-        for (uint64_t i = 1; i < count; i++) {
-            uint8_t d[32], ctr[8], lo[32] = {0};
-            for (int b = 0; b < 8; b++) ctr[b] = (uint8_t)(i >> (8 * b));
-            hs.reset(); hs.update(seed, 32); hs.update(ctr, 8); hs.final(d);
-            memcpy(lo + 16, d, 16);
-            rho[i] = fr_mod(lo);
-        }
+        const std::vector<Fr> rho = batch_weights(proofs, proof_len, pubs, pub_len, count);
         return pair_is_one(vk, lincomb(lhs, rho), lincomb(rhs, rho), why);
     }
 };

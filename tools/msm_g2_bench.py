@@ -28,7 +28,7 @@ if __name__ == "__main__":
         P = opair.g2_add(cv, P, gen)
     sc = [rng.randrange(cv.r) for _ in range(n)]
     raw = api.g2_to_mont_bytes(curve, pts)
-    api.msm_g2_raw(curve, raw[: 4 * 2 * cv.fp_bytes * 4], sc[:4])          # warm-up: context, module load
+    api.msm_g2_raw(curve, raw[: 4 * 4 * cv.fp_bytes], sc[:4])          # warm-up: context, module load
     best = 1e9
     for _ in range(3):
         t0 = time.perf_counter()
