@@ -88,6 +88,8 @@ SYMBOLS = [
     ("b2p_verify", _int, [_int, _u64, _u32, _u32, C.POINTER(_u64), _vp, _vp, _vp, _vp, _u64, _vp, _u64]),
     ("b2p_verify_batch", _int, [_int, _u64, _u32, _u32, C.POINTER(_u64), _vp, _vp, _vp, _vp, _u64, _vp, _u64, _u64,
                           C.POINTER(_u64)]),
+    ("b2p_verify_batch_dev", _int, [_int, _u64, _u32, _u32, C.POINTER(_u64), _vp, _vp, _vp, _vp, _u64, _vp, _u64, _u64,
+                              C.POINTER(_u64)]),
     ("b2p_pairing_check", _int, [_int, _vp, _vp, _u64, C.POINTER(_int)]),
     ("b2p_kzg_vk_load", _int, [_int, _vp, _u64, _vp, _vp]),
     ("b2p_g2_generate_unsafe", _int, [_int, _vp, _vp]),

@@ -172,9 +172,11 @@ def verify(curve: str, n: int, nb_public: int, commitment_indexes: Sequence[int]
 
 
 def verify_batch(curve: str, n: int, nb_public: int, commitment_indexes: Sequence[int], vk_points_raw: bytes,
-                 kzg_g1_raw: bytes, kzg_g2_raw: bytes, proofs: Sequence[bytes], public_inputs: Sequence[bytes]) -> None:
-    """Many proofs of one circuit, one pairing check (b2p_verify_batch).  Raises ValueError naming the first proof
-    rejected before the pairing, or "batch" when only the folded pairing check failed."""
+                 kzg_g1_raw: bytes, kzg_g2_raw: bytes, proofs: Sequence[bytes], public_inputs: Sequence[bytes],
+                 device: bool = False) -> None:
+    """Many proofs of one circuit, one pairing check (b2p_verify_batch; device=True: b2p_verify_batch_dev, the point
+    combinations on the GPU).  Raises ValueError naming the first proof rejected before the pairing, or "batch" when
+    only the folded pairing check failed."""
     if len(proofs) != len(public_inputs):
         raise ValueError("one public-input blob per proof")
     if len({len(p) for p in proofs}) > 1 or len({len(p) for p in public_inputs}) > 1:
@@ -185,9 +187,11 @@ def verify_batch(curve: str, n: int, nb_public: int, commitment_indexes: Sequenc
     ql = len(public_inputs[0]) if public_inputs else 0
     pj, qj = b"".join(proofs), b"".join(public_inputs)
     bad = C.c_uint64(0)
-    rc = _lib.load().b2p_verify_batch(CURVE_ID[curve], n, nb_public, k, cidx, _buf(vk_points_raw), _buf(kzg_g1_raw),
-                                      _buf(kzg_g2_raw), _buf(pj) if pj else None, pl, _buf(qj) if qj else None, ql,
-                                      len(proofs), C.byref(bad))
+    if device:
+        _lib.init()
+    fn = _lib.load().b2p_verify_batch_dev if device else _lib.load().b2p_verify_batch
+    rc = fn(CURVE_ID[curve], n, nb_public, k, cidx, _buf(vk_points_raw), _buf(kzg_g1_raw),
+            _buf(kzg_g2_raw), _buf(pj) if pj else None, pl, _buf(qj) if qj else None, ql, len(proofs), C.byref(bad))
     if rc == _lib.ERR_VERIFY:
         raise ValueError(_lib.load().b2p_last_error().decode())
     _lib.check(rc)
@@ -403,11 +407,12 @@ class CompiledCircuit:
             raise ValueError("error verifying proof")
         return VerifiedProof(proof, public)
 
-    def VerifyProofs(self, proofs: Sequence[bytes], publics: Sequence[bytes]) -> None:
-        """Many proofs of this circuit, one folded pairing check (b2p_verify_batch); raises ValueError when rejected."""
+    def VerifyProofs(self, proofs: Sequence[bytes], publics: Sequence[bytes], device: bool = False) -> None:
+        """Many proofs of this circuit, one folded pairing check (b2p_verify_batch, or b2p_verify_batch_dev with
+        device=True); raises ValueError when rejected."""
         self._key_material()
         verify_batch(self.Curve, self.trace.n, self.trace.nb_public, self.trace.commitment_constraint_indexes,
-                     self._vk_raw, self._g1_raw, self.srs.g2, proofs, publics)
+                     self._vk_raw, self._g1_raw, self.srs.g2, proofs, publics, device=device)
 
     def VerifyProof(self, proof_bytes: bytes, public_bytes: bytes) -> None:
         """plonk.Verify(proof, cc.Vk, publicWitness) on marshalled bytes; raises ValueError when rejected."""

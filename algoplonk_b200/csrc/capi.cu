@@ -568,6 +568,29 @@ API int b2p_verify_batch(int curve, uint64_t n, uint32_t nb_public, uint32_t k, 
                                             (bad < count ? " " + std::to_string(bad) : std::string(" batch")) + ": " + why);
     });
 }
+API int b2p_verify_batch_dev(int curve, uint64_t n, uint32_t nb_public, uint32_t k, const uint64_t* commitment_indexes,
+                             const void* vk_points, const void* kzg_g1, const void* kzg_g2, const void* proofs,
+                             uint64_t proof_len, const void* public_inputs, uint64_t public_len, uint64_t count,
+                             uint64_t* first_bad) {
+    return guarded([&] {
+        require_curve(curve);
+        require(vk_points && kzg_g1 && kzg_g2 && (count == 0 || proofs) && (k == 0 || commitment_indexes) &&
+                    (public_len == 0 || count == 0 || public_inputs), "null argument");
+        require(k <= 64, "too many BSB22 commitments");
+        require(count <= (1u << 20), "too many proofs in one batch");
+        current_device();                          // fails loudly without a usable GPU: no fallback to the host batch
+        HostVerifyKey vk{n, nb_public, k, commitment_indexes, vk_points, kzg_g1, kzg_g2};
+        std::string why;
+        uint64_t bad = count;
+        static const uint8_t none = 0;
+        const bool ok = device_verify_batch(curve, vk, proofs ? proofs : &none, proof_len,
+                                            public_inputs ? public_inputs : &none, public_len, count, &bad, &why);
+        if (first_bad) *first_bad = bad;
+        if (!ok)
+            throw Error(B2P_ERR_VERIFY, "error verifying proof" +
+                                            (bad < count ? " " + std::to_string(bad) : std::string(" batch")) + ": " + why);
+    });
+}
 API int b2p_pairing_check(int curve, const void* g1_points, const void* g2_points, uint64_t n, int* is_one) {
     return guarded([&] {
         require_curve(curve);

@@ -131,6 +131,9 @@ bool host_verify(int curve, const HostVerifyKey& vk, const void* proof, uint64_t
                  uint64_t pub_len, std::string* why);
 bool host_verify_batch(int curve, const HostVerifyKey& vk, const void* proofs, uint64_t proof_len, const void* pubs,
                        uint64_t pub_len, uint64_t count, uint64_t* first_bad, std::string* why);
+// the same with the point combinations of the whole batch on the GPU (verify_batch.cuh, inst_verify_batch.cu)
+bool device_verify_batch(int curve, const HostVerifyKey& vk, const void* proofs, uint64_t proof_len, const void* pubs,
+                         uint64_t pub_len, uint64_t count, uint64_t* first_bad, std::string* why);
 bool host_pairing_check(int curve, const void* g1s, const void* g2s, uint64_t n, std::string* why);
 const char* host_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g2, void* out_g1);
 void host_g2_unsafe(int curve, const void* tau_mont, void* out_two_g2);

@@ -469,10 +469,17 @@ def run_b200(args):
         one_ms = (time.perf_counter() - t0) / 5 * 1e3
         t0 = time.perf_counter()
         ccs[0].VerifyProofs([blob] * 16, [pub] * 16)
+        batch16_ms = (time.perf_counter() - t0) / 16 * 1e3
+        ccs[0].VerifyProofs([blob] * 8, [pub] * 8, device=True)            # module load, stream
+        t0 = time.perf_counter()
+        ccs[0].VerifyProofs([blob] * 1024, [pub] * 1024, device=True)
+        dev_us = (time.perf_counter() - t0) / 1024 * 1e6
         line["verify"] = {"accepted": True, "ms_per_proof": one_ms,
-                          "ms_per_proof_batch_of_16": (time.perf_counter() - t0) / 16 * 1e3,
-                          "where": "host thread, b2p_verify; not part of value / e2e (the reference arm times "
-                                   "plonk.Prove only)"}
+                          "ms_per_proof_batch_of_16": batch16_ms,
+                          "us_per_proof_device_batch_of_1024": dev_us,
+                          "where": "b2p_verify / b2p_verify_batch: host threads; b2p_verify_batch_dev: point "
+                                   "combinations on the GPU, transcript on host threads; none of it is part of value / "
+                                   "e2e (the reference arm times plonk.Prove only)"}
     except Exception as e:  # noqa: BLE001 -- reported in the line
         line["verify"] = {"accepted": False, "error": f"{type(e).__name__}: {e}"[:300]}
     if sharded_line is not None:

@@ -326,6 +326,15 @@ int b2p_verify_batch(int curve, uint64_t n, uint32_t nb_public, uint32_t k, cons
                      const void* vk_points, const void* kzg_g1, const void* kzg_g2,
                      const void* proofs, uint64_t proof_len,
                      const void* public_inputs, uint64_t public_len, uint64_t count, uint64_t* first_bad);
+/* The same batch with the group arithmetic on the GPU (needs b2p_init): the three point combinations of every proof
+ * -- [Lin], the folded digest, the pairing pair, 9+k / 5+k / 7 points with full-width scalars -- and BLS12-381's
+ * r-torsion tests run as one warp per combination, three launches per batch; the SHA-256 transcript and the scalar
+ * work stay on host threads; one host pairing check at the end.  Same verdicts and error reporting as
+ * b2p_verify_batch (a point outside the r-torsion subgroup is reported as such instead of as a parse failure). */
+int b2p_verify_batch_dev(int curve, uint64_t n, uint32_t nb_public, uint32_t k, const uint64_t* commitment_indexes,
+                         const void* vk_points, const void* kzg_g1, const void* kzg_g2,
+                         const void* proofs, uint64_t proof_len,
+                         const void* public_inputs, uint64_t public_len, uint64_t count, uint64_t* first_bad);
 /* prod_i e(g1_points[i], g2_points[i]) == 1 ?  (replaces the curve package's PairingCheck, the last line of
  * kzg.BatchVerifyMultiPoints; setup/trusted_setup_test.go checks its setups with the same equation).
  * Points off their curve give B2P_ERR_ARG. */
