@@ -184,12 +184,18 @@ struct DeviceBatchVerifier {
                 if (!res[j].inf) { okv[i] = 0; whys[i] = "a point of the proof is not in the r-torsion subgroup"; }
         if (first_failure()) return false;
         // ---- stage 2: fold challenge (hashes [Lin]), the folded digest
-        parallel_for(count, [&](uint64_t i) { V::stage2(vk, sts[i], res[i]); });
+        // (nothing may escape a worker thread: an exception there would be std::terminate across the C ABI)
+        auto guarded_stage = [&](uint64_t i, auto&& fn) {
+            try { fn(); } catch (...) { okv[i] = 0; try { whys[i] = "internal error while reducing the proof (out of memory?)"; } catch (...) {} }
+        };
+        parallel_for(count, [&](uint64_t i) { guarded_stage(i, [&] { V::stage2(vk, sts[i], res[i]); }); });
+        if (first_failure()) return false;
         sg = Segments();
         for (uint64_t i = 0; i < count; i++) pack(sg, sts[i]);
         res = run(sg);
         // ---- stage 3: last challenge (hashes the digest), the pair of every proof, weighted by the batch's rho_i
-        parallel_for(count, [&](uint64_t i) { V::stage3(sts[i], res[i]); });
+        parallel_for(count, [&](uint64_t i) { guarded_stage(i, [&] { V::stage3(sts[i], res[i]); }); });
+        if (first_failure()) return false;
         const std::vector<HFr> rho = V::batch_weights(proofs, proof_len, pubs, pub_len, count);
         sg = Segments();
         for (uint64_t i = 0; i < count; i++) {
