@@ -1,9 +1,8 @@
-"""GPU tests written after the round's GPU budget was spent: they have NOT run on a B200 yet.
-
-Their CPU halves are green (`tests/test_oracle.py` random-dense circuits, `tests/test_sharded.py` cyclic gloo
-collective, `tests/test_sharded_ntt.py` host run of the kernel bodies).  They live in this file so that pytest
-collects them last: under `-x` an unconfirmed case cannot hide the results of the confirmed ones.  Move each
-back next to its siblings once it has passed on hardware.
+"""GPU parity: random-dense circuits (full-width selectors, irregular copy cycles) against the C++ oracle, the cyclic
+SRS layout of the sharded MSM, and the sharded NTT's composition with it.  Written at the end of round 1 (when they
+could not run on hardware any more -- hence a file of their own); green in the round-1 driver run and throughout
+round 2.  Their CPU halves: `tests/test_oracle.py` (random-dense circuits), `tests/test_sharded.py` (cyclic gloo
+collective), `tests/test_sharded_ntt.py` (host run of the kernel bodies).
 """
 import random
 

@@ -4,7 +4,7 @@
 CPU (gloo): the committer's protocol -- header, scalar broadcast, per-rank slices of ragged vectors, all_gather of one
 point per rank, host add, STOP -- with the local sums supplied by the big-int oracle (no GPU compute on this path).
 The GPU half (a whole proof through the hook, world 1, byte-identical to the plain prover) is in
-tests/test_zz_gpu_unconfirmed.py: it was written after the round's GPU budget was spent.
+tests/test_gpu_dense_and_cyclic.py.
 """
 import json
 import os
