@@ -147,6 +147,7 @@ struct Solver : SolverBase {
     std::vector<HF> h_values;
 
     ~Solver() override {
+        if (graph) cudaGraphExecDestroy(graph);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -317,15 +318,12 @@ struct Solver : SolverBase {
         last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
 
-    void solve_device(const void* inputs) {
+    // the fixed part of a device solve: flags, input scatter, one launch per plan entry, gather + check
+    void queue_levels() {
         const SolverCols<Fr> c = dcols();
-        const uint32_t init[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        B2P_CUDA(cudaMemcpyAsync(d_flags.p, init, sizeof init, cudaMemcpyHostToDevice, st));
-        // only the inputs travel; every other variable is written by the row that determines it (create() checked that)
-        if (nb_inputs) {
-            B2P_CUDA(cudaMemcpyAsync(d_in.p, inputs, nb_inputs * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        B2P_CUDA(cudaMemsetAsync(d_flags.p, 0xFF, 2 * sizeof(uint32_t), st));
+        if (nb_inputs)
             B2P_LAUNCH((k_solver_inputs<Fr>), div_up(nb_inputs, 128), 128, 0, st, d_values.p, d_in.p, d_inputs.p, nb_inputs);
-        }
         for (const SolverLaunch& s : plan) {
             if (s.narrow)
                 B2P_LAUNCH((k_solve_narrow<Fr>), 1, SOLVER_NARROW_THREADS, 0, st, c, d_values.p, d_ops.p, d_level_off.p,
@@ -336,6 +334,33 @@ struct Solver : SolverBase {
         }
         B2P_LAUNCH((k_solver_gather<Fr>), div_up(n, 128), 128, 0, st, c, d_values.p, dL.p, dR.p, dO.p, n, nb_public,
                    d_flags.p + 1);
+    }
+    // A shallow circuit is hundreds of short launches with fixed arguments: captured once into a CUDA graph, a solve is
+    // one graph launch (B2P_SOLVER_GRAPH=0 keeps the plain launches; so does any failure to capture).
+    cudaGraphExec_t graph = nullptr;
+    bool graph_tried = false;
+    void build_graph() {
+        graph_tried = true;
+        const char* e = getenv("B2P_SOLVER_GRAPH");
+        if ((e && atoi(e) == 0) || plan.size() < 8) return;
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return; }
+        bool ok = true;
+        try { queue_levels(); } catch (...) { ok = false; }
+        if (cudaStreamEndCapture(st, &g) != cudaSuccess || !ok || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return; }
+        if (cudaGraphInstantiate(&graph, g, 0) != cudaSuccess) { cudaGetLastError(); graph = nullptr; }
+        cudaGraphDestroy(g);
+    }
+    void solve_device(const void* inputs) {
+        // only the inputs travel; every other variable is written by the row that determines it (create() checked that)
+        if (nb_inputs) B2P_CUDA(cudaMemcpyAsync(d_in.p, inputs, nb_inputs * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        if (!graph_tried) build_graph();
+        if (graph) {
+            B2P_CUDA(cudaGraphLaunch(graph, st));
+            g_launch_count += plan.size() + 2;
+        } else {
+            queue_levels();
+        }
         uint32_t flags[2];
         B2P_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
         B2P_CUDA(cudaStreamSynchronize(st));

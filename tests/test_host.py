@@ -427,3 +427,26 @@ def test_fp2_device_code_on_host(hostfield, curve):
         assert call(7, a) == (2 * a[0] % p, 2 * a[1] % p)
         inv = call(5, a)
         assert (a == (0, 0) and inv == (0, 0)) or mul(a, inv) == (1, 0)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="the point is the behaviour on a box without a GPU")
+def test_device_entry_points_fail_loudly_without_a_gpu():
+    """No CPU fallback behind the device entry points added in round 2: the device batch verifier does not quietly run
+    the host batch, and the solver (whose host path still keeps its key material in HBM) refuses to be created."""
+    import helpers as H
+    import test_verify_host as tvh
+    case = H.golden_proofs()[0]
+    (curve, n, nbp, cidx, vk, g1, g2), _, _ = tvh._verify_args(case)
+    proof, pub = bytes.fromhex(case["proof"]), bytes.fromhex(case["public_inputs"])
+    lib = _lib.load()
+    bad = C.c_uint64()
+    args = (api.CURVE_ID[curve], n, nbp, 0, None, vk, g1, g2, proof, len(proof), pub, len(pub), 1, C.byref(bad))
+    assert lib.b2p_verify_batch(*args) == 0                                  # host arithmetic: works anywhere
+    assert lib.b2p_verify_batch_dev(*args) == _lib.ERR_CUDA and b"CUDA" in lib.b2p_last_error()
+    out = C.c_void_p()
+    z = b"\0" * 256
+    w = (C.c_uint32 * 8)()
+    assert lib.b2p_solver_create(0, 8, 1, 4, (C.c_uint32 * 1)(0), 1, z, z, z, z, z, w, w, w, C.byref(out)) == _lib.ERR_CUDA
+    with pytest.raises(_lib.B200PlonkError):
+        api.msm_g2_raw("BN254", b"", [])
+
