@@ -98,6 +98,11 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            # nvidia-smi's own start-up (NVML initialisation) holds driver locks for a few hundred ms and would land in
+            # the first timed pass: wait until it delivers its first sample
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 3.0 and self.proc.poll() is None:
+                time.sleep(0.02)
         except OSError:
             self.proc = None
 
