@@ -137,83 +137,100 @@ struct DeviceBatchVerifier {
         for (auto& th : pool) th.join();
     }
 
+    static constexpr uint64_t CHUNK = 4096;      // proofs whose staged state is alive at once (a few KB each)
+
     bool verify(const typename V::Key& vk, const uint8_t* proofs, uint64_t proof_len, const uint8_t* pubs, uint64_t pub_len,
                 uint64_t count, uint64_t* bad, std::string* why) {
         if (bad) *bad = count;
         if (count == 0) return true;
-        std::vector<Staged> sts(count);
-        std::vector<std::string> whys(count);
-        std::vector<uint8_t> okv(count, 1);
-        auto first_failure = [&]() -> bool {
-            for (uint64_t i = 0; i < count; i++)
+        const std::vector<HFr> rho = V::batch_weights(proofs, proof_len, pubs, pub_len, count);
+        typename V::Ext lhs = V::Ext::inf(), rhs = V::Ext::inf();
+        for (uint64_t first = 0; first < count; first += CHUNK)
+            if (!reduce_chunk(vk, proofs, proof_len, pubs, pub_len, first, std::min(CHUNK, count - first), rho, lhs, rhs, bad, why))
+                return false;
+        return V::pair_is_one(vk, lhs.to_affine(), V::neg(rhs.to_affine()), why);
+    }
+
+    // proofs [first, first + cnt): all pre-pairing checks, then lhs += sum rho_i lhs_i, rhs += sum rho_i (W_zeta + u W_omega-zeta)_i
+    bool reduce_chunk(const typename V::Key& vk, const uint8_t* proofs, uint64_t proof_len, const uint8_t* pubs,
+                      uint64_t pub_len, uint64_t first, uint64_t cnt, const std::vector<HFr>& rho, typename V::Ext& lhs,
+                      typename V::Ext& rhs, uint64_t* bad, std::string* why) {
+        std::vector<Staged> sts(cnt);
+        std::vector<std::string> whys(cnt);
+        std::vector<uint8_t> okv(cnt, 1);
+        auto first_failure = [&]() -> bool {     // the smallest index wins, as in the host batch
+            for (uint64_t i = 0; i < cnt; i++)
                 if (!okv[i]) {
-                    if (bad) *bad = i;
+                    if (bad) *bad = first + i;
                     if (why) *why = whys[i];
                     return true;
                 }
             return false;
         };
+        // nothing may escape a worker thread: an exception there would be std::terminate across the C ABI
+        auto guarded_stage = [&](uint64_t i, auto&& fn) {
+            try { fn(); } catch (...) { okv[i] = 0; try { whys[i] = "internal error while reducing the proof (out of memory?)"; } catch (...) {} }
+        };
         // ---- stage 1: parse, challenges, the scalars of [Lin]; r-torsion tests deferred to the device
-        parallel_for(count, [&](uint64_t i) {
-            try {
-                okv[i] = V::stage1(vk, proofs + i * proof_len, proof_len, pubs + i * pub_len, pub_len, sts[i], &whys[i], true);
-            } catch (...) { okv[i] = 0; try { whys[i] = "internal error while reducing the proof (out of memory?)"; } catch (...) {} }
+        parallel_for(cnt, [&](uint64_t i) {
+            guarded_stage(i, [&] {
+                const uint64_t g = first + i;
+                okv[i] = V::stage1(vk, proofs + g * proof_len, proof_len, pubs + g * pub_len, pub_len, sts[i], &whys[i], true);
+            });
         });
-        if (first_failure()) return false;
         uint32_t order[8];
         for (int i = 0; i < 4; i++) {
             order[2 * i] = (uint32_t)HFr::M(i);
             order[2 * i + 1] = (uint32_t)(HFr::M(i) >> 32);
         }
-        auto pack = [&](Segments& sg, const Staged& s) {
-            for (size_t j = 0; j < s.pts.size(); j++) sg.pair(s.pts[j], s.sc[j]);
-            for (const HAff& p : s.plus) sg.one(p);
+        auto pack = [&](Segments& sg, uint64_t i) {       // a proof already rejected keeps its (empty) segment
+            const Staged& s = sts[i];
+            if (okv[i]) {
+                for (size_t j = 0; j < s.pts.size(); j++) sg.pair(s.pts[j], s.sc[j]);
+                for (const HAff& p : s.plus) sg.one(p);
+            }
             sg.close();
         };
         Segments sg;
-        std::vector<uint32_t> first_check(count + 1, 0);
-        for (uint64_t i = 0; i < count; i++) pack(sg, sts[i]);
-        for (uint64_t i = 0; i < count; i++) {                 // after the `count` combinations: one segment per point to test
+        std::vector<uint32_t> first_check(cnt + 1, 0);
+        for (uint64_t i = 0; i < cnt; i++) pack(sg, i);
+        for (uint64_t i = 0; i < cnt; i++) {                  // after the cnt combinations: one segment per point to test
             first_check[i] = (uint32_t)sg.count();
-            for (const HAff& p : sts[i].to_check) { sg.raw(p, order); sg.close(); }
+            if (okv[i])
+                for (const HAff& p : sts[i].to_check) { sg.raw(p, order); sg.close(); }
         }
-        first_check[count] = (uint32_t)sg.count();
+        first_check[cnt] = (uint32_t)sg.count();
         std::vector<HAff> res = run(sg);
-        for (uint64_t i = 0; i < count; i++)
+        for (uint64_t i = 0; i < cnt; i++)
             for (uint32_t j = first_check[i]; j < first_check[i + 1]; j++)
                 if (!res[j].inf) { okv[i] = 0; whys[i] = "a point of the proof is not in the r-torsion subgroup"; }
         if (first_failure()) return false;
         // ---- stage 2: fold challenge (hashes [Lin]), the folded digest
-        // (nothing may escape a worker thread: an exception there would be std::terminate across the C ABI)
-        auto guarded_stage = [&](uint64_t i, auto&& fn) {
-            try { fn(); } catch (...) { okv[i] = 0; try { whys[i] = "internal error while reducing the proof (out of memory?)"; } catch (...) {} }
-        };
-        parallel_for(count, [&](uint64_t i) { guarded_stage(i, [&] { V::stage2(vk, sts[i], res[i]); }); });
+        parallel_for(cnt, [&](uint64_t i) { guarded_stage(i, [&] { V::stage2(vk, sts[i], res[i]); }); });
         if (first_failure()) return false;
         sg = Segments();
-        for (uint64_t i = 0; i < count; i++) pack(sg, sts[i]);
+        for (uint64_t i = 0; i < cnt; i++) pack(sg, i);
         res = run(sg);
         // ---- stage 3: last challenge (hashes the digest), the pair of every proof, weighted by the batch's rho_i
-        parallel_for(count, [&](uint64_t i) { guarded_stage(i, [&] { V::stage3(sts[i], res[i]); }); });
+        parallel_for(cnt, [&](uint64_t i) { guarded_stage(i, [&] { V::stage3(sts[i], res[i]); }); });
         if (first_failure()) return false;
-        const std::vector<HFr> rho = V::batch_weights(proofs, proof_len, pubs, pub_len, count);
         sg = Segments();
-        for (uint64_t i = 0; i < count; i++) {
+        for (uint64_t i = 0; i < cnt; i++) {
             const Staged& s = sts[i];
-            for (size_t j = 0; j < s.pts.size(); j++) sg.pair(s.pts[j], s.sc[j] * rho[i]);
-            for (const HAff& p : s.plus) sg.pair(p, rho[i]);
+            const HFr& w = rho[first + i];
+            for (size_t j = 0; j < s.pts.size(); j++) sg.pair(s.pts[j], s.sc[j] * w);
+            for (const HAff& p : s.plus) sg.pair(p, w);
             sg.close();
-            for (size_t j = 0; j < s.pts2.size(); j++) sg.pair(s.pts2[j], s.sc2[j] * rho[i]);
-            for (const HAff& p : s.plus2) sg.pair(p, rho[i]);
+            for (size_t j = 0; j < s.pts2.size(); j++) sg.pair(s.pts2[j], s.sc2[j] * w);
+            for (const HAff& p : s.plus2) sg.pair(p, w);
             sg.close();
         }
         res = run(sg);
-        typename V::Ext lhs = V::Ext::inf(), rhs = V::Ext::inf();
-        for (uint64_t i = 0; i < count; i++) {
+        for (uint64_t i = 0; i < cnt; i++) {
             lhs = lhs.add_affine(res[2 * i]);
             rhs = rhs.add_affine(res[2 * i + 1]);
         }
-        return V::pair_is_one(vk, lhs.to_affine(), V::neg(rhs.to_affine()), why);
+        return true;
     }
 };
 
