@@ -21,7 +21,9 @@ import (
 
 	"github.com/consensys/gnark-crypto/ecc"
 	"github.com/consensys/gnark/backend/plonk"
+	plonk_bn254 "github.com/consensys/gnark/backend/plonk/bn254"
 	"github.com/consensys/gnark/constraint"
+	cs_bn254 "github.com/consensys/gnark/constraint/bn254"
 )
 
 // WarmKey is what LoadCompiledCircuit returns: the constraint system (for gnark's solver), the verifying key, and
@@ -95,7 +97,13 @@ func (w *WarmKey) Circuit(keyPath string) (*C.b2p_circuit, error) {
 			return c, nil
 		}
 	}
-	return uploadTraceAndSave(w, snap) // prove_<curve>.go: NewTrace -> b2p_circuit_save -> b2p_circuit_load
+	// no usable snapshot: build the trace once, write the snapshot for the next start, make the circuit resident
+	switch spr := w.Ccs.(type) {
+	case *cs_bn254.SparseR1CS:
+		return loadCircuitBN254(w.srs, spr, w.Vk.(*plonk_bn254.VerifyingKey), snap)
+	default:
+		return loadCircuitOtherCurves(w, snap) // prove_bls12381.go
+	}
 }
 
 func shouldRecompile(target string, sources ...string) bool {

@@ -65,9 +65,20 @@ func uploadBls(spr *cs_bls12381.SparseR1CS, pk *plonk_bls12381.ProvingKey) (*gpu
 	}); err != nil {
 		return nil, err
 	}
-	// gnark v0.15: NewTrace(spr *cs.SparseR1CS, domain *fft.Domain) -- Lagrange-form ql qr qm qo qk, S, qcp
-	trace := plonk_bls12381.NewTrace(spr, fft_bls12381.NewDomain(pk.Vk.Size))
-	n := C.uint64_t(pk.Vk.Size)
+	var err error
+	if k.circuit, err = loadCircuitBLS12381(k.srs, spr, pk.Vk, ""); err != nil {
+		C.b2p_srs_free(k.srs)
+		return nil, err
+	}
+	k.allocColumns(int(pk.Vk.Size))
+	remember(pk, k) // may evict the least recently used key (MaxResidentKeys)
+	return k, nil
+}
+
+// loadCircuitBLS12381: prove_bn254.go's loadCircuitBN254 with the bls12-381 packages.
+func loadCircuitBLS12381(srs *C.b2p_srs, spr *cs_bls12381.SparseR1CS, vk *plonk_bls12381.VerifyingKey, snapshotPath string) (*C.b2p_circuit, error) {
+	trace := plonk_bls12381.NewTrace(spr, fft_bls12381.NewDomain(vk.Size))
+	n := C.uint64_t(vk.Size)
 	col := func(p interface{ Coefficients() []fr.Element }) unsafe.Pointer {
 		return unsafe.Pointer(&p.Coefficients()[0])
 	}
@@ -76,32 +87,51 @@ func uploadBls(spr *cs_bls12381.SparseR1CS, pk *plonk_bls12381.ProvingKey) (*gpu
 	for i := range trace.Qcp {
 		qcpPtrs[i] = col(trace.Qcp[i])
 	}
-	qcp, unpin := pointerArray(qcpPtrs) // Go pointers inside an array handed to C: pinned for the call
+	qcp, unpin := pointerArray(qcpPtrs)
 	defer unpin()
 	var cidx *C.uint64_t
 	if nq > 0 {
-		cidx = (*C.uint64_t)(unsafe.Pointer(&pk.Vk.CommitmentConstraintIndexes[0]))
+		cidx = (*C.uint64_t)(unsafe.Pointer(&vk.CommitmentConstraintIndexes[0]))
 	}
-	// the VK digests gnark binds into gamma: S1 S2 S3 Ql Qr Qm Qo Qk Qcp*, Marshal() each
 	var vkb []byte
-	for _, p := range append(append([]bls12381.G1Affine{}, pk.Vk.S[:]...), pk.Vk.Ql, pk.Vk.Qr, pk.Vk.Qm, pk.Vk.Qo, pk.Vk.Qk) {
+	for _, p := range append(append([]bls12381.G1Affine{}, vk.S[:]...), vk.Ql, vk.Qr, vk.Qm, vk.Qo, vk.Qk) {
 		vkb = append(vkb, p.Marshal()...)
 	}
-	for _, p := range pk.Vk.Qcp {
+	for _, p := range vk.Qcp {
 		vkb = append(vkb, p.Marshal()...)
 	}
+	if snapshotPath != "" {
+		cs := C.CString(snapshotPath)
+		defer C.free(unsafe.Pointer(cs))
+		if err := call(func() C.int {
+			return C.b2p_circuit_save(cs, C.B2P_BLS12_381, n, C.uint32_t(vk.NbPublicVariables),
+				col(trace.Ql), col(trace.Qr), col(trace.Qm), col(trace.Qo), col(trace.Qk),
+				(*C.int64_t)(unsafe.Pointer(&trace.S[0])), C.uint32_t(nq), (*unsafe.Pointer)(unsafe.Pointer(qcp)), cidx,
+				unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)))
+		}); err != nil {
+			return nil, err
+		}
+	}
+	var c *C.b2p_circuit
 	if err := call(func() C.int {
-		return C.b2p_circuit_load(k.srs, n, C.uint32_t(pk.Vk.NbPublicVariables),
+		return C.b2p_circuit_load(srs, n, C.uint32_t(vk.NbPublicVariables),
 			col(trace.Ql), col(trace.Qr), col(trace.Qm), col(trace.Qo), col(trace.Qk),
 			(*C.int64_t)(unsafe.Pointer(&trace.S[0])), C.uint32_t(nq), (*unsafe.Pointer)(unsafe.Pointer(qcp)), cidx,
-			unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)), &k.circuit)
+			unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)), &c)
 	}); err != nil {
-		C.b2p_srs_free(k.srs)
 		return nil, err
 	}
-	k.allocColumns(int(pk.Vk.Size))
-	remember(pk, k) // may evict the least recently used key (MaxResidentKeys)
-	return k, nil
+	return c, nil
+}
+
+// loadCircuitOtherCurves is persist.go's dispatch for keys that are not BN254.
+func loadCircuitOtherCurves(w *WarmKey, snapshotPath string) (*C.b2p_circuit, error) {
+	spr, ok1 := w.Ccs.(*cs_bls12381.SparseR1CS)
+	vk, ok2 := w.Vk.(*plonk_bls12381.VerifyingKey)
+	if !ok1 || !ok2 {
+		return nil, errors.New("gpuplonk: compiled circuit is on a curve AlgoPlonk does not support")
+	}
+	return loadCircuitBLS12381(w.srs, spr, vk, snapshotPath)
 }
 
 func proveBLS12381(spr *cs_bls12381.SparseR1CS, pk *plonk_bls12381.ProvingKey, fullWitness witness.Witness,

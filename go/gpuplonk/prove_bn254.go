@@ -53,15 +53,29 @@ func upload(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey) (*gpuKey, erro
 		return nil, err
 	}
 	k := &gpuKey{}
+	var err error
 	g1 := pk.Kzg.G1 // canonical SRS, n+3 points, gnark in-memory layout == library layout
 	if err := call(func() C.int {
 		return C.b2p_srs_load(C.B2P_BN254, unsafe.Pointer(&g1[0]), C.uint64_t(len(g1)), nil, 0, &k.srs)
 	}); err != nil {
 		return nil, err
 	}
+	if k.circuit, err = loadCircuitBN254(k.srs, spr, pk.Vk, ""); err != nil {
+		C.b2p_srs_free(k.srs)
+		return nil, err
+	}
+	k.allocColumns(int(pk.Vk.Size))
+	remember(pk, k) // may evict the least recently used key (MaxResidentKeys)
+	return k, nil
+}
+
+// loadCircuitBN254 builds the trace of a constraint system (gnark's NewTrace) and makes it resident on the SRS handle's
+// GPU; with a non-empty snapshotPath it also writes the library's own snapshot of it (b2p_circuit_save), which
+// persist.go's warm start reads back with b2p_circuit_load_file instead of rebuilding the trace.
+func loadCircuitBN254(srs *C.b2p_srs, spr *cs_bn254.SparseR1CS, vk *plonk_bn254.VerifyingKey, snapshotPath string) (*C.b2p_circuit, error) {
 	// gnark v0.15: NewTrace(spr *cs.SparseR1CS, domain *fft.Domain) -- Lagrange-form ql qr qm qo qk, S, qcp
-	trace := plonk_bn254.NewTrace(spr, fft_bn254.NewDomain(pk.Vk.Size))
-	n := C.uint64_t(pk.Vk.Size)
+	trace := plonk_bn254.NewTrace(spr, fft_bn254.NewDomain(vk.Size))
+	n := C.uint64_t(vk.Size)
 	col := func(p interface{ Coefficients() []fr.Element }) unsafe.Pointer {
 		return unsafe.Pointer(&p.Coefficients()[0])
 	}
@@ -74,28 +88,38 @@ func upload(spr *cs_bn254.SparseR1CS, pk *plonk_bn254.ProvingKey) (*gpuKey, erro
 	defer unpin()
 	var cidx *C.uint64_t
 	if nq > 0 {
-		cidx = (*C.uint64_t)(unsafe.Pointer(&pk.Vk.CommitmentConstraintIndexes[0]))
+		cidx = (*C.uint64_t)(unsafe.Pointer(&vk.CommitmentConstraintIndexes[0]))
 	}
 	// the VK digests gnark binds into gamma: S1 S2 S3 Ql Qr Qm Qo Qk Qcp*, Marshal() each
 	var vkb []byte
-	for _, p := range append(append([]bn254.G1Affine{}, pk.Vk.S[:]...), pk.Vk.Ql, pk.Vk.Qr, pk.Vk.Qm, pk.Vk.Qo, pk.Vk.Qk) {
+	for _, p := range append(append([]bn254.G1Affine{}, vk.S[:]...), vk.Ql, vk.Qr, vk.Qm, vk.Qo, vk.Qk) {
 		vkb = append(vkb, p.Marshal()...)
 	}
-	for _, p := range pk.Vk.Qcp {
+	for _, p := range vk.Qcp {
 		vkb = append(vkb, p.Marshal()...)
 	}
+	if snapshotPath != "" {
+		cs := C.CString(snapshotPath)
+		defer C.free(unsafe.Pointer(cs))
+		if err := call(func() C.int {
+			return C.b2p_circuit_save(cs, C.B2P_BN254, n, C.uint32_t(vk.NbPublicVariables),
+				col(trace.Ql), col(trace.Qr), col(trace.Qm), col(trace.Qo), col(trace.Qk),
+				(*C.int64_t)(unsafe.Pointer(&trace.S[0])), C.uint32_t(nq), (*unsafe.Pointer)(unsafe.Pointer(qcp)), cidx,
+				unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)))
+		}); err != nil {
+			return nil, err
+		}
+	}
+	var c *C.b2p_circuit
 	if err := call(func() C.int {
-		return C.b2p_circuit_load(k.srs, n, C.uint32_t(pk.Vk.NbPublicVariables),
+		return C.b2p_circuit_load(srs, n, C.uint32_t(vk.NbPublicVariables),
 			col(trace.Ql), col(trace.Qr), col(trace.Qm), col(trace.Qo), col(trace.Qk),
 			(*C.int64_t)(unsafe.Pointer(&trace.S[0])), C.uint32_t(nq), (*unsafe.Pointer)(unsafe.Pointer(qcp)), cidx,
-			unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)), &k.circuit)
+			unsafe.Pointer(&vkb[0]), C.uint64_t(len(vkb)), &c)
 	}); err != nil {
-		C.b2p_srs_free(k.srs)
 		return nil, err
 	}
-	k.allocColumns(int(pk.Vk.Size))
-	remember(pk, k) // may evict the least recently used key (MaxResidentKeys)
-	return k, nil
+	return c, nil
 }
 
 // Prove has plonk.Prove's signature.  Any failure of the GPU path falls back to gnark's CPU prover
