@@ -9,9 +9,10 @@
 //    them with __syncthreads() -- a dependency chain costs one barrier per link instead of one launch.
 //  * solve(): inputs up, levels, then one gather kernel writes L, R, O (n rows, padding rows = variable 0 as
 //    gnark's NewTrace pads) and checks EVERY row's gate equation; L, R, O stay in HBM for b2p_prove_dev.
-//  * A chain is still a chain: a depth-2^20 squaring chain takes ~2 us per link on one SM against 46 ns on a host
-//    core (profiles/solver_floor_r2.json), so solve() also has a host path (same rows, 64-bit limbs, one thread) and
-//    B2P_SOLVE_AUTO picks by a cost model of the level structure.  The device pays for wide, shallow circuits.
+//  * A chain is still a chain: a depth-2^20 squaring chain takes ~2 us per link on one SM, so solve() also has a host
+//    path -- the rows in their original order on one thread, 64-bit limbs, one product per common gate (26 ns per link),
+//    the values then uploaded and L, R, O gathered / checked by the same device kernel -- and B2P_SOLVE_AUTO picks by
+//    a cost model of the level structure.  The device pays for wide, shallow circuits (20x a host core at 2^20 rows).
 //  * Not handled: hints (BSB22 commitments, gnark's hint functions): a row whose unassigned wire occurs twice, or
 //    that has two unassigned wires, is refused at create().
 #pragma once
@@ -144,10 +145,14 @@ struct Solver : SolverBase {
     DevBuf<Fr> d_cols[5], d_ninv, d_values, dL, dR, dO, d_in;
     DevBuf<uint32_t> d_x[3], d_ops, d_level_off, d_flags, d_inputs;
     DevBuf<uint8_t> d_kind;
-    std::vector<HF> h_values;
+    HF* h_pinned = nullptr;            // the host path's variable vector, page-locked (nb_variables entries)
+    std::vector<uint32_t> h_rows;      // the solving rows in their original order ...
+    std::vector<uint8_t> h_cls;        // ... and their class: kind in the low two bits, then which coefficients matter
+    static constexpr uint8_t CLS_KIND = 3, CLS_QL = 4, CLS_QR = 8, CLS_QM = 16, CLS_QM_ONE = 32, CLS_QK = 64, CLS_NINV_ONE = 128;
 
     ~Solver() override {
         if (graph) cudaGraphExecDestroy(graph);
+        if (h_pinned) cudaFreeHost(h_pinned);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -244,7 +249,7 @@ struct Solver : SolverBase {
             l = e;
         }
         est_dev_us += 10 + n * 1e-4;
-        est_host_us = h_ops.size() * 0.15 + n * 0.05;        // measured: solve + gather + upload of L, R, O
+        est_host_us = h_ops.size() * 0.06 + nb_variables * 0.004 + 300;   // one product per common row + upload of the values
         // ---- device copies
         B2P_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (int k = 0; k < 5; k++) {
@@ -267,6 +272,20 @@ struct Solver : SolverBase {
         B2P_LAUNCH((k_solver_ninv<Fr>), div_up(n, 128), 128, 0, st, d_ninv.p, d_cols[3].p, d_kind.p, n);
         h_ninv.resize(n);
         B2P_CUDA(cudaMemcpyAsync(h_ninv.data(), d_ninv.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        B2P_CUDA(cudaStreamSynchronize(st));                 // h_ninv is complete
+        for (uint64_t i = nb_public; i < n; i++) {
+            if (!h_kind[i]) continue;
+            uint8_t cls = h_kind[i];
+            if (!h_cols[0][i].is_zero()) cls |= CLS_QL;
+            if (!h_cols[1][i].is_zero()) cls |= CLS_QR;
+            if (!h_cols[2][i].is_zero()) cls |= CLS_QM;
+            if (h_cols[2][i] == HF::one()) cls |= CLS_QM_ONE;
+            if (!h_cols[4][i].is_zero()) cls |= CLS_QK;
+            if (h_ninv[i] == HF::one()) cls |= CLS_NINV_ONE;
+            h_rows.push_back((uint32_t)i);
+            h_cls.push_back(cls);
+        }
+        B2P_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_pinned), nb_variables * sizeof(HF)));
         d_values.alloc(nb_variables);
         d_in.alloc(std::max<uint32_t>(nb_inputs, 1));
         dL.alloc(n); dR.alloc(n); dO.alloc(n);
@@ -295,24 +314,15 @@ struct Solver : SolverBase {
         where = choose(where);
         last_where = where;
         const auto t0 = std::chrono::steady_clock::now();
+        // either way L, R, O are gathered -- and every row checked -- by k_solver_gather on the device
         if (where == B2P_SOLVE_DEVICE) solve_device(inputs);
         else solve_host(inputs);
         if (device_out) {
             dptrs[0] = dL.p; dptrs[1] = dR.p; dptrs[2] = dO.p;
-        } else if (where == B2P_SOLVE_DEVICE) {
+        } else {
             B2P_CUDA(cudaMemcpyAsync(L, dL.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
             B2P_CUDA(cudaMemcpyAsync(R, dR.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
             B2P_CUDA(cudaMemcpyAsync(O, dO.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
-            B2P_CUDA(cudaStreamSynchronize(st));
-        } else {
-            gather_host(static_cast<HF*>(L), static_cast<HF*>(R), static_cast<HF*>(O));
-        }
-        if (device_out && where == B2P_SOLVE_HOST) {        // host-solved columns up to the device for b2p_prove_dev
-            std::vector<HF> l(n), r(n), o(n);
-            gather_host(l.data(), r.data(), o.data());
-            B2P_CUDA(cudaMemcpyAsync(dL.p, l.data(), n * sizeof(Fr), cudaMemcpyHostToDevice, st));
-            B2P_CUDA(cudaMemcpyAsync(dR.p, r.data(), n * sizeof(Fr), cudaMemcpyHostToDevice, st));
-            B2P_CUDA(cudaMemcpyAsync(dO.p, o.data(), n * sizeof(Fr), cudaMemcpyHostToDevice, st));
             B2P_CUDA(cudaStreamSynchronize(st));
         }
         last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -374,47 +384,52 @@ struct Solver : SolverBase {
             throw Error(B2P_ERR_VERIFY, "constraint #" + std::to_string(unsat_row) + " is not satisfied");
     }
 
+    // The rows in their original order on one host thread (a dependency chain is the whole job: 0.05 us per link here
+    // against 2 us on an SM).  Row classes computed at create() keep the common gates at one product per row: a
+    // coefficient that is 0 or 1 is neither loaded nor multiplied.  The values then go up (page-locked, 32 B per
+    // variable) and the device gathers L, R, O and checks every row, exactly as after a device solve.
     void solve_host(const void* inputs) {
-        h_values.assign(nb_variables, HF::zero());
+        HF* v = h_pinned;
         const HF* in = static_cast<const HF*>(inputs);
-        for (uint32_t i = 0; i < nb_inputs; i++) h_values[h_inputs[i]] = in[i];
-        HF* v = h_values.data();
+        for (uint32_t i = 0; i < nb_inputs; i++) v[h_inputs[i]] = in[i];
         uint32_t div0 = 0xFFFFFFFFu;
-        for (uint64_t i = nb_public; i < n; i++) {
-            const uint32_t kind = h_kind[i];
-            if (!kind) continue;
-            const HF &ql = h_cols[0][i], &qr = h_cols[1][i], &qm = h_cols[2][i], &qo = h_cols[3][i], &qk = h_cols[4][i];
+        const uint32_t nops = (uint32_t)h_rows.size();
+        for (uint32_t k = 0; k < nops; k++) {
+            const uint64_t i = h_rows[k];
+            const uint8_t cls = h_cls[k];
             const uint32_t ia = h_x[0][i], ib = h_x[1][i], ic = h_x[2][i];
-            if (kind == SOLVE_O) {
-                HF t = qk;
-                if (!ql.is_zero()) t = t + ql * v[ia];
-                if (!qr.is_zero()) t = t + qr * v[ib];
-                if (!qm.is_zero()) t = t + qm * (v[ia] * v[ib]);
-                v[ic] = t * h_ninv[i];
+            if ((cls & CLS_KIND) == SOLVE_O) {
+                HF t;
+                if (cls & CLS_QM) {
+                    t = v[ia] * v[ib];
+                    if (!(cls & CLS_QM_ONE)) t = t * h_cols[2][i];
+                    if (cls & CLS_QK) t = t + h_cols[4][i];
+                } else {
+                    t = (cls & CLS_QK) ? h_cols[4][i] : HF::zero();
+                }
+                if (cls & CLS_QL) t = t + h_cols[0][i] * v[ia];
+                if (cls & CLS_QR) t = t + h_cols[1][i] * v[ib];
+                v[ic] = (cls & CLS_NINV_ONE) ? t : t * h_ninv[i];
                 continue;
             }
-            const HF other = v[kind == SOLVE_A ? ib : ia];
-            HF num = qk + (kind == SOLVE_A ? qr : ql) * other;
+            const bool solve_a = (cls & CLS_KIND) == SOLVE_A;
+            const HF &ql = h_cols[0][i], &qr = h_cols[1][i], &qm = h_cols[2][i], &qo = h_cols[3][i], &qk = h_cols[4][i];
+            const HF other = v[solve_a ? ib : ia];
+            HF num = qk + (solve_a ? qr : ql) * other;
             if (!qo.is_zero()) num = num + qo * v[ic];
-            const HF den = (kind == SOLVE_A ? ql : qr) + qm * other;
+            const HF den = (solve_a ? ql : qr) + qm * other;
             if (den.is_zero()) { div0 = std::min<uint32_t>(div0, (uint32_t)i); continue; }
-            v[kind == SOLVE_A ? ia : ib] = (num * den.inverse()).neg();
+            v[solve_a ? ia : ib] = (num * den.inverse()).neg();
         }
-        uint32_t unsat = 0xFFFFFFFFu;
-        for (uint64_t i = 0; i < n && unsat == 0xFFFFFFFFu; i++) {
-            const HF a = v[h_x[0][i]], b = v[h_x[1][i]], o = v[h_x[2][i]];
-            HF t = h_cols[0][i] * a + h_cols[1][i] * b + h_cols[2][i] * (a * b) + h_cols[3][i] * o;
-            t = t + (i < nb_public ? a : h_cols[4][i]);
-            if (!t.is_zero()) unsat = (uint32_t)i;
-        }
-        report(div0, unsat);
-    }
-    void gather_host(HF* L, HF* R, HF* O) const {
-        for (uint64_t i = 0; i < n; i++) {
-            L[i] = h_values[h_x[0][i]];
-            R[i] = h_values[h_x[1][i]];
-            O[i] = h_values[h_x[2][i]];
-        }
+        if (div0 != 0xFFFFFFFFu) report(div0, 0xFFFFFFFFu);
+        B2P_CUDA(cudaMemcpyAsync(d_values.p, v, nb_variables * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        B2P_CUDA(cudaMemsetAsync(d_flags.p, 0xFF, 2 * sizeof(uint32_t), st));
+        B2P_LAUNCH((k_solver_gather<Fr>), div_up(n, 128), 128, 0, st, dcols(), d_values.p, dL.p, dR.p, dO.p, n, nb_public,
+                   d_flags.p + 1);
+        uint32_t flags[2];
+        B2P_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+        B2P_CUDA(cudaStreamSynchronize(st));
+        report(flags[0], flags[1]);
     }
 };
 

@@ -392,6 +392,49 @@ def run_b200(args):
         for o in outs:
             assert bytes(o.raw) == proof_resident, f"{name}: proof differs"
 
+    # pass 5 ("end-to-end incl. solve"): the caller hands over the circuit's INPUTS only; the library's solver
+    # (b2p_solver_solve_dev, placement by its own cost model: a dependency chain like this workload is solved on a host
+    # thread, a wide circuit on the GPU) fills L, R, O in HBM and b2p_prove_dev proves them.  One solver per lane.
+    from_inputs = None
+    if getattr(cs, "input_vars", None) is not None and not cs.commitments and not args.no_solver_leg:
+        try:
+            import numpy as np
+            from algoplonk_b200 import frontend as fe
+            cols_b = [C.create_string_buffer(api.fr_to_mont_bytes(curve, c)) for c in (tc.ql, tc.qr, tc.qm, tc.qo, tc.qk)]
+            wires = [np.asarray(w, dtype=np.uint32) for w in fe.solver_wires(cs, n)]
+            ids = np.asarray(cs.input_vars, dtype=np.uint32)
+            values_in = C.create_string_buffer(api.fr_to_mont_bytes(curve, [L[0], L[tc.nb_public]]))
+            assert list(cs.input_vars) == [0, 1], "the squaring chain assigns y and x0"
+            solvers = []
+            for _ in range(F):
+                h = C.c_void_p()
+                _lib.check(lib.b2p_solver_create(cid, n, tc.nb_public, cs.nb_variables, ids.ctypes.data, len(ids), *cols_b,
+                                                 *[w.ctypes.data for w in wires], C.byref(h)))
+                solvers.append(h)
+
+            def prove_from_inputs(i):
+                ptrs = [C.c_void_p() for _ in range(3)]
+                _lib.check(lib.b2p_solver_solve_dev(solvers[i], values_in, _lib.SOLVE_AUTO, *[C.byref(p) for p in ptrs]))
+                _lib.check(lib.b2p_prove_dev(ccs[i].handle, ptrs[0], ptrs[1], ptrs[2], None, None, blinding, outs[i]))
+            for i in range(F):
+                prove_from_inputs(i)
+            ms_in = timed(prove_from_inputs, args.steps, F)
+            tot_in, units_in = reduce_over_ranks(ms_in, args.steps, world, device)
+            for o in outs:
+                assert bytes(o.raw) == proof_resident, "from inputs: proof differs"
+            info = (C.c_uint64 * 8)()
+            _lib.check(lib.b2p_solver_info(solvers[0], info))
+            from_inputs = {"value": units_in / (tot_in / 1e3), "unit": UNIT, "ms_per_step": tot_in / args.steps,
+                           "solver": {"levels": int(info[0]), "widest_level": int(info[1]),
+                                      "ran_on": "device" if info[7] == _lib.SOLVE_DEVICE else "host thread",
+                                      "last_solve_ms": info[6] / 1e3},
+                           "what": "circuit inputs (64 bytes) -> b2p_solver_solve_dev -> b2p_prove_dev: solving included; "
+                                   "same proof bytes"}
+            for h in solvers:
+                lib.b2p_solver_free(h)
+        except Exception as e:  # noqa: BLE001 -- reported in the line
+            from_inputs = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     sharded_line = measure_sharded_msm(args, rank, world, device) if world > 1 else None
     # one proof over all the GPUs (commitments sharded over the point set, native peer-memory path)
     proof_sharded_line = None
@@ -487,6 +530,8 @@ def run_b200(args):
                                    "e2e (the reference arm times plonk.Prove only)"}
     except Exception as e:  # noqa: BLE001 -- reported in the line
         line["verify"] = {"accepted": False, "error": f"{type(e).__name__}: {e}"[:300]}
+    if from_inputs is not None:
+        line["e2e_from_inputs"] = from_inputs
     if sharded_line is not None:
         line["msm_sharded"] = sharded_line
     if proof_sharded_line is not None:
@@ -776,6 +821,7 @@ def main():
     ap.add_argument("--log2", type=int, default=20, help="log2 of the constraint count (BASELINE: 20)")
     ap.add_argument("--curve", default="BN254", choices=["BN254", "BLS12_381"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solver-leg", action="store_true", help="skip the e2e_from_inputs leg (solver + prover)")
     ap.add_argument("--no-proof-sharded", action="store_true",
                     help="skip the one-proof-over-all-GPUs leg of a multi-GPU run")
     ap.add_argument("--shard-c", type=int, default=0,
