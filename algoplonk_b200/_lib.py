@@ -94,6 +94,9 @@ SYMBOLS = [
     ("b2p_kzg_vk_load", _int, [_int, _vp, _u64, _vp, _vp]),
     ("b2p_g2_generate_unsafe", _int, [_int, _vp, _vp]),
     ("b2p_solver_create", _int, [_int, _u64, _u32, _u64, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    ("b2p_solver_create_hinted", _int, [_int, _u64, _u32, _u64, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _u32, _vp, C.POINTER(_vp)]),
+    ("b2p_solver_set_hint_fn", _int, [_vp, _vp, _vp]),
     ("b2p_solver_solve", _int, [_vp, _vp, _int, _vp, _vp, _vp]),
     ("b2p_solver_solve_dev", _int, [_vp, _vp, _int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     ("b2p_solver_info", _int, [_vp, C.POINTER(_u64)]),
@@ -130,6 +133,15 @@ class GnarkPk(C.Structure):
     """b2p_gnark_pk"""
     _fields_ = [("vk", GnarkVk), ("kzg_off", _u64), ("kzg_count", _u64), ("lagrange_off", _u64),
                 ("lagrange_count", _u64)]
+
+
+class Hint(C.Structure):
+    """b2p_hint"""
+    _fields_ = [("id", _u32), ("n_in", _u32), ("n_out", _u32), ("in_vars", C.POINTER(_u32)), ("out_vars", C.POINTER(_u32))]
+
+
+# b2p_hint_fn: int fn(void* ctx, uint32_t id, const void* inputs, uint32_t n_in, void* outputs, uint32_t n_out)
+HINT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32)
 
 
 # b2p_commit_fn: int fn(void* ctx, const void* d_scalars, uint64_t n, void* out_affine)

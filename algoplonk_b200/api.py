@@ -481,11 +481,17 @@ class Solver:
     (or on one host thread when the circuit is a dependency chain), and hands L, R, O to the prover."""
     INFO = ["levels", "widest_level", "solved_rows", "launches", "est_host_us", "est_device_us", "last_us", "last_where"]
 
-    def __init__(self, cs: fe.SparseR1CS, trace: Optional[fe.TraceColumns] = None):
-        if cs.commitments:
-            raise ValueError("circuits with BSB22 commitments need gnark's hint: not solved by the library")
+    def __init__(self, cs: fe.SparseR1CS, trace: Optional[fe.TraceColumns] = None,
+                 hint_fn: Optional[Callable[[int, List[int], int], Sequence[int]]] = None):
+        """hint_fn(hint id, input values, n_out) -> n_out output values: the caller's hint functions (gnark:
+        solver.WithHints); std_hint_fn below covers the front end's NBits.  Needed only when the constraint system
+        records hints."""
         if cs.input_vars is None:
             raise ValueError("the constraint system does not say which variables are inputs")
+        if (cs.commitments or cs.hints) and not cs.hints:
+            raise ValueError("circuits with BSB22 commitments need the commitment hint recorded in the constraint system")
+        if cs.hints and hint_fn is None:
+            raise ValueError("the circuit uses solver hints: pass hint_fn")
         _lib.init()
         tc = trace if trace is not None else fe.build_trace(cs)
         self.curve, self.n, self.nb_public, self.nb_inputs = cs.curve, tc.n, cs.nb_public, len(cs.input_vars)
@@ -493,10 +499,40 @@ class Solver:
         cols = [_buf(fr_to_mont_bytes(cs.curve, c)) for c in (tc.ql, tc.qr, tc.qm, tc.qo, tc.qk)]
         xa, xb, xc = ((C.c_uint32 * n)(*w) for w in fe.solver_wires(cs, n))
         ids = (C.c_uint32 * max(self.nb_inputs, 1))(*cs.input_vars)
+        # hints: b2p_hint records pointing into arrays this object keeps alive
+        self._hint_arrays = [((C.c_uint32 * max(len(h.in_vars), 1))(*h.in_vars), (C.c_uint32 * len(h.out_vars))(*h.out_vars))
+                             for h in cs.hints]
+        hints = (_lib.Hint * max(len(cs.hints), 1))()
+        for rec, h, (ia, oa) in zip(hints, cs.hints, self._hint_arrays):
+            rec.id, rec.n_in, rec.n_out = h.id, len(h.in_vars), len(h.out_vars)
+            rec.in_vars, rec.out_vars = C.cast(ia, C.POINTER(C.c_uint32)), C.cast(oa, C.POINTER(C.c_uint32))
+        unchecked = None
+        if cs.unchecked_rows:
+            mask = bytearray(n)
+            for j in cs.unchecked_rows:
+                mask[cs.nb_public + j] = 1
+            unchecked = _buf(bytes(mask))
         h = C.c_void_p()
-        _lib.check(_lib.load().b2p_solver_create(CURVE_ID[cs.curve], n, cs.nb_public, cs.nb_variables, ids, self.nb_inputs,
-                                                 *cols, xa, xb, xc, C.byref(h)))
+        _lib.check(_lib.load().b2p_solver_create_hinted(CURVE_ID[cs.curve], n, cs.nb_public, cs.nb_variables, ids,
+                                                        self.nb_inputs, *cols, xa, xb, xc,
+                                                        hints if cs.hints else None, len(cs.hints), unchecked, C.byref(h)))
         self.handle = h.value
+        self._hint_cb = None
+        if cs.hints:
+            curve = cs.curve
+
+            def trampoline(_ctx, hid, inp, n_in, outp, n_out):
+                try:
+                    vals = fr_from_mont_bytes(curve, C.string_at(inp, 32 * n_in)) if n_in else []
+                    got = list(hint_fn(hid, vals, n_out))
+                    if len(got) != n_out:
+                        return 1
+                    C.memmove(outp, fr_to_mont_bytes(curve, got), 32 * n_out)
+                    return 0
+                except Exception:  # noqa: BLE001 -- reported by the library as a failed hint
+                    return 2
+            self._hint_cb = _lib.HINT_FN(trampoline)
+            _lib.check(_lib.load().b2p_solver_set_hint_fn(self.handle, C.cast(self._hint_cb, C.c_void_p), None))
 
     def info(self) -> dict:
         out = (C.c_uint64 * 8)()
@@ -525,6 +561,18 @@ class Solver:
         if self.handle:
             _lib.load().b2p_solver_free(self.handle)
             self.handle = None
+
+
+def std_hint_fn(extra: Optional[Callable[[int, List[int], int], Sequence[int]]] = None):
+    """hint_fn for api.Solver covering the front end's standard hints (HINT_NBITS: the low n_out bits of the input,
+    gnark's bits.NBits); other ids go to `extra` (e.g. the BSB22 commitment hint, which needs the SRS)."""
+    def fn(hid: int, vals: List[int], n_out: int):
+        if hid == fe.HINT_NBITS:
+            return [(vals[0] >> i) & 1 for i in range(n_out)]
+        if extra is None:
+            raise ValueError(f"no function for hint {hid}")
+        return extra(hid, vals, n_out)
+    return fn
 
 
 def VerifyFromInputs(cc: CompiledCircuit, solver: Solver, inputs: Sequence[int], blinding: Sequence[int],

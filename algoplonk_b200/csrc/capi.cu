@@ -610,17 +610,34 @@ API int b2p_kzg_vk_load(int curve, const void* vk_bin, uint64_t len, void* out_g
     });
 }
 // ---- witness solver ---------------------------------------------------------------------------------------
+API int b2p_solver_create_hinted(int curve, uint64_t n, uint32_t nb_public, uint64_t nb_variables, const uint32_t* input_ids,
+                                 uint32_t nb_inputs, const void* ql, const void* qr, const void* qm, const void* qo,
+                                 const void* qk, const uint32_t* xa, const uint32_t* xb, const uint32_t* xc,
+                                 const b2p_hint* hints, uint32_t n_hints, const uint8_t* unchecked_rows, b2p_solver** out) {
+    return guarded([&] {
+        require_curve(curve);
+        require(ql && qr && qm && qo && qk && xa && xb && xc && out && (input_ids || nb_inputs == 0) && (hints || n_hints == 0),
+                "null argument");
+        const void* cols[5] = {ql, qr, qm, qo, qk};
+        const int dev = current_device();
+        SolverBase* s = new_solver(curve, n, nb_public, nb_variables, input_ids, nb_inputs, cols, xa, xb, xc, hints, n_hints,
+                                   unchecked_rows);
+        s->device = dev;
+        *out = reinterpret_cast<b2p_solver*>(s);
+    });
+}
 API int b2p_solver_create(int curve, uint64_t n, uint32_t nb_public, uint64_t nb_variables, const uint32_t* input_ids,
                           uint32_t nb_inputs, const void* ql, const void* qr, const void* qm, const void* qo,
                           const void* qk, const uint32_t* xa, const uint32_t* xb, const uint32_t* xc, b2p_solver** out) {
+    return b2p_solver_create_hinted(curve, n, nb_public, nb_variables, input_ids, nb_inputs, ql, qr, qm, qo, qk, xa, xb, xc,
+                                    nullptr, 0, nullptr, out);
+}
+API int b2p_solver_set_hint_fn(b2p_solver* s, b2p_hint_fn fn, void* ctx) {
     return guarded([&] {
-        require_curve(curve);
-        require(ql && qr && qm && qo && qk && xa && xb && xc && out && (input_ids || nb_inputs == 0), "null argument");
-        const void* cols[5] = {ql, qr, qm, qo, qk};
-        const int dev = current_device();
-        SolverBase* s = new_solver(curve, n, nb_public, nb_variables, input_ids, nb_inputs, cols, xa, xb, xc);
-        s->device = dev;
-        *out = reinterpret_cast<b2p_solver*>(s);
+        require(s, "null argument");
+        SolverBase* b = reinterpret_cast<SolverBase*>(s);
+        std::lock_guard<std::mutex> lk(b->mu);
+        b->set_hint_fn(fn, ctx);
     });
 }
 API int b2p_solver_solve(b2p_solver* s, const void* inputs, int where, void* L, void* R, void* O) {

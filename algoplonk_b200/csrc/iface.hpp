@@ -94,10 +94,11 @@ struct SolverBase {
     virtual ~SolverBase() {}
     virtual void solve(const void* inputs, int where, void* L, void* R, void* O, bool device_out, void** dptrs) = 0;
     virtual void info(uint64_t* out8) const = 0;
+    virtual void set_hint_fn(b2p_hint_fn fn, void* ctx) = 0;
 };
 SolverBase* new_solver(int curve, uint64_t n, uint32_t nb_public, uint64_t nb_variables, const uint32_t* input_ids,
                        uint32_t nb_inputs, const void* const cols[5], const uint32_t* xa, const uint32_t* xb,
-                       const uint32_t* xc);
+                       const uint32_t* xc, const b2p_hint* hints, uint32_t n_hints, const uint8_t* unchecked);
 
 struct CurveOps {
     virtual ~CurveOps() {}

@@ -13,12 +13,17 @@
 //    path -- the rows in their original order on one thread, 64-bit limbs, one product per common gate (26 ns per link),
 //    the values then uploaded and L, R, O gathered / checked by the same device kernel -- and B2P_SOLVE_AUTO picks by
 //    a cost model of the level structure.  The device pays for wide, shallow circuits (20x a host core at 2^20 rows).
-//  * Not handled: hints (BSB22 commitments, gnark's hint functions): a row whose unassigned wire occurs twice, or
-//    that has two unassigned wires, is refused at create().
+//  * Hints (gnark's hint functions: bit decompositions, inverses-or-zero, the BSB22 commitment hint, ...) are the
+//    caller's: create() is told which variables a hint produces from which, places the hint at the level where its
+//    inputs are known, and solve() calls the registered function there (inputs down, outputs up: a hint is a
+//    synchronisation point of the device path).  Rows the caller marks unchecked (BSB22's committed rows, whose
+//    qcp * pi2 term and hash the prover adds) are left out of the final gate check.  A row whose unassigned wire occurs
+//    twice, or that has two unassigned wires no hint produces, is refused at create().
 #pragma once
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -107,13 +112,14 @@ __global__ void k_solver_ninv(F* ninv, const F* __restrict__ qo, const uint8_t* 
 // L, R, O of every row and the gate check; public rows: the public value enters through qk (gnark's completeQk)
 template <class F>
 __global__ void k_solver_gather(SolverCols<F> c, const F* __restrict__ values, F* L, F* R, F* O, uint64_t n,
-                                uint32_t nb_public, uint32_t* first_unsat) {
+                                uint32_t nb_public, uint32_t* first_unsat, const uint8_t* __restrict__ unchecked) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const F a = ld_field(values + c.xa[i]), b = ld_field(values + c.xb[i]), o = ld_field(values + c.xc[i]);
     st_field(L + i, a);
     st_field(R + i, b);
     st_field(O + i, o);
+    if (unchecked && unchecked[i]) return;
     F t = ld_field(c.ql + i) * a + ld_field(c.qr + i) * b + ld_field(c.qm + i) * (a * b) + ld_field(c.qo + i) * o;
     t = t + (i < nb_public ? a : ld_field(c.qk + i));
     if (!t.is_zero()) atomicMin(first_unsat, (uint32_t)i);
@@ -122,6 +128,13 @@ __global__ void k_solver_gather(SolverCols<F> c, const F* __restrict__ values, F
 struct SolverLaunch {
     uint32_t first_level, levels, first_op, ops;
     bool narrow;
+    uint32_t hint_first = 0, hint_count = 0;   // hint_count > 0: not a launch but "call hints [hint_first, +count) of hint_order"
+};
+struct SolverHint {
+    uint32_t id;
+    std::vector<uint32_t> in, out;
+    uint32_t level = 0;          // 1 + deepest input
+    uint32_t trigger_op = 0;     // host path: runs before this entry of h_rows
 };
 
 template <class Fr>
@@ -145,6 +158,14 @@ struct Solver : SolverBase {
     DevBuf<Fr> d_cols[5], d_ninv, d_values, dL, dR, dO, d_in;
     DevBuf<uint32_t> d_x[3], d_ops, d_level_off, d_flags, d_inputs;
     DevBuf<uint8_t> d_kind;
+    std::vector<SolverHint> hints;
+    std::vector<uint32_t> hint_order;  // hints sorted by level (device path) -- and by trigger row inside a level
+    std::vector<uint32_t> hint_by_trigger;   // the same hints in the order the host path meets them
+    b2p_hint_fn hint_fn = nullptr;
+    void* hint_ctx = nullptr;
+    DevBuf<uint8_t> d_unchecked;
+    bool has_unchecked = false;
+    std::vector<HF> hint_in, hint_out;
     HF* h_pinned = nullptr;            // the host path's variable vector, page-locked (nb_variables entries)
     std::vector<uint32_t> h_rows;      // the solving rows in their original order ...
     std::vector<uint8_t> h_cls;        // ... and their class: kind in the low two bits, then which coefficients matter
@@ -157,7 +178,8 @@ struct Solver : SolverBase {
     }
 
     void create(uint64_t n_, uint32_t nb_public_, uint64_t nb_variables_, const uint32_t* input_ids, uint32_t nb_inputs_,
-                const void* const cols[5], const uint32_t* xa, const uint32_t* xb, const uint32_t* xc) {
+                const void* const cols[5], const uint32_t* xa, const uint32_t* xb, const uint32_t* xc,
+                const b2p_hint* hint_list, uint32_t n_hints, const uint8_t* unchecked) {
         n = n_; nb_public = nb_public_; nb_variables = nb_variables_; nb_inputs = nb_inputs_;
         B2P_REQUIRE(n >= 1 && n <= (1ull << 30), "solver: at most 2^30 rows");
         B2P_REQUIRE(nb_variables >= 1 && nb_variables < (1ull << 32), "solver: variable count out of range");
@@ -184,10 +206,49 @@ struct Solver : SolverBase {
             B2P_REQUIRE(var_level[h_x[0][i]] == 0, "solver: a public row's L wire is not an input");
         h_kind.assign(n, SOLVE_NONE);
         std::vector<uint32_t> row_level(n, 0);
+        // hints: which variable comes out of which hint; a hint is placed when a row first needs one of its outputs
+        std::vector<int32_t> hint_of_var(n_hints ? nb_variables : 0, -1);
+        std::vector<uint8_t> hint_placed(n_hints, 0);
+        std::vector<uint64_t> hint_trigger_row(n_hints, 0);
+        hints.resize(n_hints);
+        for (uint32_t h = 0; h < n_hints; h++) {
+            B2P_REQUIRE(hint_list[h].n_out >= 1 && (hint_list[h].in_vars || hint_list[h].n_in == 0) && hint_list[h].out_vars,
+                        "solver: a hint needs outputs");
+            hints[h].id = hint_list[h].id;
+            hints[h].in.assign(hint_list[h].in_vars, hint_list[h].in_vars + hint_list[h].n_in);
+            hints[h].out.assign(hint_list[h].out_vars, hint_list[h].out_vars + hint_list[h].n_out);
+            for (uint32_t v : hints[h].in) B2P_REQUIRE(v < nb_variables, "solver: hint input out of range");
+            for (uint32_t v : hints[h].out) {
+                B2P_REQUIRE(v < nb_variables, "solver: hint output out of range");
+                B2P_REQUIRE(var_level[v] == UNKNOWN && hint_of_var[v] < 0, "solver: a hint output is an input or another hint's output");
+                hint_of_var[v] = (int32_t)h;
+            }
+        }
+        std::function<void(uint32_t, uint64_t)> place_hint = [&](uint32_t var, uint64_t row) {
+            if (hint_of_var.empty() || hint_of_var[var] < 0 || hint_placed[hint_of_var[var]]) return;
+            const uint32_t h = (uint32_t)hint_of_var[var];
+            hint_placed[h] = 1;                          // (also ends a cycle of hints feeding each other)
+            uint32_t lvl = 0;
+            for (uint32_t v : hints[h].in) {
+                if (var_level[v] == UNKNOWN) place_hint(v, row);     // an input that is itself a hint's output
+                if (var_level[v] == UNKNOWN)
+                    throw Error(B2P_ERR_ARG, "solver: hint " + std::to_string(h) + " is needed at row " + std::to_string(row) +
+                                                 " before its input variable " + std::to_string(v) + " is assigned");
+                lvl = std::max(lvl, var_level[v]);
+            }
+            hints[h].level = lvl + 1;
+            for (uint32_t v : hints[h].out) var_level[v] = lvl + 1;
+            hint_placed[h] = 1;
+            hint_trigger_row[h] = row;
+            hint_by_trigger.push_back(h);
+            depth = std::max(depth, lvl + 1);
+        };
         for (uint64_t i = nb_public; i < n; i++) {
             const bool use[3] = {!h_cols[0][i].is_zero() || !h_cols[2][i].is_zero(),
                                  !h_cols[1][i].is_zero() || !h_cols[2][i].is_zero(), !h_cols[3][i].is_zero()};
             const uint32_t w[3] = {h_x[0][i], h_x[1][i], h_x[2][i]};
+            for (int k = 0; k < 3; k++)
+                if (use[k] && var_level[w[k]] == UNKNOWN) place_hint(w[k], i);
             uint32_t unknown_var = UNKNOWN, lvl = 0;
             int unknown_pos = -1, occurrences = 0;
             bool two = false;
@@ -213,10 +274,12 @@ struct Solver : SolverBase {
             depth = std::max(depth, lvl + 1);
         }
         for (uint64_t i = 0; i < n; i++)
-            for (int k = 0; k < 3; k++)
+            for (int k = 0; k < 3; k++) {
+                if (var_level[h_x[k][i]] == UNKNOWN) place_hint(h_x[k][i], n);     // only ever read through a zero selector
                 if (var_level[h_x[k][i]] == UNKNOWN)
                     throw Error(B2P_ERR_ARG, "solver: variable " + std::to_string(h_x[k][i]) + " (row " + std::to_string(i) +
                                                  ") is neither an input nor determined by a row");
+            }
         // ---- rows by level (counting sort keeps the row order inside a level)
         h_level_off.assign(depth + 2, 0);
         for (uint64_t i = 0; i < n; i++)
@@ -228,25 +291,64 @@ struct Solver : SolverBase {
             for (uint64_t i = 0; i < n; i++)
                 if (h_kind[i]) h_ops[cur[row_level[i]]++] = (uint32_t)i | ((uint32_t)h_kind[i] << 30);
         }
-        // ---- launch plan + cost model (us): a wide level = one launch, a run of narrow levels = one block
+        // ---- launch plan + cost model (us): a wide level = one launch, a run of narrow levels = one block; the hints
+        // of level l run after the rows of the levels below it and before anything that can read their outputs
         est_dev_us = 0;
-        for (uint32_t l = 1; l <= depth;) {
-            const uint32_t w = h_level_off[l + 1] - h_level_off[l];
-            widest = std::max(widest, w);
-            if (w > SOLVER_NARROW_MAX) {
-                plan.push_back({l, 1, h_level_off[l], w, false});
-                est_dev_us += 4.0 + w * 2.5e-4;
-                l++;
-                continue;
+        auto emit_rows = [&](uint32_t l0, uint32_t l1) {            // levels [l0, l1)
+            for (uint32_t l = l0; l < l1;) {
+                const uint32_t w = h_level_off[l + 1] - h_level_off[l];
+                widest = std::max(widest, w);
+                if (w > SOLVER_NARROW_MAX) {
+                    plan.push_back({l, 1, h_level_off[l], w, false});
+                    est_dev_us += 4.0 + w * 2.5e-4;
+                    l++;
+                    continue;
+                }
+                uint32_t e = l;
+                while (e < l1 && h_level_off[e + 1] - h_level_off[e] <= SOLVER_NARROW_MAX) {
+                    widest = std::max(widest, h_level_off[e + 1] - h_level_off[e]);
+                    e++;
+                }
+                plan.push_back({l, e - l, h_level_off[l], h_level_off[e] - h_level_off[l], true});
+                est_dev_us += 4.0 + (e - l) * 2.2;
+                l = e;
             }
-            uint32_t e = l;
-            while (e <= depth && h_level_off[e + 1] - h_level_off[e] <= SOLVER_NARROW_MAX) {
-                widest = std::max(widest, h_level_off[e + 1] - h_level_off[e]);
-                e++;
+        };
+        for (uint32_t h = 0; h < n_hints; h++)
+            if (hint_placed[h]) hint_order.push_back(h);
+        std::stable_sort(hint_order.begin(), hint_order.end(),
+                         [&](uint32_t x, uint32_t y) { return hints[x].level < hints[y].level; });
+        {
+            uint32_t start = 1;
+            for (size_t k = 0; k < hint_order.size();) {
+                const uint32_t l = hints[hint_order[k]].level;
+                size_t e = k;
+                while (e < hint_order.size() && hints[hint_order[e]].level == l) e++;
+                emit_rows(start, l);
+                SolverLaunch item{l, 0, 0, 0, false};
+                item.hint_first = (uint32_t)k;
+                item.hint_count = (uint32_t)(e - k);
+                plan.push_back(item);
+                est_dev_us += 30.0 * (e - k);
+                start = l;
+                k = e;
             }
-            plan.push_back({l, e - l, h_level_off[l], h_level_off[e] - h_level_off[l], true});
-            est_dev_us += 4.0 + (e - l) * 2.2;
-            l = e;
+            emit_rows(start, depth + 1);
+        }
+        // host path: a hint runs before the first solving row at or after the trace row that first needed it
+        {
+            size_t k = 0;
+            std::vector<uint32_t> solving;
+            for (uint64_t i = nb_public; i < n; i++)
+                if (h_kind[i]) solving.push_back((uint32_t)i);
+            for (uint32_t h : hint_by_trigger) {
+                while (k < solving.size() && solving[k] < hint_trigger_row[h]) k++;
+                hints[h].trigger_op = (uint32_t)k;
+            }
+        }
+        if (unchecked) {
+            has_unchecked = true;
+            d_unchecked.alloc(n);
         }
         est_dev_us += 10 + n * 1e-4;
         est_host_us = h_ops.size() * 0.06 + nb_variables * 0.004 + 300;   // one product per common row + upload of the values
@@ -262,6 +364,7 @@ struct Solver : SolverBase {
         }
         d_kind.alloc(n);
         B2P_CUDA(cudaMemcpyAsync(d_kind.p, h_kind.data(), n, cudaMemcpyHostToDevice, st));
+        if (has_unchecked) B2P_CUDA(cudaMemcpyAsync(d_unchecked.p, unchecked, n, cudaMemcpyHostToDevice, st));
         d_ops.alloc(std::max<size_t>(h_ops.size(), 1));
         if (!h_ops.empty()) B2P_CUDA(cudaMemcpyAsync(d_ops.p, h_ops.data(), h_ops.size() * 4, cudaMemcpyHostToDevice, st));
         d_level_off.alloc(h_level_off.size());
@@ -297,6 +400,7 @@ struct Solver : SolverBase {
         return {d_cols[0].p, d_cols[1].p, d_cols[2].p, d_cols[3].p, d_cols[4].p, d_ninv.p, d_x[0].p, d_x[1].p, d_x[2].p};
     }
 
+    void set_hint_fn(b2p_hint_fn fn, void* ctx) override { hint_fn = fn; hint_ctx = ctx; }
     void info(uint64_t* out) const override {
         out[0] = depth; out[1] = widest; out[2] = h_ops.size(); out[3] = plan.size();
         out[4] = (uint64_t)est_host_us; out[5] = (uint64_t)est_dev_us; out[6] = (uint64_t)(last_ms * 1000.0); out[7] = last_where;
@@ -328,22 +432,50 @@ struct Solver : SolverBase {
         last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
 
-    // the fixed part of a device solve: flags, input scatter, one launch per plan entry, gather + check
+    // the fixed part of a device solve: flags, input scatter, one launch per plan entry (hints: a round trip through
+    // the caller's function), gather + check
     void queue_levels() {
         const SolverCols<Fr> c = dcols();
         B2P_CUDA(cudaMemsetAsync(d_flags.p, 0xFF, 2 * sizeof(uint32_t), st));
         if (nb_inputs)
             B2P_LAUNCH((k_solver_inputs<Fr>), div_up(nb_inputs, 128), 128, 0, st, d_values.p, d_in.p, d_inputs.p, nb_inputs);
         for (const SolverLaunch& s : plan) {
-            if (s.narrow)
+            if (s.hint_count) {
+                for (uint32_t k = 0; k < s.hint_count; k++) run_hint_device(hints[hint_order[s.hint_first + k]]);
+            } else if (s.narrow) {
                 B2P_LAUNCH((k_solve_narrow<Fr>), 1, SOLVER_NARROW_THREADS, 0, st, c, d_values.p, d_ops.p, d_level_off.p,
                            s.first_level, s.levels, d_flags.p);
-            else
+            } else {
                 B2P_LAUNCH((k_solve_level<Fr>), div_up(s.ops, 128), 128, 0, st, c, d_values.p, d_ops.p, s.first_op, s.ops,
                            d_flags.p);
+            }
         }
         B2P_LAUNCH((k_solver_gather<Fr>), div_up(n, 128), 128, 0, st, c, d_values.p, dL.p, dR.p, dO.p, n, nb_public,
-                   d_flags.p + 1);
+                   d_flags.p + 1, has_unchecked ? d_unchecked.p : nullptr);
+    }
+    void call_hint(const SolverHint& h) {
+        if (!hint_fn) throw Error(B2P_ERR_ARG, "solver: the circuit has hints but no hint function is set (b2p_solver_set_hint_fn)");
+        if (hint_fn(hint_ctx, h.id, hint_in.data(), (uint32_t)h.in.size(), hint_out.data(), (uint32_t)h.out.size()) != 0)
+            throw Error(B2P_ERR_INTERNAL, "solver: the hint function reported a failure (hint id " + std::to_string(h.id) + ")");
+    }
+    // inputs down, the caller's function, outputs up: a synchronisation point of the device path
+    void run_hint_device(const SolverHint& h) {
+        hint_in.resize(std::max<size_t>(h.in.size(), 1));
+        hint_out.resize(h.out.size());
+        for (size_t j = 0; j < h.in.size(); j++)
+            B2P_CUDA(cudaMemcpyAsync(&hint_in[j], d_values.p + h.in[j], sizeof(Fr), cudaMemcpyDeviceToHost, st));
+        B2P_CUDA(cudaStreamSynchronize(st));
+        call_hint(h);
+        for (size_t j = 0; j < h.out.size(); j++)
+            B2P_CUDA(cudaMemcpyAsync(d_values.p + h.out[j], &hint_out[j], sizeof(Fr), cudaMemcpyHostToDevice, st));
+        B2P_CUDA(cudaStreamSynchronize(st));          // hint_out is reused by the next hint
+    }
+    void run_hint_host(const SolverHint& h, HF* v) {
+        hint_in.resize(std::max<size_t>(h.in.size(), 1));
+        hint_out.resize(h.out.size());
+        for (size_t j = 0; j < h.in.size(); j++) hint_in[j] = v[h.in[j]];
+        call_hint(h);
+        for (size_t j = 0; j < h.out.size(); j++) v[h.out[j]] = hint_out[j];
     }
     // A shallow circuit is hundreds of short launches with fixed arguments: captured once into a CUDA graph, a solve is
     // one graph launch (B2P_SOLVER_GRAPH=0 keeps the plain launches; so does any failure to capture).
@@ -352,7 +484,7 @@ struct Solver : SolverBase {
     void build_graph() {
         graph_tried = true;
         const char* e = getenv("B2P_SOLVER_GRAPH");
-        if ((e && atoi(e) == 0) || plan.size() < 8) return;
+        if ((e && atoi(e) == 0) || plan.size() < 8 || !hint_order.empty()) return;    // a hint is a host call: no capture
         cudaGraph_t g = nullptr;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return; }
         bool ok = true;
@@ -394,7 +526,10 @@ struct Solver : SolverBase {
         for (uint32_t i = 0; i < nb_inputs; i++) v[h_inputs[i]] = in[i];
         uint32_t div0 = 0xFFFFFFFFu;
         const uint32_t nops = (uint32_t)h_rows.size();
+        size_t next_hint = 0;
         for (uint32_t k = 0; k < nops; k++) {
+            while (next_hint < hint_by_trigger.size() && hints[hint_by_trigger[next_hint]].trigger_op <= k)
+                run_hint_host(hints[hint_by_trigger[next_hint++]], v);
             const uint64_t i = h_rows[k];
             const uint8_t cls = h_cls[k];
             const uint32_t ia = h_x[0][i], ib = h_x[1][i], ic = h_x[2][i];
@@ -421,11 +556,12 @@ struct Solver : SolverBase {
             if (den.is_zero()) { div0 = std::min<uint32_t>(div0, (uint32_t)i); continue; }
             v[solve_a ? ia : ib] = (num * den.inverse()).neg();
         }
+        while (next_hint < hint_by_trigger.size()) run_hint_host(hints[hint_by_trigger[next_hint++]], v);
         if (div0 != 0xFFFFFFFFu) report(div0, 0xFFFFFFFFu);
         B2P_CUDA(cudaMemcpyAsync(d_values.p, v, nb_variables * sizeof(Fr), cudaMemcpyHostToDevice, st));
         B2P_CUDA(cudaMemsetAsync(d_flags.p, 0xFF, 2 * sizeof(uint32_t), st));
         B2P_LAUNCH((k_solver_gather<Fr>), div_up(n, 128), 128, 0, st, dcols(), d_values.p, dL.p, dR.p, dO.p, n, nb_public,
-                   d_flags.p + 1);
+                   d_flags.p + 1, has_unchecked ? d_unchecked.p : nullptr);
         uint32_t flags[2];
         B2P_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
         B2P_CUDA(cudaStreamSynchronize(st));

@@ -39,6 +39,18 @@ class Commitment:
 
 
 @dataclass
+class Hint:
+    """A solver hint (gnark: solver.Hint): out_vars = f(in_vars), f identified by `id` and supplied at solve time."""
+    id: int
+    in_vars: List[int]
+    out_vars: List[int]
+
+
+HINT_NBITS = 1            # bits of one variable, least significant first (gnark: bits.NBits)
+HINT_BSB22 = 0x100        # + commitment index: hash of the commitment to the committed variables (gnark: bsb22CommitmentComputePlaceholder)
+
+
+@dataclass
 class SparseR1CS:
     curve: str
     nb_public: int
@@ -49,6 +61,8 @@ class SparseR1CS:
     # variables the caller assigns (frontend.NewWitness: public, then secret); None: the first nb_public + 1 ...
     # are not known -- circuits built by Builder / the generators below always record them
     input_vars: Optional[List[int]] = None
+    hints: List[Hint] = field(default_factory=list)
+    unchecked_rows: List[int] = field(default_factory=list)    # constraint indexes whose gate the prover completes (BSB22)
 
     @property
     def nb_constraints(self) -> int:
@@ -74,6 +88,8 @@ class Builder:
         # filled by commit(): callbacks the solver runs to obtain hash(commitment)
         self._commit_hooks: List[Callable] = []
         self.input_vars: List[int] = []          # variables assigned by the caller, in declaration order
+        self.hints: List[Hint] = []
+        self.unchecked_rows: List[int] = []
 
     # -- variables ---------------------------------------------------------
     def public(self, value: int) -> int:
@@ -114,6 +130,28 @@ class Builder:
     def assert_is_equal(self, a: int, b: int) -> None:
         self.add_constraint(ql=1, qr=-1, xa=a, xb=b, xc=0)
 
+    def hint(self, hint_id: int, in_vars: Sequence[int], out_values: Sequence[int]) -> List[int]:
+        """Variables a solver hint produces (api.Compiler.NewHint): the builder knows their values, the constraint
+        system only records which function makes them from what."""
+        outs = [self.internal(v) for v in out_values]
+        self.hints.append(Hint(hint_id, list(in_vars), outs))
+        return outs
+
+    def to_binary(self, a: int, nbits: int) -> List[int]:
+        """api.ToBinary: nbits boolean variables from the NBits hint, each constrained b*b = b, recomposing to a."""
+        bits = self.hint(HINT_NBITS, [a], [(self.values[a] >> i) & 1 for i in range(nbits)])
+        acc = None
+        for i, b in enumerate(bits):
+            self.add_constraint(qm=1, ql=-1, xa=b, xb=b)             # b * b - b = 0
+            if acc is None:
+                acc = b
+            else:
+                nxt = self.internal(self.values[acc] + (self.values[b] << i))
+                self.add_constraint(ql=1, qr=1 << i, qo=-1, xa=acc, xb=b, xc=nxt)
+                acc = nxt
+        self.assert_is_equal(acc, a)
+        return bits
+
     def assert_is_different_from_zero(self, a: int) -> None:
         v = self.values[a]
         inv = self.internal(pow(v, -1, self.r) if v else 0)
@@ -128,14 +166,15 @@ class Builder:
             rows.append(self.add_constraint(ql=-1, xa=v, xb=0, xc=0))      # -v + qcp*pi2 = 0
         commitment_row = len(self.constraints)
         h = hash_of_commitment(rows, [self.values[v] for v in variables], commitment_row)
-        cvar = self.internal(h)
+        cvar = self.hint(HINT_BSB22 + len(self.commitments), list(variables), [h])[0]
         self.add_constraint(ql=-1, xa=cvar, xb=0, xc=0)                     # -cmt + qk(=hash) = 0
         self.commitments.append(Commitment(rows, commitment_row, cvar))
+        self.unchecked_rows += rows + [commitment_row]                       # the prover adds qcp * pi2 and the hash
         return cvar
 
     def build(self) -> SparseR1CS:
         return SparseR1CS(self.curve, self.nb_public, len(self.values), list(self.constraints),
-                          list(self.commitments), list(self.input_vars))
+                          list(self.commitments), list(self.input_vars), list(self.hints), list(self.unchecked_rows))
 
 
 @dataclass
@@ -438,7 +477,7 @@ def _mimc_in_circuit(B: Builder, h: int, blocks: Sequence[int]) -> int:
     return h
 
 
-def merkle_circuit(curve: str, depth: int = 16, nb_leaves: int = 6, index: int = 3):
+def merkle_circuit(curve: str, depth: int = 16, nb_leaves: int = 6, index: int = 3, bits_from_hint: bool = False):
     """MerkleCircuit (examples/merkle/logicsigVerifier/main.go:45-61): public RootHash, secret Path[depth + 1] (the
     unhashed leaf, then the siblings up to the root) and Index; Define() = merkle.MerkleProof.VerifyProof with MiMC:
     the leaf is hashed, the index is split into bits, every level selects (left, right) by its bit and hashes them,
@@ -471,8 +510,11 @@ def merkle_circuit(curve: str, depth: int = 16, nb_leaves: int = 6, index: int =
     total = _mimc_in_circuit(B, zero_h, [v_path[0]])          # leafSum
     # api.ToBinary(index, depth): boolean bits that recompose to the index
     bits, acc = [], None
+    hinted = B.hint(HINT_NBITS, [v_index], [(index >> i) & 1 for i in range(depth)]) if bits_from_hint else None
     for i in range(depth):
-        b = B.secret((index >> i) & 1)
+        # bits_from_hint: the bits are what gnark's NBits hint produces at solve time (same variables, same rows --
+        # only who assigns them differs); else the caller supplies them with the witness
+        b = hinted[i] if bits_from_hint else B.secret((index >> i) & 1)
         B.add_constraint(qm=1, ql=-1, xa=b, xb=b)             # b * b - b = 0
         bits.append(b)
         if acc is None:

@@ -1,16 +1,21 @@
 // solver.go -- the witness solver on the GPU (SURVEY 8f rank 4; spr.Solve inside plonk.Prove,
 // /root/reference/algoplonk.go:81-89) for hint-free circuits: rows and wire ids come from the compiled
 // SparseR1CS once per key (b2p_solver_create), the assigned inputs per proof (b2p_solver_solve_dev), and L, R, O stay
-// in HBM for b2p_prove_dev.  Circuits with hints (BSB22 commitments, std gadgets that call hint functions) keep
-// gnark's solver: b2p_solver_create refuses them.  NOT COMPILED in the build container (no Go toolchain).
+// in HBM for b2p_prove_dev.  Hints stay gnark's: newDeviceSolverBN254 hands b2p_solver_create_hinted the (inputs,
+// outputs) of every hint instruction of the constraint system, and goHintTrampoline -- the b2p_hint_fn the library calls
+// during a solve -- runs the registered Go hint function (solver.GetRegisteredHint, the BSB22 override of hints.go
+// included) on big.Int copies of the values.  NOT COMPILED in the build container (no Go toolchain).
 package gpuplonk
 
 /*
 #include "b200plonk.h"
+extern int goHintTrampoline(void* ctx, uint32_t id, void* inputs, uint32_t n_in, void* outputs, uint32_t n_out);
 */
 import "C"
 
 import (
+	"math/big"
+	"runtime/cgo"
 	"unsafe"
 
 	"github.com/consensys/gnark-crypto/ecc/bn254/fr"
@@ -61,4 +66,46 @@ func (s *deviceSolver) solve(inputs []fr.Element) (l, r, o unsafe.Pointer, err e
 		return C.b2p_solver_solve_dev(s.h, unsafe.Pointer(&inputs[0]), C.B2P_SOLVE_AUTO, &l, &r, &o)
 	})
 	return
+}
+
+// ---- hints ---------------------------------------------------------------------------------------------------------
+//
+// gnark's solver executes hint instructions between constraint instructions; the library needs to know only which
+// variables each one reads and writes (b2p_hint) and calls back for the values.  The callback below is exported to C
+// (//export) and registered with b2p_solver_set_hint_fn; ctx is a cgo.Handle of the *hintTable of the key.
+
+// hintTable: per key, the hint functions by the id given to the library (the index of the hint instruction).
+type hintTable struct {
+	fns []solverHint
+}
+type solverHint struct {
+	fn      func(mod *big.Int, inputs, outputs []*big.Int) error // solver.Hint
+	nIn     int
+	nOut    int
+}
+
+//export goHintTrampoline
+func goHintTrampoline(ctx unsafe.Pointer, id C.uint32_t, inputs unsafe.Pointer, nIn C.uint32_t, outputs unsafe.Pointer, nOut C.uint32_t) C.int {
+	tbl := cgo.Handle(uintptr(ctx)).Value().(*hintTable)
+	if int(id) >= len(tbl.fns) {
+		return 1
+	}
+	h := tbl.fns[id]
+	in := unsafe.Slice((*fr.Element)(inputs), int(nIn))
+	out := unsafe.Slice((*fr.Element)(outputs), int(nOut))
+	bi := make([]*big.Int, len(in))
+	for i := range in {
+		bi[i] = in[i].BigInt(new(big.Int)) // Montgomery -> canonical
+	}
+	bo := make([]*big.Int, len(out))
+	for i := range bo {
+		bo[i] = new(big.Int)
+	}
+	if err := h.fn(fr.Modulus(), bi, bo); err != nil {
+		return 2
+	}
+	for i := range out {
+		out[i].SetBigInt(bo[i])
+	}
+	return 0
 }

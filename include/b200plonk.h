@@ -410,7 +410,7 @@ int b2p_circuit_load_file(b2p_srs* srs, const char* path, b2p_circuit** out);
  * Columns are the padded trace of b2p_circuit_load (n rows, public rows first, qk WITHOUT public inputs); xa xb xc
  * give the variable of each row's L R O wire (padding rows and unused wires: variable 0, as gnark pads).
  * input_ids: the variables assigned by the caller (public, then secret), values in the same order in `inputs`.
- * Hints (BSB22 commitments, gnark hint functions) are not solved: such rows make create fail with B2P_ERR_ARG.
+ * Rows that need a hint make b2p_solver_create fail with B2P_ERR_ARG: use b2p_solver_create_hinted.
  * solve: B2P_ERR_VERIFY "constraint #i is not satisfied" when the assignment breaks a row (every row is checked).
  * L R O: n Fr each (Montgomery), what b2p_prove takes; the _dev form leaves them in HBM (valid until the next
  * solve on this handle) for b2p_prove_dev.  One call at a time per handle. */
@@ -422,6 +422,26 @@ int b2p_solver_create(int curve, uint64_t n, uint32_t nb_public, uint64_t nb_var
                       const uint32_t* input_ids, uint32_t nb_inputs,
                       const void* ql, const void* qr, const void* qm, const void* qo, const void* qk,
                       const uint32_t* xa, const uint32_t* xb, const uint32_t* xc, b2p_solver** out);
+/* Hints -- gnark's hint functions (bit decompositions, inverse-or-zero, the BSB22 commitment hint, ...): variables a
+ * function of the CALLER's computes from other variables.  create_hinted is told which variables each hint reads and
+ * produces; the solver places a hint where its inputs are known and calls `fn(ctx, id, inputs, n_in, outputs, n_out)`
+ * there during a solve (values as Fr in Montgomery form; return 0, anything else fails the solve with B2P_ERR_INTERNAL).
+ * On the device path a hint is a synchronisation point (inputs down, outputs up).  unchecked_rows (n bytes, may be NULL):
+ * rows left out of the final gate check -- BSB22's committed rows and commitment row, whose qcp * pi2 term and hash
+ * the prover adds (b2p_prove's bsb22 arguments).  The shim passes gnark's own hint functions through a cgo callback. */
+typedef struct b2p_hint {
+    uint32_t id;                  /* the caller's name for the function (gnark: solver.HintID) */
+    uint32_t n_in, n_out;
+    const uint32_t* in_vars;      /* variables read */
+    const uint32_t* out_vars;     /* variables produced (not inputs, not another hint's outputs) */
+} b2p_hint;
+typedef int (*b2p_hint_fn)(void* ctx, uint32_t id, const void* inputs, uint32_t n_in, void* outputs, uint32_t n_out);
+int b2p_solver_create_hinted(int curve, uint64_t n, uint32_t nb_public, uint64_t nb_variables,
+                             const uint32_t* input_ids, uint32_t nb_inputs,
+                             const void* ql, const void* qr, const void* qm, const void* qo, const void* qk,
+                             const uint32_t* xa, const uint32_t* xb, const uint32_t* xc,
+                             const b2p_hint* hints, uint32_t n_hints, const uint8_t* unchecked_rows, b2p_solver** out);
+int b2p_solver_set_hint_fn(b2p_solver* s, b2p_hint_fn fn, void* ctx);
 int b2p_solver_solve(b2p_solver* s, const void* inputs, int where, void* L, void* R, void* O);
 int b2p_solver_solve_dev(b2p_solver* s, const void* inputs, int where, void** dL, void** dR, void** dO);
 /* out[8]: levels, widest level, solved rows, launches per solve, estimated host us, estimated device us,

@@ -12,15 +12,45 @@ class Unsatisfied(Exception):
 
 
 def solve(r: int, nb_public: int, nb_variables: int, constraints: Sequence[tuple], input_vars: Sequence[int],
-          inputs: Sequence[int]) -> Tuple[List[int], List[int]]:
-    """Returns (values of every variable, level of every constraint: 0 = assertion, else 1 + deepest wire it reads)."""
+          inputs: Sequence[int], hints: Sequence[tuple] = (), hint_fn=None, unchecked: Sequence[int] = ()
+          ) -> Tuple[List[int], List[int]]:
+    """Returns (values of every variable, level of every constraint: 0 = assertion, else 1 + deepest wire it reads).
+    hints: (id, in_vars, out_vars) triples; hint_fn(id, input values, n_out) -> output values runs a hint the first time a
+    constraint needs one of its outputs (gnark runs hint instructions in stream order, which comes to the same values).
+    unchecked: constraint indexes left out of the final check (BSB22 rows the prover completes)."""
     val = [None] * nb_variables
     lvl = [0] * nb_variables
     for v, x in zip(input_vars, inputs):
         val[v] = x % r
+    hint_of = {}
+    for h, (_, _, outs) in enumerate(hints):
+        for v in outs:
+            hint_of[v] = h
+    done = set()
+
+    def need(v):
+        h = hint_of.get(v)
+        if h is None or h in done:
+            return
+        hid, ins, outs = hints[h]
+        for i in ins:                       # an input may itself come out of a hint that has not run yet
+            if val[i] is None:
+                need(i)
+        if any(val[i] is None for i in ins):
+            raise ValueError(f"hint {h} needed before its inputs are assigned")
+        got = hint_fn(hid, [val[i] for i in ins], len(outs))
+        d = max([lvl[i] for i in ins], default=0) + 1
+        for v2, x in zip(outs, got):
+            val[v2] = x % r
+            lvl[v2] = d
+        done.add(h)
+
     levels = []
     for j, (ql, qr, qm, qo, qk, a, b, c) in enumerate(constraints):
         used = [(a, bool(ql or qm)), (b, bool(qr or qm)), (c, bool(qo))]
+        for w, u in used:
+            if u and val[w] is None:
+                need(w)
         unknown = sorted({w for w, u in used if u and val[w] is None})
         depth = max([lvl[w] for w, u in used if u and val[w] is not None], default=0)
         if not unknown:
@@ -45,10 +75,13 @@ def solve(r: int, nb_public: int, nb_variables: int, constraints: Sequence[tuple
         val[u] = (-num) * pow(den, -1, r) % r
         lvl[u] = depth + 1
         levels.append(depth + 1)
+    skip = set(unchecked)
     for j, (ql, qr, qm, qo, qk, a, b, c) in enumerate(constraints):
         for w in (a, b, c):
             if val[w] is None:
+                need(w)
+            if val[w] is None:
                 raise ValueError(f"variable {w} is never assigned")
-        if (ql * val[a] + qr * val[b] + qm * val[a] * val[b] + qo * val[c] + qk) % r:
+        if j not in skip and (ql * val[a] + qr * val[b] + qm * val[a] * val[b] + qo * val[c] + qk) % r:
             raise Unsatisfied(f"constraint #{nb_public + j} is not satisfied")
     return val, levels

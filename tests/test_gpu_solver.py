@@ -135,3 +135,106 @@ def test_inputs_to_verified_proof_on_the_device(gpu, curve, build):
     s.free()
     cc.free()
     srs.free()
+
+
+# ---- hints -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", CURVES)
+def test_solver_runs_the_callers_hints(gpu, curve):
+    """gnark's hint functions are the caller's: the NBits hint behind api.ToBinary (the reference's Merkle circuit takes
+    the bits of its leaf index that way, examples/merkle/logicsigVerifier/main.go:45-61) placed where its input is
+    known, on the device path (a synchronisation point) and on the host path; same witness as the oracle's solver."""
+    cv = po.CURVES[curve]
+    cases = []
+    B = fe.Builder(curve)
+    x = B.public(0b1011001)
+    y = B.secret(77)
+    bits = B.to_binary(B.mul(x, y), 14)                       # the hint's input is itself solved from a row
+    B.assert_is_equal(B.add(bits[0], bits[3]), B.add(bits[3], bits[0]))
+    cases.append(("to_binary", B.build(), B.values))
+    M, _ = fe.merkle_circuit(curve, depth=3, bits_from_hint=True)
+    cases.append(("merkle_hinted", M.build(), M.values))
+    W = fe.Builder(curve)                                      # hints between wide levels: the launch plan is cut there
+    xs = [W.secret(1000 + i) for i in range(600)]
+    sq = [W.mul(v, v) for v in xs]
+    lows = [W.to_binary(W.hint(fe.HINT_NBITS + 0, [q], [W.values[q] & 1])[0], 1)[0] for q in sq[:3]]
+    W.assert_is_equal(W.add(lows[0], lows[1]), W.add(lows[1], lows[0]))
+    cases.append(("wide_with_hints", W.build(), W.values))
+    for name, cs, values in cases:
+        tc = fe.build_trace(cs)
+        want = fe.solve_lro(cs, values, tc.n)
+        inputs = [values[v] for v in cs.input_vars]
+        hs = [(h.id, h.in_vars, h.out_vars) for h in cs.hints]
+        oval, olevels = osolver.solve(cv.r, cs.nb_public, cs.nb_variables, cs.constraints, cs.input_vars, inputs, hs,
+                                      api.std_hint_fn())
+        assert oval == [v % cv.r for v in values], name
+        s = api.Solver(cs, tc, hint_fn=api.std_hint_fn())
+        for where in WHERE:
+            assert s.solve(inputs, where) == want, (name, where)
+        s.free()
+        with pytest.raises(ValueError, match="hint"):
+            api.Solver(cs, tc)                                  # hints recorded, no function given
+    # a hint function that fails, and one that lies (the rows that constrain its outputs catch it)
+    cs, values = cases[0][1], cases[0][2]
+    inputs = [values[v] for v in cs.input_vars]
+
+    def failing(hid, vals, n_out):
+        raise RuntimeError("no such hint")
+    s = api.Solver(cs, hint_fn=failing)
+    for where in (_lib.SOLVE_HOST, _lib.SOLVE_DEVICE):
+        with pytest.raises(_lib.B200PlonkError, match="hint function reported a failure") as e:
+            s.solve(inputs, where)
+        assert e.value.code == _lib.ERR_INTERNAL
+    s.free()
+    s = api.Solver(cs, hint_fn=lambda hid, vals, n_out: [1] * n_out)
+    for where in (_lib.SOLVE_HOST, _lib.SOLVE_DEVICE):
+        with pytest.raises(_lib.B200PlonkError, match="is not satisfied"):
+            s.solve(inputs, where)
+    s.free()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("k", (1, 2))
+def test_solver_with_the_bsb22_commitment_hint(gpu, curve, k):
+    """bsb22Circuit (bsb22_test.go:18-39): the commitment hint -- commit to the committed wires on the Lagrange basis
+    (b2p_msm_g1), hash to the field -- runs as a solver hint; the committed rows and the commitment row, whose gates the
+    prover completes, are left out of the solver's check.  L, R, O then prove to the golden bytes."""
+    cv = po.CURVES[curve]
+    n_dry = fe.bsb22_circuit(curve, k, lambda a, b, c: 1).build().domain_size
+    srs = api.SRS.unsafe(curve, n_dry + 3, H.TAU)
+    cs, values, pi2s, coms = H.build_bsb22(curve, k, lambda col: srs.msm(col, basis=_lib.BASIS_LAGRANGE))
+    case = next(c for c in H.golden_proofs() if c["curve"] == curve and c["name"] == f"bsb22_k{k}" and c["srs"] == "tau")
+    off = cs.nb_public
+    calls = []
+
+    def commitment_hint(hid, vals, n_out):
+        c = hid - fe.HINT_BSB22
+        col = pi2s[c]                                            # the committed values + gnark's two blinding slots
+        assert [col[off + r] for r in cs.commitments[c].committed_rows] == vals
+        com = srs.msm(col, basis=_lib.BASIS_LAGRANGE)            # on the GPU, inside the solve
+        assert com == coms[c]
+        calls.append(c)
+        return [po.hash_fr(cv, po.fs_point(cv, com))]
+
+    s = api.Solver(cs, hint_fn=api.std_hint_fn(commitment_hint))
+    tc = fe.build_trace(cs)
+    want = fe.solve_lro(cs, values, tc.n)
+    inputs = [values[v] for v in cs.input_vars]
+    for where in WHERE:
+        assert s.solve(inputs, where) == want, where
+    assert calls == list(range(k)) * 3
+    L, R, O = s.solve(inputs)
+    cc = api.Compile(cs, curve, SETUP[curve], srs=srs)
+    assert api.MarshalProof(cc.Prove(L, R, O, case["blinding"], pi2s, coms)).hex() == case["proof"]
+    # a wrong input: this test's hint notices that the committed values changed ...
+    with pytest.raises(_lib.B200PlonkError, match="hint function reported a failure"):
+        s.solve([inputs[0] + 1] + inputs[1:])
+    s.free()
+    # ... and with a hint that does not look, the rows the solver does check (X == Y * Y) fail
+    s = api.Solver(cs, hint_fn=api.std_hint_fn(lambda hid, vals, n_out: [po.hash_fr(cv, po.fs_point(cv, coms[hid - fe.HINT_BSB22]))]))
+    for where in (_lib.SOLVE_HOST, _lib.SOLVE_DEVICE):
+        with pytest.raises(_lib.B200PlonkError, match="is not satisfied"):
+            s.solve([inputs[0] + 1] + inputs[1:], where)
+    s.free()
+    cc.free()
+    srs.free()
+

@@ -570,3 +570,39 @@ def test_oracle_solver_against_the_eager_front_end(curve):
     with pytest.raises(osolver.Unsatisfied):
         osolver.solve(cv.r, cs.nb_public, cs.nb_variables, cs.constraints, cs.input_vars, [3, 4, 6])
     assert max(osolver.solve(cv.r, 1, *(lambda c, v: (c.nb_variables, c.constraints, c.input_vars, [v[0], v[1]]))(*fe.squaring_chain(curve, 6)))[1]) == 62
+
+
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+def test_oracle_solver_with_hints(curve):
+    """Hints in the oracle's solver (the checker of b2p_solver_create_hinted): the NBits hint behind ToBinary, a hint
+    whose input is another hint's output, and the BSB22 commitment hint with its unchecked rows -- against the witness
+    the eager front end computed."""
+    from algoplonk_b200 import api, frontend as fe
+    from oracle import solver as osolver
+    cv = po.CURVES[curve]
+    M, _ = fe.merkle_circuit(curve, depth=2, bits_from_hint=True)
+    B = fe.Builder(curve)
+    x = B.public(0b1011001)
+    bits = B.to_binary(B.mul(x, B.secret(3)), 12)
+    low = B.to_binary(B.hint(fe.HINT_NBITS, [bits[2]], [B.values[bits[2]] & 1])[0], 1)
+    B.assert_is_equal(low[0], bits[2])
+    for Bd in (M, B):
+        cs, values = Bd.build(), Bd.values
+        hs = [(h.id, h.in_vars, h.out_vars) for h in cs.hints]
+        inputs = [values[v] for v in cs.input_vars]
+        val, _ = osolver.solve(cv.r, cs.nb_public, cs.nb_variables, cs.constraints, cs.input_vars, inputs, hs, api.std_hint_fn())
+        assert val == [v % cv.r for v in values]
+        with pytest.raises((ValueError, TypeError)):
+            osolver.solve(cv.r, cs.nb_public, cs.nb_variables, cs.constraints, cs.input_vars, inputs)     # hints not given
+    pts = po.srs_from_tau(cv, H.TAU, 16)
+    commit = lambda col: po.msm_naive(cv, pts, po.intt(cv, col, po.domain_generator(cv, len(col))))
+    cs, values, pi2s, coms = H.build_bsb22(curve, 2, commit)
+    assert sorted(cs.unchecked_rows) == sorted(r for c in cs.commitments for r in c.committed_rows + [c.commitment_row])
+    hs = [(h.id, h.in_vars, h.out_vars) for h in cs.hints]
+    extra = lambda hid, vals, n_out: [po.hash_fr(cv, po.fs_point(cv, coms[hid - fe.HINT_BSB22]))]
+    inputs = [values[v] for v in cs.input_vars]
+    val, _ = osolver.solve(cv.r, cs.nb_public, cs.nb_variables, cs.constraints, cs.input_vars, inputs, hs,
+                           api.std_hint_fn(extra), cs.unchecked_rows)
+    assert val == [v % cv.r for v in values]
+    with pytest.raises(osolver.Unsatisfied):      # without the exemption the committed rows read  -v + 0 = 0
+        osolver.solve(cv.r, cs.nb_public, cs.nb_variables, cs.constraints, cs.input_vars, inputs, hs, api.std_hint_fn(extra))
