@@ -19,6 +19,7 @@ import (
 	"unsafe"
 
 	"github.com/consensys/gnark-crypto/ecc/bn254/fr"
+	"github.com/consensys/gnark/constraint"
 	cs_bn254 "github.com/consensys/gnark/constraint/bn254"
 )
 
@@ -108,4 +109,42 @@ func goHintTrampoline(ctx unsafe.Pointer, id C.uint32_t, inputs unsafe.Pointer, 
 		out[i].SetBigInt(bo[i])
 	}
 	return 0
+}
+
+// hintRecords walks the instruction stream of a compiled constraint system and returns, per hint instruction, what the
+// library needs (the variables it reads and the range it writes) and what the trampoline needs (the linear
+// expressions gnark evaluates before calling the hint function).  gnark v0.15.0: hint instructions carry a blueprint
+// implementing constraint.BlueprintHint whose DecompressHint fills a constraint.HintMapping{HintID, Inputs
+// []LinearExpression, OutputRange} [UPSTREAM-RECALL: constraint/core.go, constraint/solver.go -- not compiled here].
+type hintRecord struct {
+	mapping constraint.HintMapping
+	inVars  []uint32 // distinct variables of mapping.Inputs, in first-use order: b2p_hint.in_vars
+	outVars []uint32 // mapping.OutputRange.Start .. End: b2p_hint.out_vars
+}
+
+func hintRecords(sys *constraint.System) []hintRecord {
+	var out []hintRecord
+	for i := range sys.Instructions {
+		inst := sys.Instructions[i]
+		bh, ok := sys.Blueprints[inst.BlueprintID].(constraint.BlueprintHint)
+		if !ok {
+			continue
+		}
+		var r hintRecord
+		bh.DecompressHint(&r.mapping, inst.Unpack(sys))
+		seen := map[uint32]bool{}
+		for _, le := range r.mapping.Inputs {
+			for _, t := range le {
+				if v := uint32(t.WireID()); !seen[v] {
+					seen[v] = true
+					r.inVars = append(r.inVars, v)
+				}
+			}
+		}
+		for v := r.mapping.OutputRange.Start; v < r.mapping.OutputRange.End; v++ {
+			r.outVars = append(r.outVars, v)
+		}
+		out = append(out, r)
+	}
+	return out
 }
