@@ -18,6 +18,16 @@ for curve, setup in (("BN254", api.SetupName.TestOnlyBN254), ("BLS12_381", api.S
         for where in (_lib.SOLVE_DEVICE, _lib.SOLVE_HOST):
             assert s.solve([values[v] for v in cs.input_vars], where) == want
         s.free()
+    # hints: the launch plan cut at hint levels, single values down and up (device), plain calls (host)
+    Bh = fe.Builder(curve)
+    xh = Bh.public(0b101101)
+    bits = Bh.to_binary(Bh.mul(xh, Bh.secret(3)), 10)
+    Bh.to_binary(Bh.hint(fe.HINT_NBITS, [bits[1]], [Bh.values[bits[1]] & 1])[0], 1)
+    csh = Bh.build()
+    s = api.Solver(csh, hint_fn=api.std_hint_fn())
+    for where in (_lib.SOLVE_DEVICE, _lib.SOLVE_HOST):
+        assert s.solve([Bh.values[v] for v in csh.input_vars], where) == fe.solve_lro(csh, Bh.values, s.n)
+    s.free()
     B = fe.Builder(curve)
     x = B.public(5)
     B.assert_is_different_from_zero(x)
