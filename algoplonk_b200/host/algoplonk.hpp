@@ -10,6 +10,9 @@
 //   VerifiedProof::ExportProofAndPublicInputs /root/reference/algoplonk.go:103-131
 //   MarshalProof / MarshalPublicInputs        /root/reference/helper.go:13-24,91-110
 //   setup::Name                               /root/reference/setup/setup.go:23-36
+//   CompiledCircuit::VerifyFromInputs(inputs)   the same with the witness solved by the library (b2p_solver_*),
+//                                               L R O staying in HBM (algoplonk.go:81-89: NewWitness + spr.Solve)
+//   SaveKey / Compile(..., snapshot)            /root/reference/utils/utils.go:97-157 (persisted proving key)
 //
 // The circuit front end (gnark's frontend.Compile + NewTrace) is restated minimally: public rows first,
 // last-seen-position permutation, padding rows on variable 0 -- enough for the circuits of the reference's
@@ -75,6 +78,7 @@ struct SparseR1CS {
     uint32_t nb_public = 0;
     std::vector<Fr> values;                 // solved witness, public variables first
     std::vector<Constraint> constraints;
+    std::vector<uint32_t> input_vars;       // the variables an assignment gives (public, then secret)
 
     uint64_t domain_size() const {          // NextPowerOfTwo(nbConstraints + nbPublic), setup.go:113
         uint64_t need = constraints.size() + nb_public, n = 1;
@@ -91,19 +95,27 @@ struct Builder {
     uint32_t Public(const Fr& v) {
         if (secret_started) throw Error("public variables first (gnark witness order)");
         cs.values.push_back(v);
+        cs.input_vars.push_back(cs.nb_public);
         return cs.nb_public++;
     }
-    uint32_t Secret(const Fr& v) { secret_started = true; cs.values.push_back(v); return (uint32_t)cs.values.size() - 1; }
+    uint32_t Secret(const Fr& v) {
+        secret_started = true;
+        cs.values.push_back(v);
+        cs.input_vars.push_back((uint32_t)cs.values.size() - 1);
+        return (uint32_t)cs.values.size() - 1;
+    }
+    // a variable the solver determines from a row (not part of the assignment)
+    uint32_t Internal(const Fr& v) { secret_started = true; cs.values.push_back(v); return (uint32_t)cs.values.size() - 1; }
     void Constrain(const Fr& ql, const Fr& qr, const Fr& qm, const Fr& qo, const Fr& qk, uint32_t a, uint32_t b, uint32_t c) {
         cs.constraints.push_back({ql, qr, qm, qo, qk, a, b, c});
     }
     uint32_t Mul(uint32_t a, uint32_t b) {
-        const uint32_t c = Secret(cs.values[a] * cs.values[b]);
+        const uint32_t c = Internal(cs.values[a] * cs.values[b]);
         Constrain(Fr::zero(), Fr::zero(), Fr::one(), Fr::one().neg(), Fr::zero(), a, b, c);
         return c;
     }
     uint32_t Add(uint32_t a, uint32_t b) {
-        const uint32_t c = Secret(cs.values[a] + cs.values[b]);
+        const uint32_t c = Internal(cs.values[a] + cs.values[b]);
         Constrain(Fr::one(), Fr::one(), Fr::zero(), Fr::one().neg(), Fr::zero(), a, b, c);
         return c;
     }
@@ -148,8 +160,44 @@ public:
     CompiledCircuit(const CompiledCircuit&) = delete;
     CompiledCircuit& operator=(const CompiledCircuit&) = delete;
     ~CompiledCircuit() {
+        if (solver_) b2p_solver_free(solver_);
         if (circuit_) b2p_circuit_free(circuit_);
         if (srs_) b2p_srs_free(srs_);
+    }
+
+    // (*CompiledCircuit).Verify as the reference runs it (algoplonk.go:79-98): `inputs` are the values of the circuit's
+    // public and secret variables in declaration order; the library solves the rest (b2p_solver_solve_dev: a wide
+    // circuit on the GPU, a dependency chain on a host thread), proves from HBM (b2p_prove_dev) and verifies.
+    // Hint-free circuits only in this mirror (its Builder has no hints); throws "constraint #i is not satisfied" like gnark.
+    VerifiedProof<CURVE> VerifyFromInputs(const std::vector<Fr>& inputs, const std::vector<Fr>& blinding, bool self_check = true) {
+        if (blinding.size() != 9) throw Error("9 blinding scalars expected");
+        if (inputs.size() != ccs.input_vars.size()) throw Error("one value per public / secret variable expected");
+        if (!solver_) {
+            std::vector<uint32_t> xa(n, 0), xb(n, 0), xc(n, 0);
+            for (uint32_t i = 0; i < ccs.nb_public; i++) xa[i] = i;
+            for (size_t j = 0; j < ccs.constraints.size(); j++) {
+                xa[ccs.nb_public + j] = ccs.constraints[j].xa;
+                xb[ccs.nb_public + j] = ccs.constraints[j].xb;
+                xc[ccs.nb_public + j] = ccs.constraints[j].xc;
+            }
+            check(b2p_solver_create(CURVE, n, ccs.nb_public, ccs.values.size(), ccs.input_vars.data(),
+                                    (uint32_t)ccs.input_vars.size(), ql_.data(), qr_.data(), qm_.data(), qo_.data(), qk_.data(),
+                                    xa.data(), xb.data(), xc.data(), &solver_), "solver");
+        }
+        void *dL = nullptr, *dR = nullptr, *dO = nullptr;
+        check(b2p_solver_solve_dev(solver_, inputs.data(), B2P_SOLVE_AUTO, &dL, &dR, &dO), "spr.Solve");
+        VerifiedProof<CURVE> vp;
+        vp.raw.resize(b2p_proof_raw_size(CURVE, 0));
+        check(b2p_prove_dev(circuit_, dL, dR, dO, nullptr, nullptr, blinding.data(), vp.raw.data()), "plonk.Prove");
+        vp.witness.assign(inputs.begin(), inputs.begin() + ccs.nb_public);
+        if (self_check) VerifyProof(vp.MarshalProof(), vp.MarshalPublicInputs());
+        return vp;
+    }
+    // utils.SerializeCompiledCircuit (utils/utils.go:97-121) for the circuit half of the key: the library's snapshot,
+    // which Compile(..., snapshot_path) loads back instead of rebuilding the trace
+    void SaveKey(const std::string& path) const {
+        check(b2p_circuit_save(path.c_str(), CURVE, n, ccs.nb_public, ql_.data(), qr_.data(), qm_.data(), qo_.data(),
+                               qk_.data(), perm_.data(), 0, nullptr, nullptr, nullptr, 0), "SerializeCompiledCircuit");
     }
 
     // plonk.Prove alone (algoplonk.go:89 without :93): the explicit opt-out of the self-check below
@@ -218,17 +266,21 @@ public:
     }
 
     template <int C> friend CompiledCircuit<C>* CompileInto(CompiledCircuit<C>*, const SparseR1CS<typename ScalarField<C>::Fr>&,
-                                                           setup::Name, const typename ScalarField<C>::Fr*, const void*, uint64_t);
+                                                           setup::Name, const typename ScalarField<C>::Fr*, const void*, uint64_t,
+                                                           const char*);
 private:
     b2p_srs* srs_ = nullptr;
     b2p_circuit* circuit_ = nullptr;
+    b2p_solver* solver_ = nullptr;
     std::vector<uint8_t> kzg_g2_;
+    std::vector<Fr> ql_, qr_, qm_, qo_, qk_;     // the trace (the solver's rows, SaveKey)
+    std::vector<int64_t> perm_;
 };
 
 template <int CURVE>
 inline CompiledCircuit<CURVE>* CompileInto(CompiledCircuit<CURVE>* cc, const SparseR1CS<typename ScalarField<CURVE>::Fr>& cs,
                                            setup::Name name, const typename ScalarField<CURVE>::Fr* test_tau,
-                                           const void* pk_bin, uint64_t pk_len) {
+                                           const void* pk_bin, uint64_t pk_len, const char* snapshot_path = nullptr) {
     using Fr = typename ScalarField<CURVE>::Fr;
     if ((int)name < 0 || (int)name > (int)setup::Name::DuskBLS12381) throw Error("unknown setup");   // compile_test.go:22-30
     if (setup::curve_of(name) != CURVE) throw Error("curve and trusted setup do not match");          // algoplonk.go:46-48
@@ -263,8 +315,13 @@ inline CompiledCircuit<CURVE>* CompileInto(CompiledCircuit<CURVE>* cc, const Spa
     }
     for (uint64_t i = 0; i < 3 * n; i++)
         if (perm[i] == -1) perm[i] = cycle[lro[i]];
-    check(b2p_circuit_load(cc->srs_, n, cs.nb_public, ql.data(), qr.data(), qm.data(), qo.data(), qk.data(), perm.data(), 0,
-                           nullptr, nullptr, nullptr, 0, &cc->circuit_), "plonk.Setup");
+    // utils.DeserializeCompiledCircuit (utils/utils.go:124-157): a snapshot written by SaveKey goes from the page cache
+    // to HBM; without one (or if it does not load) the columns built above are uploaded
+    if (!snapshot_path || b2p_circuit_load_file(cc->srs_, snapshot_path, &cc->circuit_) != B2P_OK)
+        check(b2p_circuit_load(cc->srs_, n, cs.nb_public, ql.data(), qr.data(), qm.data(), qo.data(), qk.data(), perm.data(), 0,
+                               nullptr, nullptr, nullptr, 0, &cc->circuit_), "plonk.Setup");
+    cc->ql_ = std::move(ql); cc->qr_ = std::move(qr); cc->qm_ = std::move(qm); cc->qo_ = std::move(qo); cc->qk_ = std::move(qk);
+    cc->perm_ = std::move(perm);
     return cc;
 }
 
@@ -272,8 +329,9 @@ inline CompiledCircuit<CURVE>* CompileInto(CompiledCircuit<CURVE>* cc, const Spa
 // the embedded setup/<name>/pk.bin.
 template <int CURVE>
 inline void Compile(CompiledCircuit<CURVE>& out, const SparseR1CS<typename ScalarField<CURVE>::Fr>& cs, setup::Name name,
-                    const typename ScalarField<CURVE>::Fr* test_tau = nullptr, const void* pk_bin = nullptr, uint64_t pk_len = 0) {
-    CompileInto<CURVE>(&out, cs, name, test_tau, pk_bin, pk_len);
+                    const typename ScalarField<CURVE>::Fr* test_tau = nullptr, const void* pk_bin = nullptr, uint64_t pk_len = 0,
+                    const char* snapshot_path = nullptr) {
+    CompileInto<CURVE>(&out, cs, name, test_tau, pk_bin, pk_len, snapshot_path);
 }
 
 }  // namespace algoplonk

@@ -13,10 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
-def _build(tmp_path_factory):
-    out = tmp_path_factory.mktemp("cpp") / "basic"
+def _build(tmp_path_factory, name="basic"):
+    out = tmp_path_factory.mktemp("cpp") / name
     lib_dir = os.path.join(ROOT, "algoplonk_b200")
-    subprocess.run([GXX, "-O2", "-std=c++17", "-o", str(out), os.path.join(ROOT, "examples", "cpp", "basic.cpp"),
+    subprocess.run([GXX, "-O2", "-std=c++17", "-o", str(out), os.path.join(ROOT, "examples", "cpp", name + ".cpp"),
                     "-L" + lib_dir, "-lb200plonk", "-Wl,-rpath," + lib_dir], check=True)
     return str(out)
 
@@ -45,3 +45,19 @@ def test_cpp_mirror_reproduces_golden_basic_proof(gpu, tmp_path_factory, curve):
     proof_hex, public_hex = out.stdout.split()
     assert proof_hex == case["proof"]
     assert public_hex == case["public_inputs"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("curve", ("BN254", "BLS12_381"))
+def test_cpp_caller_solver_and_persisted_key(gpu, tmp_path_factory, tmp_path, curve):
+    """examples/cpp/bench_prove.cpp: a compiled caller proves the squaring chain from pageable columns, from the
+    circuit's inputs alone (library solver, L R O in HBM) and from a reloaded key snapshot -- one proof, three ways --
+    and a wrong input is refused with gnark's message."""
+    import json
+    exe = _build(tmp_path_factory, "bench_prove")
+    out = subprocess.run([exe, curve, "12", "3", str(tmp_path / "key.b2pk")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout)
+    assert line["same_bytes"] and line["bad_input_rejected"] and line["log2"] == 12
+    assert os.path.getsize(tmp_path / "key.b2pk") == 64 + 5 * 32 * 4096 + 3 * 8 * 4096
+
