@@ -488,7 +488,7 @@ class Solver:
         records hints."""
         if cs.input_vars is None:
             raise ValueError("the constraint system does not say which variables are inputs")
-        if (cs.commitments or cs.hints) and not cs.hints:
+        if cs.commitments and not cs.hints:
             raise ValueError("circuits with BSB22 commitments need the commitment hint recorded in the constraint system")
         if cs.hints and hint_fn is None:
             raise ValueError("the circuit uses solver hints: pass hint_fn")
