@@ -38,9 +38,10 @@ METRIC = "plonk_proofs_per_sec"
 UNIT = "proofs/s"
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_msm_accumulate launch, from `ncu --set full` captures
-# (profiles/ncu_r1_full_summary.csv; the kernel is unchanged since), keyed by (curve, log2 rows): the gather reads W = 13
+# (profiles/ncu_r2_accum_summary.csv; round 1's capture read the same), keyed by (curve, log2 rows): the gather reads W = 13
 # table points per scalar, so ~13x the algorithmic bytes.  A configuration nobody captured reports null and says so.
-ACCUM_DRAM_TRAFFIC = {("BN254", 20): 1_872_500_000}
+ACCUM_DRAM_TRAFFIC = {("BN254", 20): 1_873_200_000,        # 1.8033 GB read + 69.9 MB written
+                      ("BLS12_381", 20): 2_724_300_000}    # 2.6286 GB read + 95.7 MB written
 # The roof that binds the accumulation: the SM's multiplier pipe.  IMAD issues at 1.84e13 lanes/s on 148 SMs
 # (tools/microbench.cu, profiles/microbench_r2.json); a 32x32->64 product takes two such slots in whichever form ptxas
 # emits it (IMAD.WIDE.U32.X, measured at half the IMAD rate, or IMAD + IMAD.HI).  One XYZZ mixed addition executes
@@ -495,7 +496,7 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic,
                 "traffic_source": ("ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one launch "
-                                   "(profiles/ncu_r1_full_summary.csv)" if traffic else
+                                   "(profiles/ncu_r2_accum_summary.csv; round 1 read the same: ncu_r1_full_summary.csv)" if traffic else
                                    f"null: no ncu --set full capture exists for ({curve}, 2^{args.log2})"),
                 "peak_source": peak_src, "launch_ms": accum_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "measured_in": "the one-proof-at-a-time pass (CUDA events around every launch of the kernel)",
