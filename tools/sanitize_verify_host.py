@@ -1,7 +1,7 @@
 """AddressSanitizer + UndefinedBehaviorSanitizer, then ThreadSanitizer, over the host verifier (csrc/verify_host.hpp, pairing_host.hpp,
 verify.cu): the translation unit is rebuilt with g++ -fsanitize=address,undefined next to a few extern "C" wrappers,
-and every golden proof, a tampered copy of each, the pairing on the ceremony files and the vk.bin decoder (good and
-damaged input) go through it.  CPU only.
+and every golden proof, a tampered copy of each, the pairing on the ceremony files, the vk.bin decoder and the
+persisted-key parsers of keyfile.hpp (good and damaged input) go through it.  CPU only.
 
     python tools/sanitize_verify_host.py          # prints "sanitizers: 0 reports" and exits 0 when clean
 """
@@ -38,6 +38,10 @@ int s_pairing(int curve, const void* g1s, const void* g2s, uint64_t n) {
 }
 int s_vk_load(int curve, const void* in, uint64_t len, void* g2, void* g1) { return host_kzg_vk_load(curve, in, len, g2, g1) ? 1 : 0; }
 void s_g2_unsafe(int curve, const void* tau, void* out) { host_g2_unsafe(curve, tau, out); }
+// persisted keys (keyfile.hpp): parsers of file input
+int s_file_parse(const void* f, uint64_t len, b2p_gnark_file* out) { return host_gnark_file_parse(f, len, out) ? 1 : 0; }
+int s_vk_parse(int curve, const void* b, uint64_t len, b2p_gnark_vk* out) { return host_gnark_vk_parse(curve, b, len, out) ? 1 : 0; }
+int s_pk_parse(int curve, const void* b, uint64_t len, b2p_gnark_pk* out) { return host_gnark_pk_parse(curve, b, len, out) ? 1 : 0; }
 }
 """
 
@@ -105,8 +109,38 @@ def workload(lib_path):
         assert lib.s_pairing(cid, buf(g1s), g2, C.c_uint64(2)) == 1
         out = C.create_string_buffer(8 * nb)
         lib.s_g2_unsafe(cid, buf(api.fr_to_mont_bytes(curve, [cv.r - 1])), out)
+    # persisted keys: the gob container and gnark's key layouts, good input and a few thousand damaged copies
+    # (bit flips, truncations, garbage): any verdict, no report; exact-length heap copies so that an over-read shows
+    import gnark_format as gf
+    import test_keyfile as TK
+    from algoplonk_b200 import _lib
+    n_keys = 0
+    for curve in ("BN254", "BLS12_381"):
+        cid = api.CURVE_ID[curve]
+        key = TK._key(curve, 2)
+        blob = gf.compiled_circuit_bytes(b"\xa1ccs-bytes", key["pk"], key["vk"], gf.ECC_ID[curve])
+        fi, vki, pki = _lib.GnarkFile(), _lib.GnarkVk(), _lib.GnarkPk()
+        assert lib.s_file_parse(buf(blob), C.c_uint64(len(blob)), C.byref(fi)) == 0
+        assert lib.s_vk_parse(cid, buf(key["vk"]), C.c_uint64(len(key["vk"])), C.byref(vki)) == 0 and vki.k == 2
+        assert lib.s_pk_parse(cid, buf(key["pk"]), C.c_uint64(len(key["pk"])), C.byref(pki)) == 0
+        rng = random.Random(cid)
+        for data, fn in ((blob, lambda d: lib.s_file_parse(buf(d), C.c_uint64(len(d)), C.byref(fi))),
+                         (key["vk"], lambda d: lib.s_vk_parse(cid, buf(d), C.c_uint64(len(d)), C.byref(vki))),
+                         (key["pk"], lambda d: lib.s_pk_parse(cid, buf(d), C.c_uint64(len(d)), C.byref(pki)))):
+            for cut in list(range(0, min(len(data), 300))) + [len(data) - j for j in range(1, 40)]:
+                fn(data[:cut]) if cut else None
+                n_keys += 1
+            for _ in range(400):
+                bad = bytearray(data)
+                for _ in range(rng.randrange(1, 4)):
+                    bad[rng.randrange(len(bad))] ^= 1 << rng.randrange(8)
+                fn(bytes(bad))
+                n_keys += 1
+            for _ in range(50):
+                fn(bytes(rng.randrange(256) for _ in range(rng.randrange(1, 400))))
+                n_keys += 1
     print(f"sanitizers: 0 reports ({n_ok} proofs accepted, {n_bad} tampered proofs rejected, vk.bin fuzzed, "
-          f"ceremony pairings checked)")
+          f"ceremony pairings checked, {n_keys} damaged key files / keys parsed)")
 
 
 if __name__ == "__main__":
